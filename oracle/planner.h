@@ -1,0 +1,50 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+//
+// One planning problem end to end on the CPU: reach-set build (KPR/armour_main.cu:86-216),
+// collision hyper-planes (KPR/CollisionChecking.cu:26-39,136-228), the NLP rows and Jacobian
+// (KPR/NLPclass.cu:45-396, KPR/CollisionChecking.cu:230-299), bounds and the feasibility verdict
+// (KPR/NLPclass.cu:116-165,449-537), cost and cost gradient (:207-268).
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "dynamics.h"
+
+namespace orc {
+
+constexpr int kBufGen = 9;   // 3 obstacle generators + 3 link generators + 3 radius generators
+constexpr int kComb = 36;    // C(9,2)
+
+struct Problem {
+    RobotModel model;
+    PlannerParams params;
+    int T = 0, NJ = 0, O = 0;
+    std::unique_ptr<BezierCurve> traj;
+    std::unique_ptr<KinematicsDynamics> kd;
+    std::vector<double> link_gens;      // [T*NJ][18] column-major 3x6        (armour_main.cu:113,126)
+    std::vector<double> torque_radius;  // [NF*T], index j*T + t               (armour_main.cu:168-201)
+    std::vector<double> obstacles;      // [O*12]: c, g1, g2, g3
+    std::vector<double> A, d, delta;    // [((t*NJ + l)*O + o)*36 + p] (A has 3 per entry)
+    std::vector<double> link_sliced_center;     // [T*NJ*3]   (NLPclass.h:150)
+    std::vector<double> dk_link_sliced_center;  // [T*NJ*NF*3]
+    Stats stats;
+    double build_ms = 0;
+
+    Problem(int model_id, const PlannerParams& p);
+    // armour_main.cu sections II.A-II.D.  nthreads <= 0: OpenMP default.
+    void build(const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int nobs, int nthreads);
+    int num_constraints() const { return NF * T + NJ * T * O + NF * 4; }
+    void eval_g(const double* k, double* g);                 // NLPclass.cu:272-324
+    void eval_jac_g(const double* k, double* values);        // NLPclass.cu:330-396
+    void bounds(double* g_l, double* g_u) const;             // NLPclass.cu:116-165
+    // verdict of finalize_solution: returns 1 feasible / 0 infeasible; first violated row or -1
+    int verdict(const double* g, int* first_violation) const;  // NLPclass.cu:449-537
+    double cost(const double* q_des, const double* k) const;    // NLPclass.cu:207-236
+    void cost_grad(const double* q_des, const double* k, double* grad) const;  // :241-268
+
+private:
+    void init_hyperplanes();
+    void link_constraints(bool with_grad, double* link_c, double* grad_link_c);
+};
+
+}  // namespace orc
