@@ -1,0 +1,616 @@
+// C ABI of libarmour_b200.so (see include/armour_b200.h).  One translation unit: the kernels are
+// included below so they share the __constant__ block.  No CPU fallback anywhere: every compute entry
+// point launches CUDA kernels on the context's stream and reports CUDA errors as ARMOUR_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/armour_b200.h"
+#include "bezier.cuh"
+#include "device_constants.cuh"
+#include "k1_reachsets.cuh"
+#include "k3_constraints.cuh"
+#include "layout.h"
+
+using namespace armour;
+
+struct armour_ctx {
+    armour_config cfg;
+    RobotConstants rc;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    Batch B;                 // device pointers + dimensions of the current batch
+    int built_nprob = 0;     // problems with valid reach sets
+    size_t hp_capacity = 0;  // doubles allocated for B.hp
+    size_t obs_capacity = 0;
+    double* d_in = nullptr;  // [3][max_problems][NF] q0, qd0, qdd0
+    double* d_obs = nullptr;
+    double* d_k = nullptr;   // staging for the host-pointer evaluation calls
+    double* d_g = nullptr;
+    double* d_jac = nullptr;
+    size_t g_capacity = 0, jac_capacity = 0;
+    int* d_verdict = nullptr;  // [2][max_problems]
+    K1Scratch k1;
+    long long launches = 0;
+    std::string last_error;
+    std::vector<double> h_torque_radius;  // host mirror of problem 0..built_nprob-1 (lazy)
+    bool h_torque_valid = false;
+    std::vector<double> h_q0, h_qd0, h_qdd0;
+};
+
+namespace {
+
+int fail(armour_ctx* c, int code, const std::string& msg) {
+    if (c) c->last_error = msg;
+    return code;
+}
+#define CU(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(ctx, ARMOUR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+int ensure_eval_buffers(armour_ctx* ctx, int nprob, bool need_g, bool need_jac) {
+    const size_t m = size_t(ctx->B.m());
+    if (need_g && ctx->g_capacity < nprob * m) {
+        if (ctx->d_g) cudaFree(ctx->d_g);
+        ctx->d_g = nullptr;
+        CU(dalloc(&ctx->d_g, nprob * m));
+        ctx->g_capacity = nprob * m;
+    }
+    if (need_jac && ctx->jac_capacity < nprob * m * NF) {
+        if (ctx->d_jac) cudaFree(ctx->d_jac);
+        ctx->d_jac = nullptr;
+        CU(dalloc(&ctx->d_jac, nprob * m * NF));
+        ctx->jac_capacity = nprob * m * NF;
+    }
+    return ARMOUR_OK;
+}
+
+int ensure_obstacle_buffers(armour_ctx* ctx, int nprob, int nobs) {
+    const size_t need_obs = size_t(nprob) * nobs * 12;
+    if (ctx->obs_capacity < need_obs) {
+        if (ctx->d_obs) cudaFree(ctx->d_obs);
+        ctx->d_obs = nullptr;
+        CU(dalloc(&ctx->d_obs, need_obs));
+        ctx->obs_capacity = need_obs;
+    }
+    Batch& B = ctx->B;
+    B.O = nobs;
+    B.nprob = nprob;
+    const size_t need_hp = size_t(nprob) * (B.T / TB) * B.hp_chunk();
+    if (ctx->hp_capacity < need_hp) {
+        if (B.hp) cudaFree(B.hp);
+        B.hp = nullptr;
+        CU(dalloc(&B.hp, need_hp));
+        ctx->hp_capacity = need_hp;
+    }
+    B.obstacles = ctx->d_obs;
+    return ARMOUR_OK;
+}
+
+int check_batch(armour_ctx* ctx, int nprob, int nobs) {
+    if (!ctx) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->cfg.max_problems)
+        return fail(ctx, ARMOUR_ERR_STATE, "nprob outside [1, max_problems]");
+    if (nobs < 0) return fail(ctx, ARMOUR_ERR_ARG, "negative obstacle count");
+    if (nobs > ctx->cfg.max_obstacles)
+        return fail(ctx, ARMOUR_ERR_OBSTACLES, "number of obstacles larger than max_obstacles");
+    return ARMOUR_OK;
+}
+
+int fetch_torque_radius(armour_ctx* ctx) {
+    if (ctx->h_torque_valid) return ARMOUR_OK;
+    const size_t n = size_t(ctx->built_nprob) * NF * ctx->B.T;
+    ctx->h_torque_radius.resize(n);
+    CU(cudaMemcpyAsync(ctx->h_torque_radius.data(), ctx->B.torque_radius, n * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->h_torque_valid = true;
+    return ARMOUR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int armour_abi_version(void) { return ARMOUR_ABI_VERSION; }
+
+const char* armour_status_string(int s) {
+    switch (s) {
+        case ARMOUR_OK: return "ok";
+        case ARMOUR_ERR_ARG: return "invalid argument";
+        case ARMOUR_ERR_CUDA: return "CUDA error";
+        case ARMOUR_ERR_OBSTACLES: return "too many obstacles";
+        case ARMOUR_ERR_CAPACITY: return "monomial table capacity exceeded";
+        case ARMOUR_ERR_STATE: return "invalid call order or batch size";
+        case ARMOUR_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+int armour_config_default(armour_config* cfg) {
+    if (!cfg) return ARMOUR_ERR_ARG;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = int(sizeof(armour_config));
+    cfg->device = 0;
+    cfg->robot_model = 0;
+    cfg->num_time_steps = 128;
+    cfg->max_obstacles = 40;
+    cfg->max_problems = 1;
+    cfg->cap_link_monomials = 32;
+    cfg->cap_torque_monomials = 64;
+    cfg->cap_work_monomials = 768;
+    cfg->simplify_threshold = 5e-4;
+    for (int i = 0; i < NF; i++) cfg->k_range[i] = M_PI / 48;
+    cfg->mass_uncertainty = -1;
+    cfg->inertia_uncertainty = -1;
+    return ARMOUR_OK;
+}
+
+int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
+    if (!cfg || !out) return ARMOUR_ERR_ARG;
+    *out = nullptr;
+    if (cfg->struct_size != int(sizeof(armour_config))) return ARMOUR_ERR_ARG;
+    if (cfg->num_time_steps < TB || cfg->num_time_steps > 128 || cfg->num_time_steps % TB != 0) return ARMOUR_ERR_ARG;
+    if (cfg->max_problems < 1 || cfg->max_obstacles < 0) return ARMOUR_ERR_ARG;
+    if (cfg->robot_model < 0 || cfg->robot_model > 1) return ARMOUR_ERR_ARG;
+    if (cfg->cap_link_monomials < 1 || cfg->cap_torque_monomials < 1 || cfg->cap_work_monomials < 64)
+        return ARMOUR_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) return ARMOUR_ERR_CUDA;
+    armour_ctx* ctx = new (std::nothrow) armour_ctx();
+    if (!ctx) return ARMOUR_ERR_NOMEM;
+    ctx->cfg = *cfg;
+    ctx->rc = make_robot_constants(cfg->robot_model);
+    ctx->rc.num_time_steps = cfg->num_time_steps;
+    ctx->rc.simplify_threshold = cfg->simplify_threshold;
+    for (int i = 0; i < NF; i++) ctx->rc.k_range[i] = cfg->k_range[i];
+    if (cfg->mass_uncertainty >= 0) ctx->rc.mass_uncertainty = cfg->mass_uncertainty;
+    if (cfg->inertia_uncertainty >= 0) ctx->rc.inertia_uncertainty = cfg->inertia_uncertainty;
+
+    auto bail = [&](const char* what, cudaError_t e) {
+        std::fprintf(stderr, "armour_ctx_create: %s: %s\n", what, cudaGetErrorString(e));
+        armour_ctx_destroy(ctx);
+        return ARMOUR_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
+    ctx->stream = ctx->own_stream;
+    if ((e = upload_constants(ctx->rc, ctx->stream)) != cudaSuccess) return bail("upload_constants", e);
+
+    Batch& B = ctx->B;
+    std::memset(&B, 0, sizeof(B));
+    B.T = cfg->num_time_steps;
+    B.NJ = ctx->rc.num_joints;
+    B.capL = cfg->cap_link_monomials;
+    B.capU = cfg->cap_torque_monomials;
+    const size_t P = size_t(cfg->max_problems), T = size_t(B.T), NJ = size_t(B.NJ);
+#define ALLOC(ptr, n) \
+    if ((e = dalloc(&ptr, (n))) != cudaSuccess) return bail(#ptr, e)
+    ALLOC(ctx->d_in, 3 * P * NF);
+    ALLOC(B.link_n, P * T * NJ);
+    ALLOC(B.link_c, P * T * NJ * 3);
+    ALLOC(B.link_key, P * T * NJ * B.capL);
+    ALLOC(B.link_g, P * T * NJ * B.capL * 3);
+    ALLOC(B.u_n, P * T * NF);
+    ALLOC(B.u_c, P * T * NF);
+    ALLOC(B.u_r, P * T * NF);
+    ALLOC(B.u_key, P * T * NF * B.capU);
+    ALLOC(B.u_g, P * T * NF * B.capU);
+    ALLOC(B.torque_radius, P * NF * T);
+    ALLOC(B.link_gens, P * T * NJ * 18);
+    ALLOC(B.link_sliced, P * T * NJ * 3);
+    ALLOC(B.status, P);
+    ALLOC(ctx->d_k, P * NF);
+    ALLOC(ctx->d_verdict, 2 * P);
+#undef ALLOC
+    B.q0 = ctx->d_in;
+    B.qd0 = ctx->d_in + P * NF;
+    B.qdd0 = ctx->d_in + 2 * P * NF;
+    if ((e = cudaMemsetAsync(B.status, 0, P * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = k1_scratch_create(&ctx->k1, ctx->cfg, ctx->rc, ctx->stream)) != cudaSuccess) return bail("k1 scratch", e);
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("sync", e);
+    *out = ctx;
+    return ARMOUR_OK;
+}
+
+int armour_ctx_destroy(armour_ctx* ctx) {
+    if (!ctx) return ARMOUR_OK;
+    cudaSetDevice(ctx->cfg.device);
+    Batch& B = ctx->B;
+    void* ptrs[] = {ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
+                    B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.hp,
+                    B.link_sliced, B.status};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    k1_scratch_destroy(&ctx->k1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return ARMOUR_OK;
+}
+
+int armour_ctx_set_stream(armour_ctx* ctx, void* s) {
+    if (!ctx) return ARMOUR_ERR_ARG;
+    ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+    return ARMOUR_OK;
+}
+int armour_ctx_synchronize(armour_ctx* ctx) {
+    if (!ctx) return ARMOUR_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+const char* armour_last_error(const armour_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+long long armour_kernel_launches(const armour_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int armour_num_joints(const armour_ctx* ctx) { return ctx ? ctx->B.NJ : ARMOUR_ERR_ARG; }
+int armour_num_time_steps(const armour_ctx* ctx) { return ctx ? ctx->B.T : ARMOUR_ERR_ARG; }
+int armour_num_constraints(const armour_ctx* ctx, int nobs) {
+    if (!ctx || nobs < 0) return ARMOUR_ERR_ARG;
+    return NF * ctx->B.T + ctx->B.NJ * ctx->B.T * nobs + 4 * NF;
+}
+
+// ---- build -----------------------------------------------------------------------------------------
+int armour_batch_reachsets_build_device(armour_ctx* ctx, int nprob, const double* d_q0, const double* d_qd0,
+                                        const double* d_qdd0, const double* d_obstacles, int nobs) {
+    int rc = check_batch(ctx, nprob, nobs);
+    if (rc) return rc;
+    if (!d_q0 || !d_qd0 || !d_qdd0 || (nobs > 0 && !d_obstacles)) return fail(ctx, ARMOUR_ERR_ARG, "null input");
+    CU(cudaSetDevice(ctx->cfg.device));
+    rc = ensure_obstacle_buffers(ctx, nprob, nobs);
+    if (rc) return rc;
+    const size_t P = size_t(ctx->cfg.max_problems);
+    const size_t nb = size_t(nprob) * NF * sizeof(double);
+    CU(cudaMemcpyAsync(ctx->d_in, d_q0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_in + P * NF, d_qd0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_in + 2 * P * NF, d_qdd0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nobs > 0)
+        CU(cudaMemcpyAsync(ctx->d_obs, d_obstacles, size_t(nprob) * nobs * 12 * sizeof(double),
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    int nl = 0;
+    CU(launch_reachsets(ctx->B, ctx->k1, ctx->stream, &nl));
+    ctx->launches += nl;
+    CU(launch_hyperplanes(ctx->B, ctx->stream));
+    ctx->launches += (nobs > 0);
+    ctx->built_nprob = nprob;
+    ctx->h_torque_valid = false;
+    ctx->h_q0.clear();
+    return ARMOUR_OK;
+}
+
+int armour_batch_reachsets_build(armour_ctx* ctx, int nprob, const double* q0, const double* qd0, const double* qdd0,
+                                 const double* obstacles, int nobs) {
+    int rc = check_batch(ctx, nprob, nobs);
+    if (rc) return rc;
+    if (!q0 || !qd0 || !qdd0 || (nobs > 0 && !obstacles)) return fail(ctx, ARMOUR_ERR_ARG, "null input");
+    CU(cudaSetDevice(ctx->cfg.device));
+    rc = ensure_obstacle_buffers(ctx, nprob, nobs);
+    if (rc) return rc;
+    const size_t P = size_t(ctx->cfg.max_problems);
+    const size_t nb = size_t(nprob) * NF * sizeof(double);
+    CU(cudaMemcpyAsync(ctx->d_in, q0, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_in + P * NF, qd0, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_in + 2 * P * NF, qdd0, nb, cudaMemcpyHostToDevice, ctx->stream));
+    if (nobs > 0)
+        CU(cudaMemcpyAsync(ctx->d_obs, obstacles, size_t(nprob) * nobs * 12 * sizeof(double), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    int nl = 0;
+    CU(launch_reachsets(ctx->B, ctx->k1, ctx->stream, &nl));
+    ctx->launches += nl;
+    CU(launch_hyperplanes(ctx->B, ctx->stream));
+    ctx->launches += (nobs > 0);
+    ctx->built_nprob = nprob;
+    ctx->h_torque_valid = false;
+    ctx->h_q0.assign(q0, q0 + size_t(nprob) * NF);
+    ctx->h_qd0.assign(qd0, qd0 + size_t(nprob) * NF);
+    ctx->h_qdd0.assign(qdd0, qdd0 + size_t(nprob) * NF);
+    // surface capacity overflows of the build (never truncate silently)
+    std::vector<int> st(nprob);
+    CU(cudaMemcpyAsync(st.data(), ctx->B.status, nprob * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < nprob; p++)
+        if (st[p] != 0)
+            return fail(ctx, ARMOUR_ERR_CAPACITY,
+                        "reach-set build overflowed a monomial table (problem " + std::to_string(p) + ", code " +
+                            std::to_string(st[p]) + ")");
+    return ARMOUR_OK;
+}
+
+int armour_reachsets_build(armour_ctx* ctx, const double* q0, const double* qd0, const double* qdd0,
+                           const double* obstacles, int nobs) {
+    return armour_batch_reachsets_build(ctx, 1, q0, qd0, qdd0, obstacles, nobs);
+}
+
+int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out) {
+    if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
+    CU(cudaMemcpyAsync(out, ctx->B.status, nprob * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+
+// ---- evaluate --------------------------------------------------------------------------------------
+int armour_batch_eval_device(armour_ctx* ctx, int nprob, const double* d_k, double* d_g, double* d_values) {
+    if (!ctx || !d_k) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "evaluate before build");
+    CU(cudaSetDevice(ctx->cfg.device));
+    Batch B = ctx->B;
+    B.nprob = nprob;
+    CU(launch_constraints(B, d_k, d_g, d_values, ctx->stream));
+    ctx->launches += 1;
+    return ARMOUR_OK;
+}
+
+int armour_batch_eval(armour_ctx* ctx, int nprob, const double* k, double* g, double* values) {
+    if (!ctx || !k) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "evaluate before build");
+    CU(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_eval_buffers(ctx, nprob, g != nullptr, values != nullptr);
+    if (rc) return rc;
+    const size_t m = size_t(ctx->B.m());
+    CU(cudaMemcpyAsync(ctx->d_k, k, size_t(nprob) * NF * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = armour_batch_eval_device(ctx, nprob, ctx->d_k, g ? ctx->d_g : nullptr, values ? ctx->d_jac : nullptr);
+    if (rc) return rc;
+    if (g) CU(cudaMemcpyAsync(g, ctx->d_g, nprob * m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (values)
+        CU(cudaMemcpyAsync(values, ctx->d_jac, nprob * m * NF * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+
+int armour_eval_g(armour_ctx* ctx, const double* k, double* g) { return armour_batch_eval(ctx, 1, k, g, nullptr); }
+int armour_eval_jac_g(armour_ctx* ctx, const double* k, double* values) {
+    return armour_batch_eval(ctx, 1, k, nullptr, values);
+}
+int armour_eval_g_jac(armour_ctx* ctx, const double* k, double* g, double* values) {
+    return armour_batch_eval(ctx, 1, k, g, values);
+}
+
+int armour_batch_verdict_device(armour_ctx* ctx, int nprob, const double* d_g, int* d_feasible, int* d_first) {
+    if (!ctx || !d_g || !d_feasible || !d_first) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "verdict before build");
+    Batch B = ctx->B;
+    B.nprob = nprob;
+    CU(launch_verdict(B, d_g, d_feasible, d_first, ctx->stream));
+    ctx->launches += 1;
+    return ARMOUR_OK;
+}
+
+// ---- getters ---------------------------------------------------------------------------------------
+int armour_batch_get_torque_radius(armour_ctx* ctx, int nprob, double* out) {
+    if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
+    int rc = fetch_torque_radius(ctx);
+    if (rc) return rc;
+    std::memcpy(out, ctx->h_torque_radius.data(), size_t(nprob) * NF * ctx->B.T * sizeof(double));
+    return ARMOUR_OK;
+}
+int armour_get_torque_radius(armour_ctx* ctx, double* out) { return armour_batch_get_torque_radius(ctx, 1, out); }
+
+int armour_batch_get_link_independent_generators(armour_ctx* ctx, int nprob, double* out) {
+    if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
+    CU(cudaMemcpyAsync(out, ctx->B.link_gens, size_t(nprob) * ctx->B.T * ctx->B.NJ * 18 * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+int armour_get_link_independent_generators(armour_ctx* ctx, double* out) {
+    return armour_batch_get_link_independent_generators(ctx, 1, out);
+}
+
+int armour_get_link_sliced_center(armour_ctx* ctx, double* out) {
+    if (!ctx || !out || ctx->built_nprob < 1) return ARMOUR_ERR_ARG;
+    CU(cudaMemcpyAsync(out, ctx->B.link_sliced, size_t(ctx->B.T) * ctx->B.NJ * 3 * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+
+int armour_batch_get_bounds(armour_ctx* ctx, int nprob, double* g_l, double* g_u) {  // KPR/NLPclass.cu:116-165
+    if (!ctx || !g_l || !g_u || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
+    int rc = fetch_torque_radius(ctx);
+    if (rc) return rc;
+    const RobotConstants& R = ctx->rc;
+    const int T = ctx->B.T, NJ = ctx->B.NJ, O = ctx->B.O, m = ctx->B.m();
+    for (int p = 0; p < nprob; p++) {
+        double* gl = g_l + size_t(p) * m;
+        double* gu = g_u + size_t(p) * m;
+        const double* tr = ctx->h_torque_radius.data() + size_t(p) * NF * T;
+        for (int t = 0; t < T; t++)
+            for (int j = 0; j < NF; j++) {
+                gl[t * NF + j] = -R.torque_limits[j] + tr[j * T + t];
+                gu[t * NF + j] = R.torque_limits[j] - tr[j * T + t];
+            }
+        int off = NF * T;
+        for (int i = off; i < off + T * NJ * O; i++) {
+            gl[i] = -1e19;
+            gu[i] = 0;
+        }
+        off += T * NJ * O;
+        for (int rep = 0; rep < 2; rep++, off += NF)
+            for (int i = 0; i < NF; i++) {
+                gl[off + i] = R.state_limits_lb[i] + R.qe;
+                gu[off + i] = R.state_limits_ub[i] - R.qe;
+            }
+        for (int rep = 0; rep < 2; rep++, off += NF)
+            for (int i = 0; i < NF; i++) {
+                gl[off + i] = -R.speed_limits[i] + R.qde;
+                gu[off + i] = R.speed_limits[i] - R.qde;
+            }
+    }
+    return ARMOUR_OK;
+}
+int armour_get_bounds(armour_ctx* ctx, double* g_l, double* g_u) { return armour_batch_get_bounds(ctx, 1, g_l, g_u); }
+
+int armour_verdict(armour_ctx* ctx, const double* g, int* feasible, int* first_violation) {  // KPR/NLPclass.cu:449-537
+    if (!ctx || !g || !feasible || ctx->built_nprob < 1) return ARMOUR_ERR_ARG;
+    int rc = fetch_torque_radius(ctx);
+    if (rc) return rc;
+    const RobotConstants& R = ctx->rc;
+    const int T = ctx->B.T, NJ = ctx->B.NJ, O = ctx->B.O;
+    const double* tr = ctx->h_torque_radius.data();
+    auto done = [&](int ok, int row) {
+        *feasible = ok;
+        if (first_violation) *first_violation = row;
+        return ARMOUR_OK;
+    };
+    for (int t = 0; t < T; t++)
+        for (int j = 0; j < NF; j++) {
+            const double v = g[t * NF + j];
+            if (v < -R.torque_limits[j] + tr[j * T + t] - R.torque_violation_threshold ||
+                v > R.torque_limits[j] - tr[j * T + t] + R.torque_violation_threshold)
+                return done(0, t * NF + j);
+        }
+    int off = NF * T;
+    for (int i = 0; i < NJ * T * O; i++)
+        if (g[off + i] > R.collision_violation_threshold) return done(0, off + i);
+    off += NJ * T * O;
+    for (int rep = 0; rep < 2; rep++, off += NF)
+        for (int i = 0; i < NF; i++)
+            if (g[off + i] < R.state_limits_lb[i] + R.qe || g[off + i] > R.state_limits_ub[i] - R.qe)
+                return done(0, off + i);
+    for (int rep = 0; rep < 2; rep++, off += NF)
+        for (int i = 0; i < NF; i++)
+            if (g[off + i] < -R.speed_limits[i] + R.qde || g[off + i] > R.speed_limits[i] - R.qde)
+                return done(0, off + i);
+    return done(1, -1);
+}
+
+int armour_cost(armour_ctx* ctx, const double* q_des, const double* k, double* obj, double* grad) {
+    if (!ctx || !q_des || !k || ctx->built_nprob < 1 || ctx->h_q0.empty()) return ARMOUR_ERR_ARG;
+    const RobotConstants& R = ctx->rc;
+    auto wrap = [](double a) {  // KPR/NLPclass.cu:6-15
+        while (a < -M_PI) a += 2 * M_PI;
+        while (a > M_PI) a -= 2 * M_PI;
+        return a;
+    };
+    const double tp = R.t_plan, D = R.duration;
+    double qp[NF];
+    for (int i = 0; i < NF; i++)
+        qp[i] = bez_q(ctx->h_q0[i], ctx->h_qd0[i] * D, ctx->h_qdd0[i] * D * D, R.k_range[i] * k[i], tp);
+    if (obj) {  // KPR/NLPclass.cu:222-233
+        double v = pw2(wrap(q_des[0] - qp[0])) + pw2(wrap(q_des[2] - qp[2])) + pw2(wrap(q_des[4] - qp[4])) +
+                   pw2(wrap(q_des[6] - qp[6])) + pw2(q_des[1] - qp[1]) + pw2(q_des[3] - qp[3]) + pw2(q_des[5] - qp[5]);
+        *obj = v * R.cost_scale;
+    }
+    if (grad) {  // KPR/NLPclass.cu:252-264
+        for (int i = 0; i < NF; i++) {
+            const double dk = pw3(tp) * (6 * pw2(tp) - 15 * tp + 10) * R.k_range[i];
+            grad[i] = (i % 2 == 0) ? (2 * wrap(qp[i] - q_des[i]) * dk) : (2 * (qp[i] - q_des[i]) * dk);
+            grad[i] *= R.cost_scale;
+        }
+    }
+    return ARMOUR_OK;
+}
+
+// ---- reach-set tables ------------------------------------------------------------------------------
+int armour_export_reachsets(armour_ctx* ctx, int prob, armour_reachset_tables* out) {
+    if (!ctx || !out || prob < 0 || prob >= ctx->built_nprob) return ARMOUR_ERR_ARG;
+    const Batch& B = ctx->B;
+    const size_t T = B.T, NJ = B.NJ;
+    if (out->cap_link < B.capL || out->cap_u < B.capU) return fail(ctx, ARMOUR_ERR_ARG, "export caps too small");
+    std::vector<uint16_t> lk(T * NJ * B.capL), uk(T * NF * B.capU);
+    std::vector<double> lg(T * NJ * B.capL * 3), ug(T * NF * B.capU);
+    cudaStream_t st = ctx->stream;
+#define D2H(dst, src, n) CU(cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, st))
+    D2H(out->link_n, B.link_n + prob * T * NJ, T * NJ * sizeof(int));
+    D2H(out->link_center, B.link_c + prob * T * NJ * 3, T * NJ * 3 * sizeof(double));
+    D2H(lk.data(), B.link_key + prob * T * NJ * B.capL, lk.size() * sizeof(uint16_t));
+    D2H(lg.data(), B.link_g + prob * T * NJ * B.capL * 3, lg.size() * sizeof(double));
+    D2H(out->u_n, B.u_n + prob * T * NF, T * NF * sizeof(int));
+    D2H(out->u_center, B.u_c + prob * T * NF, T * NF * sizeof(double));
+    D2H(uk.data(), B.u_key + prob * T * NF * B.capU, uk.size() * sizeof(uint16_t));
+    D2H(ug.data(), B.u_g + prob * T * NF * B.capU, ug.size() * sizeof(double));
+    if (out->u_radius) D2H(out->u_radius, B.u_r + prob * T * NF, T * NF * sizeof(double));
+    if (out->torque_radius) D2H(out->torque_radius, B.torque_radius + prob * NF * T, NF * T * sizeof(double));
+    if (out->link_gens) D2H(out->link_gens, B.link_gens + prob * T * NJ * 18, T * NJ * 18 * sizeof(double));
+#undef D2H
+    CU(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < T * NJ; i++)
+        for (int mI = 0; mI < B.capL; mI++) {
+            out->link_key[i * out->cap_link + mI] = lk[i * B.capL + mI];
+            for (int e = 0; e < 3; e++)
+                out->link_coeff[(i * out->cap_link + mI) * 3 + e] = lg[(i * B.capL + mI) * 3 + e];
+        }
+    for (size_t i = 0; i < T * NF; i++)
+        for (int mI = 0; mI < B.capU; mI++) {
+            out->u_key[i * out->cap_u + mI] = uk[i * B.capU + mI];
+            out->u_coeff[i * out->cap_u + mI] = ug[i * B.capU + mI];
+        }
+    return ARMOUR_OK;
+}
+
+int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const armour_reachset_tables* in,
+                            const double* q0, const double* qd0, const double* qdd0, const double* obstacles, int nobs) {
+    int rc = check_batch(ctx, nprob_total, nobs);
+    if (rc) return rc;
+    if (!in || !in->u_radius || !in->torque_radius || !in->link_gens || !q0 || !qd0 || !qdd0 || prob < 0 ||
+        prob >= nprob_total)
+        return ARMOUR_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (prob == 0 || ctx->B.O != nobs || ctx->B.nprob != nprob_total) {
+        rc = ensure_obstacle_buffers(ctx, nprob_total, nobs);
+        if (rc) return rc;
+    }
+    const Batch& B = ctx->B;
+    const size_t T = B.T, NJ = B.NJ, P = size_t(ctx->cfg.max_problems);
+    std::vector<uint16_t> lk(T * NJ * B.capL, 0), uk(T * NF * B.capU, 0);
+    std::vector<double> lg(T * NJ * B.capL * 3, 0.0), ug(T * NF * B.capU, 0.0);
+    for (size_t i = 0; i < T * NJ; i++) {
+        if (in->link_n[i] > B.capL) return fail(ctx, ARMOUR_ERR_CAPACITY, "imported link table exceeds cap_link_monomials");
+        for (int mI = 0; mI < in->link_n[i]; mI++) {
+            lk[i * B.capL + mI] = uint16_t(in->link_key[i * in->cap_link + mI]);
+            for (int e = 0; e < 3; e++) lg[(i * B.capL + mI) * 3 + e] = in->link_coeff[(i * in->cap_link + mI) * 3 + e];
+        }
+    }
+    for (size_t i = 0; i < T * NF; i++) {
+        if (in->u_n[i] > B.capU) return fail(ctx, ARMOUR_ERR_CAPACITY, "imported torque table exceeds cap_torque_monomials");
+        for (int mI = 0; mI < in->u_n[i]; mI++) {
+            uk[i * B.capU + mI] = uint16_t(in->u_key[i * in->cap_u + mI]);
+            ug[i * B.capU + mI] = in->u_coeff[i * in->cap_u + mI];
+        }
+    }
+    cudaStream_t st = ctx->stream;
+#define H2D(dst, src, n) CU(cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, st))
+    H2D(B.link_n + prob * T * NJ, in->link_n, T * NJ * sizeof(int));
+    H2D(B.link_c + prob * T * NJ * 3, in->link_center, T * NJ * 3 * sizeof(double));
+    H2D(B.link_key + prob * T * NJ * B.capL, lk.data(), lk.size() * sizeof(uint16_t));
+    H2D(B.link_g + prob * T * NJ * B.capL * 3, lg.data(), lg.size() * sizeof(double));
+    H2D(B.u_n + prob * T * NF, in->u_n, T * NF * sizeof(int));
+    H2D(B.u_c + prob * T * NF, in->u_center, T * NF * sizeof(double));
+    H2D(B.u_key + prob * T * NF * B.capU, uk.data(), uk.size() * sizeof(uint16_t));
+    H2D(B.u_g + prob * T * NF * B.capU, ug.data(), ug.size() * sizeof(double));
+    H2D(B.torque_radius + prob * NF * T, in->torque_radius, NF * T * sizeof(double));
+    H2D(B.link_gens + prob * T * NJ * 18, in->link_gens, T * NJ * 18 * sizeof(double));
+    H2D(B.u_r + prob * T * NF, in->u_radius, T * NF * sizeof(double));
+    H2D(ctx->d_in + prob * NF, q0, NF * sizeof(double));
+    H2D(ctx->d_in + P * NF + prob * NF, qd0, NF * sizeof(double));
+    H2D(ctx->d_in + 2 * P * NF + prob * NF, qdd0, NF * sizeof(double));
+    if (nobs > 0) H2D(ctx->d_obs + size_t(prob) * nobs * 12, obstacles, size_t(nobs) * 12 * sizeof(double));
+#undef H2D
+    CU(cudaStreamSynchronize(st));  // the staging vectors die at return
+    if (prob == nprob_total - 1) {
+        CU(launch_hyperplanes(ctx->B, ctx->stream));
+        ctx->launches += (nobs > 0);
+        ctx->built_nprob = nprob_total;
+        ctx->h_torque_valid = false;
+    }
+    if (prob == 0) {
+        ctx->h_q0.assign(q0, q0 + NF);
+        ctx->h_qd0.assign(qd0, qd0 + NF);
+        ctx->h_qdd0.assign(qdd0, qdd0 + NF);
+    }
+    return ARMOUR_OK;
+}
+
+}  // extern "C"

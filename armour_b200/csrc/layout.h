@@ -1,0 +1,50 @@
+// Device-side data layout of a batch of planning problems (HBM, structure of arrays).
+//
+// All arrays are problem-major; inside a problem the time interval is the slow index because every
+// kernel assigns a CTA to one (problem, time interval) or one (problem, block of TB intervals), so
+// each CTA streams one contiguous chunk.
+#pragma once
+#include <cstdint>
+
+#include "robot_constants.h"
+
+namespace armour {
+
+constexpr int TB = 8;        // time intervals per CTA in the constraint kernels
+constexpr int HP_COMP = 5;   // hyper-plane record: Cx, Cy, Cz, d, delta
+
+struct Batch {
+    int nprob;     // problems in flight
+    int T;         // time intervals
+    int NJ;        // links
+    int O;         // obstacles per problem (same for the whole batch)
+    int capL;      // stored k-only monomials per link reach set
+    int capU;      // stored k-only monomials per torque reach set
+    // inputs
+    const double* q0;         // [p][NF]
+    const double* qd0;        // [p][NF]
+    const double* qdd0;       // [p][NF]
+    const double* obstacles;  // [p][O][12]
+    // reach sets written by the build kernel (or armour_import_reachsets)
+    int* link_n;              // [p][t][NJ]
+    double* link_c;           // [p][t][NJ][3]
+    uint16_t* link_key;       // [p][t][NJ][capL]   2 bits per k_j (reference degree hash, k-only part)
+    double* link_g;           // [p][t][NJ][capL][3]
+    int* u_n;                 // [p][t][NF]
+    double* u_c;              // [p][t][NF]
+    double* u_r;              // [p][t][NF]         radius of the reduced nominal torque PZ
+    uint16_t* u_key;          // [p][t][NF][capU]
+    double* u_g;              // [p][t][NF][capU]
+    double* torque_radius;    // [p][j*T + t]
+    double* link_gens;        // [p][t][NJ][18]     column-major 3x6
+    // collision hyper-planes: [p][t/TB][comp][pair][l][t%TB][o]
+    double* hp;
+    // outputs of the last evaluation
+    double* link_sliced;      // [p][t][NJ][3]
+    int* status;              // [p]
+
+    __host__ __device__ size_t hp_chunk() const { return size_t(HP_COMP) * NCOMB * NJ * TB * O; }
+    __host__ __device__ int m() const { return NF * T + NJ * T * O + 4 * NF; }
+};
+
+}  // namespace armour

@@ -1,0 +1,164 @@
+/* armour_b200.h — C ABI of the B200-native ARMOUR reach-set / constraint-evaluation hot path.
+ *
+ * The reference planner (roahmlab/armour, kinova_planner_realtime = "KPR/") has no library ABI: its
+ * boundaries are the Ipopt TNLP virtual interface implemented by armtd_NLP (KPR/NLPclass.h:11-184)
+ * and the armour.in / armour*.out text files (KPR/armour_main.cu:36-78,312-372).  This header is the
+ * thin C layer a maintainer binds instead of the bodies of those functions; every entry point names
+ * the reference code it replaces.  Conventions:
+ *   - plain pointers and sizes only; every function returns ARMOUR_OK (0) or a negative error code and
+ *     never throws across the ABI (the reference throws int / aborts: KPR/CollisionChecking.cu:10-13);
+ *   - the caller owns all host buffers; the context owns all device memory;
+ *   - one context = one CUDA device + one stream; thread-compatible, not thread-safe (Ipopt calls
+ *     eval_g / eval_jac_g serially from one thread);
+ *   - there is NO CPU fallback: without a CUDA device armour_ctx_create fails with ARMOUR_ERR_CUDA.
+ *
+ * Index conventions (T = num_time_steps = 128, NJ = links, NF = 7, O = obstacles of the problem):
+ *   constraint rows m = NF*T + NJ*T*O + 4*NF            (KPR/NLPclass.cu:45-57)
+ *     [0, NF*T)                     torque centre, row t*NF + j
+ *     [NF*T, NF*T + NJ*T*O)         collision value, row NF*T + (l*T + t)*O + o   (link-major)
+ *     next NF / NF                  min / max joint position over the horizon
+ *     next NF / NF                  min / max joint velocity
+ *   Jacobian: dense, values[row*NF + col]                (KPR/NLPclass.cu:348-357)
+ *   obstacles: O x 12 doubles, zonotope centre then 3 generators (KPR/armour_main.cu:71-75)
+ */
+#ifndef ARMOUR_B200_H
+#define ARMOUR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARMOUR_NF 7
+#define ARMOUR_ABI_VERSION 1
+
+enum {
+    ARMOUR_OK = 0,
+    ARMOUR_ERR_ARG = -1,        /* null pointer / out-of-range argument */
+    ARMOUR_ERR_CUDA = -2,       /* CUDA runtime error or no device (see armour_last_error) */
+    ARMOUR_ERR_OBSTACLES = -3,  /* more obstacles than max_obstacles (reference: throw, CollisionChecking.cu:10-13) */
+    ARMOUR_ERR_CAPACITY = -4,   /* a monomial table overflowed its configured capacity (never truncated silently) */
+    ARMOUR_ERR_STATE = -5,      /* call order: eval before build, batch larger than max_problems, ... */
+    ARMOUR_ERR_NOMEM = -6
+};
+
+typedef struct armour_ctx armour_ctx;
+
+/* Run-time form of the reference's compile-time configuration (KPR/Parameters.h:10-58,
+ * KPR/KinovaWithoutGripperInfo.h:41-61).  Fill with armour_config_default() first. */
+typedef struct armour_config {
+    int struct_size;            /* sizeof(armour_config), ABI check */
+    int device;                 /* CUDA device ordinal */
+    int robot_model;            /* 0: Kinova Gen3 without gripper (NUM_JOINTS 7); 1: with fixed gripper link (8) */
+    int num_time_steps;         /* NUM_TIME_STEPS, even, <= 128 */
+    int max_obstacles;          /* per problem (reference MAX_OBSTACLE_NUM = 40) */
+    int max_problems;           /* batch capacity of this context */
+    int cap_link_monomials;     /* capacity of the stored k-only table of one link reach set */
+    int cap_torque_monomials;   /* capacity of the stored k-only table of one torque reach set */
+    int cap_work_monomials;     /* capacity of one intermediate PZ during reach-set construction */
+    double simplify_threshold;  /* SIMPLIFY_THRESHOLD */
+    double k_range[ARMOUR_NF];  /* k_range */
+    double mass_uncertainty;    /* < 0: model default (0.03) */
+    double inertia_uncertainty; /* < 0: model default (0.03) */
+} armour_config;
+
+int armour_config_default(armour_config* cfg);
+int armour_ctx_create(const armour_config* cfg, armour_ctx** out);
+int armour_ctx_destroy(armour_ctx* ctx);
+/* Launch everything on this cudaStream_t (default: a stream owned by the context). */
+int armour_ctx_set_stream(armour_ctx* ctx, void* cuda_stream);
+int armour_ctx_synchronize(armour_ctx* ctx);
+const char* armour_status_string(int status);
+const char* armour_last_error(const armour_ctx* ctx);
+int armour_abi_version(void);
+/* Number of kernels this library has launched on the context since creation (bench.py gpu_launches). */
+long long armour_kernel_launches(const armour_ctx* ctx);
+
+/* Problem dimensions: replaces armtd_NLP::get_nlp_info (KPR/NLPclass.cu:62-84). */
+int armour_num_joints(const armour_ctx* ctx);
+int armour_num_time_steps(const armour_ctx* ctx);
+int armour_num_constraints(const armour_ctx* ctx, int nobs);
+
+/* ---- single planning problem (a batch of one) --------------------------------------------------- */
+
+/* Replaces sections II.A-II.D of main(): BezierCurve::makePolyZono, KinematicsDynamics::fk /
+ * rnea_nominal / rnea_interval, the robust-input radius and Obstacles::initializeHyperPlane
+ * (KPR/armour_main.cu:86-216).  Inputs as parsed from armour.in. */
+int armour_reachsets_build(armour_ctx* ctx, const double q0[ARMOUR_NF], const double qd0[ARMOUR_NF],
+                           const double qdd0[ARMOUR_NF], const double* obstacles, int nobs);
+/* torque_radius(j, t) at out[j*T + t] (Eigen column = time; KPR/armour_main.cu:168-201). */
+int armour_get_torque_radius(armour_ctx* ctx, double* out);
+/* 3x6 column-major generator matrix of link l, interval t at out[(t*NJ + l)*18]
+ * (link_independent_generators, KPR/armour_main.cu:113,126; written to armour_joint_position_radius.out). */
+int armour_get_link_independent_generators(armour_ctx* ctx, double* out);
+/* Replaces armtd_NLP::get_bounds_info rows g_l / g_u (KPR/NLPclass.cu:116-165). */
+int armour_get_bounds(armour_ctx* ctx, double* g_l, double* g_u);
+/* Replaces the body of armtd_NLP::eval_g (KPR/NLPclass.cu:272-324): g has m entries. */
+int armour_eval_g(armour_ctx* ctx, const double k[ARMOUR_NF], double* g);
+/* Replaces the body of armtd_NLP::eval_jac_g with values != NULL (KPR/NLPclass.cu:330-396): m*NF entries. */
+int armour_eval_jac_g(armour_ctx* ctx, const double k[ARMOUR_NF], double* values);
+/* Both at once (one launch); either output may be NULL. */
+int armour_eval_g_jac(armour_ctx* ctx, const double k[ARMOUR_NF], double* g, double* values);
+/* armtd_NLP::link_sliced_center of the last evaluation, out[(t*NJ + l)*3] (KPR/NLPclass.h:150). */
+int armour_get_link_sliced_center(armour_ctx* ctx, double* out);
+/* Feasibility predicate of armtd_NLP::finalize_solution (KPR/NLPclass.cu:449-537) applied to g:
+ * *feasible = 1/0, *first_violation = first violated row in the reference's check order, or -1. */
+int armour_verdict(armour_ctx* ctx, const double* g, int* feasible, int* first_violation);
+/* Cost and its gradient: armtd_NLP::eval_f / eval_grad_f (KPR/NLPclass.cu:207-268); host arithmetic. */
+int armour_cost(armour_ctx* ctx, const double q_des[ARMOUR_NF], const double k[ARMOUR_NF], double* obj,
+                double grad[ARMOUR_NF]);
+
+/* ---- batched planning problems (worlds x replans), problem-major arrays ------------------------- */
+
+/* nprob independent problems with the same obstacle count: q0/qd0/qdd0 [nprob*NF],
+ * obstacles [nprob*nobs*12].  Host pointers; the H2D copy is part of the call. */
+int armour_batch_reachsets_build(armour_ctx* ctx, int nprob, const double* q0, const double* qd0, const double* qdd0,
+                                 const double* obstacles, int nobs);
+/* One eval_g + eval_jac_g per problem: k [nprob*NF] -> g [nprob*m], values [nprob*m*NF] (either may be
+ * NULL).  Host pointers; H2D of k and D2H of the results are part of the call. */
+int armour_batch_eval(armour_ctx* ctx, int nprob, const double* k, double* g, double* values);
+/* Same with DEVICE pointers; asynchronous on the context's stream, no copies. */
+int armour_batch_eval_device(armour_ctx* ctx, int nprob, const double* d_k, double* d_g, double* d_values);
+/* Inputs already on the device (same layout as the host variant); asynchronous. */
+int armour_batch_reachsets_build_device(armour_ctx* ctx, int nprob, const double* d_q0, const double* d_qd0,
+                                        const double* d_qdd0, const double* d_obstacles, int nobs);
+/* Per-problem verdict on the device from device g: feasible[nprob], first_violation[nprob] (int32). */
+int armour_batch_verdict_device(armour_ctx* ctx, int nprob, const double* d_g, int* d_feasible, int* d_first);
+int armour_batch_get_torque_radius(armour_ctx* ctx, int nprob, double* out /* [nprob][NF*T] */);
+int armour_batch_get_link_independent_generators(armour_ctx* ctx, int nprob, double* out /* [nprob][T*NJ*18] */);
+int armour_batch_get_bounds(armour_ctx* ctx, int nprob, double* g_l, double* g_u);
+/* Status of the last build per problem (ARMOUR_OK or ARMOUR_ERR_CAPACITY), out[nprob]. */
+int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out);
+
+/* ---- reach-set tables (k-only monomials after reduce / reduce_link_PZ) -------------------------- */
+
+/* Padded neutral layout shared with the test oracle:
+ *   links : n[t*NJ+l], center[(t*NJ+l)*3+e], key[(t*NJ+l)*cap_link+m], coeff[((t*NJ+l)*cap_link+m)*3+e]
+ *   torque: n[t*NF+j], center[t*NF+j],       key[(t*NF+j)*cap_u+m],    coeff[(t*NF+j)*cap_u+m]
+ * key = the reference's degree hash (KPR/PZsparse.h:23-40), < 2^14 for k-only monomials. */
+typedef struct armour_reachset_tables {
+    int cap_link, cap_u;
+    int* link_n;
+    double* link_center;
+    unsigned long long* link_key;
+    double* link_coeff;
+    int* u_n;
+    double* u_center;
+    unsigned long long* u_key;
+    double* u_coeff;
+    double* u_radius;        /* [t*NF + j] radius of the reduced nominal torque PZ (u_nom.independent) */
+    double* torque_radius;   /* [j*T + t] */
+    double* link_gens;       /* [(t*NJ + l)*18] */
+} armour_reachset_tables;
+
+/* Download the tables of problem `prob` (debugging / parity tests / *_joint_position_*.out files). */
+int armour_export_reachsets(armour_ctx* ctx, int prob, armour_reachset_tables* out);
+/* Upload externally built tables for problem `prob` together with the inputs the Bezier rows need, then
+ * build its collision hyper-planes.  Lets the constraint kernels be exercised in isolation. */
+int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const armour_reachset_tables* in,
+                            const double q0[ARMOUR_NF], const double qd0[ARMOUR_NF], const double qdd0[ARMOUR_NF],
+                            const double* obstacles, int nobs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARMOUR_B200_H */

@@ -177,3 +177,12 @@ class OracleProblem:
             raise RuntimeError(f"reach-set export capacity exceeded (largest table {-mx})")
         r["max_monos"] = mx
         return r
+
+    def tables(self, cap_link=64, cap_u=128):
+        """k-only reach-set tables in the neutral layout of armour_import_reachsets (include/armour_b200.h)."""
+        r = self.export_reachsets(cap_link, cap_u)
+        r["torque_radius"] = np.ascontiguousarray(self.torque_radius())
+        raw = np.empty((self.T, self.NJ, 18))
+        lib().orc_get_link_gens(self._h, _dp(raw))
+        r["link_gens"] = raw
+        return r
