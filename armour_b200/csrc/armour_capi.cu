@@ -536,16 +536,19 @@ int armour_export_reachsets(armour_ctx* ctx, int prob, armour_reachset_tables* o
     if (out->link_gens) D2H(out->link_gens, B.link_gens + prob * T * NJ * 18, T * NJ * 18 * sizeof(double));
 #undef D2H
     CU(cudaStreamSynchronize(st));
+    // entries past the monomial count are padding: export them as zero
     for (size_t i = 0; i < T * NJ; i++)
-        for (int mI = 0; mI < B.capL; mI++) {
-            out->link_key[i * out->cap_link + mI] = lk[i * B.capL + mI];
+        for (int mI = 0; mI < out->cap_link; mI++) {
+            const bool valid = mI < out->link_n[i] && mI < B.capL;
+            out->link_key[i * out->cap_link + mI] = valid ? lk[i * B.capL + mI] : 0;
             for (int e = 0; e < 3; e++)
-                out->link_coeff[(i * out->cap_link + mI) * 3 + e] = lg[(i * B.capL + mI) * 3 + e];
+                out->link_coeff[(i * out->cap_link + mI) * 3 + e] = valid ? lg[(i * B.capL + mI) * 3 + e] : 0.0;
         }
     for (size_t i = 0; i < T * NF; i++)
-        for (int mI = 0; mI < B.capU; mI++) {
-            out->u_key[i * out->cap_u + mI] = uk[i * B.capU + mI];
-            out->u_coeff[i * out->cap_u + mI] = ug[i * B.capU + mI];
+        for (int mI = 0; mI < out->cap_u; mI++) {
+            const bool valid = mI < out->u_n[i] && mI < B.capU;
+            out->u_key[i * out->cap_u + mI] = valid ? uk[i * B.capU + mI] : 0;
+            out->u_coeff[i * out->cap_u + mI] = valid ? ug[i * B.capU + mI] : 0.0;
         }
     return ARMOUR_OK;
 }

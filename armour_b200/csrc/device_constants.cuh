@@ -1,6 +1,8 @@
 // __constant__ block shared by every kernel of the library (single translation unit: kernels.cu).
 #pragma once
+#ifndef ARMOUR_EMU
 #include <cuda_runtime.h>
+#endif
 
 #include "robot_constants.h"
 
@@ -10,6 +12,7 @@ __constant__ RobotConstants c_robot;
 __constant__ unsigned char c_combA[NCOMB];  // generator-pair enumeration (0,1),(0,2)...(7,8)
 __constant__ unsigned char c_combB[NCOMB];  // reference KPR/CollisionChecking.cu:26-39
 
+#ifndef ARMOUR_EMU
 inline cudaError_t upload_constants(const RobotConstants& rc, cudaStream_t stream) {
     unsigned char a[NCOMB], b[NCOMB];
     int ai = 0, bi = 1;
@@ -31,5 +34,6 @@ inline cudaError_t upload_constants(const RobotConstants& rc, cudaStream_t strea
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(stream);  // a, b are stack temporaries
 }
+#endif
 
 }  // namespace armour

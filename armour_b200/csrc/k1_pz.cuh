@@ -1,0 +1,1011 @@
+// K1 building blocks: a sparse polynomial zonotope (PZ) algebra executed by one CTA on tables that live
+// in shared memory.
+//
+// What it replaces: the reference's host-side PZsparse class (KPR/PZsparse.h:50-183, KPR/PZsparse.cu),
+// whose every operation ends in simplify() = std::sort over heap-allocated monomials + merge + prune
+// (KPR/PZsparse.cu:284-350).  Here a PZ is a block of doubles in a CTA-private arena
+//     [centre: sz][radius lane 0: sz][radius lane 1: sz][keys: n x u64][coeff: n x sz]
+// (sz = 1, 3 or 9 = scalar, 3-vector, 3x3 column-major) and simplify() is a pass through an
+// open-addressing hash table keyed by the reference's 63-bit degree hash (KPR/PZsparse.h:23-40):
+//   * keys are inserted with atomicMax ("larger key keeps the slot, the smaller one moves on") — the
+//     ordered-hashing rule makes the final slot layout a function of the key SET only, never of the
+//     thread schedule, so every result of this file is bitwise reproducible run to run;
+//   * coefficients of equal keys are summed in a fixed order (one __syncthreads between the term
+//     groups that can collide; two-term sums use a commutative atomic add);
+//   * a finalize pass applies the reference's prune rule (Frobenius norm of the whole coefficient
+//     <= threshold -> |coeff| moves into the radius) and compacts the survivors in slot order.
+// Two radius lanes are carried so that the nominal and the interval-parameter Newton-Euler passes
+// (KPR/Dynamics.h:41-47) are one pass: their polynomial parts are bit-identical (only radii differ).
+// Coefficient / centre arithmetic is round-to-nearest without FMA contraction (-fmad=false), like
+// the host reference; radii are accumulated with round-up intrinsics so the outer bound stays sound.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#include "robot_constants.h"
+
+#ifndef ARMOUR_EMU
+#include <cuda_runtime.h>
+#define K1_DI __device__ __forceinline__
+#define K1_OP __device__ __noinline__
+#else
+#define K1_DI inline
+#define K1_OP inline
+#endif
+
+namespace armour {
+namespace k1 {
+
+typedef unsigned long long u64;
+
+constexpr int NT = 256;      // threads per CTA
+constexpr int NW = NT / 32;  // warps per CTA
+constexpr int RED_STRIDE = 12;
+
+// failure codes written to Batch::status (a build never truncates silently)
+enum { FAIL_ARENA = 1, FAIL_TABLE = 2, FAIL_SCRATCH = 3, FAIL_LINK_CAP = 4, FAIL_TORQUE_CAP = 5 };
+
+constexpr u64 KEY_K_ONLY = 1ull << 14;       // max_hash_dependent_k_only        (KPR/PZsparse.h:37)
+constexpr u64 KEY_K_LINKS = 1ull << 35;      // max_hash_dependent_k_links_only  (KPR/PZsparse.h:39)
+constexpr u64 KEY_K_MASK = KEY_K_ONLY - 1;   // dependent_k_mask                 (KPR/PZsparse.h:40)
+K1_DI u64 key_k(int i) { return 1ull << (2 * i); }
+K1_DI u64 key_qde(int i) { return 1ull << (14 + i); }
+K1_DI u64 key_qdae(int i) { return 1ull << (21 + i); }
+K1_DI u64 key_qddae(int i) { return 1ull << (28 + i); }
+K1_DI u64 key_cosqe(int i) { return 1ull << (35 + 2 * i); }
+K1_DI u64 key_sinqe(int i) { return 1ull << (49 + 2 * i); }
+
+// ---- PZ handle ------------------------------------------------------------------------------------
+struct PZH {
+    double* p;
+    int n;
+    int sz;
+};
+K1_DI double* pz_c(const PZH& h) { return h.p; }
+K1_DI double* pz_r(const PZH& h, int lane) { return h.p + (1 + lane) * h.sz; }
+K1_DI u64* pz_keys(const PZH& h) { return reinterpret_cast<u64*>(h.p + 3 * h.sz); }
+K1_DI double* pz_coef(const PZH& h) { return h.p + 3 * h.sz + h.n; }
+K1_DI int pz_words(int n, int sz) { return 3 * sz + n * (1 + sz); }
+
+struct Tab {
+    u64* keys;
+    double* acc;
+    int cap, shift;  // home slot = (key * golden) >> shift
+};
+
+// per-CTA state; every field is uniform across the threads of the CTA
+struct Ctx {
+    double* arena;   // CTA-private PZ arena (shared memory in the fast tier)
+    int arena_words;
+    int top;
+    int top_max;
+    double* garena;  // global-memory continuation of the arena (spill space)
+    int garena_words;
+    double* gscr;    // global scratch for the per-joint F / N blocks kept until the backward pass
+    int gscr_words;
+    int gtop;
+    char* tab_s;     // shared-memory hash-table pool (all zero between operations)
+    int tab_s_bytes;
+    char* tab_g;     // global-memory pool for the rare table that does not fit (all zero between operations)
+    int tab_g_bytes;
+    double* red;     // [NW][RED_STRIDE] partial sums (prune amounts)
+    double* red2;    // [NW][RED_STRIDE] partial sums (|coefficient| sums)
+    int* cnt;        // [NW] survivor counts
+    double thr;
+    int fail;
+    int tid, lane, warp;
+    int n_tab_global;  // statistics
+};
+
+K1_DI void set_fail(Ctx& c, int code) {
+    if (!c.fail) c.fail = code;
+}
+
+// The arena is one virtual offset space over two segments: [0, arena_words) in shared memory, then
+// [arena_words, arena_words + garena_words) in the CTA's global scratch (L2-resident spill space for the
+// few long intervals whose live set outgrows shared memory).  A block never straddles the boundary.
+K1_DI double* arena_ptr(const Ctx& c, int off) {
+    return off < c.arena_words ? c.arena + off : c.garena + (off - c.arena_words);
+}
+K1_DI int arena_place(const Ctx& c, int off, int w) {  // first offset >= off where a block of w words may start
+    return (off < c.arena_words && off + w > c.arena_words) ? c.arena_words : off;
+}
+K1_DI PZH pz_alloc(Ctx& c, int n, int sz) {
+    PZH h;
+    h.n = n;
+    h.sz = sz;
+    const int w = pz_words(n, sz);
+    const int at = arena_place(c, c.top, w);
+    if (c.fail || at + w > c.arena_words + c.garena_words) {
+        set_fail(c, FAIL_ARENA);
+        h.p = c.arena;
+        h.n = 0;
+        return h;
+    }
+    h.p = arena_ptr(c, at);
+    c.top = at + w;
+    if (c.top > c.top_max) c.top_max = c.top;
+    return h;
+}
+
+// ---- small helpers --------------------------------------------------------------------------------
+K1_DI double frob(const double* v, int n) {  // Frobenius norm, entries in storage order (oracle frob_norm)
+    double s = 0;
+    for (int i = 0; i < n; i++) s += v[i] * v[i];
+    return sqrt(s);
+}
+template <int N>
+K1_DI double frobN(const double* v) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) s += v[i] * v[i];
+    return sqrt(s);
+}
+// C(3 x P) = A(3x3) * B(3 x P), column-major, inner index ascending, no FMA (Eigen-like: KPR/PZsparse.cu:864-994)
+template <int P, bool TRANS>
+K1_DI void matmul3(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int j = 0; j < P; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double acc = (TRANS ? A[i * 3] : A[i]) * B[j * 3];
+#pragma unroll
+            for (int k = 1; k < 3; k++) acc += (TRANS ? A[k + i * 3] : A[i + k * 3]) * B[k + j * 3];
+            C[i + j * 3] = acc;
+        }
+}
+// same with every product and sum rounded up (all inputs non-negative): sound radius propagation
+template <int P, bool TRANS>
+K1_DI void matmul3_up(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int j = 0; j < P; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double acc = __dmul_ru(TRANS ? A[i * 3] : A[i], B[j * 3]);
+#pragma unroll
+            for (int k = 1; k < 3; k++)
+                acc = __dadd_ru(acc, __dmul_ru(TRANS ? A[k + i * 3] : A[i + k * 3], B[k + j * 3]));
+            C[i + j * 3] = acc;
+        }
+}
+
+K1_DI double warp_sum_up(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_ru(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- hash table -----------------------------------------------------------------------------------
+K1_DI int tab_home(const Tab& t, u64 key) { return int((key * 0x9E3779B97F4A7C15ull) >> t.shift); }
+
+K1_DI void tab_insert(const Tab& t, u64 key) {
+    int h = tab_home(t, key);
+    u64 carry = key;
+    for (;;) {
+        const u64 old = atomicMax(&t.keys[h], carry);
+        if (old == 0 || old == carry) return;
+        if (old < carry) carry = old;  // the slot now holds our (larger) key; move the displaced one on
+        h = (h + 1) & (t.cap - 1);
+    }
+}
+K1_DI int tab_find(const Tab& t, u64 key) {
+    int h = tab_home(t, key);
+    while (t.keys[h] != key) h = (h + 1) & (t.cap - 1);
+    return h;
+}
+
+// Pick a table for `nterms` candidate keys with `na` accumulators per slot.  Shared memory when it
+// fits (load <= 2/3, or <= 0.8 at half the size), else the CTA's global pool.
+K1_DI bool tab_select(Ctx& c, int nterms, int na, Tab& t) {
+    int cap = 64, lg = 6;
+    while (cap * 2 < nterms * 3) {
+        cap <<= 1;
+        lg++;
+    }
+    const int slot_bytes = 8 * (1 + na);
+    char* base = nullptr;
+    if (cap * slot_bytes <= c.tab_s_bytes) {
+        base = c.tab_s;
+    } else if (cap > 64 && nterms * 5 <= (cap / 2) * 4 && (cap / 2) * slot_bytes <= c.tab_s_bytes) {
+        cap >>= 1;
+        lg--;
+        base = c.tab_s;
+    } else if (cap * slot_bytes <= c.tab_g_bytes) {
+        base = c.tab_g;
+        c.n_tab_global++;
+    } else {
+        set_fail(c, FAIL_TABLE);
+        return false;
+    }
+    t.keys = reinterpret_cast<u64*>(base);
+    t.acc = reinterpret_cast<double*>(base + size_t(cap) * 8);
+    t.cap = cap;
+    t.shift = 64 - lg;
+    return true;
+}
+
+// Finalize a table: `fin(acc[NA] -> out[SZ], rad[SZ])` decides keep / prune per occupied slot.
+// Pass 1 rewrites kept slots with their output coefficients, clears pruned ones, counts survivors per
+// warp segment and reduces the pruned amounts; pass 2 compacts the survivors (slot order) into a new
+// arena block and leaves the table all-zero.  On return every thread holds the handle and
+// rad_total[SZ] (block-wide pruned amounts, rounded up); the caller fills centre / radii and must
+// __syncthreads() before the block is read.
+template <int NA, int SZ, class Fin>
+K1_DI PZH tab_finalize(Ctx& c, const Tab& t, Fin fin, double* rad_total) {
+    const int seg = (t.cap / NW) < 32 ? 32 : (t.cap / NW);
+    const int s0 = c.warp * seg;
+    const int s1 = (s0 + seg) < t.cap ? (s0 + seg) : t.cap;
+    double rad[SZ];
+#pragma unroll
+    for (int e = 0; e < SZ; e++) rad[e] = 0.0;
+    int count = 0;
+    for (int s = s0 + c.lane; s < s1; s += 32) {
+        const u64 key = t.keys[s];
+        bool keep = false;
+        if (key != 0) {
+            double a[NA], out[SZ];
+#pragma unroll
+            for (int e = 0; e < NA; e++) a[e] = t.acc[size_t(s) * NA + e];
+            keep = fin(a, out, rad);
+            if (keep) {
+#pragma unroll
+                for (int e = 0; e < SZ; e++) t.acc[size_t(s) * NA + e] = out[e];
+#pragma unroll
+                for (int e = SZ; e < NA; e++) t.acc[size_t(s) * NA + e] = 0.0;
+            } else {
+                t.keys[s] = 0;
+#pragma unroll
+                for (int e = 0; e < NA; e++) t.acc[size_t(s) * NA + e] = 0.0;
+            }
+        }
+        count += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+#pragma unroll
+    for (int e = 0; e < SZ; e++) rad[e] = warp_sum_up(rad[e]);
+    if (c.lane == 0) {
+        c.cnt[c.warp] = count;
+#pragma unroll
+        for (int e = 0; e < SZ; e++) c.red[c.warp * RED_STRIDE + e] = rad[e];
+    }
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        const int v = c.cnt[w];
+        if (w < c.warp) before += v;
+        total += v;
+    }
+#pragma unroll
+    for (int e = 0; e < SZ; e++) {
+        double v = c.red[e];
+#pragma unroll
+        for (int w = 1; w < NW; w++) v = __dadd_ru(v, c.red[w * RED_STRIDE + e]);
+        rad_total[e] = v;
+    }
+    PZH h = pz_alloc(c, total, SZ);
+    const bool ok = !c.fail;
+    u64* ok_keys = pz_keys(h);
+    double* ok_coef = pz_coef(h);
+    int run = before;
+    for (int s = s0 + c.lane; s < s1; s += 32) {
+        const u64 key = t.keys[s];
+        const bool keep = key != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = run + __popc(b & ((1u << c.lane) - 1u));
+            if (ok) ok_keys[pos] = key;
+#pragma unroll
+            for (int e = 0; e < SZ; e++) {
+                if (ok) ok_coef[size_t(pos) * SZ + e] = t.acc[size_t(s) * NA + e];
+                t.acc[size_t(s) * NA + e] = 0.0;
+            }
+            t.keys[s] = 0;
+        }
+        run += __popc(b);
+    }
+    return h;
+}
+
+// block-wide sum over the monomials of |coeff| per component (rounded up), NOT including |centre|.
+// Writes warp partials to c.red2; the caller syncs, then calls abs_sum_collect.
+template <int SZ>
+K1_DI void abs_sum_partial(Ctx& c, const PZH& h) {
+    double s[SZ];
+#pragma unroll
+    for (int e = 0; e < SZ; e++) s[e] = 0.0;
+    const double* cf = pz_coef(h);
+    for (int m = c.tid; m < h.n; m += NT)
+#pragma unroll
+        for (int e = 0; e < SZ; e++) s[e] = __dadd_ru(s[e], fabs(cf[size_t(m) * SZ + e]));
+#pragma unroll
+    for (int e = 0; e < SZ; e++) s[e] = warp_sum_up(s[e]);
+    if (c.lane == 0)
+#pragma unroll
+        for (int e = 0; e < SZ; e++) c.red2[c.warp * RED_STRIDE + e] = s[e];
+}
+template <int SZ>
+K1_DI void abs_sum_collect(Ctx& c, const PZH& h, double* out) {  // |centre| + sum |coeff|
+#pragma unroll
+    for (int e = 0; e < SZ; e++) {
+        double v = fabs(pz_c(h)[e]);
+#pragma unroll
+        for (int w = 0; w < NW; w++) v = __dadd_ru(v, c.red2[w * RED_STRIDE + e]);
+        out[e] = v;
+    }
+}
+// every thread walks a (small) operand itself
+template <int SZ>
+K1_DI void abs_sum_serial(const PZH& h, double* out) {
+    const double* cf = pz_coef(h);
+#pragma unroll
+    for (int e = 0; e < SZ; e++) out[e] = fabs(pz_c(h)[e]);
+    for (int m = 0; m < h.n; m++)
+#pragma unroll
+        for (int e = 0; e < SZ; e++) out[e] = __dadd_ru(out[e], fabs(cf[size_t(m) * SZ + e]));
+}
+
+// ---- arena management -----------------------------------------------------------------------------
+// Slide the listed blocks (ascending addresses, all at or above `mark`) down to `mark`; everything
+// else above `mark` is released.
+K1_OP void arena_keep(Ctx& c, int mark, PZH** hs, int k) {
+    if (c.fail) return;
+    int nt = mark;
+    for (int b = 0; b < k; b++) {
+        PZH& h = *hs[b];
+        const int w = pz_words(h.n, h.sz);
+        nt = arena_place(c, nt, w);
+        double* dst = arena_ptr(c, nt);
+        double* src = h.p;
+        if (dst != src) {
+            for (int base = 0; base < w; base += NT * 4) {
+                double v[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = base + q * NT + c.tid;
+                    v[q] = (i < w) ? src[i] : 0.0;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = base + q * NT + c.tid;
+                    if (i < w) dst[i] = v[q];
+                }
+            }
+            __syncthreads();
+            h.p = dst;
+        }
+        nt += w;
+    }
+    c.top = nt;
+}
+K1_DI void arena_keep1(Ctx& c, int mark, PZH& a) {
+    PZH* l[1] = {&a};
+    arena_keep(c, mark, l, 1);
+}
+
+// copy a block to the CTA's global scratch (F_i / N_i of the forward pass)
+K1_OP PZH spill_global(Ctx& c, const PZH& h) {
+    PZH g = h;
+    const int w = pz_words(h.n, h.sz);
+    if (c.fail || c.gtop + w > c.gscr_words) {
+        set_fail(c, FAIL_SCRATCH);
+        g.n = 0;
+        return g;
+    }
+    g.p = c.gscr + c.gtop;
+    c.gtop += w;
+    for (int i = c.tid; i < w; i += NT) g.p[i] = h.p[i];
+    __syncthreads();
+    return g;
+}
+
+K1_DI PZH pz_zero(Ctx& c, int sz) {  // PZ with no monomials, zero centre and radii
+    PZH h = pz_alloc(c, 0, sz);
+    if (!c.fail && c.tid < 3 * sz) h.p[c.tid] = 0.0;
+    __syncthreads();
+    return h;
+}
+
+// ---- linear operations (operator+, operator-, addOneDimPZ, element extraction, double*PZ) -------
+// out = src0 (+) src1 with, per source: optional scalar extraction (comp_in >= 0 -> placed at comp_out of
+// the output) and a scale factor.  Mirrors KPR/PZsparse.cu:743-834 (+,-), :996-1030 (double*PZ, no
+// simplify), :678-697 (operator()), :1068-1085 (addOneDimPZ): one simplify() at the end.
+struct LinSrc {
+    PZH h;
+    int comp_in;   // -1: whole coefficient (sz_in == SZ); else scalar element of the source
+    int comp_out;  // destination component when comp_in >= 0 or the source is a scalar placed into a vector
+    double scale;  // coefficient = scale * c  (1.0 for plain add, -1.0 for subtraction)
+};
+
+template <int SZ>
+K1_DI void lin_value(const LinSrc& s, const double* v, double* out) {  // v: source coefficient / centre
+#pragma unroll
+    for (int e = 0; e < SZ; e++) out[e] = 0.0;
+    if (s.comp_in < 0 && s.h.sz == SZ) {
+#pragma unroll
+        for (int e = 0; e < SZ; e++) out[e] = s.scale * v[e];
+    } else {
+        const double x = s.scale * v[s.comp_in < 0 ? 0 : s.comp_in];
+#pragma unroll
+        for (int e = 0; e < SZ; e++)
+            if (e == s.comp_out) out[e] = x;
+    }
+}
+
+template <int SZ>
+K1_OP PZH op_lin2(Ctx& c, const LinSrc& s0, const LinSrc& s1) {
+    PZH dummy = {c.arena, 0, SZ};
+    if (c.fail) return dummy;
+    Tab t;
+    if (!tab_select(c, s0.h.n + s1.h.n, SZ, t)) return dummy;
+    const double thr = c.thr;
+    // keys
+    for (int srcI = 0; srcI < 2; srcI++) {
+        const LinSrc& s = srcI ? s1 : s0;
+        const u64* keys = pz_keys(s.h);
+        const double* cf = pz_coef(s.h);
+        for (int m = c.tid; m < s.h.n; m += NT) {
+            if (s.comp_in >= 0 && cf[size_t(m) * s.h.sz + s.comp_in] == 0.0) continue;  // extracted zero: no effect
+            tab_insert(t, keys[m]);
+        }
+    }
+    __syncthreads();
+    // at most two contributions per (key, component): a commutative atomic add is order-independent
+    for (int srcI = 0; srcI < 2; srcI++) {
+        const LinSrc& s = srcI ? s1 : s0;
+        const u64* keys = pz_keys(s.h);
+        const double* cf = pz_coef(s.h);
+        for (int m = c.tid; m < s.h.n; m += NT) {
+            if (s.comp_in >= 0 && cf[size_t(m) * s.h.sz + s.comp_in] == 0.0) continue;
+            double v[SZ];
+            lin_value<SZ>(s, cf + size_t(m) * s.h.sz, v);
+            const int slot = tab_find(t, keys[m]);
+#pragma unroll
+            for (int e = 0; e < SZ; e++)
+                if (v[e] != 0.0) atomicAdd(&t.acc[size_t(slot) * SZ + e], v[e]);
+        }
+    }
+    __syncthreads();
+    double rad[SZ];
+    PZH h = tab_finalize<SZ, SZ>(
+        c, t,
+        [thr](const double* a, double* out, double* r) {
+            if (frobN<SZ>(a) <= thr) {
+#pragma unroll
+                for (int e = 0; e < SZ; e++) r[e] = __dadd_ru(r[e], fabs(a[e]));
+                return false;
+            }
+#pragma unroll
+            for (int e = 0; e < SZ; e++) out[e] = a[e];
+            return true;
+        },
+        rad);
+    if (!c.fail && c.tid < SZ) {
+        const int e = c.tid;
+        double c0[SZ], c1[SZ];
+        lin_value<SZ>(s0, pz_c(s0.h), c0);
+        lin_value<SZ>(s1, pz_c(s1.h), c1);
+        pz_c(h)[e] = c0[e] + c1[e];
+        for (int lane = 0; lane < 2; lane++) {
+            double r0[SZ], r1[SZ];
+            LinSrc a0 = s0, a1 = s1;
+            a0.scale = fabs(s0.scale);
+            a1.scale = fabs(s1.scale);
+            // radius * |scale| (rounded up)
+            {
+                const double* rv = pz_r(s0.h, lane);
+#pragma unroll
+                for (int q = 0; q < SZ; q++) r0[q] = 0.0;
+                if (a0.comp_in < 0 && a0.h.sz == SZ) {
+#pragma unroll
+                    for (int q = 0; q < SZ; q++) r0[q] = __dmul_ru(a0.scale, rv[q]);
+                } else {
+                    const double x = __dmul_ru(a0.scale, rv[a0.comp_in < 0 ? 0 : a0.comp_in]);
+#pragma unroll
+                    for (int q = 0; q < SZ; q++)
+                        if (q == a0.comp_out) r0[q] = x;
+                }
+            }
+            {
+                const double* rv = pz_r(s1.h, lane);
+#pragma unroll
+                for (int q = 0; q < SZ; q++) r1[q] = 0.0;
+                if (a1.comp_in < 0 && a1.h.sz == SZ) {
+#pragma unroll
+                    for (int q = 0; q < SZ; q++) r1[q] = __dmul_ru(a1.scale, rv[q]);
+                } else {
+                    const double x = __dmul_ru(a1.scale, rv[a1.comp_in < 0 ? 0 : a1.comp_in]);
+#pragma unroll
+                    for (int q = 0; q < SZ; q++)
+                        if (q == a1.comp_out) r1[q] = x;
+                }
+            }
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(r0[e], r1[e]), rad[e]);
+        }
+    }
+    __syncthreads();
+    return h;
+}
+
+template <int SZ>
+K1_DI PZH op_add(Ctx& c, const PZH& a, const PZH& b) {  // KPR/PZsparse.cu:743-764
+    LinSrc s0 = {a, -1, 0, 1.0}, s1 = {b, -1, 0, 1.0};
+    return op_lin2<SZ>(c, s0, s1);
+}
+// a.addOneDimPZ(s, comp, 0) for a 3-vector a and a scalar s (KPR/PZsparse.cu:1068-1085)
+K1_DI PZH op_add_one_dim(Ctx& c, const PZH& a, const PZH& s, int comp) {
+    LinSrc s0 = {a, -1, 0, 1.0}, s1 = {s, 0, comp, 1.0};
+    return op_lin2<3>(c, s0, s1);
+}
+
+// ---- element-wise ("map") operations: the key set does not change, so no table is needed ---------
+// Generic driver: fn(m, out[SZ], rad[SZ]) -> keep.  Two passes (count, then recompute + write) keep the
+// monomials in their input order.
+template <int SZ, class Fn>
+K1_DI PZH map_op(Ctx& c, int n_in, const u64* keys_in, Fn fn, double* rad_total) {
+    PZH dummy = {c.arena, 0, SZ};
+    if (c.fail) return dummy;
+    const int chunk = ((n_in + NW - 1) / NW + 31) & ~31;  // per-warp contiguous chunk, multiple of 32
+    const int m0 = c.warp * chunk;
+    const int m1 = (m0 + chunk) < n_in ? (m0 + chunk) : n_in;
+    double rad[SZ];
+#pragma unroll
+    for (int e = 0; e < SZ; e++) rad[e] = 0.0;
+    int count = 0;
+    for (int mb = m0; mb < m1; mb += 32) {
+        const int m = mb + c.lane;
+        bool keep = false;
+        if (m < m1) {
+            double out[SZ];
+            keep = fn(m, out, rad);
+        }
+        count += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+#pragma unroll
+    for (int e = 0; e < SZ; e++) rad[e] = warp_sum_up(rad[e]);
+    if (c.lane == 0) {
+        c.cnt[c.warp] = count;
+#pragma unroll
+        for (int e = 0; e < SZ; e++) c.red[c.warp * RED_STRIDE + e] = rad[e];
+    }
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        const int v = c.cnt[w];
+        if (w < c.warp) before += v;
+        total += v;
+    }
+#pragma unroll
+    for (int e = 0; e < SZ; e++) {
+        double v = c.red[e];
+#pragma unroll
+        for (int w = 1; w < NW; w++) v = __dadd_ru(v, c.red[w * RED_STRIDE + e]);
+        rad_total[e] = v;
+    }
+    PZH h = pz_alloc(c, total, SZ);
+    if (c.fail) return h;
+    u64* ok = pz_keys(h);
+    double* oc = pz_coef(h);
+    int run = before;
+    for (int mb = m0; mb < m1; mb += 32) {
+        const int m = mb + c.lane;
+        bool keep = false;
+        double out[SZ], dump[SZ];
+#pragma unroll
+        for (int e = 0; e < SZ; e++) dump[e] = 0.0;
+        if (m < m1) keep = fn(m, out, dump);
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = run + __popc(b & ((1u << c.lane) - 1u));
+            ok[pos] = keys_in[m];
+#pragma unroll
+            for (int e = 0; e < SZ; e++) oc[size_t(pos) * SZ + e] = out[e];
+        }
+        run += __popc(b);
+    }
+    return h;  // caller writes the header, then __syncthreads()
+}
+
+// prune rule for one merged coefficient (KPR/PZsparse.cu:321-336)
+template <int SZ>
+K1_DI bool prune_or_keep(const double* v, double thr, double* rad) {
+    if (frobN<SZ>(v) <= thr) {
+#pragma unroll
+        for (int e = 0; e < SZ; e++) rad[e] = __dadd_ru(rad[e], fabs(v[e]));
+        return false;
+    }
+    return true;
+}
+
+// cross(PZ a, const b) and cross(const a, PZ b): three scaled scalar subtractions (each simplified on its
+// own: a component with |c| <= thr moves to that component's radius) and a stack (KPR/PZsparse.cu:1118-1132,
+// 1153-1167, 1087-1116).  left_const == false: result = x (PZ) cross v (const)  [cross_pz_mat]
+//                         left_const == true : result = v (const) cross x (PZ)  [cross_mat_pz]
+K1_DI void cross_const_coef(bool left_const, const double* v, const double* g, double thr, double* out, double* rad,
+                            bool* any) {
+    double c[3];
+    if (!left_const) {  // r_e = v[(e+2)%3] * g[(e+1)%3] - v[(e+1)%3] * g[(e+2)%3]
+        c[0] = v[2] * g[1] - v[1] * g[2];
+        c[1] = v[0] * g[2] - v[2] * g[0];
+        c[2] = v[1] * g[0] - v[0] * g[1];
+    } else {  // r_e = v[(e+1)%3] * g[(e+2)%3] - v[(e+2)%3] * g[(e+1)%3]
+        c[0] = v[1] * g[2] - v[2] * g[1];
+        c[1] = v[2] * g[0] - v[0] * g[2];
+        c[2] = v[0] * g[1] - v[1] * g[0];
+    }
+    bool a = false;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        if (sqrt(c[e] * c[e]) <= thr) {
+            rad[e] = __dadd_ru(rad[e], fabs(c[e]));
+            out[e] = 0.0;
+        } else {
+            out[e] = c[e];
+            a = true;
+        }
+    }
+    *any = a;
+}
+K1_OP PZH op_cross_const(Ctx& c, const PZH& x, const double* v, bool left_const) {
+    const double thr = c.thr;
+    const double* cf = pz_coef(x);
+    const double v0 = v[0], v1 = v[1], v2 = v[2];
+    double rad[3];
+    PZH h = map_op<3>(
+        c, x.n, pz_keys(x),
+        [=](int m, double* out, double* r) {
+            const double vv[3] = {v0, v1, v2};
+            bool any;
+            cross_const_coef(left_const, vv, cf + size_t(m) * 3, thr, out, r, &any);
+            if (!any) return false;
+            return prune_or_keep<3>(out, thr, r);  // stack3's own simplify (3-vector norm)
+        },
+        rad);
+    if (!c.fail && c.tid < 3) {
+        const int e = c.tid, e1 = (e + 1) % 3, e2 = (e + 2) % 3;
+        const double* xc = pz_c(x);
+        // centre: scale() multiplies centre * s (KPR/PZsparse.cu:1004), then the subtraction
+        pz_c(h)[e] = !left_const ? (xc[e1] * v[e2] - xc[e2] * v[e1]) : (xc[e2] * v[e1] - xc[e1] * v[e2]);
+        for (int lane = 0; lane < 2; lane++) {
+            const double* xr = pz_r(x, lane);
+            const double a = !left_const ? __dmul_ru(xr[e1], fabs(v[e2])) : __dmul_ru(xr[e2], fabs(v[e1]));
+            const double b = !left_const ? __dmul_ru(xr[e2], fabs(v[e1])) : __dmul_ru(xr[e1], fabs(v[e2]));
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(a, b), rad[e]);
+        }
+    }
+    __syncthreads();
+    return h;
+}
+
+// PZ(constant, radius = pct*|constant|) * x  for a scalar constant (mass) or a 3x3 constant (inertia), and
+// x * PZ(constant 3-vector) for a 3x3 x.  The constant operand has no monomials, so the product keeps the
+// key set of x (KPR/PZsparse.cu:864-994 with an empty polynomial on one side); lane 1 carries the
+// uncertain-parameter radius (KPR/PZsparse.cu:93-98, KPR/Dynamics.cu:30-40).
+//   kind 0: scalar s * vec3 x        kind 1: mat3 M * vec3 x        kind 2: mat3 x * const vec3 P
+template <int KIND>
+K1_OP PZH op_const_mul(Ctx& c, const double* K, double pct_lane1, const PZH& x) {
+    PZH dummy = {c.arena, 0, 3};
+    if (c.fail) return dummy;
+    const double thr = c.thr;
+    const double* cf = pz_coef(x);
+    constexpr int XS = (KIND == 2) ? 9 : 3;
+    double kk[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) kk[i] = (KIND == 0) ? ((i == 0) ? K[0] : 0.0) : ((KIND == 1 || i < 3) ? K[i] : 0.0);
+    abs_sum_partial<XS>(c, x);  // collected after map_op's internal barrier
+    double rad[3];
+    PZH h = map_op<3>(
+        c, x.n, pz_keys(x),
+        [=](int m, double* out, double* r) {
+            const double* g = cf + size_t(m) * XS;
+            if (KIND == 0) {
+#pragma unroll
+                for (int e = 0; e < 3; e++) out[e] = kk[0] * g[e];
+            } else if (KIND == 1) {
+                matmul3<1, false>(kk, g, out);
+            } else {
+                matmul3<1, false>(g, kk, out);
+            }
+            return prune_or_keep<3>(out, thr, r);
+        },
+        rad);
+    if (!c.fail && c.tid < 3) {
+        const int e = c.tid;
+        double absx[XS];
+        abs_sum_collect<XS>(c, x, absx);
+        const double* xc = pz_c(x);
+        double cen[3];
+        if (KIND == 0) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) cen[q] = kk[0] * xc[q];
+        } else if (KIND == 1) {
+            matmul3<1, false>(kk, xc, cen);
+        } else {
+            matmul3<1, false>(xc, kk, cen);
+        }
+        pz_c(h)[e] = cen[e];
+        for (int lane = 0; lane < 2; lane++) {
+            const double* xr = pz_r(x, lane);
+            const double pct = lane ? pct_lane1 : 0.0;
+            double absK[9], radK[9], ra2[3], ra3[3], rr[3];
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                absK[i] = fabs(kk[i]);
+                radK[i] = __dmul_ru(pct, absK[i]);
+            }
+            if (KIND == 0) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    ra2[q] = __dmul_ru(absK[0], xr[q]);
+                    ra3[q] = __dmul_ru(radK[0], absx[q]);
+                    rr[q] = __dmul_ru(radK[0], xr[q]);
+                }
+            } else if (KIND == 1) {
+                matmul3_up<1, false>(absK, xr, ra2);
+                matmul3_up<1, false>(radK, absx, ra3);
+                matmul3_up<1, false>(radK, xr, rr);
+            } else {  // x (3x3 PZ) * constant vector: the constant has no radius
+                matmul3_up<1, false>(xr, absK, ra3);
+#pragma unroll
+                for (int q = 0; q < 3; q++) ra2[q] = rr[q] = 0.0;
+            }
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr[e], __dadd_ru(ra2[e], ra3[e])), rad[e]);
+        }
+    }
+    __syncthreads();
+    return h;
+}
+
+// ---- PZ * PZ with a 3x3 left operand (KPR/PZsparse.cu:864-994) -----------------------------------
+// P = 1: 3x3 * 3x1, P = 3: 3x3 * 3x3.  TRANS: the left operand is used transposed (R_t = R.transpose(),
+// KPR/Trajectory.cu:143).  The operand with fewer monomials is the "outer" one: its monomials are
+// visited one after the other (a barrier between them, so equal keys are summed in a fixed order), the
+// other operand's monomials are spread over the threads.
+template <int P, bool TRANS>
+K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
+    constexpr int SZ = 3 * P;
+    PZH dummy = {c.arena, 0, SZ};
+    if (c.fail) return dummy;
+    const int nL = L.n, nR = R.n;
+    Tab t;
+    if (!tab_select(c, nL + nR + nL * nR, SZ, t)) return dummy;
+    const double thr = c.thr;
+    const u64* kL = pz_keys(L);
+    const u64* kR = pz_keys(R);
+    const double* cL = pz_coef(L);
+    const double* cR = pz_coef(R);
+    const bool outerL = nL <= nR;
+    const PZH& O = outerL ? L : R;
+    const PZH& I = outerL ? R : L;
+    const u64* kO = outerL ? kL : kR;
+    const u64* kI = outerL ? kR : kL;
+    // keys
+    for (int j = c.tid; j < I.n; j += NT) {
+        const u64 kj = kI[j];
+        tab_insert(t, kj);
+        for (int o = 0; o < O.n; o++) tab_insert(t, kj + kO[o]);  // degree hashes add without carry (:938-940)
+    }
+    for (int o = c.tid; o < O.n; o += NT) tab_insert(t, kO[o]);
+    if (outerL) abs_sum_partial<SZ>(c, R); else abs_sum_partial<9>(c, L);
+    __syncthreads();
+    // polynomial * centre of the other side, centre * polynomial: keys within each group are distinct
+    {
+        double cen[9];
+        const double* cc = pz_c(R);
+#pragma unroll
+        for (int q = 0; q < SZ; q++) cen[q] = cc[q];
+        for (int i = c.tid; i < nL; i += NT) {
+            double v[SZ];
+            matmul3<P, TRANS>(cL + size_t(i) * 9, cen, v);
+            const int slot = tab_find(t, kL[i]);
+#pragma unroll
+            for (int e = 0; e < SZ; e++) t.acc[size_t(slot) * SZ + e] += v[e];
+        }
+    }
+    __syncthreads();
+    {
+        double cen[9];
+        const double* cc = pz_c(L);
+#pragma unroll
+        for (int q = 0; q < 9; q++) cen[q] = cc[q];
+        for (int j = c.tid; j < nR; j += NT) {
+            double v[SZ];
+            matmul3<P, TRANS>(cen, cR + size_t(j) * SZ, v);
+            const int slot = tab_find(t, kR[j]);
+#pragma unroll
+            for (int e = 0; e < SZ; e++) t.acc[size_t(slot) * SZ + e] += v[e];
+        }
+    }
+    __syncthreads();
+    for (int o = 0; o < O.n; o++) {
+        const u64 ko = kO[o];
+        for (int j = c.tid; j < I.n; j += NT) {
+            double v[SZ];
+            if (outerL)
+                matmul3<P, TRANS>(cL + size_t(o) * 9, cR + size_t(j) * SZ, v);
+            else
+                matmul3<P, TRANS>(cL + size_t(j) * 9, cR + size_t(o) * SZ, v);
+            const int slot = tab_find(t, ko + kI[j]);
+#pragma unroll
+            for (int e = 0; e < SZ; e++) t.acc[size_t(slot) * SZ + e] += v[e];
+        }
+        __syncthreads();
+    }
+    double rad[SZ];
+    PZH h = tab_finalize<SZ, SZ>(
+        c, t,
+        [thr](const double* a, double* out, double* r) {
+            if (frobN<SZ>(a) <= thr) {
+#pragma unroll
+                for (int e = 0; e < SZ; e++) r[e] = __dadd_ru(r[e], fabs(a[e]));
+                return false;
+            }
+#pragma unroll
+            for (int e = 0; e < SZ; e++) out[e] = a[e];
+            return true;
+        },
+        rad);
+    if (!c.fail && c.tid < SZ) {
+        const int e = c.tid;
+        double absL[9], absR[SZ], cen[SZ];
+        if (outerL) {
+            abs_sum_serial<9>(L, absL);
+            abs_sum_collect<SZ>(c, R, absR);
+        } else {
+            abs_sum_collect<9>(c, L, absL);
+            abs_sum_serial<SZ>(R, absR);
+        }
+        matmul3<P, TRANS>(pz_c(L), pz_c(R), cen);
+        pz_c(h)[e] = cen[e];
+        for (int lane = 0; lane < 2; lane++) {
+            double ra2[SZ], ra3[SZ], rr[SZ];
+            matmul3_up<P, TRANS>(absL, pz_r(R, lane), ra2);
+            matmul3_up<P, TRANS>(pz_r(L, lane), absR, ra3);
+            matmul3_up<P, TRANS>(pz_r(L, lane), pz_r(R, lane), rr);
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr[e], __dadd_ru(ra2[e], ra3[e])), rad[e]);
+        }
+    }
+    __syncthreads();
+    return h;
+}
+
+// ---- cross(PZ a, PZ b) (KPR/PZsparse.cu:1134-1151) ------------------------------------------------
+// Six scalar PZ products a_x * b_y (each with its own simplify), three scalar subtractions (simplify)
+// and a stack (simplify), fused: the six products share ONE key set {a_i + b_j}, so one table with six
+// accumulators per slot reproduces all ten simplify() calls slot by slot.
+//   P0 = a1*b2, P1 = a2*b1, P2 = a2*b0, P3 = a0*b2, P4 = a0*b1, P5 = a1*b0;  r_e = P_{2e} - P_{2e+1}
+K1_DI void cross_six(const double* a, const double* b, double* v) {
+    v[0] = a[1] * b[2];
+    v[1] = a[2] * b[1];
+    v[2] = a[2] * b[0];
+    v[3] = a[0] * b[2];
+    v[4] = a[0] * b[1];
+    v[5] = a[1] * b[0];
+}
+K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
+    PZH dummy = {c.arena, 0, 3};
+    if (c.fail) return dummy;
+    const int nA = A.n, nB = B.n;
+    Tab t;
+    if (!tab_select(c, nA + nB + nA * nB, 6, t)) return dummy;
+    const double thr = c.thr;
+    const u64* kA = pz_keys(A);
+    const u64* kB = pz_keys(B);
+    const double* cA = pz_coef(A);
+    const double* cB = pz_coef(B);
+    const bool outerA = nA <= nB;
+    const PZH& O = outerA ? A : B;
+    const PZH& I = outerA ? B : A;
+    const u64* kO = outerA ? kA : kB;
+    const u64* kI = outerA ? kB : kA;
+    for (int j = c.tid; j < I.n; j += NT) {
+        const u64 kj = kI[j];
+        tab_insert(t, kj);
+        for (int o = 0; o < O.n; o++) tab_insert(t, kj + kO[o]);
+    }
+    for (int o = c.tid; o < O.n; o += NT) tab_insert(t, kO[o]);
+    abs_sum_partial<3>(c, I);
+    __syncthreads();
+    {
+        const double* cc = pz_c(B);
+        const double cen[3] = {cc[0], cc[1], cc[2]};
+        for (int i = c.tid; i < nA; i += NT) {
+            double v[6];
+            cross_six(cA + size_t(i) * 3, cen, v);
+            const int slot = tab_find(t, kA[i]);
+#pragma unroll
+            for (int e = 0; e < 6; e++) t.acc[size_t(slot) * 6 + e] += v[e];
+        }
+    }
+    __syncthreads();
+    {
+        const double* cc = pz_c(A);
+        const double cen[3] = {cc[0], cc[1], cc[2]};
+        for (int j = c.tid; j < nB; j += NT) {
+            double v[6];
+            cross_six(cen, cB + size_t(j) * 3, v);
+            const int slot = tab_find(t, kB[j]);
+#pragma unroll
+            for (int e = 0; e < 6; e++) t.acc[size_t(slot) * 6 + e] += v[e];
+        }
+    }
+    __syncthreads();
+    for (int o = 0; o < O.n; o++) {
+        const u64 ko = kO[o];
+        const double* co = (outerA ? cA : cB) + size_t(o) * 3;
+        const double ov[3] = {co[0], co[1], co[2]};
+        for (int j = c.tid; j < I.n; j += NT) {
+            double v[6];
+            if (outerA)
+                cross_six(ov, cB + size_t(j) * 3, v);
+            else
+                cross_six(cA + size_t(j) * 3, ov, v);
+            const int slot = tab_find(t, ko + kI[j]);
+#pragma unroll
+            for (int e = 0; e < 6; e++) t.acc[size_t(slot) * 6 + e] += v[e];
+        }
+        __syncthreads();
+    }
+    double rad[3];
+    PZH h = tab_finalize<6, 3>(
+        c, t,
+        [thr](const double* a, double* out, double* r) {
+            double p[6];
+            bool have[6];
+#pragma unroll
+            for (int x = 0; x < 6; x++) {  // simplify() of each scalar product
+                have[x] = !(sqrt(a[x] * a[x]) <= thr);
+                p[x] = have[x] ? a[x] : 0.0;
+                if (!have[x]) r[x >> 1] = __dadd_ru(r[x >> 1], fabs(a[x]));
+            }
+            bool any = false;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {  // simplify() of P_{2e} - P_{2e+1}
+                out[e] = 0.0;
+                if (have[2 * e] || have[2 * e + 1]) {
+                    const double d = p[2 * e] + (-p[2 * e + 1]);
+                    if (sqrt(d * d) <= thr) {
+                        r[e] = __dadd_ru(r[e], fabs(d));
+                    } else {
+                        out[e] = d;
+                        any = true;
+                    }
+                }
+            }
+            if (!any) return false;
+            return prune_or_keep<3>(out, thr, r);  // simplify() of the stack
+        },
+        rad);
+    if (!c.fail && c.tid < 3) {
+        const int e = c.tid;
+        double absA[3], absB[3];
+        if (outerA) {
+            abs_sum_serial<3>(A, absA);
+            abs_sum_collect<3>(c, B, absB);
+        } else {
+            abs_sum_collect<3>(c, A, absA);
+            abs_sum_serial<3>(B, absB);
+        }
+        const double* ca = pz_c(A);
+        const double* cb = pz_c(B);
+        const int e1 = (e + 1) % 3, e2 = (e + 2) % 3;
+        // r_e = a_{e1} b_{e2} - a_{e2} b_{e1}
+        pz_c(h)[e] = ca[e1] * cb[e2] - ca[e2] * cb[e1];
+        for (int lane = 0; lane < 2; lane++) {
+            const double* ra = pz_r(A, lane);
+            const double* rb = pz_r(B, lane);
+            // radius of a scalar product x*y: rx*ry + (|x|*ry + rx*|y|)   (KPR/PZsparse.cu:944-989)
+            const double p0 = __dadd_ru(__dmul_ru(ra[e1], rb[e2]),
+                                        __dadd_ru(__dmul_ru(absA[e1], rb[e2]), __dmul_ru(ra[e1], absB[e2])));
+            const double p1 = __dadd_ru(__dmul_ru(ra[e2], rb[e1]),
+                                        __dadd_ru(__dmul_ru(absA[e2], rb[e1]), __dmul_ru(ra[e2], absB[e1])));
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(p0, p1), rad[e]);
+        }
+    }
+    __syncthreads();
+    return h;
+}
+
+}  // namespace k1
+}  // namespace armour

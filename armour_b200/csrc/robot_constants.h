@@ -23,6 +23,7 @@ struct RobotConstants {
     int axes[MAXJ];
     double trans[(MAXJ + 1) * 3];
     double rots[MAXJ * 3];
+    double rrpy[MAXJ * 9];  // constant joint-frame rotations Rrpy(rots), column-major (KPR/PZsparse.cu:160-176)
     double mass[MAXJ];
     double com[MAXJ * 3];
     double inertia[MAXJ * 9];
@@ -54,6 +55,21 @@ inline RobotConstants make_robot_constants(int model_id) {
     if (gripper) m.trans[7 * 3 + 2] = -0.061525 - 0.10155;
     m.rots[0] = M_PI;
     for (int i = 1; i < MAXJ; i++) m.rots[i * 3] = (i % 2 == 1) ? M_PI * 0.5 : -M_PI * 0.5;
+    for (int i = 0; i < MAXJ; i++) {
+        const double roll = m.rots[i * 3], pitch = m.rots[i * 3 + 1], yaw = m.rots[i * 3 + 2];
+        double* R = &m.rrpy[i * 9];
+        using std::cos;
+        using std::sin;
+        R[0 + 0 * 3] = cos(pitch) * cos(yaw);
+        R[0 + 1 * 3] = -cos(pitch) * sin(yaw);
+        R[0 + 2 * 3] = sin(pitch);
+        R[1 + 0 * 3] = cos(roll) * sin(yaw) + cos(yaw) * sin(pitch) * sin(roll);
+        R[1 + 1 * 3] = cos(roll) * cos(yaw) - sin(pitch) * sin(roll) * sin(yaw);
+        R[1 + 2 * 3] = -cos(pitch) * sin(roll);
+        R[2 + 0 * 3] = sin(roll) * sin(yaw) - cos(roll) * cos(yaw) * sin(pitch);
+        R[2 + 1 * 3] = cos(yaw) * sin(roll) + cos(roll) * sin(pitch) * sin(yaw);
+        R[2 + 2 * 3] = cos(pitch) * cos(roll);
+    }
     const double mass[8] = {1.3773, 1.1636, 1.1636, 0.9302, 0.6781, 0.6781, 0.5, 1.72};
     std::memcpy(m.mass, mass, sizeof(mass));
     const double com[8 * 3] = {-0.000023, -0.010364, -0.07336,  -0.000044,  -0.09958,     -0.013278,

@@ -1,0 +1,110 @@
+"""GPU parity of the reach-set construction kernel (K1/K2) through the C ABI, against the CPU oracle.
+
+Tolerances (BASELINE north_star): every exported radius must CONTAIN the oracle's (>=) and differ by at
+most 1e-10 relative; centres and monomial coefficients (which feed g and the Jacobian) within 1e-9
+absolute (observed: <= 1e-15); the k-only monomial key sets must be identical; verdicts identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import WORLDS
+
+pytestmark = pytest.mark.gpu
+K_TEST = np.array([0.5, 0.6, 0.7, 0.0, -0.5, -0.6, -0.7])  # reference PZ_tests.cu:198
+REL = 1e-10
+
+
+def _compare_tables(r, tb, T, NJ):
+    NF = 7
+    assert np.array_equal(r["nl"], tb["nl"]), "link monomial counts differ"
+    assert np.array_equal(r["nu"], tb["nu"]), "torque monomial counts differ"
+    for i in range(T * NJ):
+        n = r["nl"][i]
+        assert np.array_equal(r["hl"][i, :n], tb["hl"][i, :n])
+        if n:
+            assert np.max(np.abs(r["gl"][i, :n] - tb["gl"][i, :n])) <= 1e-12
+    for i in range(T * NF):
+        n = r["nu"][i]
+        assert np.array_equal(r["hu"][i, :n], tb["hu"][i, :n])
+        if n:
+            assert np.max(np.abs(r["gu"][i, :n] - tb["gu"][i, :n])) <= 1e-12
+    assert np.max(np.abs(r["cl"] - tb["cl"])) <= 1e-12
+    assert np.max(np.abs(r["cu"] - tb["cu"])) <= 1e-11
+    # radii: containment and 1e-10 relative
+    for name in ("ru", "torque_radius"):
+        a, b = np.asarray(r[name]).ravel(), np.asarray(tb[name]).ravel()
+        assert np.all(a >= b), f"{name}: GPU radius does not contain the oracle's"
+        assert np.max((a - b) / b) <= REL, name
+    G, Gr = r["link_gens"].reshape(T, NJ, 6, 3), tb["link_gens"].reshape(T, NJ, 6, 3)
+    assert np.max(np.abs(G[:, :, :3] - Gr[:, :, :3])) <= 1e-12        # link generator columns
+    rad, rad_r = G[:, :, 3:], Gr[:, :, 3:]
+    assert np.all(rad >= rad_r)
+    nz = rad_r > 0
+    assert np.max((rad[nz] - rad_r[nz]) / rad_r[nz]) <= REL
+
+
+def _problems():
+    from armour_b200 import worlds
+    probs = [worlds.config1_problem(os.path.join(WORLDS, "scene_016_006.csv"))]
+    q0, qd0, qdd0, qdes, obs = worlds.random_problems(3, 10, seed=5)
+    for p in range(3):
+        probs.append((q0[p], qd0[p], qdd0[p], qdes[p], obs[p]))
+    return probs
+
+
+@pytest.mark.parametrize("pi", range(4))
+def test_build_matches_oracle(built, pi):
+    from armour_b200 import ReachSetEngine
+    from oracle.pyoracle import OracleProblem
+    q0, qd0, qdd0, q_des, obs = _problems()[pi]
+    ref = OracleProblem().build(q0, qd0, qdd0, obs)
+    eng = ReachSetEngine(max_problems=1, max_obstacles=obs.shape[0], cap_link=64, cap_torque=128)
+    eng.build(q0, qd0, qdd0, obs)
+    _compare_tables(eng.export_reachsets(0), ref.tables(64, 128), eng.T, eng.NJ)
+    # end to end: constraints, Jacobian and verdict from GPU-built reach sets
+    for k in (np.zeros(7), K_TEST, -K_TEST):
+        g, jac = eng.eval(k)
+        g_ref, j_ref = ref.eval_g(k), ref.eval_jac_g(k)
+        assert np.max(np.abs(g[0] - g_ref)) <= 1e-9
+        assert np.max(np.abs(jac[0] - j_ref)) <= 1e-9
+        assert eng.finalize_solution(g[0]) == ref.verdict(g_ref)
+    gl, gu = eng.get_bounds_info()
+    gl_ref, gu_ref = ref.bounds()
+    fin = np.abs(gl_ref) < 1e18
+    assert np.max(np.abs(gl[0][fin] - gl_ref[fin]) / np.maximum(1, np.abs(gl_ref[fin]))) <= REL
+    assert np.max(np.abs(gu[0] - gu_ref) / np.maximum(1, np.abs(gu_ref))) <= REL
+
+
+def test_batched_build_is_deterministic_and_matches(built):
+    """A batch of 6 problems in one launch: same tables as one-at-a-time builds, bit for bit, twice."""
+    from armour_b200 import ReachSetEngine, worlds
+    q0, qd0, qdd0, qdes, obs = worlds.random_problems(6, 10, seed=77)
+    eng = ReachSetEngine(max_problems=6, max_obstacles=10, cap_link=64, cap_torque=128)
+    eng.build(q0, qd0, qdd0, obs)
+    first = [eng.export_reachsets(p) for p in range(6)]
+    eng.build(q0, qd0, qdd0, obs)
+    again = [eng.export_reachsets(p) for p in range(6)]
+    single = ReachSetEngine(max_problems=1, max_obstacles=10, cap_link=64, cap_torque=128)
+    for p in range(6):
+        single.build(q0[p], qd0[p], qdd0[p], obs[p])
+        one = single.export_reachsets(0)
+        for key in first[p]:
+            assert np.array_equal(first[p][key], again[p][key]), f"run-to-run difference in {key}"
+            assert np.array_equal(first[p][key], one[key]), f"batch vs single difference in {key}"
+
+
+def test_gripper_model_and_uncertainty(built):
+    """8-link model (fixed gripper link, KinovaInfo.h) with 10 % inertial uncertainty."""
+    from armour_b200 import ReachSetEngine, worlds
+    from oracle.pyoracle import OracleProblem
+    q0, qd0, qdd0, qdes, obs = worlds.random_problems(1, 5, seed=3)
+    ref = OracleProblem(model_id=1, mass_uncertainty=0.10, inertia_uncertainty=0.10).build(q0[0], qd0[0], qdd0[0], obs[0])
+    eng = ReachSetEngine(max_problems=1, max_obstacles=5, robot_model=1, mass_uncertainty=0.10, inertia_uncertainty=0.10,
+                         cap_link=64, cap_torque=128)
+    eng.build(q0[0], qd0[0], qdd0[0], obs[0])
+    _compare_tables(eng.export_reachsets(0), ref.tables(64, 128), eng.T, eng.NJ)
+    g, jac = eng.eval(K_TEST)
+    assert np.max(np.abs(g[0] - ref.eval_g(K_TEST))) <= 1e-9
+    assert np.max(np.abs(jac[0] - ref.eval_jac_g(K_TEST))) <= 1e-9
