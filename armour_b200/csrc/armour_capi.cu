@@ -45,6 +45,21 @@ struct armour_ctx {
 
 namespace {
 
+// FP64 FMA throughput probe: 8 independent accumulator chains per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = double(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = __fma_rn(x[i], a, 0.5);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+
 int fail(armour_ctx* c, int code, const std::string& msg) {
     if (c) c->last_error = msg;
     return code;
@@ -337,6 +352,46 @@ int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out) {
     if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
     CU(cudaMemcpyAsync(out, ctx->B.status, nprob * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+
+int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, int* u_n) {
+    if (!ctx || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
+    const size_t T = ctx->B.T, NJ = ctx->B.NJ;
+    if (link_n)
+        CU(cudaMemcpyAsync(link_n, ctx->B.link_n, nprob * T * NJ * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (u_n) CU(cudaMemcpyAsync(u_n, ctx->B.u_n, nprob * T * NF * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+
+int armour_measure_fp64_peak(armour_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return ARMOUR_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
+    double* d_out = nullptr;
+    CU(dalloc(&d_out, 1));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 4096, grid = sms * 8, block = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        k_fp64_peak<<<grid, block, 0, ctx->stream>>>(d_out, iters, 1.0000001);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8 * double(iters) * double(grid) * block;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
     return ARMOUR_OK;
 }
 

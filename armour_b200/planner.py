@@ -108,6 +108,20 @@ class ReachSetEngine:
         self._check(self.lib.armour_batch_get_build_status(self._h, self.nprob, out.ctypes.data_as(_lib.ip)))
         return out
 
+    def monomial_counts(self):
+        """(link_n [nprob, T, NJ], u_n [nprob, T, 7]) stored k-only monomial counts of the built reach sets."""
+        ln = np.zeros((self.nprob, self.T, self.NJ), np.int32)
+        un = np.zeros((self.nprob, self.T, NF), np.int32)
+        self._check(self.lib.armour_batch_get_monomial_counts(self._h, self.nprob, ln.ctypes.data_as(_lib.ip),
+                                                              un.ctypes.data_as(_lib.ip)))
+        return ln, un
+
+    def measure_fp64_peak(self):
+        """Sustained non-tensor FP64 rate of the device in TFLOP/s (FMA probe kernel in the library)."""
+        v = C.c_double(0)
+        self._check(self.lib.armour_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
     def torque_radius(self):
         out = np.empty((self.nprob, NF, self.T))
         self._check(self.lib.armour_batch_get_torque_radius(self._h, self.nprob, _dp(out)))

@@ -128,6 +128,12 @@ int armour_batch_get_link_independent_generators(armour_ctx* ctx, int nprob, dou
 int armour_batch_get_bounds(armour_ctx* ctx, int nprob, double* g_l, double* g_u);
 /* Status of the last build per problem (ARMOUR_OK or ARMOUR_ERR_CAPACITY), out[nprob]. */
 int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out);
+/* Stored k-only monomial counts of the built reach sets: link_n[nprob*T*NJ], u_n[nprob*T*NF] (either may
+ * be NULL).  bench.py derives the algorithmic bytes of one evaluation from them (SURVEY.md 8d B_eval). */
+int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, int* u_n);
+/* Measurement aid: runs a dependent-chain-free FP64 FMA kernel on the context's device and returns the
+ * sustained non-tensor FP64 rate in TFLOP/s (the FP64 roofline denominator). */
+int armour_measure_fp64_peak(armour_ctx* ctx, double* tflops);
 
 /* ---- reach-set tables (k-only monomials after reduce / reduce_link_PZ) -------------------------- */
 
