@@ -26,7 +26,7 @@ struct armour_ctx {
     cudaStream_t own_stream = nullptr;
     Batch B;                 // device pointers + dimensions of the current batch
     int built_nprob = 0;     // problems with valid reach sets
-    size_t hp_capacity = 0;  // doubles allocated for B.hp
+    size_t hp_capacity = 0;  // doubles allocated for B.hp_cand
     size_t obs_capacity = 0;
     double* d_in = nullptr;  // [3][max_problems][NF] q0, qd0, qdd0
     double* d_obs = nullptr;
@@ -106,9 +106,13 @@ int ensure_obstacle_buffers(armour_ctx* ctx, int nprob, int nobs) {
     B.nprob = nprob;
     const size_t need_hp = size_t(nprob) * (B.T / TB) * B.hp_chunk();
     if (ctx->hp_capacity < need_hp) {
-        if (B.hp) cudaFree(B.hp);
-        B.hp = nullptr;
-        CU(dalloc(&B.hp, need_hp));
+        if (B.hp_cand) cudaFree(B.hp_cand);
+        if (B.hp_cnt) cudaFree(B.hp_cnt);
+        B.hp_cand = nullptr;
+        B.hp_cnt = nullptr;
+        ctx->hp_capacity = 0;
+        CU(dalloc(&B.hp_cand, need_hp));
+        CU(dalloc(&B.hp_cnt, need_hp / (HP_CAP * 4)));
         ctx->hp_capacity = need_hp;
     }
     B.obstacles = ctx->d_obs;
@@ -248,7 +252,7 @@ int armour_ctx_destroy(armour_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     Batch& B = ctx->B;
     void* ptrs[] = {ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
-                    B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.hp,
+                    B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.hp_cand, B.hp_cnt,
                     B.link_sliced, B.status};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -1,8 +1,8 @@
 // Constraint-side kernels of the hot path (sm_100a, FP64 SIMT, HBM-streaming):
 //
-//   k_hyperplanes  — K3a: buffered obstacle zonotope -> 36 half-space normals per (link, interval,
-//                    obstacle).  Replaces bufferObstaclesKernel + polytope_PH
-//                    (reference KPR/CollisionChecking.cu:136-228), which the reference launches 14 times.
+//   k_hyperplanes  — K3a: buffered obstacle zonotope -> the half-spaces that can attain the maximum of a
+//                    (link, interval, obstacle) row for some k in the box.  Replaces bufferObstaclesKernel +
+//                    polytope_PH (reference KPR/CollisionChecking.cu:136-228, 14 launches).
 //   k_constraints  — K3: slice every link / torque reach set at k (value and d/dk), evaluate the
 //                    collision rows and their gradients, append the Bezier joint-limit rows; writes the
 //                    whole g(k) and dense Jacobian.  Replaces PZsparse::slice (KPR/PZsparse.cu:404-555),
@@ -25,70 +25,170 @@
 namespace armour {
 
 // ---------------------------------------------------------------------------------------------------
-// K3a
-__global__ void __launch_bounds__(256) k_hyperplanes(Batch B) {
-    const int tb = blockIdx.x, p = blockIdx.y;
-    const int NJ = B.NJ, O = B.O;
-    const int per_pair = NJ * TB * O;
-    const int items = NCOMB * per_pair;
-    const double* obs = B.obstacles + size_t(p) * O * 12;
-    const double* LGs = B.link_gens + (size_t(p) * B.T + size_t(tb) * TB) * NJ * 18;
-    double* out = B.hp + (size_t(p) * (B.T / TB) + tb) * B.hp_chunk();
+// Collision half-spaces of one (link, interval, obstacle) row.
+//
+// The buffered obstacle zonotope has 9 generators: 3 of the obstacle, the <= 3 pure link-generator
+// columns and diag(radius) of the link reach set (KPR/CollisionChecking.cu:136-167).  Each of the
+// C(9,2) = 36 generator pairs gives a unit normal C = g_a x g_b / |g_a x g_b| (zero if degenerate),
+// an offset d = C . c_obs and a half-width delta = sum_j |C . g_j| (polytope_PH, :169-228); the
+// constraint of the row is h(k) = -max_i max(C_i.p(k) - (d_i + delta_i), -C_i.p(k) - (-d_i + delta_i))
+// with strict '>' in the scan order pos_0, neg_0, pos_1, ... (checkCollisionKernel, :230-299).
+// for_each_plane() enumerates the pairs in the reference order (0,1),(0,2)...(7,8) with every index a
+// compile-time constant, so the 27 generator components stay in registers.
+template <class F>
+__device__ __forceinline__ void for_each_plane(const double (&G)[9][3], const double (&oc)[3], F f) {
+    int i = 0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+#pragma unroll
+        for (int b = a + 1; b < 9; b++) {
+            const double cx = G[a][1] * G[b][2] - G[a][2] * G[b][1];
+            const double cy = G[a][2] * G[b][0] - G[a][0] * G[b][2];
+            const double cz = G[a][0] * G[b][1] - G[a][1] * G[b][0];
+            const double nrm = sqrt(cx * cx + cy * cy + cz * cz);
+            double C0 = 0, C1 = 0, C2 = 0;
+            if (nrm > 0) {
+                C0 = cx / nrm;
+                C1 = cy / nrm;
+                C2 = cz / nrm;
+            }
+            const double d = C0 * oc[0] + C1 * oc[1] + C2 * oc[2];
+            double delta = 0.0;
+#pragma unroll
+            for (int gI = 0; gI < 9; gI++) delta += fabs(C0 * G[gI][0] + C1 * G[gI][1] + C2 * G[gI][2]);
+            const bool nz = sqrt(C0 * C0 + C1 * C1 + C2 * C2) > 0;  // the test of checkCollisionKernel (:259)
+            f(i, C0, C1, C2, d, delta, nz);
+            i++;
+        }
+    }
+}
 
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int i = it / per_pair;
-        const int x = it - i * per_pair;  // (l*TB + tt)*O + o
+__device__ __forceinline__ void load_row_generators(const double* __restrict__ ob, const double* __restrict__ LG,
+                                                    double (&G)[9][3], double (&oc)[3]) {
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        oc[e] = ob[e];
+#pragma unroll
+        for (int gI = 0; gI < 3; gI++) G[gI][e] = ob[(gI + 1) * 3 + e];
+#pragma unroll
+        for (int gI = 0; gI < 6; gI++) G[gI + 3][e] = LG[e + gI * 3];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3a: half-space candidate lists.  Replaces bufferObstaclesKernel + polytope_PH (14 launches in the
+// reference).  The reference stores all 72 half-spaces of every row (12.9 MB per problem at 10
+// obstacles) and scans them at every constraint evaluation.  Here the scan is bounded at build time:
+// the link centre p(k) is a polynomial in k with known coefficients, so each half-space value
+//     v_i(k) = s_i C_i . p(k) - b_i     lies in   [vc_i - rho_i, vc_i + rho_i]   for all |k_j| <= K_DOMAIN,
+// rho_i = sum_m |C_i . g_m|.  A half-space whose upper bound is below the best lower bound can never
+// be the maximum; neither can one that repeats the normal of an earlier candidate with a larger
+// offset.  Only the survivors are stored, in scan order, as 32-byte records (s_i C_i, b_i), so that the
+// evaluation kernel returns bit-identical values and gradients while reading ~100 B per row instead
+// of 1440 B.  Rows with more than HP_CAP survivors are flagged and evaluated from the generators.
+__global__ void __launch_bounds__(128) k_hyperplanes(Batch B) {
+    const int tb = blockIdx.x, p = blockIdx.y;
+    const int NJ = B.NJ, O = B.O, T = B.T;
+    const int per_pair = NJ * TB * O;
+    const double* obs = B.obstacles + size_t(p) * O * 12;
+    const size_t chunk = size_t(p) * (T / TB) + tb;
+    double* cand = B.hp_cand + chunk * B.hp_chunk();
+    unsigned char* cnt = B.hp_cnt + chunk * per_pair;
+
+    for (int x = threadIdx.x; x < per_pair; x += blockDim.x) {
         const int o = x % O;
         const int ltt = x / O;
         const int tt = ltt % TB, l = ltt / TB;
-        const double* LG = LGs + size_t(tt * NJ + l) * 18;
-        const double* ob = obs + o * 12;
-        double G[9][3];
-#pragma unroll
-        for (int e = 0; e < 3; e++) {
-#pragma unroll
-            for (int gI = 0; gI < 3; gI++) G[gI][e] = ob[(gI + 1) * 3 + e];
-#pragma unroll
-            for (int gI = 0; gI < 6; gI++) G[gI + 3][e] = LG[e + gI * 3];
-        }
-        const int a = c_combA[i], b = c_combB[i];
-        double ga[3], gb[3];
-#pragma unroll
-        for (int e = 0; e < 3; e++) {  // dynamic row select without local-memory indexing
-            double va = 0, vb = 0;
-#pragma unroll
-            for (int gI = 0; gI < 9; gI++) {
-                va = (gI == a) ? G[gI][e] : va;
-                vb = (gI == b) ? G[gI][e] : vb;
+        const size_t idx = (size_t(p) * T + size_t(tb) * TB + tt) * NJ + l;
+        double G[9][3], oc[3];
+        load_row_generators(obs + o * 12, B.link_gens + idx * 18, G, oc);
+        const int n = B.link_n[idx];
+        const double* __restrict__ lg = B.link_g + idx * B.capL * 3;
+        const double c0 = B.link_c[idx * 3 + 0], c1 = B.link_c[idx * 3 + 1], c2 = B.link_c[idx * 3 + 2];
+
+        auto bounds = [&](double C0, double C1, double C2, double d, double delta, double& vpos, double& vneg,
+                          double& rho) {
+            const double dot = C0 * c0 + C1 * c1 + C2 * c2;
+            vpos = dot - (d + delta);
+            vneg = -dot - (-d + delta);
+            double r = 0.0;
+            for (int mI = 0; mI < n; mI++)
+                r += fabs(C0 * lg[mI * 3 + 0] + C1 * lg[mI * 3 + 1] + C2 * lg[mI * 3 + 2]);
+            // |k_j| <= K_DOMAIN, total degree <= 21; plus evaluation round-off (values are O(1))
+            rho = r * HP_RHO_SCALE + (1e-10 + 1e-12 * (fabs(dot) + fabs(d) + delta));
+        };
+
+        // pass 1: the best guaranteed lower bound
+        double lo_max = -100000000;
+        for_each_plane(G, oc, [&](int, double C0, double C1, double C2, double d, double delta, bool nz) {
+            if (!nz) return;
+            double vpos, vneg, rho;
+            bounds(C0, C1, C2, d, delta, vpos, vneg, rho);
+            lo_max = fmax(lo_max, fmax(vpos, vneg) - rho);
+        });
+        // pass 2: emit the survivors in scan order
+        int count = 0;
+        bool overflow = false;
+        double* row = cand + size_t(x) * 4;
+        const size_t cstride = size_t(per_pair) * 4;
+        auto emit = [&](double A0, double A1, double A2, double b) {
+            for (int q = 0; q < count; q++) {  // an earlier candidate with the same normal and b_q <= b dominates
+                const double* e = row + q * cstride;
+                if (e[0] == A0 && e[1] == A1 && e[2] == A2 && e[3] <= b) return;
             }
-            ga[e] = va;
-            gb[e] = vb;
-        }
-        const double cx = ga[1] * gb[2] - ga[2] * gb[1];
-        const double cy = ga[2] * gb[0] - ga[0] * gb[2];
-        const double cz = ga[0] * gb[1] - ga[1] * gb[0];
-        const double nrm = sqrt(cx * cx + cy * cy + cz * cz);
-        double C0 = 0, C1 = 0, C2 = 0;
-        if (nrm > 0) {
-            C0 = cx / nrm;
-            C1 = cy / nrm;
-            C2 = cz / nrm;
-        }
-        const double d = C0 * ob[0] + C1 * ob[1] + C2 * ob[2];
-        double delta = 0.0;
-#pragma unroll
-        for (int gI = 0; gI < 9; gI++) delta += fabs(C0 * G[gI][0] + C1 * G[gI][1] + C2 * G[gI][2]);
-        const size_t stride = size_t(NCOMB) * per_pair;
-        out[it] = C0;
-        out[it + stride] = C1;
-        out[it + 2 * stride] = C2;
-        out[it + 3 * stride] = d;
-        out[it + 4 * stride] = delta;
+            if (count == HP_CAP) {
+                overflow = true;
+                return;
+            }
+            double* e = row + count * cstride;
+            e[0] = A0;
+            e[1] = A1;
+            e[2] = A2;
+            e[3] = b;
+            count++;
+        };
+        for_each_plane(G, oc, [&](int, double C0, double C1, double C2, double d, double delta, bool nz) {
+            if (!nz || overflow) return;
+            double vpos, vneg, rho;
+            bounds(C0, C1, C2, d, delta, vpos, vneg, rho);
+            if (vpos + rho >= lo_max) emit(C0, C1, C2, d + delta);
+            if (vneg + rho >= lo_max) emit(-C0, -C1, -C2, -d + delta);
+        });
+        cnt[x] = overflow ? (unsigned char)HP_OVERFLOW : (unsigned char)count;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // K3
+// Slow path of one collision row: scan all 72 half-spaces computed from the generators
+// (checkCollisionKernel, KPR/CollisionChecking.cu:230-299).  Kept out of line so that the streaming
+// path of k_constraints keeps its register budget.
+__device__ __noinline__ void row_from_generators(const double* __restrict__ ob, const double* __restrict__ LG,
+                                                 double c0, double c1, double c2, double* max_out, double* A0o,
+                                                 double* A1o, double* A2o) {
+    double G[9][3], oc[3];
+    load_row_generators(ob, LG, G, oc);
+    double max_elt = -100000000, A0 = 0, A1 = 0, A2 = 0;
+    for_each_plane(G, oc, [&](int, double a0, double a1, double a2, double d, double dl, bool nz) {
+        if (!nz) return;
+        const double dot = a0 * c0 + a1 * c1 + a2 * c2;
+        const double pos = dot - (d + dl);
+        const double neg = -dot - (-d + dl);
+        if (pos > max_elt) {
+            max_elt = pos;
+            A0 = -a0; A1 = -a1; A2 = -a2;
+        }
+        if (neg > max_elt) {
+            max_elt = neg;
+            A0 = a0; A1 = a1; A2 = a2;
+        }
+    });
+    *max_out = max_elt;
+    *A0o = A0;
+    *A1o = A1;
+    *A2o = A2;
+}
+
 template <int NC>  // NC = 3 (link) or 1 (torque)
 __device__ __forceinline__ void slice_one(const uint16_t* __restrict__ keys, const double* __restrict__ coef, int n,
                                           int v, const double (*kp)[4], const double (*dkp)[4], double* acc) {
@@ -117,7 +217,7 @@ __device__ __forceinline__ void slice_one(const uint16_t* __restrict__ keys, con
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
     const int tb = blockIdx.x, p = blockIdx.y;
     const int NJ = B.NJ, O = B.O, T = B.T;
@@ -125,7 +225,13 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     __shared__ double kp[NF][4], dkp[NF][4];
     __shared__ double s_lc[TB][MAXJ][3];
     __shared__ double s_dlc[TB][MAXJ][NF][3];
+    __shared__ int s_in_domain;
 
+    if (threadIdx.x == 0) {
+        bool in = true;
+        for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
+        s_in_domain = in ? 1 : 0;
+    }
     if (threadIdx.x < NF) {
         const double k = kin[size_t(p) * NF + threadIdx.x];
         kp[threadIdx.x][0] = 1.0;
@@ -191,44 +297,45 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 
     // phase 2: collision rows.  item x = (l*TB + tt)*O + o
     const int per_pair = NJ * TB * O;
-    const double* hp = B.hp + (size_t(p) * (T / TB) + tb) * B.hp_chunk();
-    const size_t cstride = size_t(NCOMB) * per_pair;
+    const size_t chunk = size_t(p) * (T / TB) + tb;
+    const double* cand = B.hp_cand + chunk * B.hp_chunk();
+    const unsigned char* cnt = B.hp_cnt + chunk * per_pair;
+    const size_t cstride = size_t(per_pair) * 4;
     for (int x = threadIdx.x; x < per_pair; x += blockDim.x) {
         const int o = x % O;
         const int ltt = x / O;
         const int tt = ltt % TB, l = ltt / TB;
         const double c0 = s_lc[tt][l][0], c1 = s_lc[tt][l][1], c2 = s_lc[tt][l][2];
         double max_elt = -100000000;
-        double A0 = 0, A1 = 0, A2 = 0;  // winning normal, sign folded in
-#pragma unroll 4
-        for (int i = 0; i < NCOMB; i++) {
-            const double* h = hp + size_t(i) * per_pair + x;
-            const double a0 = h[0], a1 = h[cstride], a2 = h[2 * cstride];
-            const double d = h[3 * cstride], dl = h[4 * cstride];
-            double pos = -100000000, neg = -100000000;
-            if (sqrt(a0 * a0 + a1 * a1 + a2 * a2) > 0) {
-                const double dot = a0 * c0 + a1 * c1 + a2 * c2;
-                pos = dot - (d + dl);
-                neg = -dot - (-d + dl);
+        double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
+        const int n = cnt[x];
+        if (n != HP_OVERFLOW && s_in_domain) {
+            const double2* row = reinterpret_cast<const double2*>(cand + size_t(x) * 4);
+            for (int q = 0; q < n; q++) {
+                const double2 u = __ldg(row + q * (cstride / 2));
+                const double2 w = __ldg(row + q * (cstride / 2) + 1);
+                const double v = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
+                if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
+                    max_elt = v;
+                    A0 = -u.x; A1 = -u.y; A2 = -w.x;
+                }
             }
-            if (pos > max_elt) {  // strict '>' and pos-before-neg: KPR/CollisionChecking.cu:264-276
-                max_elt = pos;
-                A0 = -a0; A1 = -a1; A2 = -a2;
-            }
-            if (neg > max_elt) {
-                max_elt = neg;
-                A0 = a0; A1 = a1; A2 = a2;
-            }
+        } else {
+            // all 72 half-spaces from the generators: rows with more than HP_CAP candidates, or k outside
+            // the box the candidate lists were built for
+            const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+            row_from_generators(B.obstacles + (size_t(p) * O + o) * 12, B.link_gens + idx * 18, c0, c1, c2, &max_elt,
+                                &A0, &A1, &A2);
         }
         const int t = tb * TB + tt;
-        const size_t row = size_t(NF) * T + (size_t(l) * T + t) * O + o;
-        if (gp) gp[row] = -max_elt;
+        const size_t row_i = size_t(NF) * T + (size_t(l) * T + t) * O + o;
+        if (gp) gp[row_i] = -max_elt;
         if (jp) {
 #pragma unroll
             for (int v = 0; v < NF; v++) {
                 const double* dk = s_dlc[tt][l][v];
-                // -(A.dk) for a 'pos' winner, +(A.dk) for 'neg' (:286-295); the sign was folded into A
-                jp[row * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+                // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
+                jp[row_i * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
             }
         }
     }
@@ -305,7 +412,7 @@ k_verdict(Batch B, const double* __restrict__ g, int* __restrict__ feasible, int
 cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
     if (B.O == 0 || B.nprob == 0) return cudaSuccess;
     dim3 grid(B.T / TB, B.nprob);
-    k_hyperplanes<<<grid, 256, 0, st>>>(B);
+    k_hyperplanes<<<grid, 128, 0, st>>>(B);
     return cudaGetLastError();
 }
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {

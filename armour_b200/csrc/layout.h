@@ -11,7 +11,10 @@
 namespace armour {
 
 constexpr int TB = 8;        // time intervals per CTA in the constraint kernels
-constexpr int HP_COMP = 5;   // hyper-plane record: Cx, Cy, Cz, d, delta
+constexpr int HP_CAP = 16;         // stored candidate half-spaces per (link, interval, obstacle) row
+constexpr int HP_OVERFLOW = 255;   // row count marker: more than HP_CAP candidates, evaluate from the generators
+constexpr double K_DOMAIN = 1.0 + 1e-6;        // the candidate lists are exact for |k_j| <= K_DOMAIN
+constexpr double HP_RHO_SCALE = 1.0 + 3e-5;    // >= K_DOMAIN^21 (largest total degree of a link monomial)
 
 struct Batch {
     int nprob;     // problems in flight
@@ -37,13 +40,15 @@ struct Batch {
     double* u_g;              // [p][t][NF][capU]
     double* torque_radius;    // [p][j*T + t]
     double* link_gens;        // [p][t][NJ][18]     column-major 3x6
-    // collision hyper-planes: [p][t/TB][comp][pair][l][t%TB][o]
-    double* hp;
+    // collision half-space candidates: records [p][t/TB][candidate][l][t%TB][o][4] = (s*Cx, s*Cy, s*Cz, b),
+    // and the number of candidates per row [p][t/TB][l][t%TB][o]
+    double* hp_cand;
+    unsigned char* hp_cnt;
     // outputs of the last evaluation
     double* link_sliced;      // [p][t][NJ][3]
     int* status;              // [p]
 
-    __host__ __device__ size_t hp_chunk() const { return size_t(HP_COMP) * NCOMB * NJ * TB * O; }
+    __host__ __device__ size_t hp_chunk() const { return size_t(HP_CAP) * 4 * NJ * TB * O; }
     __host__ __device__ int m() const { return NF * T + NJ * T * O + 4 * NF; }
 };
 

@@ -217,7 +217,11 @@ def run_b200(args):
     # ---- inputs (synthetic, config-2 generator), reach sets built once per problem -------------------
     q0, qd0, qdd0, q_des, obs = worlds.random_problems(nprob, nobs, seed=20261017 + rank)
     eng = ReachSetEngine(max_problems=nprob, max_obstacles=nobs, device=local)
-    stream = torch.cuda.current_stream()
+    # the library launches on THIS stream and the CUDA events below are recorded on it (a NULL handle would
+    # make the context fall back to its own stream, which torch events do not see)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     tq0, tqd0, tqdd0, tobs = (torch.tensor(a, dtype=torch.float64, device=dev) for a in (q0, qd0, qdd0, obs))
     launches0 = eng.kernel_launches

@@ -95,6 +95,22 @@ def test_batched_import_eval(built):
     assert np.array_equal(g2, g) and np.array_equal(j2, jac)
 
 
+def test_k_outside_the_box_uses_the_full_scan(built):
+    """The stored half-space candidate lists are exact for |k_j| <= 1 (the NLP's variable bounds,
+    NLPclass.cu:86-110).  Outside the box the kernel scans all 72 half-spaces from the generators: same answer
+    as the oracle there too, and the two paths agree on the boundary."""
+    from armour_b200 import ReachSetEngine
+    from oracle.pyoracle import OracleProblem
+    q0, qd0, qdd0, q_des, obs = _problems()[2]
+    ref = OracleProblem().build(q0, qd0, qdd0, obs)
+    eng = ReachSetEngine(max_problems=1, max_obstacles=obs.shape[0])
+    eng.import_reachsets(0, 1, ref.tables(), q0, qd0, qdd0, obs)
+    for k in (1.5 * K_TEST, np.full(7, -1.25), np.array([1.0, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0 + 2e-6])):
+        g, jac = eng.eval(k)
+        assert np.max(np.abs(g[0] - ref.eval_g(k))) <= TOL
+        assert np.max(np.abs(jac[0] - ref.eval_jac_g(k))) <= TOL
+
+
 def test_error_paths(built):
     from armour_b200 import ReachSetEngine, ArmourError
     eng = ReachSetEngine(max_problems=1, max_obstacles=2)
