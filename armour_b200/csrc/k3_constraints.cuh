@@ -189,160 +189,178 @@ __device__ __noinline__ void row_from_generators(const double* __restrict__ ob, 
     *A2o = A2;
 }
 
-template <int NC>  // NC = 3 (link) or 1 (torque)
-__device__ __forceinline__ void slice_one(const uint16_t* __restrict__ keys, const double* __restrict__ coef, int n,
-                                          int v, const double (*kp)[4], const double (*dkp)[4], double* acc) {
-    // acc[] enters holding the centre (v == 0) or zero (v > 0: derivative w.r.t. k_{v-1})
+// One component of one reach set sliced at k: value and all seven d/dk in a single pass over the
+// monomials.  Per monomial the factors k_j^{d_j} are applied in ascending j exactly like
+// PZsparse::slice (KPR/PZsparse.cu:404-435) and its gradient overloads (:477-555); a factor with
+// d_j = 0 is 1.0 and is skipped (exact).  D[v] carries coef * prod_{j<v} f_j * f'_v * prod_{v<j} f_j.
+__device__ __forceinline__ void slice_component(const uint16_t* __restrict__ keys, const double* __restrict__ coef,
+                                                int n, int cstride, const double (*kp)[4], const double (*dkp)[4],
+                                                double& value, double (&grad)[NF]) {
     for (int mI = 0; mI < n; mI++) {
         const unsigned key = keys[mI];
-        double t[NC];
-#pragma unroll
-        for (int e = 0; e < NC; e++) t[e] = coef[mI * NC + e];
-        bool zero = false;
+        double val = coef[mI * cstride];
+        double D[NF];
 #pragma unroll
         for (int j = 0; j < NF; j++) {
             const int dg = (key >> (2 * j)) & 3;
-            double f;
-            if (j == v - 1) {
-                zero = zero || (dg == 0);
-                f = dkp[j][dg];
-            } else {
-                f = kp[j][dg];
+            D[j] = 0.0;
+            if (dg) {
+                const double f = kp[j][dg], df = dkp[j][dg];
+                D[j] = val * df;
+#pragma unroll
+                for (int v = 0; v < j; v++) D[v] *= f;
+                val *= f;
             }
-#pragma unroll
-            for (int e = 0; e < NC; e++) t[e] *= f;
         }
+        value += val;
 #pragma unroll
-        for (int e = 0; e < NC; e++) acc[e] += zero ? 0.0 : t[e];
+        for (int v = 0; v < NF; v++) grad[v] += D[v];
     }
 }
 
-__global__ void __launch_bounds__(256, 4)
+constexpr int K3_THREADS = 256;
+constexpr int K3_WARPS = K3_THREADS / 32;
+constexpr int K3_TORQUE_T0 = 192;  // first thread of the torque slices (warp aligned; link slices use 0..TB*3*NJ-1)
+static_assert(TB * 3 * MAXJ <= K3_TORQUE_T0 && K3_TORQUE_T0 + TB * NF <= K3_THREADS, "thread map of the slice phase");
+
+__global__ void __launch_bounds__(K3_THREADS, 4)
 k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
     const int tb = blockIdx.x, p = blockIdx.y;
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int m = B.m();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double kp[NF][4], dkp[NF][4];
     __shared__ double s_lc[TB][MAXJ][3];
     __shared__ double s_dlc[TB][MAXJ][NF][3];
+    __shared__ double s_stage[K3_WARPS][32 * NF];  // per-warp transpose buffer: Jacobian rows leave coalesced
     __shared__ int s_in_domain;
 
-    if (threadIdx.x == 0) {
+    if (tid == 32) {
         bool in = true;
         for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
         s_in_domain = in ? 1 : 0;
     }
-    if (threadIdx.x < NF) {
-        const double k = kin[size_t(p) * NF + threadIdx.x];
-        kp[threadIdx.x][0] = 1.0;
-        kp[threadIdx.x][1] = k;
-        kp[threadIdx.x][2] = k * k;
-        kp[threadIdx.x][3] = k * k * k;
-        dkp[threadIdx.x][0] = 0.0;
-        dkp[threadIdx.x][1] = 1.0;
-        dkp[threadIdx.x][2] = 2.0 * k;
-        dkp[threadIdx.x][3] = 3.0 * (k * k);
+    if (tid < NF) {
+        const double k = kin[size_t(p) * NF + tid];
+        kp[tid][0] = 1.0;
+        kp[tid][1] = k;
+        kp[tid][2] = k * k;
+        kp[tid][3] = k * k * k;
+        dkp[tid][0] = 0.0;
+        dkp[tid][1] = 1.0;
+        dkp[tid][2] = 2.0 * k;
+        dkp[tid][3] = 3.0 * (k * k);
     }
     __syncthreads();
 
     double* gp = g ? g + size_t(p) * m : nullptr;
     double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
 
-    // phase 1: slices.  item = (tt, s, v): s < NJ link slices, then NF torque slices; v = 0 value, 1..7 d/dk
-    const int nsl = NJ + NF;
-    for (int it = threadIdx.x; it < TB * nsl * 8; it += blockDim.x) {
-        const int v = it & 7;
-        const int s = (it >> 3) % nsl;
-        const int tt = (it >> 3) / nsl;
-        const int t = tb * TB + tt;
-        if (s < NJ) {
-            const size_t idx = (size_t(p) * T + t) * NJ + s;
-            const int n = B.link_n[idx];
-            double acc[3] = {0, 0, 0};
-            if (v == 0) {
-                acc[0] = B.link_c[idx * 3 + 0];
-                acc[1] = B.link_c[idx * 3 + 1];
-                acc[2] = B.link_c[idx * 3 + 2];
-            }
-            slice_one<3>(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3, n, v, kp, dkp, acc);
-            if (v == 0) {
-                // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
-                const double* LG = B.link_gens + idx * 18;
+    // ---- phase 1: slices.  Threads [0, TB*NJ*3): link component (tt, l, e); threads [192, 192+TB*NF): torque (tt, j)
+    if (tid < TB * NJ * 3) {
+        const int e = tid % 3;
+        const int l = (tid / 3) % NJ;
+        const int tt = tid / (3 * NJ);
+        const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+        double value = B.link_c[idx * 3 + e];
+        double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
+        slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 3, kp, dkp, value,
+                        grad);
+        // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
+        const double r = B.link_gens[idx * 18 + e + (3 + e) * 3];
+        const double c = ((value - r) + (value + r)) * 0.5;
+        s_lc[tt][l][e] = c;
+        B.link_sliced[idx * 3 + e] = c;
 #pragma unroll
-                for (int e = 0; e < 3; e++) {
-                    const double r = LG[e + (3 + e) * 3];
-                    const double c = ((acc[e] - r) + (acc[e] + r)) * 0.5;
-                    s_lc[tt][s][e] = c;
-                    B.link_sliced[idx * 3 + e] = c;
-                }
-            } else {
+        for (int v = 0; v < NF; v++) s_dlc[tt][l][v][e] = grad[v];
+    } else if (tid >= K3_TORQUE_T0 && tid < K3_TORQUE_T0 + TB * NF) {
+        const int i = tid - K3_TORQUE_T0;  // tt*NF + j
+        const size_t idx = (size_t(p) * T + tb * TB) * NF + i;
+        double value = B.u_c[idx];
+        double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
+        slice_component(B.u_key + idx * B.capU, B.u_g + idx * B.capU, B.u_n[idx], 1, kp, dkp, value, grad);
+        const double r = B.u_r[idx];
+        if (gp) gp[tb * TB * NF + i] = ((value - r) + (value + r)) * 0.5;
+        if (jp) {  // rows tb*TB*NF + i, i < 56: 392 contiguous doubles, transposed through the stage of warps 6 and 7
+            double* st = &s_stage[K3_TORQUE_T0 / 32][0];
 #pragma unroll
-                for (int e = 0; e < 3; e++) s_dlc[tt][s][v - 1][e] = acc[e];
-            }
-        } else {
-            const int j = s - NJ;
-            const size_t idx = (size_t(p) * T + t) * NF + j;
-            const int n = B.u_n[idx];
-            double acc[1] = {v == 0 ? B.u_c[idx] : 0.0};
-            slice_one<1>(B.u_key + idx * B.capU, B.u_g + idx * B.capU, n, v, kp, dkp, acc);
-            if (v == 0) {
-                const double r = B.u_r[idx];
-                if (gp) gp[t * NF + j] = ((acc[0] - r) + (acc[0] + r)) * 0.5;
-            } else if (jp) {
-                jp[size_t(t * NF + j) * NF + (v - 1)] = acc[0];
-            }
+            for (int v = 0; v < NF; v++) st[i * NF + v] = grad[v];
         }
     }
     __syncthreads();
+    if (jp && tid >= K3_TORQUE_T0) {
+        const double* st = &s_stage[K3_TORQUE_T0 / 32][0];
+        double* dst = jp + size_t(tb) * TB * NF * NF;
+        for (int i = tid - K3_TORQUE_T0; i < TB * NF * NF; i += K3_THREADS - K3_TORQUE_T0) dst[i] = st[i];
+    }
+    __syncthreads();
 
-    // phase 2: collision rows.  item x = (l*TB + tt)*O + o
+    // ---- phase 2: collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
     const int per_pair = NJ * TB * O;
     const size_t chunk = size_t(p) * (T / TB) + tb;
     const double* cand = B.hp_cand + chunk * B.hp_chunk();
     const unsigned char* cnt = B.hp_cnt + chunk * per_pair;
-    const size_t cstride = size_t(per_pair) * 4;
-    for (int x = threadIdx.x; x < per_pair; x += blockDim.x) {
-        const int o = x % O;
-        const int ltt = x / O;
-        const int tt = ltt % TB, l = ltt / TB;
-        const double c0 = s_lc[tt][l][0], c1 = s_lc[tt][l][1], c2 = s_lc[tt][l][2];
+    const size_t cstride2 = size_t(per_pair) * 2;  // candidate stride in double2 units
+    const bool in_domain = s_in_domain != 0;
+    double* stage = &s_stage[warp][0];
+    for (int x0 = warp * 32; x0 < per_pair; x0 += K3_THREADS) {
+        const int x = x0 + lane;
+        const bool active = x < per_pair;
         double max_elt = -100000000;
         double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
-        const int n = cnt[x];
-        if (n != HP_OVERFLOW && s_in_domain) {
-            const double2* row = reinterpret_cast<const double2*>(cand + size_t(x) * 4);
-            for (int q = 0; q < n; q++) {
-                const double2 u = __ldg(row + q * (cstride / 2));
-                const double2 w = __ldg(row + q * (cstride / 2) + 1);
-                const double v = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
-                if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
-                    max_elt = v;
-                    A0 = -u.x; A1 = -u.y; A2 = -w.x;
+        int l = 0, tt = 0, o = 0;
+        if (active) {
+            o = x % O;
+            const int ltt = x / O;
+            tt = ltt % TB;
+            l = ltt / TB;
+            const double c0 = s_lc[tt][l][0], c1 = s_lc[tt][l][1], c2 = s_lc[tt][l][2];
+            const int n = cnt[x];
+            if (n != HP_OVERFLOW && in_domain) {
+                const double2* row = reinterpret_cast<const double2*>(cand) + size_t(x) * 2;
+                for (int q = 0; q < n; q++) {
+                    const double2 u = __ldg(row + q * cstride2);
+                    const double2 w = __ldg(row + q * cstride2 + 1);
+                    const double v = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
+                    if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
+                        max_elt = v;
+                        A0 = -u.x; A1 = -u.y; A2 = -w.x;
+                    }
+                }
+            } else {
+                // all 72 half-spaces from the generators: rows with more than HP_CAP candidates, or k outside
+                // the box the candidate lists were built for
+                const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+                row_from_generators(B.obstacles + (size_t(p) * O + o) * 12, B.link_gens + idx * 18, c0, c1, c2,
+                                    &max_elt, &A0, &A1, &A2);
+            }
+        }
+        const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
+        if (gp && active) gp[row_i] = -max_elt;
+        if (jp) {
+            if (active) {
+#pragma unroll
+                for (int v = 0; v < NF; v++) {
+                    const double* dk = s_dlc[tt][l][v];
+                    // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
+                    stage[lane * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
                 }
             }
-        } else {
-            // all 72 half-spaces from the generators: rows with more than HP_CAP candidates, or k outside
-            // the box the candidate lists were built for
-            const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
-            row_from_generators(B.obstacles + (size_t(p) * O + o) * 12, B.link_gens + idx * 18, c0, c1, c2, &max_elt,
-                                &A0, &A1, &A2);
-        }
-        const int t = tb * TB + tt;
-        const size_t row_i = size_t(NF) * T + (size_t(l) * T + t) * O + o;
-        if (gp) gp[row_i] = -max_elt;
-        if (jp) {
+            __syncwarp();
 #pragma unroll
-            for (int v = 0; v < NF; v++) {
-                const double* dk = s_dlc[tt][l][v];
-                // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
-                jp[row_i * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+            for (int q = 0; q < NF; q++) {
+                const int e = q * 32 + lane;
+                const int r = e / NF;
+                const long long rr = __shfl_sync(0xffffffffu, row_i, r);
+                if (rr >= 0) jp[rr * NF + (e - r * NF)] = stage[e];
             }
+            __syncwarp();
         }
     }
 
     // Bezier joint-limit rows (KPR/Trajectory.cu:256-540), once per problem
-    if (tb == 0 && threadIdx.x < NF) {
-        const int i = threadIdx.x;
+    if (tb == 0 && tid < NF) {
+        const int i = tid;
         const double D = c_robot.duration;
         const double q0 = B.q0[size_t(p) * NF + i];
         const double a = B.qd0[size_t(p) * NF + i] * D;
@@ -418,7 +436,7 @@ cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
     dim3 grid(B.T / TB, B.nprob);
-    k_constraints<<<grid, 256, 0, st>>>(B, d_k, d_g, d_jac);
+    k_constraints<<<grid, K3_THREADS, 0, st>>>(B, d_k, d_g, d_jac);
     return cudaGetLastError();
 }
 cudaError_t launch_verdict(const Batch& B, const double* d_g, int* d_feasible, int* d_first, cudaStream_t st) {
