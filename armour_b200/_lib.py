@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarmour_b200.so")
+# ARMOUR_B200_LIB: developer override used by tools/exp_k1.py to compare differently tuned builds of the SAME CUDA library
+LIB_PATH = os.environ.get("ARMOUR_B200_LIB") or os.path.join(_HERE, "libarmour_b200.so")
 NF = 7
 
 OK, ERR_ARG, ERR_CUDA, ERR_OBSTACLES, ERR_CAPACITY, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6

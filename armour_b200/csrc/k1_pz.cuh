@@ -38,7 +38,14 @@ namespace k1 {
 
 typedef unsigned long long u64;
 
-constexpr int NT = 256;      // threads per CTA
+#ifndef K1_NT
+#define K1_NT 256
+#endif
+#ifndef K1_CTAS
+#define K1_CTAS 2
+#endif
+constexpr int NT = K1_NT;    // threads per CTA
+constexpr int CTAS_PER_SM = K1_CTAS;  // resident CTAs per SM (shared memory is split evenly)
 constexpr int NW = NT / 32;  // warps per CTA
 constexpr int RED_STRIDE = 12;
 

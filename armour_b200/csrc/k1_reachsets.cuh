@@ -606,7 +606,7 @@ K1_DI void build_unit(Ctx& c, const Batch& B, int p, int t, double* jrs_mem, int
 
 constexpr int K1_FIXED_BYTES = 64 * 4 + 2 * NW * RED_STRIDE * 8 + 16 * 8 + JRS_WORDS * 8;
 
-__global__ void __launch_bounds__(NT, 2) k_reachsets(K1Params P) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_reachsets(K1Params P) {
     K1_SMEM_DECL;
     unsigned char* sm = K1_SMEM_PTR;
     int* s_int = reinterpret_cast<int*>(sm);                 // [0..8) cnt, [8] unit, [16..40) jrs counts
@@ -710,13 +710,13 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     // two CTAs per SM: half of the SM's shared memory each (1 KB per CTA is reserved by the system)
-    int per_cta = (smem_optin + 1024) / 2 - 1024;
+    int per_cta = (smem_optin + 1024) / CTAS_PER_SM - 1024;
     per_cta &= ~1023;
     const int dyn = per_cta - K1_FIXED_BYTES;
     s->tab_s_bytes = (dyn * 5 / 8) & ~1023;
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
     s->smem_bytes = size_t(K1_FIXED_BYTES) + size_t(s->arena_words) * 8 + s->tab_s_bytes;
-    s->grid = 2 * sms;
+    s->grid = CTAS_PER_SM * sms;
     // per-CTA global scratch: F_i / N_i of one unit, and the overflow hash-table pool
     const int capw = cfg.cap_work_monomials;
     s->fn_words = 2 * MAXJ * (9 + capw * 2);
