@@ -92,7 +92,8 @@ class ReachSetEngine:
         """Batched build.  q0/qd0/qdd0: [nprob, 7] (or [7]); obstacles: [nprob, nobs, 12] (or [nobs, 12])."""
         q0, qd0, qdd0 = _f64(q0).reshape(-1, NF), _f64(qd0).reshape(-1, NF), _f64(qdd0).reshape(-1, NF)
         nprob = q0.shape[0]
-        obs = _f64(obstacles).reshape(nprob, -1, 12)
+        obs = _f64(obstacles)
+        obs = obs.reshape(nprob, -1, 12) if obs.size else np.zeros((nprob, 0, 12))
         nobs = obs.shape[1]
         self._check(self.lib.armour_batch_reachsets_build(self._h, nprob, _dp(q0), _dp(qd0), _dp(qdd0), _dp(obs), nobs))
         self.nprob, self.nobs = nprob, nobs

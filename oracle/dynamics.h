@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned: bit-identical to the reference's own sources (oracle/_ref, tests/test_oracle_pinned.py, tests/golden/ref).
 //
 // PZ forward kinematics and PZ recursive Newton-Euler, restating KPR/Dynamics.h:6-48 and
 // KPR/Dynamics.cu:6-181.

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned: bit-identical to the reference's own sources (oracle/_ref, tests/test_oracle_pinned.py, tests/golden/ref).
 //
 // Restatement of the Boost.Interval type the reference uses
 // (KPR/Headers.h:30-36: interval<double, policies<save_state<rounded_transc_std<double>>,

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned for the reach-set build, slices and Bezier rows (oracle/_ref, tests/test_oracle_pinned.py); the collision rows (KPR/CollisionChecking.cu, CUDA) are restated only: parity unpinned for those rows.
 // See planner.h.
 #include "planner.h"
 

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned for the reach-set build, slices and Bezier rows (oracle/_ref, tests/test_oracle_pinned.py); the collision rows (KPR/CollisionChecking.cu, CUDA) are restated only: parity unpinned for those rows.
 //
 // One planning problem end to end on the CPU: reach-set build (KPR/armour_main.cu:86-216),
 // collision hyper-planes (KPR/CollisionChecking.cu:26-39,136-228), the NLP rows and Jacobian

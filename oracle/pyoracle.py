@@ -1,4 +1,4 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned for the reach-set build, slices and Bezier rows (oracle/_ref, tests/test_oracle_pinned.py); the collision rows (KPR/CollisionChecking.cu, CUDA) are restated only: parity unpinned for those rows.
 
 ctypes binding of oracle/liboracle.so (the CPU restatement of the reference planner's hot path).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import

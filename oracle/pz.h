@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned: bit-identical to the reference's own sources (oracle/_ref, tests/test_oracle_pinned.py, tests/golden/ref).
 //
 // CPU restatement of the reference's sparse polynomial zonotope (KPR/PZsparse.h:50-183,
 // KPR/PZsparse.cu).  A PZ is  centre + sum_i coeff_i * prod_j x_j^{d_ij} + [-indep, +indep]

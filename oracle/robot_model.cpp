@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned: bit-identical to the reference's own sources (oracle/_ref, tests/test_oracle_pinned.py, tests/golden/ref).
 // Physical constants of the Kinova Gen3 arm as used by the reference planner
 // (values from KPR/KinovaWithoutGripperInfo.h:17-112 and KPR/KinovaInfo.h:17-121).
 #include "robot_model.h"

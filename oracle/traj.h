@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned: bit-identical to the reference's own sources (oracle/_ref, tests/test_oracle_pinned.py, tests/golden/ref).
 //
 // Degree-5 Bezier desired trajectory and its per-interval joint reachable set (JRS),
 // restating KPR/Trajectory.h:10-95 and KPR/Trajectory.cu:15-822.
