@@ -62,8 +62,17 @@ K1_DI u64 key_qddae(int i) { return 1ull << (28 + i); }
 K1_DI u64 key_cosqe(int i) { return 1ull << (35 + 2 * i); }
 K1_DI u64 key_sinqe(int i) { return 1ull << (49 + 2 * i); }
 
-// ---- PZ handle ------------------------------------------------------------------------------------
-struct PZH {
+// ---- PZ handles -----------------------------------------------------------------------------------
+// A PZ is referred to by an 8-byte handle (virtual arena offset in words, monomial count) that is passed BY
+// VALUE and lives in registers; the element size (1, 3, 9) is a template parameter of the operation.
+// Nothing in this file takes the address of a handle or of per-thread state, so the kernel has no stack
+// frame: all CTA-uniform state sits in the shared-memory control block K1S below.  (Round-1 profile: the
+// previous by-reference plumbing cost 3 KB of local memory per thread and 1.5 G local loads per 64 problems.)
+struct PZ8 {
+    int off;
+    int n;
+};
+struct PZH {  // resolved view of a block (registers only; built by view<SZ>())
     double* p;
     int n;
     int sz;
@@ -80,58 +89,85 @@ struct Tab {
     int cap, shift;  // home slot = (key * golden) >> shift
 };
 
-// per-CTA state; every field is uniform across the threads of the CTA
-struct Ctx {
-    double* arena;   // CTA-private PZ arena (shared memory in the fast tier)
-    int arena_words;
-    int top;
-    int top_max;
-    double* garena;  // global-memory continuation of the arena (spill space)
-    int garena_words;
-    double* gscr;    // global scratch for the per-joint F / N blocks kept until the backward pass
-    int gscr_words;
-    int gtop;
-    char* tab_s;     // shared-memory hash-table pool (all zero between operations)
-    int tab_s_bytes;
-    char* tab_g;     // global-memory pool for the rare table that does not fit (all zero between operations)
-    int tab_g_bytes;
-    double* red;     // [NW][RED_STRIDE] partial sums (prune amounts)
-    double* red2;    // [NW][RED_STRIDE] partial sums (|coefficient| sums)
-    int* cnt;        // [NW] survivor counts
+// Per-CTA control block at the start of dynamic shared memory.  Written by thread 0 at kernel start (the
+// immutable part) or by all threads with identical values (fail); read by everybody.
+struct K1S {
+    double* gbase;   // global continuation of the virtual arena: [spill space GW words | F/N scratch FW words]
+    char* tab_g;     // global-memory pool for the rare hash table that does not fit (all zero between operations)
     double thr;
-    int fail;
-    int tid, lane, warp;
+    int AW;          // words of the shared-memory part of the virtual arena (JRS region + working arena)
+    int GW, FW;
+    int tab_s_bytes, tab_g_bytes;
+    int fail;        // first failure code of the current unit (0 = none)
     int n_tab_global;  // statistics
+    int unit;
+    int cnt[NW];     // survivor counts per warp
+    int jrs_n[40];   // monomial counts of the joint reachable set blocks: R at [0..8], qd/qda/qdda at [16+8g+i]
+    PZ8 Fg[MAXJ], Ng[MAXJ];  // F_i / N_i of the forward Newton-Euler pass (blocks in the F/N scratch)
+    double red[NW * RED_STRIDE];   // partial sums (prune amounts)
+    double red2[NW * RED_STRIDE];  // partial sums (|coefficient| sums)
+    double misc[16];               // [0..7) u_nom radius, [8..15) disturbance radius
 };
+constexpr int K1S_BYTES = (int(sizeof(K1S)) + 15) & ~15;
 
-K1_DI void set_fail(Ctx& c, int code) {
-    if (!c.fail) c.fail = code;
+#ifndef ARMOUR_EMU
+K1_DI unsigned char* smem_base() {
+    extern __shared__ __align__(16) unsigned char k1_smem[];
+    return k1_smem;
+}
+K1_DI int k1_tid() { return threadIdx.x; }
+#else
+inline unsigned char* smem_base() { return reinterpret_cast<unsigned char*>(emu::S().dyn_smem); }
+inline int k1_tid() { return int(threadIdx.x); }
+#endif
+K1_DI K1S& k1s() { return *reinterpret_cast<K1S*>(smem_base()); }
+K1_DI double* arena0() { return reinterpret_cast<double*>(smem_base() + K1S_BYTES); }
+K1_DI char* tab_s0() { return reinterpret_cast<char*>(arena0() + k1s().AW); }
+
+K1_DI void set_fail(int code) {
+    K1S& S = k1s();
+    if (!S.fail) S.fail = code;  // every thread writes the same value
 }
 
-// The arena is one virtual offset space over two segments: [0, arena_words) in shared memory, then
-// [arena_words, arena_words + garena_words) in the CTA's global scratch (L2-resident spill space for the
-// few long intervals whose live set outgrows shared memory).  A block never straddles the boundary.
-K1_DI double* arena_ptr(const Ctx& c, int off) {
-    return off < c.arena_words ? c.arena + off : c.garena + (off - c.arena_words);
+// The arena is one virtual offset space over two segments: [0, AW) in shared memory (the fixed JRS region
+// first), then the CTA's global scratch: [AW, AW + GW) is spill space for the few long intervals whose live
+// set outgrows shared memory (L2-resident), [AW + GW, AW + GW + FW) holds the F_i / N_i blocks.  A block never
+// straddles the shared / global boundary.
+K1_DI double* vptr(int off) {
+    const K1S& S = k1s();
+    return off < S.AW ? arena0() + off : S.gbase + (off - S.AW);
 }
-K1_DI int arena_place(const Ctx& c, int off, int w) {  // first offset >= off where a block of w words may start
-    return (off < c.arena_words && off + w > c.arena_words) ? c.arena_words : off;
+template <int SZ>
+K1_DI PZH view(PZ8 h) {
+    PZH v;
+    v.p = vptr(h.off);
+    v.n = h.n;
+    v.sz = SZ;
+    return v;
 }
-K1_DI PZH pz_alloc(Ctx& c, int n, int sz) {
-    PZH h;
-    h.n = n;
-    h.sz = sz;
-    const int w = pz_words(n, sz);
-    const int at = arena_place(c, c.top, w);
-    if (c.fail || at + w > c.arena_words + c.garena_words) {
-        set_fail(c, FAIL_ARENA);
-        h.p = c.arena;
+template <int SZ>
+K1_DI int end_of(PZ8 h) { return h.off + pz_words(h.n, SZ); }  // arena top after an operation that produced h
+K1_DI int arena_place(int off, int w) {  // first offset >= off where a block of w words may start
+    const int AW = k1s().AW;
+    return (off < AW && off + w > AW) ? AW : off;
+}
+// allocate a block for n monomials at the arena top `top` (uniform); h.n = 0 and a failure code on overflow
+template <int SZ>
+K1_DI PZ8 pz_alloc(int top, int n, bool* ok) {
+    const K1S& S = k1s();
+    const int w = pz_words(n, SZ);
+    const int at = arena_place(top, w);
+    PZ8 h;
+    if (S.fail || at + w > S.AW + S.GW) {
+        set_fail(FAIL_ARENA);
+        h.off = 0;
         h.n = 0;
+        *ok = false;
         return h;
     }
-    h.p = arena_ptr(c, at);
-    c.top = at + w;
-    if (c.top > c.top_max) c.top_max = c.top;
+    h.off = at;
+    h.n = n;
+    *ok = true;
     return h;
 }
 
@@ -203,7 +239,8 @@ K1_DI int tab_find(const Tab& t, u64 key) {
 
 // Pick a table for `nterms` candidate keys with `na` accumulators per slot.  Shared memory when it
 // fits (load <= 2/3, or <= 0.8 at half the size), else the CTA's global pool.
-K1_DI bool tab_select(Ctx& c, int nterms, int na, Tab& t) {
+K1_DI bool tab_select(int nterms, int na, Tab& t) {
+    K1S& S = k1s();
     int cap = 64, lg = 6;
     while (cap * 2 < nterms * 3) {
         cap <<= 1;
@@ -211,17 +248,17 @@ K1_DI bool tab_select(Ctx& c, int nterms, int na, Tab& t) {
     }
     const int slot_bytes = 8 * (1 + na);
     char* base = nullptr;
-    if (cap * slot_bytes <= c.tab_s_bytes) {
-        base = c.tab_s;
-    } else if (cap > 64 && nterms * 5 <= (cap / 2) * 4 && (cap / 2) * slot_bytes <= c.tab_s_bytes) {
+    if (cap * slot_bytes <= S.tab_s_bytes) {
+        base = tab_s0();
+    } else if (cap > 64 && nterms * 5 <= (cap / 2) * 4 && (cap / 2) * slot_bytes <= S.tab_s_bytes) {
         cap >>= 1;
         lg--;
-        base = c.tab_s;
-    } else if (cap * slot_bytes <= c.tab_g_bytes) {
-        base = c.tab_g;
-        c.n_tab_global++;
+        base = tab_s0();
+    } else if (cap * slot_bytes <= S.tab_g_bytes) {
+        base = S.tab_g;
+        if (k1_tid() == 0) S.n_tab_global++;
     } else {
-        set_fail(c, FAIL_TABLE);
+        set_fail(FAIL_TABLE);
         return false;
     }
     t.keys = reinterpret_cast<u64*>(base);
@@ -234,19 +271,21 @@ K1_DI bool tab_select(Ctx& c, int nterms, int na, Tab& t) {
 // Finalize a table: `fin(acc[NA] -> out[SZ], rad[SZ])` decides keep / prune per occupied slot.
 // Pass 1 rewrites kept slots with their output coefficients, clears pruned ones, counts survivors per
 // warp segment and reduces the pruned amounts; pass 2 compacts the survivors (slot order) into a new
-// arena block and leaves the table all-zero.  On return every thread holds the handle and
+// arena block at `top` and leaves the table all-zero.  On return every thread holds the handle and
 // rad_total[SZ] (block-wide pruned amounts, rounded up); the caller fills centre / radii and must
 // __syncthreads() before the block is read.
 template <int NA, int SZ, class Fin>
-K1_DI PZH tab_finalize(Ctx& c, const Tab& t, Fin fin, double* rad_total) {
+K1_DI PZ8 tab_finalize(int top, const Tab& t, Fin fin, double* rad_total, bool* ok_out) {
+    K1S& S = k1s();
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
     const int seg = (t.cap / NW) < 32 ? 32 : (t.cap / NW);
-    const int s0 = c.warp * seg;
+    const int s0 = warp * seg;
     const int s1 = (s0 + seg) < t.cap ? (s0 + seg) : t.cap;
     double rad[SZ];
 #pragma unroll
     for (int e = 0; e < SZ; e++) rad[e] = 0.0;
     int count = 0;
-    for (int s = s0 + c.lane; s < s1; s += 32) {
+    for (int s = s0 + lane; s < s1; s += 32) {
         const u64 key = t.keys[s];
         bool keep = false;
         if (key != 0) {
@@ -269,37 +308,38 @@ K1_DI PZH tab_finalize(Ctx& c, const Tab& t, Fin fin, double* rad_total) {
     }
 #pragma unroll
     for (int e = 0; e < SZ; e++) rad[e] = warp_sum_up(rad[e]);
-    if (c.lane == 0) {
-        c.cnt[c.warp] = count;
+    if (lane == 0) {
+        S.cnt[warp] = count;
 #pragma unroll
-        for (int e = 0; e < SZ; e++) c.red[c.warp * RED_STRIDE + e] = rad[e];
+        for (int e = 0; e < SZ; e++) S.red[warp * RED_STRIDE + e] = rad[e];
     }
     __syncthreads();
     int before = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        const int v = c.cnt[w];
-        if (w < c.warp) before += v;
+        const int v = S.cnt[w];
+        if (w < warp) before += v;
         total += v;
     }
 #pragma unroll
     for (int e = 0; e < SZ; e++) {
-        double v = c.red[e];
+        double v = S.red[e];
 #pragma unroll
-        for (int w = 1; w < NW; w++) v = __dadd_ru(v, c.red[w * RED_STRIDE + e]);
+        for (int w = 1; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE + e]);
         rad_total[e] = v;
     }
-    PZH h = pz_alloc(c, total, SZ);
-    const bool ok = !c.fail;
+    bool ok;
+    const PZ8 h8 = pz_alloc<SZ>(top, total, &ok);
+    const PZH h = view<SZ>(h8);
     u64* ok_keys = pz_keys(h);
     double* ok_coef = pz_coef(h);
     int run = before;
-    for (int s = s0 + c.lane; s < s1; s += 32) {
+    for (int s = s0 + lane; s < s1; s += 32) {
         const u64 key = t.keys[s];
         const bool keep = key != 0;
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            const int pos = run + __popc(b & ((1u << c.lane) - 1u));
+            const int pos = run + __popc(b & ((1u << lane) - 1u));
             if (ok) ok_keys[pos] = key;
 #pragma unroll
             for (int e = 0; e < SZ; e++) {
@@ -310,33 +350,37 @@ K1_DI PZH tab_finalize(Ctx& c, const Tab& t, Fin fin, double* rad_total) {
         }
         run += __popc(b);
     }
-    return h;
+    *ok_out = ok;
+    return h8;
 }
 
 // block-wide sum over the monomials of |coeff| per component (rounded up), NOT including |centre|.
-// Writes warp partials to c.red2; the caller syncs, then calls abs_sum_collect.
+// Writes warp partials to S.red2; the caller syncs, then calls abs_sum_collect.
 template <int SZ>
-K1_DI void abs_sum_partial(Ctx& c, const PZH& h) {
+K1_DI void abs_sum_partial(const PZH& h) {
+    K1S& S = k1s();
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
     double s[SZ];
 #pragma unroll
     for (int e = 0; e < SZ; e++) s[e] = 0.0;
     const double* cf = pz_coef(h);
-    for (int m = c.tid; m < h.n; m += NT)
+    for (int m = tid; m < h.n; m += NT)
 #pragma unroll
         for (int e = 0; e < SZ; e++) s[e] = __dadd_ru(s[e], fabs(cf[size_t(m) * SZ + e]));
 #pragma unroll
     for (int e = 0; e < SZ; e++) s[e] = warp_sum_up(s[e]);
-    if (c.lane == 0)
+    if (lane == 0)
 #pragma unroll
-        for (int e = 0; e < SZ; e++) c.red2[c.warp * RED_STRIDE + e] = s[e];
+        for (int e = 0; e < SZ; e++) S.red2[warp * RED_STRIDE + e] = s[e];
 }
 template <int SZ>
-K1_DI void abs_sum_collect(Ctx& c, const PZH& h, double* out) {  // |centre| + sum |coeff|
+K1_DI void abs_sum_collect(const PZH& h, double* out) {  // |centre| + sum |coeff|
+    const K1S& S = k1s();
 #pragma unroll
     for (int e = 0; e < SZ; e++) {
         double v = fabs(pz_c(h)[e]);
 #pragma unroll
-        for (int w = 0; w < NW; w++) v = __dadd_ru(v, c.red2[w * RED_STRIDE + e]);
+        for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red2[w * RED_STRIDE + e]);
         out[e] = v;
     }
 }
@@ -352,63 +396,66 @@ K1_DI void abs_sum_serial(const PZH& h, double* out) {
 }
 
 // ---- arena management -----------------------------------------------------------------------------
-// Slide the listed blocks (ascending addresses, all at or above `mark`) down to `mark`; everything
-// else above `mark` is released.
-K1_OP void arena_keep(Ctx& c, int mark, PZH** hs, int k) {
-    if (c.fail) return;
-    int nt = mark;
-    for (int b = 0; b < k; b++) {
-        PZH& h = *hs[b];
-        const int w = pz_words(h.n, h.sz);
-        nt = arena_place(c, nt, w);
-        double* dst = arena_ptr(c, nt);
-        double* src = h.p;
-        if (dst != src) {
-            for (int base = 0; base < w; base += NT * 4) {
-                double v[4];
+// Move w words from virtual offset src to dst (dst < src; the ranges may overlap): chunks are read by
+// all threads, then written after a barrier.
+K1_OP void move_words(int dst_off, int src_off, int w) {
+    const int tid = k1_tid();
+    double* dst = vptr(dst_off);
+    const double* src = vptr(src_off);
+    for (int base = 0; base < w; base += NT * 4) {
+        double v[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int i = base + q * NT + c.tid;
-                    v[q] = (i < w) ? src[i] : 0.0;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int i = base + q * NT + c.tid;
-                    if (i < w) dst[i] = v[q];
-                }
-            }
-            __syncthreads();
-            h.p = dst;
+        for (int q = 0; q < 4; q++) {
+            const int i = base + q * NT + tid;
+            v[q] = (i < w) ? src[i] : 0.0;
         }
-        nt += w;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = base + q * NT + tid;
+            if (i < w) dst[i] = v[q];
+        }
     }
-    c.top = nt;
+    __syncthreads();
 }
-K1_DI void arena_keep1(Ctx& c, int mark, PZH& a) {
-    PZH* l[1] = {&a};
-    arena_keep(c, mark, l, 1);
+// Slide block h down to the cursor (blocks are kept in ascending address order); advances the cursor.
+template <int SZ>
+K1_DI void keep(int& cursor, PZ8& h) {
+    if (k1s().fail) return;
+    const int w = pz_words(h.n, SZ);
+    const int at = arena_place(cursor, w);
+    if (at != h.off) {
+        move_words(at, h.off, w);
+        h.off = at;
+    }
+    cursor = at + w;
 }
 
-// copy a block to the CTA's global scratch (F_i / N_i of the forward pass)
-K1_OP PZH spill_global(Ctx& c, const PZH& h) {
-    PZH g = h;
-    const int w = pz_words(h.n, h.sz);
-    if (c.fail || c.gtop + w > c.gscr_words) {
-        set_fail(c, FAIL_SCRATCH);
+// copy a block to the CTA's F / N scratch (kept until the backward pass); gtop is the scratch cursor
+template <int SZ>
+K1_DI PZ8 spill_global(int& gtop, PZ8 h8) {
+    const K1S& S = k1s();
+    const int w = pz_words(h8.n, SZ);
+    PZ8 g = h8;
+    if (S.fail || gtop + w > S.FW) {
+        set_fail(FAIL_SCRATCH);
         g.n = 0;
         return g;
     }
-    g.p = c.gscr + c.gtop;
-    c.gtop += w;
-    for (int i = c.tid; i < w; i += NT) g.p[i] = h.p[i];
+    g.off = S.AW + S.GW + gtop;
+    gtop += w;
+    const double* src = vptr(h8.off);
+    double* dst = vptr(g.off);
+    for (int i = k1_tid(); i < w; i += NT) dst[i] = src[i];
     __syncthreads();
     return g;
 }
 
-K1_DI PZH pz_zero(Ctx& c, int sz) {  // PZ with no monomials, zero centre and radii
-    PZH h = pz_alloc(c, 0, sz);
-    if (!c.fail && c.tid < 3 * sz) h.p[c.tid] = 0.0;
+template <int SZ>
+K1_DI PZ8 pz_zero(int top) {  // PZ with no monomials, zero centre and radii
+    bool ok;
+    const PZ8 h = pz_alloc<SZ>(top, 0, &ok);
+    if (ok && k1_tid() < 3 * SZ) vptr(h.off)[k1_tid()] = 0.0;
     __syncthreads();
     return h;
 }
@@ -438,31 +485,56 @@ K1_DI void lin_value(const LinSrc& s, const double* v, double* out) {  // v: sou
             if (e == s.comp_out) out[e] = x;
     }
 }
-
 template <int SZ>
-K1_OP PZH op_lin2(Ctx& c, const LinSrc& s0, const LinSrc& s1) {
-    PZH dummy = {c.arena, 0, SZ};
-    if (c.fail) return dummy;
+K1_DI void lin_radius(const LinSrc& s, int lane, double* out) {  // radius * |scale| (rounded up)
+    const double* rv = pz_r(s.h, lane);
+    const double sc = fabs(s.scale);
+#pragma unroll
+    for (int q = 0; q < SZ; q++) out[q] = 0.0;
+    if (s.comp_in < 0 && s.h.sz == SZ) {
+#pragma unroll
+        for (int q = 0; q < SZ; q++) out[q] = __dmul_ru(sc, rv[q]);
+    } else {
+        const double x = __dmul_ru(sc, rv[s.comp_in < 0 ? 0 : s.comp_in]);
+#pragma unroll
+        for (int q = 0; q < SZ; q++)
+            if (q == s.comp_out) out[q] = x;
+    }
+}
+
+// sources are described by scalars passed by value: (handle, element size, comp_in, comp_out, scale)
+template <int SZ>
+K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale, PZ8 b8, int b_sz, int b_in, int b_out,
+                  double b_scale) {
+    const PZ8 dummy = {0, 0};
+    K1S& S = k1s();
+    if (S.fail) return dummy;
+    const int tid = k1_tid();
+    LinSrc s0, s1;
+    s0.h.p = vptr(a8.off); s0.h.n = a8.n; s0.h.sz = a_sz; s0.comp_in = a_in; s0.comp_out = a_out; s0.scale = a_scale;
+    s1.h.p = vptr(b8.off); s1.h.n = b8.n; s1.h.sz = b_sz; s1.comp_in = b_in; s1.comp_out = b_out; s1.scale = b_scale;
     Tab t;
-    if (!tab_select(c, s0.h.n + s1.h.n, SZ, t)) return dummy;
-    const double thr = c.thr;
+    if (!tab_select(s0.h.n + s1.h.n, SZ, t)) return dummy;
+    const double thr = S.thr;
     // keys
+#pragma unroll
     for (int srcI = 0; srcI < 2; srcI++) {
         const LinSrc& s = srcI ? s1 : s0;
         const u64* keys = pz_keys(s.h);
         const double* cf = pz_coef(s.h);
-        for (int m = c.tid; m < s.h.n; m += NT) {
+        for (int m = tid; m < s.h.n; m += NT) {
             if (s.comp_in >= 0 && cf[size_t(m) * s.h.sz + s.comp_in] == 0.0) continue;  // extracted zero: no effect
             tab_insert(t, keys[m]);
         }
     }
     __syncthreads();
     // at most two contributions per (key, component): a commutative atomic add is order-independent
+#pragma unroll
     for (int srcI = 0; srcI < 2; srcI++) {
         const LinSrc& s = srcI ? s1 : s0;
         const u64* keys = pz_keys(s.h);
         const double* cf = pz_coef(s.h);
-        for (int m = c.tid; m < s.h.n; m += NT) {
+        for (int m = tid; m < s.h.n; m += NT) {
             if (s.comp_in >= 0 && cf[size_t(m) * s.h.sz + s.comp_in] == 0.0) continue;
             double v[SZ];
             lin_value<SZ>(s, cf + size_t(m) * s.h.sz, v);
@@ -474,8 +546,9 @@ K1_OP PZH op_lin2(Ctx& c, const LinSrc& s0, const LinSrc& s1) {
     }
     __syncthreads();
     double rad[SZ];
-    PZH h = tab_finalize<SZ, SZ>(
-        c, t,
+    bool ok;
+    const PZ8 h8 = tab_finalize<SZ, SZ>(
+        top, t,
         [thr](const double* a, double* out, double* r) {
             if (frobN<SZ>(a) <= thr) {
 #pragma unroll
@@ -486,81 +559,49 @@ K1_OP PZH op_lin2(Ctx& c, const LinSrc& s0, const LinSrc& s1) {
             for (int e = 0; e < SZ; e++) out[e] = a[e];
             return true;
         },
-        rad);
-    if (!c.fail && c.tid < SZ) {
-        const int e = c.tid;
+        rad, &ok);
+    if (ok && tid < SZ) {
+        const PZH h = view<SZ>(h8);
+        const int e = tid;
         double c0[SZ], c1[SZ];
         lin_value<SZ>(s0, pz_c(s0.h), c0);
         lin_value<SZ>(s1, pz_c(s1.h), c1);
         pz_c(h)[e] = c0[e] + c1[e];
+#pragma unroll
         for (int lane = 0; lane < 2; lane++) {
             double r0[SZ], r1[SZ];
-            LinSrc a0 = s0, a1 = s1;
-            a0.scale = fabs(s0.scale);
-            a1.scale = fabs(s1.scale);
-            // radius * |scale| (rounded up)
-            {
-                const double* rv = pz_r(s0.h, lane);
-#pragma unroll
-                for (int q = 0; q < SZ; q++) r0[q] = 0.0;
-                if (a0.comp_in < 0 && a0.h.sz == SZ) {
-#pragma unroll
-                    for (int q = 0; q < SZ; q++) r0[q] = __dmul_ru(a0.scale, rv[q]);
-                } else {
-                    const double x = __dmul_ru(a0.scale, rv[a0.comp_in < 0 ? 0 : a0.comp_in]);
-#pragma unroll
-                    for (int q = 0; q < SZ; q++)
-                        if (q == a0.comp_out) r0[q] = x;
-                }
-            }
-            {
-                const double* rv = pz_r(s1.h, lane);
-#pragma unroll
-                for (int q = 0; q < SZ; q++) r1[q] = 0.0;
-                if (a1.comp_in < 0 && a1.h.sz == SZ) {
-#pragma unroll
-                    for (int q = 0; q < SZ; q++) r1[q] = __dmul_ru(a1.scale, rv[q]);
-                } else {
-                    const double x = __dmul_ru(a1.scale, rv[a1.comp_in < 0 ? 0 : a1.comp_in]);
-#pragma unroll
-                    for (int q = 0; q < SZ; q++)
-                        if (q == a1.comp_out) r1[q] = x;
-                }
-            }
+            lin_radius<SZ>(s0, lane, r0);
+            lin_radius<SZ>(s1, lane, r1);
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(r0[e], r1[e]), rad[e]);
         }
     }
     __syncthreads();
-    return h;
+    return h8;
 }
 
 template <int SZ>
-K1_DI PZH op_add(Ctx& c, const PZH& a, const PZH& b) {  // KPR/PZsparse.cu:743-764
-    LinSrc s0 = {a, -1, 0, 1.0}, s1 = {b, -1, 0, 1.0};
-    return op_lin2<SZ>(c, s0, s1);
+K1_DI PZ8 op_add(int top, PZ8 a, PZ8 b) {  // KPR/PZsparse.cu:743-764
+    return op_lin2<SZ>(top, a, SZ, -1, 0, 1.0, b, SZ, -1, 0, 1.0);
 }
 // a.addOneDimPZ(s, comp, 0) for a 3-vector a and a scalar s (KPR/PZsparse.cu:1068-1085)
-K1_DI PZH op_add_one_dim(Ctx& c, const PZH& a, const PZH& s, int comp) {
-    LinSrc s0 = {a, -1, 0, 1.0}, s1 = {s, 0, comp, 1.0};
-    return op_lin2<3>(c, s0, s1);
-}
+K1_DI PZ8 op_add_one_dim(int top, PZ8 a, PZ8 s, int comp) { return op_lin2<3>(top, a, 3, -1, 0, 1.0, s, 1, 0, comp, 1.0); }
 
 // ---- element-wise ("map") operations: the key set does not change, so no table is needed ---------
 // Generic driver: fn(m, out[SZ], rad[SZ]) -> keep.  Two passes (count, then recompute + write) keep the
 // monomials in their input order.
 template <int SZ, class Fn>
-K1_DI PZH map_op(Ctx& c, int n_in, const u64* keys_in, Fn fn, double* rad_total) {
-    PZH dummy = {c.arena, 0, SZ};
-    if (c.fail) return dummy;
+K1_DI PZ8 map_op(int top, int n_in, const u64* keys_in, Fn fn, double* rad_total, bool* ok_out) {
+    K1S& S = k1s();
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
     const int chunk = ((n_in + NW - 1) / NW + 31) & ~31;  // per-warp contiguous chunk, multiple of 32
-    const int m0 = c.warp * chunk;
+    const int m0 = warp * chunk;
     const int m1 = (m0 + chunk) < n_in ? (m0 + chunk) : n_in;
     double rad[SZ];
 #pragma unroll
     for (int e = 0; e < SZ; e++) rad[e] = 0.0;
     int count = 0;
     for (int mb = m0; mb < m1; mb += 32) {
-        const int m = mb + c.lane;
+        const int m = mb + lane;
         bool keep = false;
         if (m < m1) {
             double out[SZ];
@@ -570,33 +611,36 @@ K1_DI PZH map_op(Ctx& c, int n_in, const u64* keys_in, Fn fn, double* rad_total)
     }
 #pragma unroll
     for (int e = 0; e < SZ; e++) rad[e] = warp_sum_up(rad[e]);
-    if (c.lane == 0) {
-        c.cnt[c.warp] = count;
+    if (lane == 0) {
+        S.cnt[warp] = count;
 #pragma unroll
-        for (int e = 0; e < SZ; e++) c.red[c.warp * RED_STRIDE + e] = rad[e];
+        for (int e = 0; e < SZ; e++) S.red[warp * RED_STRIDE + e] = rad[e];
     }
     __syncthreads();
     int before = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        const int v = c.cnt[w];
-        if (w < c.warp) before += v;
+        const int v = S.cnt[w];
+        if (w < warp) before += v;
         total += v;
     }
 #pragma unroll
     for (int e = 0; e < SZ; e++) {
-        double v = c.red[e];
+        double v = S.red[e];
 #pragma unroll
-        for (int w = 1; w < NW; w++) v = __dadd_ru(v, c.red[w * RED_STRIDE + e]);
+        for (int w = 1; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE + e]);
         rad_total[e] = v;
     }
-    PZH h = pz_alloc(c, total, SZ);
-    if (c.fail) return h;
-    u64* ok = pz_keys(h);
+    bool ok;
+    const PZ8 h8 = pz_alloc<SZ>(top, total, &ok);
+    *ok_out = ok;
+    if (!ok) return h8;
+    const PZH h = view<SZ>(h8);
+    u64* okk = pz_keys(h);
     double* oc = pz_coef(h);
     int run = before;
     for (int mb = m0; mb < m1; mb += 32) {
-        const int m = mb + c.lane;
+        const int m = mb + lane;
         bool keep = false;
         double out[SZ], dump[SZ];
 #pragma unroll
@@ -604,14 +648,14 @@ K1_DI PZH map_op(Ctx& c, int n_in, const u64* keys_in, Fn fn, double* rad_total)
         if (m < m1) keep = fn(m, out, dump);
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            const int pos = run + __popc(b & ((1u << c.lane) - 1u));
-            ok[pos] = keys_in[m];
+            const int pos = run + __popc(b & ((1u << lane) - 1u));
+            okk[pos] = keys_in[m];
 #pragma unroll
             for (int e = 0; e < SZ; e++) oc[size_t(pos) * SZ + e] = out[e];
         }
         run += __popc(b);
     }
-    return h;  // caller writes the header, then __syncthreads()
+    return h8;  // caller writes the header, then __syncthreads()
 }
 
 // prune rule for one merged coefficient (KPR/PZsparse.cu:321-336)
@@ -654,13 +698,19 @@ K1_DI void cross_const_coef(bool left_const, const double* v, const double* g, d
     }
     *any = a;
 }
-K1_OP PZH op_cross_const(Ctx& c, const PZH& x, const double* v, bool left_const) {
-    const double thr = c.thr;
+K1_OP PZ8 op_cross_const(int top, PZ8 x8, const double* v, bool left_const) {
+    const PZ8 dummy = {0, 0};
+    K1S& S = k1s();
+    if (S.fail) return dummy;
+    const int tid = k1_tid();
+    const PZH x = view<3>(x8);
+    const double thr = S.thr;
     const double* cf = pz_coef(x);
     const double v0 = v[0], v1 = v[1], v2 = v[2];
     double rad[3];
-    PZH h = map_op<3>(
-        c, x.n, pz_keys(x),
+    bool ok;
+    const PZ8 h8 = map_op<3>(
+        top, x.n, pz_keys(x),
         [=](int m, double* out, double* r) {
             const double vv[3] = {v0, v1, v2};
             bool any;
@@ -668,21 +718,24 @@ K1_OP PZH op_cross_const(Ctx& c, const PZH& x, const double* v, bool left_const)
             if (!any) return false;
             return prune_or_keep<3>(out, thr, r);  // stack3's own simplify (3-vector norm)
         },
-        rad);
-    if (!c.fail && c.tid < 3) {
-        const int e = c.tid, e1 = (e + 1) % 3, e2 = (e + 2) % 3;
+        rad, &ok);
+    if (ok && tid < 3) {
+        const PZH h = view<3>(h8);
+        const int e = tid, e1 = (e + 1) % 3, e2 = (e + 2) % 3;
         const double* xc = pz_c(x);
+        const double vv[3] = {v0, v1, v2};
         // centre: scale() multiplies centre * s (KPR/PZsparse.cu:1004), then the subtraction
-        pz_c(h)[e] = !left_const ? (xc[e1] * v[e2] - xc[e2] * v[e1]) : (xc[e2] * v[e1] - xc[e1] * v[e2]);
+        pz_c(h)[e] = !left_const ? (xc[e1] * vv[e2] - xc[e2] * vv[e1]) : (xc[e2] * vv[e1] - xc[e1] * vv[e2]);
+#pragma unroll
         for (int lane = 0; lane < 2; lane++) {
             const double* xr = pz_r(x, lane);
-            const double a = !left_const ? __dmul_ru(xr[e1], fabs(v[e2])) : __dmul_ru(xr[e2], fabs(v[e1]));
-            const double b = !left_const ? __dmul_ru(xr[e2], fabs(v[e1])) : __dmul_ru(xr[e1], fabs(v[e2]));
+            const double a = !left_const ? __dmul_ru(xr[e1], fabs(vv[e2])) : __dmul_ru(xr[e2], fabs(vv[e1]));
+            const double b = !left_const ? __dmul_ru(xr[e2], fabs(vv[e1])) : __dmul_ru(xr[e1], fabs(vv[e2]));
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(a, b), rad[e]);
         }
     }
     __syncthreads();
-    return h;
+    return h8;
 }
 
 // PZ(constant, radius = pct*|constant|) * x  for a scalar constant (mass) or a 3x3 constant (inertia), and
@@ -691,19 +744,23 @@ K1_OP PZH op_cross_const(Ctx& c, const PZH& x, const double* v, bool left_const)
 // uncertain-parameter radius (KPR/PZsparse.cu:93-98, KPR/Dynamics.cu:30-40).
 //   kind 0: scalar s * vec3 x        kind 1: mat3 M * vec3 x        kind 2: mat3 x * const vec3 P
 template <int KIND>
-K1_OP PZH op_const_mul(Ctx& c, const double* K, double pct_lane1, const PZH& x) {
-    PZH dummy = {c.arena, 0, 3};
-    if (c.fail) return dummy;
-    const double thr = c.thr;
-    const double* cf = pz_coef(x);
+K1_OP PZ8 op_const_mul(int top, const double* K, double pct_lane1, PZ8 x8) {
+    const PZ8 dummy = {0, 0};
+    K1S& S = k1s();
+    if (S.fail) return dummy;
+    const int tid = k1_tid();
     constexpr int XS = (KIND == 2) ? 9 : 3;
+    const PZH x = view<XS>(x8);
+    const double thr = S.thr;
+    const double* cf = pz_coef(x);
     double kk[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) kk[i] = (KIND == 0) ? ((i == 0) ? K[0] : 0.0) : ((KIND == 1 || i < 3) ? K[i] : 0.0);
-    abs_sum_partial<XS>(c, x);  // collected after map_op's internal barrier
+    abs_sum_partial<XS>(x);  // collected after map_op's internal barrier
     double rad[3];
-    PZH h = map_op<3>(
-        c, x.n, pz_keys(x),
+    bool ok;
+    const PZ8 h8 = map_op<3>(
+        top, x.n, pz_keys(x),
         [=](int m, double* out, double* r) {
             const double* g = cf + size_t(m) * XS;
             if (KIND == 0) {
@@ -716,11 +773,12 @@ K1_OP PZH op_const_mul(Ctx& c, const double* K, double pct_lane1, const PZH& x) 
             }
             return prune_or_keep<3>(out, thr, r);
         },
-        rad);
-    if (!c.fail && c.tid < 3) {
-        const int e = c.tid;
+        rad, &ok);
+    if (ok && tid < 3) {
+        const PZH h = view<3>(h8);
+        const int e = tid;
         double absx[XS];
-        abs_sum_collect<XS>(c, x, absx);
+        abs_sum_collect<XS>(x, absx);
         const double* xc = pz_c(x);
         double cen[3];
         if (KIND == 0) {
@@ -732,6 +790,7 @@ K1_OP PZH op_const_mul(Ctx& c, const double* K, double pct_lane1, const PZH& x) 
             matmul3<1, false>(xc, kk, cen);
         }
         pz_c(h)[e] = cen[e];
+#pragma unroll
         for (int lane = 0; lane < 2; lane++) {
             const double* xr = pz_r(x, lane);
             const double pct = lane ? pct_lane1 : 0.0;
@@ -761,7 +820,7 @@ K1_OP PZH op_const_mul(Ctx& c, const double* K, double pct_lane1, const PZH& x) 
         }
     }
     __syncthreads();
-    return h;
+    return h8;
 }
 
 // ---- PZ * PZ with a 3x3 left operand (KPR/PZsparse.cu:864-994) -----------------------------------
@@ -770,31 +829,33 @@ K1_OP PZH op_const_mul(Ctx& c, const double* K, double pct_lane1, const PZH& x) 
 // visited one after the other (a barrier between them, so equal keys are summed in a fixed order), the
 // other operand's monomials are spread over the threads.
 template <int P, bool TRANS>
-K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
+K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
     constexpr int SZ = 3 * P;
-    PZH dummy = {c.arena, 0, SZ};
-    if (c.fail) return dummy;
+    const PZ8 dummy = {0, 0};
+    K1S& S = k1s();
+    if (S.fail) return dummy;
+    const int tid = k1_tid();
+    const PZH L = view<9>(L8), R = view<SZ>(R8);
     const int nL = L.n, nR = R.n;
     Tab t;
-    if (!tab_select(c, nL + nR + nL * nR, SZ, t)) return dummy;
-    const double thr = c.thr;
+    if (!tab_select(nL + nR + nL * nR, SZ, t)) return dummy;
+    const double thr = S.thr;
     const u64* kL = pz_keys(L);
     const u64* kR = pz_keys(R);
     const double* cL = pz_coef(L);
     const double* cR = pz_coef(R);
     const bool outerL = nL <= nR;
-    const PZH& O = outerL ? L : R;
-    const PZH& I = outerL ? R : L;
+    const int nO = outerL ? nL : nR, nI = outerL ? nR : nL;
     const u64* kO = outerL ? kL : kR;
     const u64* kI = outerL ? kR : kL;
     // keys
-    for (int j = c.tid; j < I.n; j += NT) {
+    for (int j = tid; j < nI; j += NT) {
         const u64 kj = kI[j];
         tab_insert(t, kj);
-        for (int o = 0; o < O.n; o++) tab_insert(t, kj + kO[o]);  // degree hashes add without carry (:938-940)
+        for (int o = 0; o < nO; o++) tab_insert(t, kj + kO[o]);  // degree hashes add without carry (:938-940)
     }
-    for (int o = c.tid; o < O.n; o += NT) tab_insert(t, kO[o]);
-    if (outerL) abs_sum_partial<SZ>(c, R); else abs_sum_partial<9>(c, L);
+    for (int o = tid; o < nO; o += NT) tab_insert(t, kO[o]);
+    if (outerL) abs_sum_partial<SZ>(R); else abs_sum_partial<9>(L);
     __syncthreads();
     // polynomial * centre of the other side, centre * polynomial: keys within each group are distinct
     {
@@ -802,7 +863,7 @@ K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
         const double* cc = pz_c(R);
 #pragma unroll
         for (int q = 0; q < SZ; q++) cen[q] = cc[q];
-        for (int i = c.tid; i < nL; i += NT) {
+        for (int i = tid; i < nL; i += NT) {
             double v[SZ];
             matmul3<P, TRANS>(cL + size_t(i) * 9, cen, v);
             const int slot = tab_find(t, kL[i]);
@@ -816,7 +877,7 @@ K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
         const double* cc = pz_c(L);
 #pragma unroll
         for (int q = 0; q < 9; q++) cen[q] = cc[q];
-        for (int j = c.tid; j < nR; j += NT) {
+        for (int j = tid; j < nR; j += NT) {
             double v[SZ];
             matmul3<P, TRANS>(cen, cR + size_t(j) * SZ, v);
             const int slot = tab_find(t, kR[j]);
@@ -825,9 +886,9 @@ K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
         }
     }
     __syncthreads();
-    for (int o = 0; o < O.n; o++) {
+    for (int o = 0; o < nO; o++) {
         const u64 ko = kO[o];
-        for (int j = c.tid; j < I.n; j += NT) {
+        for (int j = tid; j < nI; j += NT) {
             double v[SZ];
             if (outerL)
                 matmul3<P, TRANS>(cL + size_t(o) * 9, cR + size_t(j) * SZ, v);
@@ -840,8 +901,9 @@ K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
         __syncthreads();
     }
     double rad[SZ];
-    PZH h = tab_finalize<SZ, SZ>(
-        c, t,
+    bool ok;
+    const PZ8 h8 = tab_finalize<SZ, SZ>(
+        top, t,
         [thr](const double* a, double* out, double* r) {
             if (frobN<SZ>(a) <= thr) {
 #pragma unroll
@@ -852,19 +914,21 @@ K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
             for (int e = 0; e < SZ; e++) out[e] = a[e];
             return true;
         },
-        rad);
-    if (!c.fail && c.tid < SZ) {
-        const int e = c.tid;
+        rad, &ok);
+    if (ok && tid < SZ) {
+        const PZH h = view<SZ>(h8);
+        const int e = tid;
         double absL[9], absR[SZ], cen[SZ];
         if (outerL) {
             abs_sum_serial<9>(L, absL);
-            abs_sum_collect<SZ>(c, R, absR);
+            abs_sum_collect<SZ>(R, absR);
         } else {
-            abs_sum_collect<9>(c, L, absL);
+            abs_sum_collect<9>(L, absL);
             abs_sum_serial<SZ>(R, absR);
         }
         matmul3<P, TRANS>(pz_c(L), pz_c(R), cen);
         pz_c(h)[e] = cen[e];
+#pragma unroll
         for (int lane = 0; lane < 2; lane++) {
             double ra2[SZ], ra3[SZ], rr[SZ];
             matmul3_up<P, TRANS>(absL, pz_r(R, lane), ra2);
@@ -874,7 +938,7 @@ K1_OP PZH op_mul33(Ctx& c, const PZH& L, const PZH& R) {
         }
     }
     __syncthreads();
-    return h;
+    return h8;
 }
 
 // ---- cross(PZ a, PZ b) (KPR/PZsparse.cu:1134-1151) ------------------------------------------------
@@ -890,34 +954,36 @@ K1_DI void cross_six(const double* a, const double* b, double* v) {
     v[4] = a[0] * b[1];
     v[5] = a[1] * b[0];
 }
-K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
-    PZH dummy = {c.arena, 0, 3};
-    if (c.fail) return dummy;
+K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
+    const PZ8 dummy = {0, 0};
+    K1S& S = k1s();
+    if (S.fail) return dummy;
+    const int tid = k1_tid();
+    const PZH A = view<3>(A8), B = view<3>(B8);
     const int nA = A.n, nB = B.n;
     Tab t;
-    if (!tab_select(c, nA + nB + nA * nB, 6, t)) return dummy;
-    const double thr = c.thr;
+    if (!tab_select(nA + nB + nA * nB, 6, t)) return dummy;
+    const double thr = S.thr;
     const u64* kA = pz_keys(A);
     const u64* kB = pz_keys(B);
     const double* cA = pz_coef(A);
     const double* cB = pz_coef(B);
     const bool outerA = nA <= nB;
-    const PZH& O = outerA ? A : B;
-    const PZH& I = outerA ? B : A;
+    const int nO = outerA ? nA : nB, nI = outerA ? nB : nA;
     const u64* kO = outerA ? kA : kB;
     const u64* kI = outerA ? kB : kA;
-    for (int j = c.tid; j < I.n; j += NT) {
+    for (int j = tid; j < nI; j += NT) {
         const u64 kj = kI[j];
         tab_insert(t, kj);
-        for (int o = 0; o < O.n; o++) tab_insert(t, kj + kO[o]);
+        for (int o = 0; o < nO; o++) tab_insert(t, kj + kO[o]);
     }
-    for (int o = c.tid; o < O.n; o += NT) tab_insert(t, kO[o]);
-    abs_sum_partial<3>(c, I);
+    for (int o = tid; o < nO; o += NT) tab_insert(t, kO[o]);
+    if (outerA) abs_sum_partial<3>(B); else abs_sum_partial<3>(A);
     __syncthreads();
     {
         const double* cc = pz_c(B);
         const double cen[3] = {cc[0], cc[1], cc[2]};
-        for (int i = c.tid; i < nA; i += NT) {
+        for (int i = tid; i < nA; i += NT) {
             double v[6];
             cross_six(cA + size_t(i) * 3, cen, v);
             const int slot = tab_find(t, kA[i]);
@@ -929,7 +995,7 @@ K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
     {
         const double* cc = pz_c(A);
         const double cen[3] = {cc[0], cc[1], cc[2]};
-        for (int j = c.tid; j < nB; j += NT) {
+        for (int j = tid; j < nB; j += NT) {
             double v[6];
             cross_six(cen, cB + size_t(j) * 3, v);
             const int slot = tab_find(t, kB[j]);
@@ -938,11 +1004,11 @@ K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
         }
     }
     __syncthreads();
-    for (int o = 0; o < O.n; o++) {
+    for (int o = 0; o < nO; o++) {
         const u64 ko = kO[o];
         const double* co = (outerA ? cA : cB) + size_t(o) * 3;
         const double ov[3] = {co[0], co[1], co[2]};
-        for (int j = c.tid; j < I.n; j += NT) {
+        for (int j = tid; j < nI; j += NT) {
             double v[6];
             if (outerA)
                 cross_six(ov, cB + size_t(j) * 3, v);
@@ -955,8 +1021,9 @@ K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
         __syncthreads();
     }
     double rad[3];
-    PZH h = tab_finalize<6, 3>(
-        c, t,
+    bool ok;
+    const PZ8 h8 = tab_finalize<6, 3>(
+        top, t,
         [thr](const double* a, double* out, double* r) {
             double p[6];
             bool have[6];
@@ -983,15 +1050,16 @@ K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
             if (!any) return false;
             return prune_or_keep<3>(out, thr, r);  // simplify() of the stack
         },
-        rad);
-    if (!c.fail && c.tid < 3) {
-        const int e = c.tid;
+        rad, &ok);
+    if (ok && tid < 3) {
+        const PZH h = view<3>(h8);
+        const int e = tid;
         double absA[3], absB[3];
         if (outerA) {
             abs_sum_serial<3>(A, absA);
-            abs_sum_collect<3>(c, B, absB);
+            abs_sum_collect<3>(B, absB);
         } else {
-            abs_sum_collect<3>(c, A, absA);
+            abs_sum_collect<3>(A, absA);
             abs_sum_serial<3>(B, absB);
         }
         const double* ca = pz_c(A);
@@ -999,6 +1067,7 @@ K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
         const int e1 = (e + 1) % 3, e2 = (e + 2) % 3;
         // r_e = a_{e1} b_{e2} - a_{e2} b_{e1}
         pz_c(h)[e] = ca[e1] * cb[e2] - ca[e2] * cb[e1];
+#pragma unroll
         for (int lane = 0; lane < 2; lane++) {
             const double* ra = pz_r(A, lane);
             const double* rb = pz_r(B, lane);
@@ -1011,7 +1080,7 @@ K1_OP PZH op_cross(Ctx& c, const PZH& A, const PZH& B) {
         }
     }
     __syncthreads();
-    return h;
+    return h8;
 }
 
 }  // namespace k1

@@ -33,22 +33,31 @@ constexpr double RADIUS_SLACK = 1.0 + 0x1p-40;  // outward slack on exported rad
 struct K1Params {
     Batch B;
     int* work;          // global unit counter (reset before every launch)
-    double* gscr;       // [grid][gscr_words]
-    int gscr_words;     // = fn_words (F / N blocks of one unit) + spill space of the arena
-    int fn_words;
+    double* gscr;       // [grid][gscr_words]: per CTA [arena spill space | F / N blocks of one unit]
+    int gscr_words;
+    int fn_words;       // words of the F / N part (the last fn_words of a CTA's scratch)
     char* gtab;         // [grid][gtab_bytes], all zero between launches
     int gtab_bytes;
-    int arena_words;    // shared-memory arena per CTA
+    int arena_words;    // shared-memory working arena per CTA (behind the fixed JRS region)
     int tab_s_bytes;    // shared-memory table pool per CTA
     const int* units;   // optional explicit unit list (p*T + t); nullptr = all units of the batch
     int nunits;
     int* stats;         // [4]: max arena words used, tables placed in global memory, failed units, units done
 };
 
-struct Jrs {
-    PZH R[MAXJ + 1];
-    PZH qd[NF], qda[NF], qdda[NF];
-};
+// handles of the joint reachable set blocks (fixed places at the bottom of the virtual arena)
+K1_DI PZ8 jrs_R(int i) {
+    PZ8 h;
+    h.off = i * ROT_WORDS;
+    h.n = k1s().jrs_n[i];
+    return h;
+}
+K1_DI PZ8 jrs_scalar(int g, int i) {  // g = 0: qd_des, 1: qda_des, 2: qdda_des
+    PZ8 h;
+    h.off = (MAXJ + 1) * ROT_WORDS + (g * NF + i) * SCL_WORDS;
+    h.n = k1s().jrs_n[16 + 8 * g + i];
+    return h;
+}
 
 K1_DI void indep_range(double v_lb, double v_ub, double s_lb, double s_ub, double e1s, double e1v, double e2s,
                        double e2v, double* radius, double* center) {  // KPR/Trajectory.cu:80-94
@@ -264,8 +273,11 @@ K1_OP void jrs_joint(int i, int t, int T, double q0, double qd0, double qdd0, do
 
 // ---- exports --------------------------------------------------------------------------------------
 // reduce_link_PZ (KPR/PZsparse.cu:370-402) + the k-only table of one link reach set, sorted by key.
-K1_OP void export_link(Ctx& c, const PZH& L, const Batch& B, int p, int t, int l) {
-    if (c.fail) return;
+K1_OP void export_link(PZ8 L8, const Batch& B, int p, int t, int l) {
+    K1S& S = k1s();
+    if (S.fail) return;
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
+    const PZH L = view<3>(L8);
     const u64* keys = pz_keys(L);
     const double* cf = pz_coef(L);
     const size_t idx = (size_t(p) * B.T + t) * B.NJ + l;
@@ -273,13 +285,13 @@ K1_OP void export_link(Ctx& c, const PZH& L, const Batch& B, int p, int t, int l
     int nk = 0;
     for (int m = 0; m < L.n; m++) nk += (keys[m] < KEY_K_ONLY);  // uniform (broadcast reads)
     if (nk > B.capL) {
-        set_fail(c, FAIL_LINK_CAP);
+        set_fail(FAIL_LINK_CAP);
         return;
     }
     double* gens = B.link_gens + idx * 18;
-    if (c.tid < 18) gens[c.tid] = 0.0;
+    if (tid < 18) gens[tid] = 0.0;
     __syncthreads();
-    for (int m = c.tid; m < L.n; m += NT) {
+    for (int m = tid; m < L.n; m += NT) {
         const u64 key = keys[m];
         const bool konly = key < KEY_K_ONLY;
         const bool gen = !konly && key < KEY_K_LINKS && (key & KEY_K_MASK) == 0;
@@ -303,36 +315,39 @@ K1_OP void export_link(Ctx& c, const PZH& L, const Batch& B, int p, int t, int l
         }
     }
     for (int e = 0; e < 3; e++) rad[e] = warp_sum_up(rad[e]);
-    if (c.lane == 0)
-        for (int e = 0; e < 3; e++) c.red[c.warp * RED_STRIDE + e] = rad[e];
+    if (lane == 0)
+        for (int e = 0; e < 3; e++) S.red[warp * RED_STRIDE + e] = rad[e];
     __syncthreads();
-    if (c.tid < 3) {
-        const int e = c.tid;
+    if (tid < 3) {
+        const int e = tid;
         double v = pz_r(L, 0)[e];
-        for (int w = 0; w < NW; w++) v = __dadd_ru(v, c.red[w * RED_STRIDE + e]);
+        for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE + e]);
         gens[e + (3 + e) * 3] = __dmul_ru(v, RADIUS_SLACK);
         B.link_c[idx * 3 + e] = pz_c(L)[e];
     }
-    if (c.tid == 0) B.link_n[idx] = nk;
+    if (tid == 0) B.link_n[idx] = nk;
     __syncthreads();
 }
 
-// u_nom.reduce() (KPR/PZsparse.cu:352-368) + the k-only table of one torque reach set; returns through
-// shared memory the radius of the reduced nominal PZ and the disturbance radius
-// toInterval(u_nom_int - u_nom) = r_int + r_nom before the reduce (KPR/armour_main.cu:134-141).
-K1_OP void export_torque(Ctx& c, const PZH& U, const Batch& B, int p, int t, int j, double* s_unom_r, double* s_dist) {
-    if (c.fail) return;
+// u_nom.reduce() (KPR/PZsparse.cu:352-368) + the k-only table of one torque reach set; leaves in S.misc the
+// radius of the reduced nominal PZ ([j]) and the disturbance radius toInterval(u_nom_int - u_nom) =
+// r_int + r_nom before the reduce ([8 + j]) (KPR/armour_main.cu:134-141).
+K1_OP void export_torque(PZ8 U8, const Batch& B, int p, int t, int j) {
+    K1S& S = k1s();
+    if (S.fail) return;
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
+    const PZH U = view<1>(U8);
     const u64* keys = pz_keys(U);
     const double* cf = pz_coef(U);
     const size_t idx = (size_t(p) * B.T + t) * NF + j;
     int nk = 0;
     for (int m = 0; m < U.n; m++) nk += (keys[m] < KEY_K_ONLY);
     if (nk > B.capU) {
-        set_fail(c, FAIL_TORQUE_CAP);
+        set_fail(FAIL_TORQUE_CAP);
         return;
     }
     double rad = 0.0;
-    for (int m = c.tid; m < U.n; m += NT) {
+    for (int m = tid; m < U.n; m += NT) {
         const u64 key = keys[m];
         if (key < KEY_K_ONLY) {
             int rank = 0;
@@ -344,15 +359,15 @@ K1_OP void export_torque(Ctx& c, const PZH& U, const Batch& B, int p, int t, int
         }
     }
     rad = warp_sum_up(rad);
-    if (c.lane == 0) c.red[c.warp * RED_STRIDE] = rad;
+    if (lane == 0) S.red[warp * RED_STRIDE] = rad;
     __syncthreads();
-    if (c.tid == 0) {
+    if (tid == 0) {
         double v = 0.0;
-        for (int w = 0; w < NW; w++) v = __dadd_ru(v, c.red[w * RED_STRIDE]);
+        for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE]);
         const double r_nom = pz_r(U, 0)[0], r_int = pz_r(U, 1)[0];
         const double reduced = __dadd_ru(r_nom, v);
-        s_unom_r[j] = reduced;
-        s_dist[j] = __dadd_ru(r_int, r_nom);
+        S.misc[j] = reduced;
+        S.misc[8 + j] = __dadd_ru(r_int, r_nom);
         B.u_n[idx] = nk;
         B.u_c[idx] = pz_c(U)[0];
         B.u_r[idx] = __dmul_ru(reduced, RADIUS_SLACK);
@@ -361,69 +376,69 @@ K1_OP void export_torque(Ctx& c, const PZH& U, const Batch& B, int p, int t, int
 }
 
 // ---- one (problem, interval) unit -----------------------------------------------------------------
-K1_DI void build_unit(Ctx& c, const Batch& B, int p, int t, double* jrs_mem, int* jrs_n, double* s_unom_r,
-                      double* s_dist) {
+// `top` (the arena top, a CTA-uniform register) is threaded through the operations: every operation
+// allocates exactly one block at `top` and the new top is the end of the block it returns.
+#define K1_OP_DO(h, SZ, ...)      \
+    const PZ8 h = (__VA_ARGS__);  \
+    top = end_of<SZ>(h);          \
+    top_max = top > top_max ? top : top_max
+#define K1_OP_VAR(h, SZ, ...) \
+    h = (__VA_ARGS__);        \
+    top = end_of<SZ>(h);      \
+    top_max = top > top_max ? top : top_max
+
+K1_DI int build_unit(const Batch& B, int p, int t) {
     const RobotConstants& rc = c_robot;
+    K1S& S = k1s();
+    const int tid = k1_tid();
     const int NJ = B.NJ, T = B.T;
-    const double thr = c.thr;
-    c.top = 0;
-    c.gtop = 0;
+    const double thr = S.thr;
+    constexpr int B0 = JRS_WORDS;  // bottom of the working arena
+    int top = B0, top_max = B0, gtop = 0;
 
     // ---- K2: joint reachable set ----
-    double* rot_mem = jrs_mem;
-    double* scl_mem = jrs_mem + (MAXJ + 1) * ROT_WORDS;
-    if (c.tid < NF) {
-        const int i = c.tid;
+    double* rot_mem = arena0();
+    double* scl_mem = arena0() + (MAXJ + 1) * ROT_WORDS;
+    if (tid < NF) {
+        const int i = tid;
         jrs_joint(i, t, T, B.q0[size_t(p) * NF + i], B.qd0[size_t(p) * NF + i], B.qdd0[size_t(p) * NF + i], thr,
-                  rot_mem + i * ROT_WORDS, &jrs_n[i], scl_mem + (0 * NF + i) * SCL_WORDS, &jrs_n[16 + i],
-                  scl_mem + (1 * NF + i) * SCL_WORDS, &jrs_n[24 + i], scl_mem + (2 * NF + i) * SCL_WORDS,
-                  &jrs_n[32 + i]);
-    } else if (c.tid >= 32 && c.tid < 32 + (NJ + 1 - NF)) {  // fixed joints and the identity after the last one
-        const int i = NF + (c.tid - 32);
+                  rot_mem + i * ROT_WORDS, &S.jrs_n[i], scl_mem + (0 * NF + i) * SCL_WORDS, &S.jrs_n[16 + i],
+                  scl_mem + (1 * NF + i) * SCL_WORDS, &S.jrs_n[24 + i], scl_mem + (2 * NF + i) * SCL_WORDS,
+                  &S.jrs_n[32 + i]);
+    } else if (tid >= 32 && tid < 32 + (NJ + 1 - NF)) {  // fixed joints and the identity after the last one
+        const int i = NF + (tid - 32);
         double* blk = rot_mem + i * ROT_WORDS;
         for (int e = 0; e < 9; e++) {
             blk[e] = (i < NJ) ? rc.rrpy[i * 9 + e] : ((e % 4 == 0) ? 1.0 : 0.0);
             blk[9 + e] = 0.0;
             blk[18 + e] = 0.0;
         }
-        jrs_n[i] = 0;
+        S.jrs_n[i] = 0;
     }
     __syncthreads();
-    Jrs J;
-    for (int i = 0; i <= NJ; i++) {
-        J.R[i].p = rot_mem + i * ROT_WORDS;
-        J.R[i].n = jrs_n[i];
-        J.R[i].sz = 9;
-    }
-    for (int i = 0; i < NF; i++) {
-        J.qd[i].p = scl_mem + (0 * NF + i) * SCL_WORDS;
-        J.qd[i].n = jrs_n[16 + i];
-        J.qd[i].sz = 1;
-        J.qda[i].p = scl_mem + (1 * NF + i) * SCL_WORDS;
-        J.qda[i].n = jrs_n[24 + i];
-        J.qda[i].sz = 1;
-        J.qdda[i].p = scl_mem + (2 * NF + i) * SCL_WORDS;
-        J.qdda[i].n = jrs_n[32 + i];
-        J.qdda[i].sz = 1;
-    }
 
     // ---- forward kinematics of the link volumes (KPR/Dynamics.cu:69-81) ----
     {
-        PZH FK_R = pz_alloc(c, 0, 9);
-        PZH FK_T = pz_alloc(c, 0, 3);
-        if (!c.fail) {
-            if (c.tid < 27) FK_R.p[c.tid] = (c.tid < 9 && c.tid % 4 == 0) ? 1.0 : 0.0;
-            if (c.tid >= 32 && c.tid < 41) FK_T.p[c.tid - 32] = 0.0;
+        bool ok;
+        PZ8 FK_R = pz_alloc<9>(top, 0, &ok);
+        top = end_of<9>(FK_R);
+        PZ8 FK_T = pz_alloc<3>(top, 0, &ok);
+        top = end_of<3>(FK_T);
+        if (ok) {
+            if (tid < 27) vptr(FK_R.off)[tid] = (tid < 9 && tid % 4 == 0) ? 1.0 : 0.0;
+            if (tid >= 32 && tid < 41) vptr(FK_T.off)[tid - 32] = 0.0;
         }
         __syncthreads();
         for (int i = 0; i < NJ; i++) {
-            PZH t1 = op_const_mul<2>(c, &rc.trans[3 * i], 0.0, FK_R);
-            PZH FK_T2 = op_add<3>(c, FK_T, t1);
-            PZH FK_R2 = op_mul33<3, false>(c, FK_R, J.R[i]);
+            K1_OP_DO(t1, 3, op_const_mul<2>(top, &rc.trans[3 * i], 0.0, FK_R));
+            PZ8 FK_T2, FK_R2;
+            K1_OP_VAR(FK_T2, 3, op_add<3>(top, FK_T, t1));
+            K1_OP_VAR(FK_R2, 9, op_mul33<3, false>(top, FK_R, jrs_R(i)));
             // link box zonotope: centre + diag(generators) on the x / y / z generator variables, which
             // reuse the hash slots of qde_0 / qdae_0 / qddae_0 (KPR/Dynamics.cu:51-66)
-            PZH box = pz_alloc(c, 3, 3);
-            if (!c.fail && c.tid == 0) {
+            PZ8 box = pz_alloc<3>(top, 3, &ok);
+            if (ok && tid == 0) {
+                double* bp = vptr(box.off);
                 double rad[3] = {0, 0, 0};
                 int n = 0;
                 u64 kk[3];
@@ -439,107 +454,147 @@ K1_DI void build_unit(Ctx& c, const Batch& B, int p, int t, double* jrs_mem, int
                     }
                 }
                 for (int e = 0; e < 3; e++) {
-                    box.p[e] = rc.link_zonotope_center[i * 3 + e];
-                    box.p[3 + e] = rad[e];
-                    box.p[6 + e] = rad[e];
+                    bp[e] = rc.link_zonotope_center[i * 3 + e];
+                    bp[3 + e] = rad[e];
+                    bp[6 + e] = rad[e];
                 }
-                u64* pk = reinterpret_cast<u64*>(box.p + 9);
+                u64* pk = reinterpret_cast<u64*>(bp + 9);
                 for (int q = 0; q < n; q++) pk[q] = kk[q];
                 for (int q = 0; q < n; q++)
-                    for (int e = 0; e < 3; e++) box.p[9 + n + q * 3 + e] = gg[q][e];
-                c.cnt[0] = n;
+                    for (int e = 0; e < 3; e++) bp[9 + n + q * 3 + e] = gg[q][e];
+                S.cnt[0] = n;
             }
             __syncthreads();
-            box.n = c.fail ? 0 : c.cnt[0];
+            box.n = ok ? S.cnt[0] : 0;
+            top = box.off + pz_words(3, 3);  // the block was sized for three generators
             __syncthreads();
-            PZH l1 = op_mul33<1, false>(c, FK_R2, box);
-            PZH link = op_add<3>(c, l1, FK_T2);
-            export_link(c, link, B, p, t, i);
-            PZH* keep[2] = {&FK_T2, &FK_R2};
-            arena_keep(c, 0, keep, 2);  // slide over the old FK_R / FK_T
+            K1_OP_DO(l1, 3, op_mul33<1, false>(top, FK_R2, box));
+            K1_OP_DO(link, 3, op_add<3>(top, l1, FK_T2));
+            export_link(link, B, p, t, i);
+            int cur = B0;  // slide over the old FK_R / FK_T
+            keep<3>(cur, FK_T2);
+            keep<9>(cur, FK_R2);
+            top = cur;
             FK_T = FK_T2;
             FK_R = FK_R2;
         }
     }
 
     // ---- recursive Newton-Euler, forward pass (KPR/Dynamics.cu:83-155) ----
-    c.top = 0;
-    PZH Fg[MAXJ], Ng[MAXJ];
-    PZH la = pz_zero(c, 3), w = pz_zero(c, 3), wa = pz_zero(c, 3), wd = pz_zero(c, 3);
-    if (!c.fail && c.tid == 0) la.p[2] = rc.gravity;
+    top = B0;
+    PZ8 la, w, wa, wd;
+    K1_OP_VAR(la, 3, pz_zero<3>(top));
+    K1_OP_VAR(w, 3, pz_zero<3>(top));
+    K1_OP_VAR(wa, 3, pz_zero<3>(top));
+    K1_OP_VAR(wd, 3, pz_zero<3>(top));
+    if (!S.fail && tid == 0) vptr(la.off)[2] = rc.gravity;
     __syncthreads();
     for (int i = 0; i < NJ; i++) {
         const double* pI = &rc.trans[3 * i];
         const double* cI = &rc.com[3 * i];
-        const PZH& Rt = J.R[i];  // used transposed
+        const PZ8 Rt = jrs_R(i);  // used transposed
         // state blocks sit at the bottom of the arena in the order of the keep lists below; each step
         // drops what has just died so the live set stays small
-        const int mark = c.top;
-        PZH la2;
+        const int mark = top;
+        PZ8 la2;
         {
-            PZH t1 = op_cross_const(c, wd, pI, false);
-            PZH t2 = op_add<3>(c, la, t1);
-            arena_keep1(c, mark, t2);
-            PZH t3 = op_cross_const(c, wa, pI, false);
-            PZH t4 = op_cross(c, w, t3);
-            PZH t5 = op_add<3>(c, t2, t4);
-            arena_keep1(c, mark, t5);
-            la2 = op_mul33<1, true>(c, Rt, t5);
+            K1_OP_DO(t1, 3, op_cross_const(top, wd, pI, false));
+            PZ8 t2;
+            K1_OP_VAR(t2, 3, op_add<3>(top, la, t1));
+            int cur = mark;
+            keep<3>(cur, t2);
+            top = cur;
+            K1_OP_DO(t3, 3, op_cross_const(top, wa, pI, false));
+            K1_OP_DO(t4, 3, op_cross(top, w, t3));
+            PZ8 t5;
+            K1_OP_VAR(t5, 3, op_add<3>(top, t2, t4));
+            cur = mark;
+            keep<3>(cur, t5);
+            top = cur;
+            K1_OP_VAR(la2, 3, op_mul33<1, true>(top, Rt, t5));
         }
-        PZH w2, wa2, wd3;
+        PZ8 w2, wa2, wd3;
         if (rc.axes[i] != 0) {
             const int ax = abs(rc.axes[i]) - 1;
-            {
-                PZH* k1l[4] = {&w, &wa, &wd, &la2};  // la is dead
-                arena_keep(c, 0, k1l, 4);
-            }
-            PZH w1 = op_mul33<1, true>(c, Rt, w);
-            w2 = op_add_one_dim(c, w1, J.qd[i], ax);
-            {
-                PZH* k2l[4] = {&wa, &wd, &la2, &w2};  // w, w1 are dead
-                arena_keep(c, 0, k2l, 4);
-            }
-            PZH wa1 = op_mul33<1, true>(c, Rt, wa);
-            PZH wd1 = op_mul33<1, true>(c, Rt, wd);
-            {
-                PZH* k3l[4] = {&la2, &w2, &wa1, &wd1};  // wa, wd are dead
-                arena_keep(c, 0, k3l, 4);
-            }
-            const int m2 = c.top;
-            PZH zero3 = pz_zero(c, 3);
-            PZH tmp = op_add_one_dim(c, zero3, J.qd[i], ax);
-            PZH t6 = op_cross(c, wa1, tmp);
-            PZH wd2 = op_add<3>(c, wd1, t6);
-            arena_keep1(c, m2, wd2);
-            wa2 = op_add_one_dim(c, wa1, J.qda[i], ax);
-            wd3 = op_add_one_dim(c, wd2, J.qdda[i], ax);
-            PZH* k4l[4] = {&la2, &w2, &wa2, &wd3};  // wa1, wd1, wd2 are dead
-            arena_keep(c, 0, k4l, 4);
+            int cur = B0;  // la is dead
+            keep<3>(cur, w);
+            keep<3>(cur, wa);
+            keep<3>(cur, wd);
+            keep<3>(cur, la2);
+            top = cur;
+            K1_OP_DO(w1, 3, op_mul33<1, true>(top, Rt, w));
+            K1_OP_VAR(w2, 3, op_add_one_dim(top, w1, jrs_scalar(0, i), ax));
+            cur = B0;  // w, w1 are dead
+            keep<3>(cur, wa);
+            keep<3>(cur, wd);
+            keep<3>(cur, la2);
+            keep<3>(cur, w2);
+            top = cur;
+            PZ8 wa1, wd1;
+            K1_OP_VAR(wa1, 3, op_mul33<1, true>(top, Rt, wa));
+            K1_OP_VAR(wd1, 3, op_mul33<1, true>(top, Rt, wd));
+            cur = B0;  // wa, wd are dead
+            keep<3>(cur, la2);
+            keep<3>(cur, w2);
+            keep<3>(cur, wa1);
+            keep<3>(cur, wd1);
+            top = cur;
+            const int m2 = top;
+            K1_OP_DO(zero3, 3, pz_zero<3>(top));
+            K1_OP_DO(tmp, 3, op_add_one_dim(top, zero3, jrs_scalar(0, i), ax));
+            K1_OP_DO(t6, 3, op_cross(top, wa1, tmp));
+            PZ8 wd2;
+            K1_OP_VAR(wd2, 3, op_add<3>(top, wd1, t6));
+            cur = m2;
+            keep<3>(cur, wd2);
+            top = cur;
+            K1_OP_VAR(wa2, 3, op_add_one_dim(top, wa1, jrs_scalar(1, i), ax));
+            K1_OP_VAR(wd3, 3, op_add_one_dim(top, wd2, jrs_scalar(2, i), ax));
+            cur = B0;  // wa1, wd1, wd2 are dead
+            keep<3>(cur, la2);
+            keep<3>(cur, w2);
+            keep<3>(cur, wa2);
+            keep<3>(cur, wd3);
+            top = cur;
         } else {
-            w2 = op_mul33<1, true>(c, Rt, w);
-            wa2 = op_mul33<1, true>(c, Rt, wa);
-            wd3 = op_mul33<1, true>(c, Rt, wd);
-            PZH* k4l[4] = {&la2, &w2, &wa2, &wd3};
-            arena_keep(c, 0, k4l, 4);
+            K1_OP_VAR(w2, 3, op_mul33<1, true>(top, Rt, w));
+            K1_OP_VAR(wa2, 3, op_mul33<1, true>(top, Rt, wa));
+            K1_OP_VAR(wd3, 3, op_mul33<1, true>(top, Rt, wd));
+            int cur = B0;
+            keep<3>(cur, la2);
+            keep<3>(cur, w2);
+            keep<3>(cur, wa2);
+            keep<3>(cur, wd3);
+            top = cur;
         }
         {
-            const int m3 = c.top;
-            PZH t7 = op_cross_const(c, wd3, cI, false);
-            PZH t8 = op_add<3>(c, la2, t7);
-            arena_keep1(c, m3, t8);
-            PZH t9 = op_cross_const(c, wa2, cI, false);
-            PZH t10 = op_cross(c, w2, t9);
-            PZH t11 = op_add<3>(c, t8, t10);
-            arena_keep1(c, m3, t11);
-            PZH F = op_const_mul<0>(c, &rc.mass[i], rc.mass_uncertainty, t11);
-            Fg[i] = spill_global(c, F);
-            c.top = m3;
-            PZH t12 = op_const_mul<1>(c, &rc.inertia[i * 9], rc.inertia_uncertainty, wd3);
-            PZH t13 = op_const_mul<1>(c, &rc.inertia[i * 9], rc.inertia_uncertainty, w2);
-            PZH t14 = op_cross(c, wa2, t13);
-            PZH N = op_add<3>(c, t12, t14);
-            Ng[i] = spill_global(c, N);
-            c.top = m3;
+            const int m3 = top;
+            K1_OP_DO(t7, 3, op_cross_const(top, wd3, cI, false));
+            PZ8 t8;
+            K1_OP_VAR(t8, 3, op_add<3>(top, la2, t7));
+            int cur = m3;
+            keep<3>(cur, t8);
+            top = cur;
+            K1_OP_DO(t9, 3, op_cross_const(top, wa2, cI, false));
+            K1_OP_DO(t10, 3, op_cross(top, w2, t9));
+            PZ8 t11;
+            K1_OP_VAR(t11, 3, op_add<3>(top, t8, t10));
+            cur = m3;
+            keep<3>(cur, t11);
+            top = cur;
+            K1_OP_DO(F, 3, op_const_mul<0>(top, &rc.mass[i], rc.mass_uncertainty, t11));
+            const PZ8 Fs = spill_global<3>(gtop, F);
+            top = m3;
+            K1_OP_DO(t12, 3, op_const_mul<1>(top, &rc.inertia[i * 9], rc.inertia_uncertainty, wd3));
+            K1_OP_DO(t13, 3, op_const_mul<1>(top, &rc.inertia[i * 9], rc.inertia_uncertainty, w2));
+            K1_OP_DO(t14, 3, op_cross(top, wa2, t13));
+            K1_OP_DO(N, 3, op_add<3>(top, t12, t14));
+            const PZ8 Ns = spill_global<3>(gtop, N);
+            if (tid == 0) {
+                S.Fg[i] = Fs;
+                S.Ng[i] = Ns;
+            }
+            top = m3;
         }
         la = la2;
         w = w2;
@@ -548,39 +603,51 @@ K1_DI void build_unit(Ctx& c, const Batch& B, int p, int t, double* jrs_mem, int
     }
 
     // ---- backward pass (KPR/Dynamics.cu:157-180) ----
-    c.top = 0;
-    PZH f = pz_zero(c, 3), n = pz_zero(c, 3);
+    top = B0;
+    PZ8 f, n;
+    K1_OP_VAR(f, 3, pz_zero<3>(top));  // the barrier inside also publishes S.Fg / S.Ng
+    K1_OP_VAR(n, 3, pz_zero<3>(top));
     for (int i = NJ - 1; i >= 0; i--) {
-        const PZH& Rn = J.R[i + 1];
-        const int mark = c.top;
-        PZH a1 = op_mul33<1, false>(c, Rn, n);
-        PZH a2 = op_add<3>(c, Ng[i], a1);
-        arena_keep1(c, mark, a2);
-        PZH a3 = op_cross_const(c, Fg[i], &rc.com[3 * i], true);
-        PZH a4 = op_add<3>(c, a2, a3);
-        arena_keep1(c, mark, a4);
-        PZH a5 = op_mul33<1, false>(c, Rn, f);
-        PZH a6 = op_cross_const(c, a5, &rc.trans[3 * (i + 1)], true);
-        PZH n2 = op_add<3>(c, a4, a6);
-        PZH f2 = op_add<3>(c, a5, Fg[i]);
-        PZH* keep[2] = {&n2, &f2};
-        arena_keep(c, 0, keep, 2);
+        const PZ8 Rn = jrs_R(i + 1);
+        const PZ8 Fi = S.Fg[i], Ni = S.Ng[i];
+        const int mark = top;
+        K1_OP_DO(a1, 3, op_mul33<1, false>(top, Rn, n));
+        PZ8 a2;
+        K1_OP_VAR(a2, 3, op_add<3>(top, Ni, a1));
+        int cur = mark;
+        keep<3>(cur, a2);
+        top = cur;
+        K1_OP_DO(a3, 3, op_cross_const(top, Fi, &rc.com[3 * i], true));
+        PZ8 a4;
+        K1_OP_VAR(a4, 3, op_add<3>(top, a2, a3));
+        cur = mark;
+        keep<3>(cur, a4);
+        top = cur;
+        K1_OP_DO(a5, 3, op_mul33<1, false>(top, Rn, f));
+        K1_OP_DO(a6, 3, op_cross_const(top, a5, &rc.trans[3 * (i + 1)], true));
+        PZ8 n2, f2;
+        K1_OP_VAR(n2, 3, op_add<3>(top, a4, a6));
+        K1_OP_VAR(f2, 3, op_add<3>(top, a5, Fi));
+        cur = B0;
+        keep<3>(cur, n2);
+        keep<3>(cur, f2);
+        top = cur;
         n = n2;
         f = f2;
         if (rc.axes[i] != 0) {
             const int ax = abs(rc.axes[i]) - 1;
-            const int m2 = c.top;
-            LinSrc s0 = {n, ax, 0, 1.0}, s1 = {J.qdda[i], 0, 0, rc.armature[i]};
-            PZH u1 = op_lin2<1>(c, s0, s1);
-            LinSrc s2 = {u1, 0, 0, 1.0}, s3 = {J.qd[i], 0, 0, rc.damping[i]};
-            PZH u2 = op_lin2<1>(c, s2, s3);
-            export_torque(c, u2, B, p, t, i, s_unom_r, s_dist);
-            c.top = m2;
+            const int m2 = top;
+            K1_OP_DO(u1, 1, op_lin2<1>(top, n, 3, ax, 0, 1.0, jrs_scalar(2, i), 1, 0, 0, rc.armature[i]));
+            K1_OP_DO(u2, 1, op_lin2<1>(top, u1, 1, 0, 0, 1.0, jrs_scalar(0, i), 1, 0, 0, rc.damping[i]));
+            export_torque(u2, B, p, t, i);
+            top = m2;
         }
     }
 
     // ---- robust-input radius (KPR/armour_main.cu:172-201) ----
-    if (!c.fail && c.tid == 0) {
+    if (!S.fail && tid == 0) {
+        const double* s_unom_r = S.misc;
+        const double* s_dist = S.misc + 8;
         double rho = 0.0;
         for (int j = 0; j < NF; j++) rho = __dadd_ru(rho, __dmul_ru(s_dist[j], s_dist[j]));
         const double nrm = __dsqrt_ru(rho);
@@ -593,63 +660,43 @@ K1_DI void build_unit(Ctx& c, const Batch& B, int p, int t, double* jrs_mem, int
         }
     }
     __syncthreads();
+    return top_max;
 }
+#undef K1_OP_DO
+#undef K1_OP_VAR
 
 // ---- kernel ---------------------------------------------------------------------------------------
-#ifndef ARMOUR_EMU
-#define K1_SMEM_DECL extern __shared__ __align__(16) unsigned char k1_smem[]
-#define K1_SMEM_PTR k1_smem
-#else
-#define K1_SMEM_DECL unsigned char* k1_smem_emu = reinterpret_cast<unsigned char*>(emu::S().dyn_smem)
-#define K1_SMEM_PTR k1_smem_emu
-#endif
-
-constexpr int K1_FIXED_BYTES = 64 * 4 + 2 * NW * RED_STRIDE * 8 + 16 * 8 + JRS_WORDS * 8;
+constexpr int K1_FIXED_BYTES = K1S_BYTES + JRS_WORDS * 8;  // control block + joint reachable set region
 
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_reachsets(K1Params P) {
-    K1_SMEM_DECL;
-    unsigned char* sm = K1_SMEM_PTR;
-    int* s_int = reinterpret_cast<int*>(sm);                 // [0..8) cnt, [8] unit, [16..40) jrs counts
-    double* s_red = reinterpret_cast<double*>(sm + 64 * 4);
-    double* s_red2 = s_red + NW * RED_STRIDE;
-    double* s_misc = s_red2 + NW * RED_STRIDE;               // [0..7) u_nom radius, [8..15) disturbance radius
-    double* s_jrs = s_misc + 16;
-    double* s_arena = s_jrs + JRS_WORDS;
-    char* s_tab = reinterpret_cast<char*>(s_arena + P.arena_words);
-
-    Ctx c;
-    c.tid = threadIdx.x;
-    c.lane = c.tid & 31;
-    c.warp = c.tid >> 5;
-    c.arena = s_arena;
-    c.arena_words = P.arena_words;
-    c.top = 0;
-    c.top_max = 0;
-    c.gscr = P.gscr + size_t(blockIdx.x) * P.gscr_words;
-    c.gscr_words = P.fn_words;
-    c.garena = c.gscr + P.fn_words;
-    c.garena_words = P.gscr_words - P.fn_words;
-    c.gtop = 0;
-    c.tab_s = s_tab;
-    c.tab_s_bytes = P.tab_s_bytes;
-    c.tab_g = P.gtab + size_t(blockIdx.x) * P.gtab_bytes;
-    c.tab_g_bytes = P.gtab_bytes;
-    c.red = s_red;
-    c.red2 = s_red2;
-    c.cnt = s_int;
-    c.thr = c_robot.simplify_threshold;
-    c.fail = 0;
-    c.n_tab_global = 0;
-
-    for (int i = c.tid; i < P.tab_s_bytes / 8; i += NT) reinterpret_cast<u64*>(s_tab)[i] = 0;
+    K1S& S = k1s();
+    const int tid = k1_tid();
+    if (tid == 0) {
+        S.gbase = P.gscr + size_t(blockIdx.x) * P.gscr_words;
+        S.tab_g = P.gtab + size_t(blockIdx.x) * P.gtab_bytes;
+        S.thr = c_robot.simplify_threshold;
+        S.AW = JRS_WORDS + P.arena_words;
+        S.GW = P.gscr_words - P.fn_words;
+        S.FW = P.fn_words;
+        S.tab_s_bytes = P.tab_s_bytes;
+        S.tab_g_bytes = P.gtab_bytes;
+        S.fail = 0;
+        S.n_tab_global = 0;
+    }
+    __syncthreads();
+    u64* s_tab = reinterpret_cast<u64*>(tab_s0());
+    for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
     __syncthreads();
 
     const int nunits = P.units ? P.nunits : P.B.nprob * P.B.T;
-    int nfail = 0, ndone = 0;
+    int nfail = 0, ndone = 0, top_max = 0;
     for (;;) {
-        if (c.tid == 0) s_int[8] = atomicAdd(P.work, 1);
+        if (tid == 0) {
+            S.unit = atomicAdd(P.work, 1);
+            S.fail = 0;
+        }
         __syncthreads();
-        int unit = s_int[8];
+        int unit = S.unit;
         __syncthreads();
         if (unit >= nunits) break;
         int p, t;
@@ -661,21 +708,22 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_reachsets(K1Params P) {
             p = unit / P.B.T;
             t = P.B.T - 1 - (unit % P.B.T);  // long intervals first
         }
-        c.fail = 0;
-        build_unit(c, P.B, p, t, s_jrs, s_int + 16, s_misc, s_misc + 8);
+        const int tm = build_unit(P.B, p, t);
+        top_max = tm > top_max ? tm : top_max;
         ndone++;
-        if (c.fail) {
+        const int failed = S.fail;
+        if (failed) {
             nfail++;
-            if (c.tid == 0) atomicMax(&P.B.status[p], c.fail);
+            if (tid == 0) atomicMax(&P.B.status[p], failed);
             // a failed operation may leave a table half-built: restore the all-zero invariant
-            for (int i = c.tid; i < P.tab_s_bytes / 8; i += NT) reinterpret_cast<u64*>(s_tab)[i] = 0;
-            for (int i = c.tid; i < P.gtab_bytes / 8; i += NT) reinterpret_cast<u64*>(c.tab_g)[i] = 0;
-            __syncthreads();
+            for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
+            for (int i = tid; i < P.gtab_bytes / 8; i += NT) reinterpret_cast<u64*>(S.tab_g)[i] = 0;
         }
+        __syncthreads();
     }
-    if (c.tid == 0 && P.stats) {
-        atomicMax(&P.stats[0], c.top_max);
-        atomicAdd(&P.stats[1], c.n_tab_global);
+    if (tid == 0 && P.stats) {
+        atomicMax(&P.stats[0], top_max - JRS_WORDS);
+        atomicAdd(&P.stats[1], S.n_tab_global);
         atomicAdd(&P.stats[2], nfail);
         atomicAdd(&P.stats[3], ndone);
     }
@@ -709,7 +757,7 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-    // two CTAs per SM: half of the SM's shared memory each (1 KB per CTA is reserved by the system)
+    // CTAS_PER_SM CTAs per SM: an equal share of the SM's shared memory each (1 KB per CTA is reserved by the system)
     int per_cta = (smem_optin + 1024) / CTAS_PER_SM - 1024;
     per_cta &= ~1023;
     const int dyn = per_cta - K1_FIXED_BYTES;
@@ -717,7 +765,7 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
     s->smem_bytes = size_t(K1_FIXED_BYTES) + size_t(s->arena_words) * 8 + s->tab_s_bytes;
     s->grid = CTAS_PER_SM * sms;
-    // per-CTA global scratch: F_i / N_i of one unit, and the overflow hash-table pool
+    // per-CTA global scratch: arena spill space, then F_i / N_i of one unit; and the overflow hash-table pool
     const int capw = cfg.cap_work_monomials;
     s->fn_words = 2 * MAXJ * (9 + capw * 2);
     s->gscr_words = s->fn_words + 24 * capw;
