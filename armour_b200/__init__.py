@@ -11,5 +11,6 @@ _lib.load()  # no CPU fallback: a missing extension is an ImportError here
 
 from .planner import ReachSetEngine  # noqa: E402
 from . import worlds  # noqa: E402
+from . import sharding  # noqa: E402
 
-__all__ = ["ReachSetEngine", "ArmourError", "NF", "worlds"]
+__all__ = ["ReachSetEngine", "ArmourError", "NF", "worlds", "sharding"]

@@ -49,6 +49,7 @@ SIGNATURES = {
     "armour_config_default": (C.c_int, [C.POINTER(Config)]),
     "armour_ctx_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "armour_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "armour_ctx_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "armour_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "armour_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "armour_status_string": (C.c_char_p, [C.c_int]),

@@ -242,6 +242,13 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     B.qdd0 = ctx->d_in + 2 * P * NF;
     if ((e = cudaMemsetAsync(B.status, 0, P * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
     if ((e = k1_scratch_create(&ctx->k1, ctx->cfg, ctx->rc, ctx->stream)) != cudaSuccess) return bail("k1 scratch", e);
+    {   // load the kernels now (CUDA loads modules lazily at first use), so that the first build is not charged for it
+        cudaFuncAttributes fa;
+        if ((e = cudaFuncGetAttributes(&fa, k1::k_reachsets)) != cudaSuccess) return bail("load k_reachsets", e);
+        if ((e = cudaFuncGetAttributes(&fa, k_hyperplanes)) != cudaSuccess) return bail("load k_hyperplanes", e);
+        if ((e = cudaFuncGetAttributes(&fa, k_constraints)) != cudaSuccess) return bail("load k_constraints", e);
+        if ((e = cudaFuncGetAttributes(&fa, k_verdict)) != cudaSuccess) return bail("load k_verdict", e);
+    }
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("sync", e);
     *out = ctx;
     return ARMOUR_OK;
@@ -279,6 +286,21 @@ int armour_num_time_steps(const armour_ctx* ctx) { return ctx ? ctx->B.T : ARMOU
 int armour_num_constraints(const armour_ctx* ctx, int nobs) {
     if (!ctx || nobs < 0) return ARMOUR_ERR_ARG;
     return NF * ctx->B.T + ctx->B.NJ * ctx->B.T * nobs + 4 * NF;
+}
+
+int armour_ctx_reserve(armour_ctx* ctx, int nprob, int nobs) {
+    int rc = check_batch(ctx, nprob, nobs);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int O = ctx->B.O, np = ctx->B.nprob;
+    rc = ensure_obstacle_buffers(ctx, nprob, nobs);
+    ctx->B.O = O;  // reserving does not change the current batch
+    ctx->B.nprob = np;
+    if (rc) return rc;
+    ctx->B.O = nobs;
+    rc = ensure_eval_buffers(ctx, nprob, true, true);
+    ctx->B.O = O;
+    return rc;
 }
 
 // ---- build -----------------------------------------------------------------------------------------

@@ -64,6 +64,10 @@ typedef struct armour_config {
 int armour_config_default(armour_config* cfg);
 int armour_ctx_create(const armour_config* cfg, armour_ctx** out);
 int armour_ctx_destroy(armour_ctx* ctx);
+/* Allocate now everything a batch of nprob problems with nobs obstacles will need (obstacle / half-space /
+ * staging buffers), so that the first build is not charged for cudaMalloc.  The reference allocates in the
+ * Obstacles constructor, before its reach-set timer starts (KPR/armour_main.cu:86-88, CollisionChecking.cu:6-55). */
+int armour_ctx_reserve(armour_ctx* ctx, int nprob, int nobs);
 /* Launch everything on this cudaStream_t (default: a stream owned by the context). */
 int armour_ctx_set_stream(armour_ctx* ctx, void* cuda_stream);
 int armour_ctx_synchronize(armour_ctx* ctx);

@@ -1,0 +1,81 @@
+"""The C++ host side (armour_b200/host): armtd_NLP twin, local solver and the armour_main CLI that keeps the
+reference's file interface (KPR/armour_main.cu:4-9,36-78,312-372; written / read by uarmtd_planner.m:158-219)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, WORLDS
+
+CLI = os.path.join(ROOT, "armour_b200", "armour_main")
+K_FILES = ("armour.out", "armour_joint_position_center.out", "armour_joint_position_radius.out",
+           "armour_control_input_radius.out", "armour_constraints.out")
+
+
+def test_selftest_host_logic(built):
+    """Parser, obstacle-count check and the local SQP solver on a problem with a known optimum (no GPU)."""
+    res = subprocess.run([CLI, "--selftest"], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "selftest: ok" in res.stdout
+
+
+def test_cli_without_gpu_writes_minus_one(built, tmp_path):
+    """No device -> exit code != 0 and a single -1 in armour.out (what uarmtd_planner.m treats as 'no plan'),
+    never a CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    from armour_b200 import worlds
+    q0, qd0, qdd0, q_des, obs = worlds.config1_problem(os.path.join(WORLDS, "scene_016_006.csv"))
+    worlds.write_armour_in(tmp_path / "armour.in", q0, qd0, qdd0, q_des, obs)
+    res = subprocess.run([CLI, str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0
+    assert (tmp_path / "armour.out").read_text().strip() == "-1"
+
+
+def test_cli_rejects_too_many_obstacles(built, tmp_path):
+    from armour_b200 import worlds
+    z = np.zeros(7)
+    worlds.write_armour_in(tmp_path / "armour.in", z, z, z, z, np.ones((41, 12)))  # MAX_OBSTACLE_NUM = 40
+    res = subprocess.run([CLI, str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0
+    assert (tmp_path / "armour.out").read_text().strip() == "-1"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["scene_016_006.csv", "scene_013_001.csv"])
+def test_cli_end_to_end_matches_oracle(built, tmp_path, scene):
+    from armour_b200 import worlds
+    from oracle.pyoracle import OracleProblem
+    q0, qd0, qdd0, q_des, obs = worlds.config1_problem(os.path.join(WORLDS, scene))
+    worlds.write_armour_in(tmp_path / "armour.in", q0, qd0, qdd0, q_des, obs)
+    q0, qd0, qdd0, q_des, obs = worlds.read_armour_in(tmp_path / "armour.in")  # what the CLI parses
+    res = subprocess.run([CLI, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    for f in K_FILES:
+        assert (tmp_path / f).exists(), f
+    ref = OracleProblem().build(q0, qd0, qdd0, obs)
+    T, NJ, m = ref.T, ref.NJ, ref.m
+    out = (tmp_path / "armour.out").read_text().split()
+    g_file = np.loadtxt(tmp_path / "armour_constraints.out")
+    assert g_file.shape == (m,)
+    if len(out) == 8:  # feasible: 7 lines of k_opt + total milliseconds
+        k = np.array([float(v) for v in out[:7]])
+        assert np.all(np.abs(k) <= 1.0)
+        g_ref = ref.eval_g(k)
+        ok, first = ref.verdict(g_ref)
+        assert ok, f"CLI reported a plan the oracle calls infeasible (row {first})"
+        assert np.max(np.abs(g_file - g_ref) / np.maximum(1.0, np.abs(g_ref))) <= 1e-5  # the file has 6 significant digits
+        assert ref.cost(q_des, k) <= ref.cost(q_des, np.zeros(7)) + 1e-12
+        centers = np.loadtxt(tmp_path / "armour_joint_position_center.out")
+        ref.eval_g(k)
+        assert np.max(np.abs(centers.reshape(T, NJ, 3) - ref.link_sliced_center())) <= 1e-9
+    else:          # infeasible: a single -1, then the time
+        assert out[0] == "-1" and len(out) == 2
+    rad = np.loadtxt(tmp_path / "armour_control_input_radius.out")  # T lines x 7
+    tr = ref.torque_radius()  # [7, T]
+    assert rad.shape == (T, 7)
+    assert np.max(np.abs(rad.T - tr) / tr) <= 1e-9
+    gens = np.loadtxt(tmp_path / "armour_joint_position_radius.out").reshape(T, NJ, 3, 6)
+    assert np.max(np.abs(gens - ref.link_gens())) <= 1e-9
