@@ -48,6 +48,7 @@ constexpr int NT = K1_NT;    // threads per CTA
 constexpr int CTAS_PER_SM = K1_CTAS;  // resident CTAs per SM (shared memory is split evenly)
 constexpr int NW = NT / 32;  // warps per CTA
 constexpr int RED_STRIDE = 12;
+constexpr int MASK_WORDS = 256;  // a merge operation handles up to 32 * MASK_WORDS candidate monomials
 
 // failure codes written to Batch::status (a build never truncates silently)
 enum { FAIL_ARENA = 1, FAIL_TABLE = 2, FAIL_SCRATCH = 3, FAIL_LINK_CAP = 4, FAIL_TORQUE_CAP = 5 };
@@ -107,6 +108,8 @@ struct K1S {
     double red[NW * RED_STRIDE];   // partial sums (prune amounts)
     double red2[NW * RED_STRIDE];  // partial sums (|coefficient| sums)
     double misc[16];               // [0..7) u_nom radius, [8..15) disturbance radius
+    int flip;                      // which survivor-mask buffer the next merge operation uses
+    unsigned mask[2][MASK_WORDS];  // survivor bits of a merge operation, by merged position (double-buffered)
 };
 constexpr int K1S_BYTES = (int(sizeof(K1S)) + 15) & ~15;
 
@@ -460,6 +463,205 @@ K1_DI PZ8 pz_zero(int top) {  // PZ with no monomials, zero centre and radii
     return h;
 }
 
+// ---- merge machinery ------------------------------------------------------------------------------
+// Every PZ keeps its monomials SORTED by key (like the reference after simplify(), KPR/PZsparse.cu:284-350).
+// Sums and products with a short operand are then merges of a few sorted lists: each candidate monomial
+// finds its place in the merged order with binary searches (no hashing, no atomics on keys), the first
+// candidate of a run of equal keys ("owner") adds up the run in a fixed order, applies the prune rule and
+// parks the survivor at its merged position in a dense scratch array; a bit mask of survivors gives the
+// output positions by a warp scan.
+struct Dense {
+    u64* keys;
+    double* coef;
+    unsigned* mask;   // survivor bits, all zero on entry
+    unsigned* other;  // the buffer of the next merge operation (zeroed here)
+    int M;
+    bool global;      // scratch lives in the global pool: give it back zeroed
+};
+K1_DI bool dense_select(int M, int sz, Dense& d) {
+    K1S& S = k1s();
+    if (M > 32 * MASK_WORDS) {
+        set_fail(FAIL_TABLE);
+        return false;
+    }
+    const int bytes = M * 8 * (1 + sz);
+    char* base;
+    d.global = false;
+    if (bytes <= S.tab_s_bytes) {
+        base = tab_s0();
+    } else if (bytes <= S.tab_g_bytes) {
+        base = S.tab_g;
+        d.global = true;
+        if (k1_tid() == 0) S.n_tab_global++;
+    } else {
+        set_fail(FAIL_TABLE);
+        return false;
+    }
+    d.keys = reinterpret_cast<u64*>(base);
+    d.coef = reinterpret_cast<double*>(base + size_t(M) * 8);
+    const int f = S.flip;
+    d.mask = S.mask[f];
+    d.other = S.mask[f ^ 1];
+    d.M = M;
+    return true;
+}
+// number of keys[0..n) that are < target (keys ascending); branch-free so that several searches interleave
+K1_DI int lower_bound(const u64* keys, int n, u64 target) {
+    int lo = 0;
+    int step = 1;
+    while (step < n) step <<= 1;
+    for (; step > 0; step >>= 1) {
+        const int probe = lo + step;
+        if (probe <= n && keys[probe - 1] < target) lo = probe;
+    }
+    return lo;
+}
+K1_DI int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+// reduce the per-thread pruned amounts to S.red (skipped when nothing was pruned in the warp)
+template <int SZ>
+K1_DI void rad_publish(const double* rad, bool pruned_any) {
+    K1S& S = k1s();
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
+    double r[SZ];
+#pragma unroll
+    for (int e = 0; e < SZ; e++) r[e] = rad[e];
+    if (__any_sync(0xffffffffu, pruned_any)) {
+#pragma unroll
+        for (int e = 0; e < SZ; e++) r[e] = warp_sum_up(r[e]);
+    }
+    if (lane == 0)
+#pragma unroll
+        for (int e = 0; e < SZ; e++) S.red[warp * RED_STRIDE + e] = r[e];
+}
+template <int SZ>
+K1_DI void rad_collect(double* rad_total) {
+    const K1S& S = k1s();
+#pragma unroll
+    for (int e = 0; e < SZ; e++) {
+        double v = S.red[e];
+#pragma unroll
+        for (int w = 1; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE + e]);
+        rad_total[e] = v;
+    }
+}
+// Second half of a merge operation (after the barrier that follows the scatter): count the survivors,
+// allocate the output block at `top` and copy them in merged (= key) order.  The caller writes the
+// centre / radii and ends with __syncthreads().
+template <int SZ>
+K1_DI PZ8 dense_emit(int top, const Dense& d, bool* ok_out) {
+    K1S& S = k1s();
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
+    constexpr int ROUNDS = MASK_WORDS / 32;
+    const int nwords = (d.M + 31) >> 5;
+    int excl[ROUNDS];
+    unsigned wv[ROUNDS];
+    int running = 0;
+#pragma unroll
+    for (int j = 0; j < ROUNDS; j++) {
+        excl[j] = 0;
+        wv[j] = 0;
+        if (j * 32 < nwords) {  // uniform
+            const unsigned w = (j * 32 + lane < nwords) ? d.mask[j * 32 + lane] : 0u;
+            const int v = __popc(w);
+            const int incl = warp_incl_scan(v, lane);
+            excl[j] = incl - v + running;
+            wv[j] = w;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    // prepare the mask buffer of the next merge operation; its last readers finished before the barrier above
+    for (int i = tid; i < MASK_WORDS; i += NT) d.other[i] = 0u;
+    if (tid == 0) S.flip ^= 1;
+    bool ok;
+    const PZ8 h8 = pz_alloc<SZ>(top, running, &ok);
+    *ok_out = ok;
+    const PZH h = view<SZ>(h8);
+    u64* out_keys = pz_keys(h);
+    double* out_coef = pz_coef(h);
+#pragma unroll
+    for (int j = 0; j < ROUNDS; j++) {
+        if (j * 32 < nwords) {
+            for (int cc = warp; cc < 32; cc += NW) {
+                const int c = j * 32 + cc;
+                if (c >= nwords) break;  // uniform per warp
+                const int base = __shfl_sync(0xffffffffu, excl[j], cc);
+                const unsigned word = __shfl_sync(0xffffffffu, wv[j], cc);
+                const int p = c * 32 + lane;
+                if ((word >> lane) & 1u) {
+                    const int rank = base + __popc(word & ((1u << lane) - 1u));
+                    if (ok) {
+                        out_keys[rank] = d.keys[p];
+#pragma unroll
+                        for (int e = 0; e < SZ; e++) out_coef[size_t(rank) * SZ + e] = d.coef[size_t(p) * SZ + e];
+                    }
+                }
+                if (d.global && p < d.M) {  // the global pool is handed back all-zero
+                    d.keys[p] = 0;
+#pragma unroll
+                    for (int e = 0; e < SZ; e++) d.coef[size_t(p) * SZ + e] = 0.0;
+                }
+            }
+        }
+    }
+    return h8;
+}
+// park a surviving candidate at merged position pos
+template <int SZ>
+K1_DI void dense_put(const Dense& d, int pos, u64 key, const double* v) {
+    d.keys[pos] = key;
+#pragma unroll
+    for (int e = 0; e < SZ; e++) d.coef[size_t(pos) * SZ + e] = v[e];
+    atomicOr(&d.mask[pos >> 5], 1u << (pos & 31));
+}
+
+// Sort the monomials of a block by key, in place (used after the hash-table product, whose survivors come out
+// in slot order): every thread ranks its monomials against all keys, then stores them at their ranks.
+template <int SZ>
+K1_DI void sort_block(PZ8 h8, bool ok) {
+    constexpr int R = 4;  // up to R * NT monomials
+    const int tid = k1_tid();
+    const PZH h = view<SZ>(h8);
+    const int n = ok ? h.n : 0;
+    if (n > R * NT) {
+        set_fail(FAIL_TABLE);
+        return;
+    }
+    u64* keys = pz_keys(h);
+    double* cf = pz_coef(h);
+    u64 k[R];
+    double v[R][SZ];
+    int rank[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = tid + r * NT;
+        rank[r] = -1;
+        if (i < n) {
+            k[r] = keys[i];
+#pragma unroll
+            for (int e = 0; e < SZ; e++) v[r][e] = cf[size_t(i) * SZ + e];
+            int c = 0;
+            for (int q = 0; q < n; q++) c += (keys[q] < k[r]);
+            rank[r] = c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (rank[r] >= 0) {
+            keys[rank[r]] = k[r];
+#pragma unroll
+            for (int e = 0; e < SZ; e++) cf[size_t(rank[r]) * SZ + e] = v[r][e];
+        }
+    }
+}
+
 // ---- linear operations (operator+, operator-, addOneDimPZ, element extraction, double*PZ) -------
 // out = src0 (+) src1 with, per source: optional scalar extraction (comp_in >= 0 -> placed at comp_out of
 // the output) and a scale factor.  Mirrors KPR/PZsparse.cu:743-834 (+,-), :996-1030 (double*PZ, no
@@ -503,6 +705,8 @@ K1_DI void lin_radius(const LinSrc& s, int lane, double* out) {  // radius * |sc
 }
 
 // sources are described by scalars passed by value: (handle, element size, comp_in, comp_out, scale)
+// A merge of two sorted lists: candidate positions = own index + rank in the other list (source 0 first on a
+// tie); the owner of a key adds s0's value and s1's value (at most two terms: order-free).
 template <int SZ>
 K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale, PZ8 b8, int b_sz, int b_in, int b_out,
                   double b_scale) {
@@ -513,54 +717,55 @@ K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale
     LinSrc s0, s1;
     s0.h.p = vptr(a8.off); s0.h.n = a8.n; s0.h.sz = a_sz; s0.comp_in = a_in; s0.comp_out = a_out; s0.scale = a_scale;
     s1.h.p = vptr(b8.off); s1.h.n = b8.n; s1.h.sz = b_sz; s1.comp_in = b_in; s1.comp_out = b_out; s1.scale = b_scale;
-    Tab t;
-    if (!tab_select(s0.h.n + s1.h.n, SZ, t)) return dummy;
+    const int na = s0.h.n, nb = s1.h.n;
+    Dense d;
+    if (!dense_select(na + nb, SZ, d)) return dummy;
     const double thr = S.thr;
-    // keys
-#pragma unroll
-    for (int srcI = 0; srcI < 2; srcI++) {
-        const LinSrc& s = srcI ? s1 : s0;
-        const u64* keys = pz_keys(s.h);
-        const double* cf = pz_coef(s.h);
-        for (int m = tid; m < s.h.n; m += NT) {
-            if (s.comp_in >= 0 && cf[size_t(m) * s.h.sz + s.comp_in] == 0.0) continue;  // extracted zero: no effect
-            tab_insert(t, keys[m]);
-        }
-    }
-    __syncthreads();
-    // at most two contributions per (key, component): a commutative atomic add is order-independent
-#pragma unroll
-    for (int srcI = 0; srcI < 2; srcI++) {
-        const LinSrc& s = srcI ? s1 : s0;
-        const u64* keys = pz_keys(s.h);
-        const double* cf = pz_coef(s.h);
-        for (int m = tid; m < s.h.n; m += NT) {
-            if (s.comp_in >= 0 && cf[size_t(m) * s.h.sz + s.comp_in] == 0.0) continue;
-            double v[SZ];
-            lin_value<SZ>(s, cf + size_t(m) * s.h.sz, v);
-            const int slot = tab_find(t, keys[m]);
-#pragma unroll
-            for (int e = 0; e < SZ; e++)
-                if (v[e] != 0.0) atomicAdd(&t.acc[size_t(slot) * SZ + e], v[e]);
-        }
-    }
-    __syncthreads();
     double rad[SZ];
-    bool ok;
-    const PZ8 h8 = tab_finalize<SZ, SZ>(
-        top, t,
-        [thr](const double* a, double* out, double* r) {
-            if (frobN<SZ>(a) <= thr) {
 #pragma unroll
-                for (int e = 0; e < SZ; e++) r[e] = __dadd_ru(r[e], fabs(a[e]));
-                return false;
+    for (int e = 0; e < SZ; e++) rad[e] = 0.0;
+    bool pruned_any = false;
+    for (int it = tid; it < na + nb; it += NT) {
+        const bool fromA = it < na;
+        const int idx = fromA ? it : it - na;
+        const LinSrc& src = fromA ? s0 : s1;
+        const LinSrc& oth = fromA ? s1 : s0;
+        const u64* ks = pz_keys(src.h);
+        const u64* ko = pz_keys(oth.h);
+        const double* cs = pz_coef(src.h) + size_t(idx) * src.h.sz;
+        const u64 key = ks[idx];
+        const int lb = lower_bound(ko, oth.h.n, key);
+        const bool hit = lb < oth.h.n && ko[lb] == key;
+        const double* co = pz_coef(oth.h) + size_t(hit ? lb : 0) * oth.h.sz;
+        // an extracted element that is exactly zero takes no part (KPR/PZsparse.cu:678-697 keeps it, simplify drops it)
+        const bool absent = src.comp_in >= 0 && cs[src.comp_in] == 0.0;
+        const bool hit_valid = hit && !(oth.comp_in >= 0 && co[oth.comp_in] == 0.0);
+        const int pos = idx + lb + ((!fromA && hit) ? 1 : 0);
+        const bool owner = !absent && (fromA || !hit_valid);
+        if (owner) {
+            double v[SZ], v2[SZ];
+            lin_value<SZ>(src, cs, v);
+            if (fromA && hit_valid) {
+                lin_value<SZ>(oth, co, v2);
+#pragma unroll
+                for (int e = 0; e < SZ; e++) v[e] = v[e] + v2[e];
             }
+            if (frobN<SZ>(v) <= thr) {
 #pragma unroll
-            for (int e = 0; e < SZ; e++) out[e] = a[e];
-            return true;
-        },
-        rad, &ok);
+                for (int e = 0; e < SZ; e++) rad[e] = __dadd_ru(rad[e], fabs(v[e]));
+                pruned_any = true;
+            } else {
+                dense_put<SZ>(d, pos, key, v);
+            }
+        }
+    }
+    rad_publish<SZ>(rad, pruned_any);
+    __syncthreads();
+    bool ok;
+    const PZ8 h8 = dense_emit<SZ>(top, d, &ok);
     if (ok && tid < SZ) {
+        double radt[SZ];
+        rad_collect<SZ>(radt);
         const PZH h = view<SZ>(h8);
         const int e = tid;
         double c0[SZ], c1[SZ];
@@ -572,7 +777,7 @@ K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale
             double r0[SZ], r1[SZ];
             lin_radius<SZ>(s0, lane, r0);
             lin_radius<SZ>(s1, lane, r1);
-            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(r0[e], r1[e]), rad[e]);
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(r0[e], r1[e]), radt[e]);
         }
     }
     __syncthreads();
@@ -825,9 +1030,15 @@ K1_OP PZ8 op_const_mul(int top, const double* K, double pct_lane1, PZ8 x8) {
 
 // ---- PZ * PZ with a 3x3 left operand (KPR/PZsparse.cu:864-994) -----------------------------------
 // P = 1: 3x3 * 3x1, P = 3: 3x3 * 3x3.  TRANS: the left operand is used transposed (R_t = R.transpose(),
-// KPR/Trajectory.cu:143).  The operand with fewer monomials is the "outer" one: its monomials are
-// visited one after the other (a barrier between them, so equal keys are summed in a fixed order), the
-// other operand's monomials are spread over the threads.
+// KPR/Trajectory.cu:143).  On this path one operand is always short (a joint rotation with <= 3 monomials, or
+// the link box): the "outer" operand O.  The product is the merge of nO + 2 sorted lists
+//     list 0      : inner monomial j times the centre of the outer operand      keys kI[j]
+//     list 1 + o  : inner monomial j times outer monomial o                      keys kI[j] + kO[o]
+//     list nO + 1 : centre of the inner operand times outer monomial o           keys kO[o]
+// (degree hashes add without carry, KPR/PZsparse.cu:938-940; adding a constant keeps a list sorted).  The
+// owner of a key adds the contributions in the fixed order: left-polynomial x right-centre, left-centre x
+// right-polynomial, then the pair products for o = 0, 1, 2.
+constexpr int MUL_MAX_OUTER = 3;
 template <int P, bool TRANS>
 K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
     constexpr int SZ = 3 * P;
@@ -837,85 +1048,131 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
     const int tid = k1_tid();
     const PZH L = view<9>(L8), R = view<SZ>(R8);
     const int nL = L.n, nR = R.n;
-    Tab t;
-    if (!tab_select(nL + nR + nL * nR, SZ, t)) return dummy;
+    const bool outerL = nL <= nR;
+    const int nO = outerL ? nL : nR, nI = outerL ? nR : nL;
+    if (nO > MUL_MAX_OUTER) {
+        set_fail(FAIL_TABLE);
+        return dummy;
+    }
+    const int M = nI * (nO + 1) + nO;
+    Dense d;
+    if (!dense_select(M, SZ, d)) return dummy;
     const double thr = S.thr;
     const u64* kL = pz_keys(L);
     const u64* kR = pz_keys(R);
     const double* cL = pz_coef(L);
     const double* cR = pz_coef(R);
-    const bool outerL = nL <= nR;
-    const int nO = outerL ? nL : nR, nI = outerL ? nR : nL;
     const u64* kO = outerL ? kL : kR;
     const u64* kI = outerL ? kR : kL;
-    // keys
-    for (int j = tid; j < nI; j += NT) {
-        const u64 kj = kI[j];
-        tab_insert(t, kj);
-        for (int o = 0; o < nO; o++) tab_insert(t, kj + kO[o]);  // degree hashes add without carry (:938-940)
+    u64 ko[MUL_MAX_OUTER];
+#pragma unroll
+    for (int o = 0; o < MUL_MAX_OUTER; o++) ko[o] = (o < nO) ? kO[o] : ~0ull;
+    double cenL[9], cenR[SZ];
+#pragma unroll
+    for (int q = 0; q < 9; q++) cenL[q] = pz_c(L)[q];
+#pragma unroll
+    for (int q = 0; q < SZ; q++) cenR[q] = pz_c(R)[q];
+    double rad[SZ];
+#pragma unroll
+    for (int e = 0; e < SZ; e++) rad[e] = 0.0;
+    bool pruned_any = false;
+    for (int it = tid; it < M; it += NT) {
+        // which list, which element
+        int a, j;
+        if (it < nI * (nO + 1)) {
+            a = it / nI;
+            j = it - a * nI;
+        } else {
+            a = nO + 1;
+            j = it - nI * (nO + 1);  // outer monomial index
+        }
+        // (select chains instead of indexing ko[] with a run-time value keep it in registers)
+        const u64 ko_a = (a == 1) ? ko[0] : ((a == 2) ? ko[1] : ko[2]);
+        const u64 ko_j = (j == 0) ? ko[0] : ((j == 1) ? ko[1] : ko[2]);
+        const u64 key = (a == 0) ? kI[j] : ((a <= nO) ? kI[j] + ko_a : ko_j);
+        // rank and hit of `key` in every list
+        int lb[MUL_MAX_OUTER + 1];
+        bool hit[MUL_MAX_OUTER + 1];
+        lb[0] = lower_bound(kI, nI, key);
+        hit[0] = lb[0] < nI && kI[lb[0]] == key;
+#pragma unroll
+        for (int o = 0; o < MUL_MAX_OUTER; o++) {
+            lb[o + 1] = 0;
+            hit[o + 1] = false;
+            if (o < nO && key >= ko[o]) {
+                const u64 target = key - ko[o];
+                lb[o + 1] = lower_bound(kI, nI, target);
+                hit[o + 1] = lb[o + 1] < nI && kI[lb[o + 1]] == target;
+            }
+        }
+        int lbH = 0, hitH = -1;
+#pragma unroll
+        for (int o = 0; o < MUL_MAX_OUTER; o++) {
+            if (o < nO) {
+                lbH += (ko[o] < key);
+                if (ko[o] == key) hitH = o;
+            }
+        }
+        // merged position: ties are ordered by list index
+        int pos = lbH, first = (hitH >= 0) ? nO + 1 : nO + 2;
+#pragma unroll
+        for (int b = MUL_MAX_OUTER; b >= 0; b--) {
+            if (b <= nO) {
+                pos += lb[b];
+                if (hit[b]) first = b;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b <= MUL_MAX_OUTER; b++)
+            if (b <= nO && b < a && hit[b]) pos += 1;
+        if (first != a) continue;   // not the owner of this key
+        // sum of the run, fixed order
+        double acc[SZ];
+#pragma unroll
+        for (int e = 0; e < SZ; e++) acc[e] = 0.0;
+        double v[SZ];
+        const bool inL = outerL ? (hitH >= 0) : hit[0];  // key among the monomials of L
+        const bool inR = outerL ? hit[0] : (hitH >= 0);  // key among the monomials of R
+        if (inL) {
+            const int i = outerL ? hitH : lb[0];
+            matmul3<P, TRANS>(cL + size_t(i) * 9, cenR, v);
+#pragma unroll
+            for (int e = 0; e < SZ; e++) acc[e] += v[e];
+        }
+        if (inR) {
+            const int jj = outerL ? lb[0] : hitH;
+            matmul3<P, TRANS>(cenL, cR + size_t(jj) * SZ, v);
+#pragma unroll
+            for (int e = 0; e < SZ; e++) acc[e] += v[e];
+        }
+#pragma unroll
+        for (int o = 0; o < MUL_MAX_OUTER; o++) {
+            if (o < nO && hit[o + 1]) {
+                const int ji = lb[o + 1];
+                if (outerL)
+                    matmul3<P, TRANS>(cL + size_t(o) * 9, cR + size_t(ji) * SZ, v);
+                else
+                    matmul3<P, TRANS>(cL + size_t(ji) * 9, cR + size_t(o) * SZ, v);
+#pragma unroll
+                for (int e = 0; e < SZ; e++) acc[e] += v[e];
+            }
+        }
+        if (frobN<SZ>(acc) <= thr) {
+#pragma unroll
+            for (int e = 0; e < SZ; e++) rad[e] = __dadd_ru(rad[e], fabs(acc[e]));
+            pruned_any = true;
+        } else {
+            dense_put<SZ>(d, pos, key, acc);
+        }
     }
-    for (int o = tid; o < nO; o += NT) tab_insert(t, kO[o]);
+    rad_publish<SZ>(rad, pruned_any);
     if (outerL) abs_sum_partial<SZ>(R); else abs_sum_partial<9>(L);
     __syncthreads();
-    // polynomial * centre of the other side, centre * polynomial: keys within each group are distinct
-    {
-        double cen[9];
-        const double* cc = pz_c(R);
-#pragma unroll
-        for (int q = 0; q < SZ; q++) cen[q] = cc[q];
-        for (int i = tid; i < nL; i += NT) {
-            double v[SZ];
-            matmul3<P, TRANS>(cL + size_t(i) * 9, cen, v);
-            const int slot = tab_find(t, kL[i]);
-#pragma unroll
-            for (int e = 0; e < SZ; e++) t.acc[size_t(slot) * SZ + e] += v[e];
-        }
-    }
-    __syncthreads();
-    {
-        double cen[9];
-        const double* cc = pz_c(L);
-#pragma unroll
-        for (int q = 0; q < 9; q++) cen[q] = cc[q];
-        for (int j = tid; j < nR; j += NT) {
-            double v[SZ];
-            matmul3<P, TRANS>(cen, cR + size_t(j) * SZ, v);
-            const int slot = tab_find(t, kR[j]);
-#pragma unroll
-            for (int e = 0; e < SZ; e++) t.acc[size_t(slot) * SZ + e] += v[e];
-        }
-    }
-    __syncthreads();
-    for (int o = 0; o < nO; o++) {
-        const u64 ko = kO[o];
-        for (int j = tid; j < nI; j += NT) {
-            double v[SZ];
-            if (outerL)
-                matmul3<P, TRANS>(cL + size_t(o) * 9, cR + size_t(j) * SZ, v);
-            else
-                matmul3<P, TRANS>(cL + size_t(j) * 9, cR + size_t(o) * SZ, v);
-            const int slot = tab_find(t, ko + kI[j]);
-#pragma unroll
-            for (int e = 0; e < SZ; e++) t.acc[size_t(slot) * SZ + e] += v[e];
-        }
-        __syncthreads();
-    }
-    double rad[SZ];
     bool ok;
-    const PZ8 h8 = tab_finalize<SZ, SZ>(
-        top, t,
-        [thr](const double* a, double* out, double* r) {
-            if (frobN<SZ>(a) <= thr) {
-#pragma unroll
-                for (int e = 0; e < SZ; e++) r[e] = __dadd_ru(r[e], fabs(a[e]));
-                return false;
-            }
-#pragma unroll
-            for (int e = 0; e < SZ; e++) out[e] = a[e];
-            return true;
-        },
-        rad, &ok);
+    const PZ8 h8 = dense_emit<SZ>(top, d, &ok);
     if (ok && tid < SZ) {
+        double radt[SZ];
+        rad_collect<SZ>(radt);
         const PZH h = view<SZ>(h8);
         const int e = tid;
         double absL[9], absR[SZ], cen[SZ];
@@ -926,7 +1183,7 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
             abs_sum_collect<9>(L, absL);
             abs_sum_serial<SZ>(R, absR);
         }
-        matmul3<P, TRANS>(pz_c(L), pz_c(R), cen);
+        matmul3<P, TRANS>(cenL, cenR, cen);
         pz_c(h)[e] = cen[e];
 #pragma unroll
         for (int lane = 0; lane < 2; lane++) {
@@ -934,7 +1191,7 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
             matmul3_up<P, TRANS>(absL, pz_r(R, lane), ra2);
             matmul3_up<P, TRANS>(pz_r(L, lane), absR, ra3);
             matmul3_up<P, TRANS>(pz_r(L, lane), pz_r(R, lane), rr);
-            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr[e], __dadd_ru(ra2[e], ra3[e])), rad[e]);
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr[e], __dadd_ru(ra2[e], ra3[e])), radt[e]);
         }
     }
     __syncthreads();
@@ -963,6 +1220,12 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
     const int nA = A.n, nB = B.n;
     Tab t;
     if (!tab_select(nA + nB + nA * nB, 6, t)) return dummy;
+    if (reinterpret_cast<char*>(t.keys) == tab_s0()) {  // merge operations leave the shared pool dirty
+        u64* z = t.keys;
+        const int words = t.cap * 7;
+        for (int i = tid; i < words; i += NT) z[i] = 0;
+        __syncthreads();
+    }
     const double thr = S.thr;
     const u64* kA = pz_keys(A);
     const u64* kB = pz_keys(B);
@@ -1079,6 +1342,8 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(p0, p1), rad[e]);
         }
     }
+    __syncthreads();
+    sort_block<3>(h8, ok);  // survivors leave the table in slot order
     __syncthreads();
     return h8;
 }

@@ -682,7 +682,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_reachsets(K1Params P) {
         S.tab_g_bytes = P.gtab_bytes;
         S.fail = 0;
         S.n_tab_global = 0;
+        S.flip = 0;
     }
+    for (int i = tid; i < 2 * MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0u;
     __syncthreads();
     u64* s_tab = reinterpret_cast<u64*>(tab_s0());
     for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
@@ -718,6 +720,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_reachsets(K1Params P) {
             // a failed operation may leave a table half-built: restore the all-zero invariant
             for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
             for (int i = tid; i < P.gtab_bytes / 8; i += NT) reinterpret_cast<u64*>(S.tab_g)[i] = 0;
+            for (int i = tid; i < 2 * MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0u;
         }
         __syncthreads();
     }

@@ -191,6 +191,7 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
     emu::warp_barrier(mask);
     return r;
 }
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 
