@@ -215,7 +215,8 @@ K1_DI void matmul3_up(const double* A, const double* B, double* C) {
         }
 }
 
-K1_DI double warp_sum_up(double v) {
+// (not inlined: the kernel is instruction-fetch bound, and this sequence used to be a quarter of its code)
+K1_OP double warp_sum_up(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = __dadd_ru(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
@@ -474,7 +475,7 @@ struct Dense {
     u64* keys;
     double* coef;
     unsigned* mask;   // survivor bits, all zero on entry
-    unsigned* other;  // the buffer of the next merge operation (zeroed here)
+    int flip;         // which mask buffer this operation uses (the other one is zeroed for the next operation)
     int M;
     bool global;      // scratch lives in the global pool: give it back zeroed
 };
@@ -501,7 +502,7 @@ K1_DI bool dense_select(int M, int sz, Dense& d) {
     d.coef = reinterpret_cast<double*>(base + size_t(M) * 8);
     const int f = S.flip;
     d.mask = S.mask[f];
-    d.other = S.mask[f ^ 1];
+    d.flip = f;
     d.M = M;
     return true;
 }
@@ -515,14 +516,6 @@ K1_DI int lower_bound(const u64* keys, int n, u64 target) {
         if (probe <= n && keys[probe - 1] < target) lo = probe;
     }
     return lo;
-}
-K1_DI int warp_incl_scan(int v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-    }
-    return v;
 }
 // reduce the per-thread pruned amounts to S.red (skipped when nothing was pruned in the warp)
 template <int SZ>
@@ -553,63 +546,72 @@ K1_DI void rad_collect(double* rad_total) {
 }
 // Second half of a merge operation (after the barrier that follows the scatter): count the survivors,
 // allocate the output block at `top` and copy them in merged (= key) order.  The caller writes the
-// centre / radii and ends with __syncthreads().
+// centre / radii and ends with __syncthreads().  Kept out of line and with run-time loops: one copy of this
+// code per element size serves every merge operation (code size is what bounds this kernel).
 template <int SZ>
-K1_DI PZ8 dense_emit(int top, const Dense& d, bool* ok_out) {
+K1_OP PZ8 dense_emit_impl(int top, u64* keys, int M, int flip, int global) {
     K1S& S = k1s();
     const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
-    constexpr int ROUNDS = MASK_WORDS / 32;
-    const int nwords = (d.M + 31) >> 5;
-    int excl[ROUNDS];
-    unsigned wv[ROUNDS];
-    int running = 0;
-#pragma unroll
-    for (int j = 0; j < ROUNDS; j++) {
-        excl[j] = 0;
-        wv[j] = 0;
-        if (j * 32 < nwords) {  // uniform
-            const unsigned w = (j * 32 + lane < nwords) ? d.mask[j * 32 + lane] : 0u;
-            const int v = __popc(w);
-            const int incl = warp_incl_scan(v, lane);
-            excl[j] = incl - v + running;
-            wv[j] = w;
-            running += __shfl_sync(0xffffffffu, incl, 31);
-        }
+    const unsigned* mask = S.mask[flip];
+    double* coef = reinterpret_cast<double*>(keys + M);
+    const int nwords = (M + 31) >> 5;
+    const int rounds = (nwords + 31) >> 5;
+    int total = 0;
+#pragma unroll 1
+    for (int j = 0; j < rounds; j++) {
+        const int wi = j * 32 + lane;
+        total += __popc(wi < nwords ? mask[wi] : 0u);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     // prepare the mask buffer of the next merge operation; its last readers finished before the barrier above
-    for (int i = tid; i < MASK_WORDS; i += NT) d.other[i] = 0u;
-    if (tid == 0) S.flip ^= 1;
+    for (int i = tid; i < MASK_WORDS; i += NT) S.mask[flip ^ 1][i] = 0u;
+    if (tid == 0) S.flip = flip ^ 1;
     bool ok;
-    const PZ8 h8 = pz_alloc<SZ>(top, running, &ok);
-    *ok_out = ok;
+    const PZ8 h8 = pz_alloc<SZ>(top, total, &ok);
     const PZH h = view<SZ>(h8);
     u64* out_keys = pz_keys(h);
     double* out_coef = pz_coef(h);
+    int running = 0;
+#pragma unroll 1
+    for (int j = 0; j < rounds; j++) {
+        const int wi = j * 32 + lane;
+        const unsigned w = wi < nwords ? mask[wi] : 0u;
+        const int v = __popc(w);
+        int incl = v;
 #pragma unroll
-    for (int j = 0; j < ROUNDS; j++) {
-        if (j * 32 < nwords) {
-            for (int cc = warp; cc < 32; cc += NW) {
-                const int c = j * 32 + cc;
-                if (c >= nwords) break;  // uniform per warp
-                const int base = __shfl_sync(0xffffffffu, excl[j], cc);
-                const unsigned word = __shfl_sync(0xffffffffu, wv[j], cc);
-                const int p = c * 32 + lane;
-                if ((word >> lane) & 1u) {
-                    const int rank = base + __popc(word & ((1u << lane) - 1u));
-                    if (ok) {
-                        out_keys[rank] = d.keys[p];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const int excl = incl - v + running;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll 1
+        for (int cc = warp; cc < 32; cc += NW) {
+            const int c = j * 32 + cc;
+            if (c >= nwords) break;  // uniform per warp
+            const int base = __shfl_sync(0xffffffffu, excl, cc);
+            const unsigned word = __shfl_sync(0xffffffffu, w, cc);
+            const int p = c * 32 + lane;
+            if (ok && ((word >> lane) & 1u)) {
+                const int rank = base + __popc(word & ((1u << lane) - 1u));
+                out_keys[rank] = keys[p];
 #pragma unroll
-                        for (int e = 0; e < SZ; e++) out_coef[size_t(rank) * SZ + e] = d.coef[size_t(p) * SZ + e];
-                    }
-                }
-                if (d.global && p < d.M) {  // the global pool is handed back all-zero
-                    d.keys[p] = 0;
+                for (int e = 0; e < SZ; e++) out_coef[size_t(rank) * SZ + e] = coef[size_t(p) * SZ + e];
+            }
+            if (global && p < M) {  // the global pool is handed back all-zero
+                keys[p] = 0;
 #pragma unroll
-                    for (int e = 0; e < SZ; e++) d.coef[size_t(p) * SZ + e] = 0.0;
-                }
+                for (int e = 0; e < SZ; e++) coef[size_t(p) * SZ + e] = 0.0;
             }
         }
     }
+    return h8;
+}
+template <int SZ>
+K1_DI PZ8 dense_emit(int top, const Dense& d, bool* ok_out) {
+    const PZ8 h8 = dense_emit_impl<SZ>(top, d.keys, d.M, d.flip, d.global ? 1 : 0);
+    *ok_out = !k1s().fail;
     return h8;
 }
 // park a surviving candidate at merged position pos
