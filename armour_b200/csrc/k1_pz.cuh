@@ -187,6 +187,16 @@ K1_DI double frobN(const double* v) {
     for (int i = 0; i < N; i++) s += v[i] * v[i];
     return sqrt(s);
 }
+template <int N>
+K1_DI double sumsqN(const double* v) {  // the argument of the square root in frobN, same order of operations
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) s += v[i] * v[i];
+    return s;
+}
+// sqrt(ss) <= thr, the prune test of simplify() (KPR/PZsparse.cu:321), out of line so that the square-root
+// expansion exists once in the kernel
+K1_OP bool norm_le(double ss, double thr) { return sqrt(ss) <= thr; }
 // C(3 x P) = A(3x3) * B(3 x P), column-major, inner index ascending, no FMA (Eigen-like: KPR/PZsparse.cu:864-994)
 template <int P, bool TRANS>
 K1_DI void matmul3(const double* A, const double* B, double* C) {
@@ -359,16 +369,16 @@ K1_DI PZ8 tab_finalize(int top, const Tab& t, Fin fin, double* rad_total, bool* 
 }
 
 // block-wide sum over the monomials of |coeff| per component (rounded up), NOT including |centre|.
-// Writes warp partials to S.red2; the caller syncs, then calls abs_sum_collect.
+// Writes warp partials to S.red2; the caller syncs, then reads entries with abs_collect_entry.
 template <int SZ>
-K1_DI void abs_sum_partial(const PZH& h) {
+K1_OP void abs_sum_partial_impl(const double* cf, int n) {
     K1S& S = k1s();
     const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
     double s[SZ];
 #pragma unroll
     for (int e = 0; e < SZ; e++) s[e] = 0.0;
-    const double* cf = pz_coef(h);
-    for (int m = tid; m < h.n; m += NT)
+#pragma unroll 1
+    for (int m = tid; m < n; m += NT)
 #pragma unroll
         for (int e = 0; e < SZ; e++) s[e] = __dadd_ru(s[e], fabs(cf[size_t(m) * SZ + e]));
 #pragma unroll
@@ -378,25 +388,22 @@ K1_DI void abs_sum_partial(const PZH& h) {
         for (int e = 0; e < SZ; e++) S.red2[warp * RED_STRIDE + e] = s[e];
 }
 template <int SZ>
-K1_DI void abs_sum_collect(const PZH& h, double* out) {  // |centre| + sum |coeff|
+K1_DI void abs_sum_partial(const PZH& h) { abs_sum_partial_impl<SZ>(pz_coef(h), h.n); }
+// |centre| + sum |coeff| of ONE component, from the partials of abs_sum_partial
+K1_DI double abs_collect_entry(const PZH& h, int comp) {
     const K1S& S = k1s();
-#pragma unroll
-    for (int e = 0; e < SZ; e++) {
-        double v = fabs(pz_c(h)[e]);
-#pragma unroll
-        for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red2[w * RED_STRIDE + e]);
-        out[e] = v;
-    }
+    double v = fabs(pz_c(h)[comp]);
+#pragma unroll 1
+    for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red2[w * RED_STRIDE + comp]);
+    return v;
 }
-// every thread walks a (small) operand itself
-template <int SZ>
-K1_DI void abs_sum_serial(const PZH& h, double* out) {
+// the same for a short operand: the calling thread walks the monomials itself
+K1_DI double abs_serial_entry(const PZH& h, int comp) {
     const double* cf = pz_coef(h);
-#pragma unroll
-    for (int e = 0; e < SZ; e++) out[e] = fabs(pz_c(h)[e]);
-    for (int m = 0; m < h.n; m++)
-#pragma unroll
-        for (int e = 0; e < SZ; e++) out[e] = __dadd_ru(out[e], fabs(cf[size_t(m) * SZ + e]));
+    double v = fabs(pz_c(h)[comp]);
+#pragma unroll 1
+    for (int m = 0; m < h.n; m++) v = __dadd_ru(v, fabs(cf[size_t(m) * h.sz + comp]));
+    return v;
 }
 
 // ---- arena management -----------------------------------------------------------------------------
@@ -649,6 +656,7 @@ K1_DI void sort_block(PZ8 h8, bool ok) {
 #pragma unroll
             for (int e = 0; e < SZ; e++) v[r][e] = cf[size_t(i) * SZ + e];
             int c = 0;
+#pragma unroll 2
             for (int q = 0; q < n; q++) c += (keys[q] < k[r]);
             rank[r] = c;
         }
@@ -752,7 +760,7 @@ K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale
 #pragma unroll
                 for (int e = 0; e < SZ; e++) v[e] = v[e] + v2[e];
             }
-            if (frobN<SZ>(v) <= thr) {
+            if (norm_le(sumsqN<SZ>(v), thr)) {
 #pragma unroll
                 for (int e = 0; e < SZ; e++) rad[e] = __dadd_ru(rad[e], fabs(v[e]));
                 pruned_any = true;
@@ -868,7 +876,7 @@ K1_DI PZ8 map_op(int top, int n_in, const u64* keys_in, Fn fn, double* rad_total
 // prune rule for one merged coefficient (KPR/PZsparse.cu:321-336)
 template <int SZ>
 K1_DI bool prune_or_keep(const double* v, double thr, double* rad) {
-    if (frobN<SZ>(v) <= thr) {
+    if (norm_le(sumsqN<SZ>(v), thr)) {
 #pragma unroll
         for (int e = 0; e < SZ; e++) rad[e] = __dadd_ru(rad[e], fabs(v[e]));
         return false;
@@ -895,7 +903,7 @@ K1_DI void cross_const_coef(bool left_const, const double* v, const double* g, d
     bool a = false;
 #pragma unroll
     for (int e = 0; e < 3; e++) {
-        if (sqrt(c[e] * c[e]) <= thr) {
+        if (norm_le(c[e] * c[e], thr)) {
             rad[e] = __dadd_ru(rad[e], fabs(c[e]));
             out[e] = 0.0;
         } else {
@@ -984,46 +992,48 @@ K1_OP PZ8 op_const_mul(int top, const double* K, double pct_lane1, PZ8 x8) {
     if (ok && tid < 3) {
         const PZH h = view<3>(h8);
         const int e = tid;
-        double absx[XS];
-        abs_sum_collect<XS>(x, absx);
         const double* xc = pz_c(x);
-        double cen[3];
+        // row e of the constant operand (scalar: the scalar itself) and |.| of it
         if (KIND == 0) {
-#pragma unroll
-            for (int q = 0; q < 3; q++) cen[q] = kk[0] * xc[q];
+            pz_c(h)[e] = kk[0] * xc[e];
         } else if (KIND == 1) {
-            matmul3<1, false>(kk, xc, cen);
+            double acc = K[e] * xc[0];
+#pragma unroll 1
+            for (int k = 1; k < 3; k++) acc += K[e + 3 * k] * xc[k];
+            pz_c(h)[e] = acc;
         } else {
-            matmul3<1, false>(xc, kk, cen);
+            double acc = xc[e] * K[0];
+#pragma unroll 1
+            for (int k = 1; k < 3; k++) acc += xc[e + 3 * k] * K[k];
+            pz_c(h)[e] = acc;
         }
-        pz_c(h)[e] = cen[e];
-#pragma unroll
+#pragma unroll 1
         for (int lane = 0; lane < 2; lane++) {
             const double* xr = pz_r(x, lane);
             const double pct = lane ? pct_lane1 : 0.0;
-            double absK[9], radK[9], ra2[3], ra3[3], rr[3];
-#pragma unroll
-            for (int i = 0; i < 9; i++) {
-                absK[i] = fabs(kk[i]);
-                radK[i] = __dmul_ru(pct, absK[i]);
-            }
+            double ra2 = 0.0, ra3 = 0.0, rr = 0.0;
             if (KIND == 0) {
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    ra2[q] = __dmul_ru(absK[0], xr[q]);
-                    ra3[q] = __dmul_ru(radK[0], absx[q]);
-                    rr[q] = __dmul_ru(radK[0], xr[q]);
-                }
+                const double aK = fabs(K[0]), rK = __dmul_ru(pct, aK);
+                ra2 = __dmul_ru(aK, xr[e]);
+                ra3 = __dmul_ru(rK, abs_collect_entry(x, e));
+                rr = __dmul_ru(rK, xr[e]);
             } else if (KIND == 1) {
-                matmul3_up<1, false>(absK, xr, ra2);
-                matmul3_up<1, false>(radK, absx, ra3);
-                matmul3_up<1, false>(radK, xr, rr);
+#pragma unroll 1
+                for (int k = 0; k < 3; k++) {
+                    const double aK = fabs(K[e + 3 * k]), rK = __dmul_ru(pct, aK);
+                    const double p2 = __dmul_ru(aK, xr[k]), p3 = __dmul_ru(rK, abs_collect_entry(x, k)), pr = __dmul_ru(rK, xr[k]);
+                    ra2 = (k == 0) ? p2 : __dadd_ru(ra2, p2);
+                    ra3 = (k == 0) ? p3 : __dadd_ru(ra3, p3);
+                    rr = (k == 0) ? pr : __dadd_ru(rr, pr);
+                }
             } else {  // x (3x3 PZ) * constant vector: the constant has no radius
-                matmul3_up<1, false>(xr, absK, ra3);
-#pragma unroll
-                for (int q = 0; q < 3; q++) ra2[q] = rr[q] = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < 3; k++) {
+                    const double p3 = __dmul_ru(xr[e + 3 * k], fabs(K[k]));
+                    ra3 = (k == 0) ? p3 : __dadd_ru(ra3, p3);
+                }
             }
-            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr[e], __dadd_ru(ra2[e], ra3[e])), rad[e]);
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr, __dadd_ru(ra2, ra3)), rad[e]);
         }
     }
     __syncthreads();
@@ -1159,7 +1169,7 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
                 for (int e = 0; e < SZ; e++) acc[e] += v[e];
             }
         }
-        if (frobN<SZ>(acc) <= thr) {
+        if (norm_le(sumsqN<SZ>(acc), thr)) {
 #pragma unroll
             for (int e = 0; e < SZ; e++) rad[e] = __dadd_ru(rad[e], fabs(acc[e]));
             pruned_any = true;
@@ -1176,24 +1186,35 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
         double radt[SZ];
         rad_collect<SZ>(radt);
         const PZH h = view<SZ>(h8);
-        const int e = tid;
-        double absL[9], absR[SZ], cen[SZ];
-        if (outerL) {
-            abs_sum_serial<9>(L, absL);
-            abs_sum_collect<SZ>(R, absR);
-        } else {
-            abs_sum_collect<9>(L, absL);
-            abs_sum_serial<SZ>(R, absR);
-        }
-        matmul3<P, TRANS>(cenL, cenR, cen);
-        pz_c(h)[e] = cen[e];
+        const int e = tid, i = e % 3, jc = e / 3;
+        // entry (i, jc) of the product: sum over k of Lm(i, k) * Rm(k, jc), k ascending
+        const double* pcL = pz_c(L);
+        const double* pcR = pz_c(R);
+        double acc = (TRANS ? pcL[i * 3] : pcL[i]) * pcR[jc * 3];
+#pragma unroll 1
+        for (int k = 1; k < 3; k++) acc += (TRANS ? pcL[k + i * 3] : pcL[i + k * 3]) * pcR[k + jc * 3];
+        pz_c(h)[e] = acc;
+        double aL[3], aR[3];
 #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int li = TRANS ? (k + i * 3) : (i + k * 3), ri = k + jc * 3;
+            aL[k] = outerL ? abs_serial_entry(L, li) : abs_collect_entry(L, li);
+            aR[k] = outerL ? abs_collect_entry(R, ri) : abs_serial_entry(R, ri);
+        }
+#pragma unroll 1
         for (int lane = 0; lane < 2; lane++) {
-            double ra2[SZ], ra3[SZ], rr[SZ];
-            matmul3_up<P, TRANS>(absL, pz_r(R, lane), ra2);
-            matmul3_up<P, TRANS>(pz_r(L, lane), absR, ra3);
-            matmul3_up<P, TRANS>(pz_r(L, lane), pz_r(R, lane), rr);
-            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr[e], __dadd_ru(ra2[e], ra3[e])), radt[e]);
+            const double* rL = pz_r(L, lane);
+            const double* rR = pz_r(R, lane);
+            double ra2 = 0.0, ra3 = 0.0, rr = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int li = TRANS ? (k + i * 3) : (i + k * 3), ri = k + jc * 3;
+                const double p2 = __dmul_ru(aL[k], rR[ri]), p3 = __dmul_ru(rL[li], aR[k]), pr = __dmul_ru(rL[li], rR[ri]);
+                ra2 = (k == 0) ? p2 : __dadd_ru(ra2, p2);
+                ra3 = (k == 0) ? p3 : __dadd_ru(ra3, p3);
+                rr = (k == 0) ? pr : __dadd_ru(rr, pr);
+            }
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr, __dadd_ru(ra2, ra3)), radt[e]);
         }
     }
     __syncthreads();
@@ -1294,7 +1315,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
             bool have[6];
 #pragma unroll
             for (int x = 0; x < 6; x++) {  // simplify() of each scalar product
-                have[x] = !(sqrt(a[x] * a[x]) <= thr);
+                have[x] = !norm_le(a[x] * a[x], thr);
                 p[x] = have[x] ? a[x] : 0.0;
                 if (!have[x]) r[x >> 1] = __dadd_ru(r[x >> 1], fabs(a[x]));
             }
@@ -1304,7 +1325,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
                 out[e] = 0.0;
                 if (have[2 * e] || have[2 * e + 1]) {
                     const double d = p[2 * e] + (-p[2 * e + 1]);
-                    if (sqrt(d * d) <= thr) {
+                    if (norm_le(d * d, thr)) {
                         r[e] = __dadd_ru(r[e], fabs(d));
                     } else {
                         out[e] = d;
@@ -1319,28 +1340,24 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
     if (ok && tid < 3) {
         const PZH h = view<3>(h8);
         const int e = tid;
-        double absA[3], absB[3];
-        if (outerA) {
-            abs_sum_serial<3>(A, absA);
-            abs_sum_collect<3>(B, absB);
-        } else {
-            abs_sum_collect<3>(A, absA);
-            abs_sum_serial<3>(B, absB);
-        }
+        const int e1 = (e + 1) % 3, e2 = (e + 2) % 3;
+        const double aA1 = outerA ? abs_serial_entry(A, e1) : abs_collect_entry(A, e1);
+        const double aA2 = outerA ? abs_serial_entry(A, e2) : abs_collect_entry(A, e2);
+        const double aB1 = outerA ? abs_collect_entry(B, e1) : abs_serial_entry(B, e1);
+        const double aB2 = outerA ? abs_collect_entry(B, e2) : abs_serial_entry(B, e2);
         const double* ca = pz_c(A);
         const double* cb = pz_c(B);
-        const int e1 = (e + 1) % 3, e2 = (e + 2) % 3;
         // r_e = a_{e1} b_{e2} - a_{e2} b_{e1}
         pz_c(h)[e] = ca[e1] * cb[e2] - ca[e2] * cb[e1];
-#pragma unroll
+#pragma unroll 1
         for (int lane = 0; lane < 2; lane++) {
             const double* ra = pz_r(A, lane);
             const double* rb = pz_r(B, lane);
             // radius of a scalar product x*y: rx*ry + (|x|*ry + rx*|y|)   (KPR/PZsparse.cu:944-989)
             const double p0 = __dadd_ru(__dmul_ru(ra[e1], rb[e2]),
-                                        __dadd_ru(__dmul_ru(absA[e1], rb[e2]), __dmul_ru(ra[e1], absB[e2])));
+                                        __dadd_ru(__dmul_ru(aA1, rb[e2]), __dmul_ru(ra[e1], aB2)));
             const double p1 = __dadd_ru(__dmul_ru(ra[e2], rb[e1]),
-                                        __dadd_ru(__dmul_ru(absA[e2], rb[e1]), __dmul_ru(ra[e2], absB[e1])));
+                                        __dadd_ru(__dmul_ru(aA2, rb[e1]), __dmul_ru(ra[e2], aB1)));
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(p0, p1), rad[e]);
         }
     }
