@@ -13,7 +13,37 @@
 #include "../../include/armour_b200.h"
 #include "bezier.cuh"
 #include "device_constants.cuh"
+// The reach-set kernel is compiled twice (see k1_pz.cuh):
+//   k1lat: one unit per CTA, 256 threads, 2 CTAs per SM  -> lowest latency for one planning problem
+//   k1thr: 8 units per CTA in lock step, 64 threads each -> highest throughput for batches (instruction fetch,
+//          the resource that bounds this kernel, is shared by the 8 units)
+#define K1_NS k1lat
+#define K1_NT 256
+#define K1_CTAS 2
+#define K1_GROUPS 1
 #include "k1_reachsets.cuh"
+#undef K1_NS
+#undef K1_NT
+#undef K1_CTAS
+#undef K1_GROUPS
+#ifndef K1THR_NT
+#define K1THR_NT 64
+#endif
+#ifndef K1THR_GROUPS
+#define K1THR_GROUPS 8
+#endif
+#ifndef K1THR_CTAS
+#define K1THR_CTAS 1
+#endif
+#define K1_NS k1thr
+#define K1_NT K1THR_NT
+#define K1_CTAS K1THR_CTAS
+#define K1_GROUPS K1THR_GROUPS
+#include "k1_reachsets.cuh"
+#undef K1_NS
+#undef K1_NT
+#undef K1_CTAS
+#undef K1_GROUPS
 #include "k3_constraints.cuh"
 #include "layout.h"
 
@@ -35,7 +65,9 @@ struct armour_ctx {
     double* d_jac = nullptr;
     size_t g_capacity = 0, jac_capacity = 0;
     int* d_verdict = nullptr;  // [2][max_problems]
-    K1Scratch k1;
+    k1lat::K1Scratch k1_lat;  // scratch of the latency configuration of k_reachsets
+    k1thr::K1Scratch k1_thr;  // scratch of the throughput configuration (allocated on first use)
+    bool k1_thr_ready = false;
     long long launches = 0;
     std::string last_error;
     std::vector<double> h_torque_radius;  // host mirror of problem 0..built_nprob-1 (lazy)
@@ -116,6 +148,23 @@ int ensure_obstacle_buffers(armour_ctx* ctx, int nprob, int nobs) {
         ctx->hp_capacity = need_hp;
     }
     B.obstacles = ctx->d_obs;
+    return ARMOUR_OK;
+}
+
+// Pick the kernel configuration by batch size: up to two waves of the latency configuration's CTAs are
+// faster there; beyond that the lock-step throughput configuration wins.
+int launch_build(armour_ctx* ctx, int* nl) {
+    const long long nunits = (long long)ctx->B.nprob * ctx->B.T;
+    const bool thr = ctx->cfg.max_problems > 1 && nunits > 2LL * ctx->k1_lat.grid;
+    if (thr) {
+        if (!ctx->k1_thr_ready) {
+            CU(k1thr::k1_scratch_create(&ctx->k1_thr, ctx->cfg, ctx->rc, ctx->stream));
+            ctx->k1_thr_ready = true;
+        }
+        CU(k1thr::launch_reachsets(ctx->B, ctx->k1_thr, ctx->stream, nl));
+    } else {
+        CU(k1lat::launch_reachsets(ctx->B, ctx->k1_lat, ctx->stream, nl));
+    }
     return ARMOUR_OK;
 }
 
@@ -241,10 +290,16 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     B.qd0 = ctx->d_in + P * NF;
     B.qdd0 = ctx->d_in + 2 * P * NF;
     if ((e = cudaMemsetAsync(B.status, 0, P * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
-    if ((e = k1_scratch_create(&ctx->k1, ctx->cfg, ctx->rc, ctx->stream)) != cudaSuccess) return bail("k1 scratch", e);
+    if ((e = k1lat::k1_scratch_create(&ctx->k1_lat, ctx->cfg, ctx->rc, ctx->stream)) != cudaSuccess) return bail("k1 scratch", e);
+    if ((long long)cfg->max_problems * B.T > 2LL * ctx->k1_lat.grid) {  // this context can see batches: set up the throughput kernel too
+        if ((e = k1thr::k1_scratch_create(&ctx->k1_thr, ctx->cfg, ctx->rc, ctx->stream)) != cudaSuccess) return bail("k1 throughput scratch", e);
+        ctx->k1_thr_ready = true;
+        cudaFuncAttributes fa2;
+        if ((e = cudaFuncGetAttributes(&fa2, k1thr::k_reachsets)) != cudaSuccess) return bail("load k_reachsets (throughput)", e);
+    }
     {   // load the kernels now (CUDA loads modules lazily at first use), so that the first build is not charged for it
         cudaFuncAttributes fa;
-        if ((e = cudaFuncGetAttributes(&fa, k1::k_reachsets)) != cudaSuccess) return bail("load k_reachsets", e);
+        if ((e = cudaFuncGetAttributes(&fa, k1lat::k_reachsets)) != cudaSuccess) return bail("load k_reachsets", e);
         if ((e = cudaFuncGetAttributes(&fa, k_hyperplanes)) != cudaSuccess) return bail("load k_hyperplanes", e);
         if ((e = cudaFuncGetAttributes(&fa, k_constraints)) != cudaSuccess) return bail("load k_constraints", e);
         if ((e = cudaFuncGetAttributes(&fa, k_verdict)) != cudaSuccess) return bail("load k_verdict", e);
@@ -263,7 +318,8 @@ int armour_ctx_destroy(armour_ctx* ctx) {
                     B.link_sliced, B.status};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    k1_scratch_destroy(&ctx->k1);
+    k1lat::k1_scratch_destroy(&ctx->k1_lat);
+    k1thr::k1_scratch_destroy(&ctx->k1_thr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ARMOUR_OK;
@@ -321,7 +377,7 @@ int armour_batch_reachsets_build_device(armour_ctx* ctx, int nprob, const double
         CU(cudaMemcpyAsync(ctx->d_obs, d_obstacles, size_t(nprob) * nobs * 12 * sizeof(double),
                            cudaMemcpyDeviceToDevice, ctx->stream));
     int nl = 0;
-    CU(launch_reachsets(ctx->B, ctx->k1, ctx->stream, &nl));
+    { int rc2 = launch_build(ctx, &nl); if (rc2) return rc2; }
     ctx->launches += nl;
     CU(launch_hyperplanes(ctx->B, ctx->stream));
     ctx->launches += (nobs > 0);
@@ -348,7 +404,7 @@ int armour_batch_reachsets_build(armour_ctx* ctx, int nprob, const double* q0, c
         CU(cudaMemcpyAsync(ctx->d_obs, obstacles, size_t(nprob) * nobs * 12 * sizeof(double), cudaMemcpyHostToDevice,
                            ctx->stream));
     int nl = 0;
-    CU(launch_reachsets(ctx->B, ctx->k1, ctx->stream, &nl));
+    { int rc2 = launch_build(ctx, &nl); if (rc2) return rc2; }
     ctx->launches += nl;
     CU(launch_hyperplanes(ctx->B, ctx->stream));
     ctx->launches += (nobs > 0);

@@ -5,11 +5,10 @@
 // (__dadd_rd/_ru, __dmul_rd/_ru, __ddiv_rd, __dsqrt_ru), not by switching a rounding mode.
 // cos(I) follows the library's published algorithm: reduce modulo the interval 2*pi, reflect by the
 // interval pi, then monotone pieces; sin(I) = cos(I - pi/2).
-#pragma once
-#include "k1_pz.cuh"
+// (included by k1_reachsets.cuh after k1_pz.cuh, once per kernel configuration; no include guard on purpose)
 
 namespace armour {
-namespace k1 {
+namespace K1_NS {
 
 struct Itv {
     double lo, hi;
@@ -82,5 +81,5 @@ K1_DI Itv iv_cos(Itv x) {
 }
 K1_DI Itv iv_sin(const Itv& x) { return iv_cos(iv_sub(x, iv(PI_LO * 0.5, PI_HI * 0.5))); }
 
-}  // namespace k1
+}  // namespace K1_NS
 }  // namespace armour

@@ -18,7 +18,6 @@
 // (KPR/Dynamics.h:41-47) are one pass: their polynomial parts are bit-identical (only radii differ).
 // Coefficient / centre arithmetic is round-to-nearest without FMA contraction (-fmad=false), like
 // the host reference; radii are accumulated with round-up intrinsics so the outer bound stays sound.
-#pragma once
 #include <cmath>
 #include <cstdint>
 
@@ -33,8 +32,15 @@
 #define K1_OP inline
 #endif
 
+// This file, k1_interval.cuh and k1_reachsets.cuh are compiled once per kernel configuration (armour_capi.cu
+// includes k1_reachsets.cuh twice: a latency configuration and a throughput configuration), each time into
+// its own namespace K1_NS; hence no include guards.
+#ifndef K1_NS
+#define K1_NS k1
+#endif
+
 namespace armour {
-namespace k1 {
+namespace K1_NS {
 
 typedef unsigned long long u64;
 
@@ -44,7 +50,12 @@ typedef unsigned long long u64;
 #ifndef K1_CTAS
 #define K1_CTAS 2
 #endif
-constexpr int NT = K1_NT;    // threads per CTA
+#ifndef K1_GROUPS
+#define K1_GROUPS 1
+#endif
+constexpr int NT = K1_NT;    // threads working on one (problem, interval) unit
+constexpr int GROUPS = K1_GROUPS;  // units built side by side by one CTA (CTA = GROUPS * NT threads), op by op in
+                                   // step, so that the instruction stream of an operation is fetched once for all
 constexpr int CTAS_PER_SM = K1_CTAS;  // resident CTAs per SM (shared memory is split evenly)
 constexpr int NW = NT / 32;  // warps per CTA
 constexpr int RED_STRIDE = 12;
@@ -113,15 +124,38 @@ struct K1S {
 };
 constexpr int K1S_BYTES = (int(sizeof(K1S)) + 15) & ~15;
 
+// Dynamic shared memory of a CTA: [16-byte CTA header: bytes per group][group 0][group 1]...; every group has
+// its own control block, arena and table pool, and its own named barrier.
 #ifndef ARMOUR_EMU
-K1_DI unsigned char* smem_base() {
+K1_DI unsigned char* smem_cta() {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     return k1_smem;
 }
-K1_DI int k1_tid() { return threadIdx.x; }
+K1_DI int k1_tid() { return GROUPS == 1 ? int(threadIdx.x) : int(threadIdx.x) % NT; }
+K1_DI int k1_group() { return GROUPS == 1 ? 0 : int(threadIdx.x) / NT; }
+K1_DI unsigned char* smem_base() {
+    if (GROUPS == 1) return smem_cta() + 16;
+    return smem_cta() + 16 + size_t(k1_group()) * size_t(*reinterpret_cast<const int*>(smem_cta()));
+}
+// barrier over the NT threads of one unit
+K1_DI void k1_sync() {
+    if (GROUPS == 1) {
+        __syncthreads();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + k1_group()), "r"(NT) : "memory");
+    }
+}
+// barrier over the whole CTA: keeps the groups in step between operations
+K1_DI void k1_sync_cta() {
+    if (GROUPS > 1) __syncthreads();
+}
 #else
-inline unsigned char* smem_base() { return reinterpret_cast<unsigned char*>(emu::S().dyn_smem); }
+inline unsigned char* smem_cta() { return reinterpret_cast<unsigned char*>(emu::S().dyn_smem); }
 inline int k1_tid() { return int(threadIdx.x); }
+inline int k1_group() { return 0; }
+inline unsigned char* smem_base() { return smem_cta() + 16; }
+inline void k1_sync() { __syncthreads(); }
+inline void k1_sync_cta() {}
 #endif
 K1_DI K1S& k1s() { return *reinterpret_cast<K1S*>(smem_base()); }
 K1_DI double* arena0() { return reinterpret_cast<double*>(smem_base() + K1S_BYTES); }
@@ -327,7 +361,7 @@ K1_DI PZ8 tab_finalize(int top, const Tab& t, Fin fin, double* rad_total, bool* 
 #pragma unroll
         for (int e = 0; e < SZ; e++) S.red[warp * RED_STRIDE + e] = rad[e];
     }
-    __syncthreads();
+    k1_sync();
     int before = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) {
@@ -420,14 +454,14 @@ K1_OP void move_words(int dst_off, int src_off, int w) {
             const int i = base + q * NT + tid;
             v[q] = (i < w) ? src[i] : 0.0;
         }
-        __syncthreads();
+        k1_sync();
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = base + q * NT + tid;
             if (i < w) dst[i] = v[q];
         }
     }
-    __syncthreads();
+    k1_sync();
 }
 // Slide block h down to the cursor (blocks are kept in ascending address order); advances the cursor.
 template <int SZ>
@@ -458,7 +492,7 @@ K1_DI PZ8 spill_global(int& gtop, PZ8 h8) {
     const double* src = vptr(h8.off);
     double* dst = vptr(g.off);
     for (int i = k1_tid(); i < w; i += NT) dst[i] = src[i];
-    __syncthreads();
+    k1_sync();
     return g;
 }
 
@@ -467,7 +501,7 @@ K1_DI PZ8 pz_zero(int top) {  // PZ with no monomials, zero centre and radii
     bool ok;
     const PZ8 h = pz_alloc<SZ>(top, 0, &ok);
     if (ok && k1_tid() < 3 * SZ) vptr(h.off)[k1_tid()] = 0.0;
-    __syncthreads();
+    k1_sync();
     return h;
 }
 
@@ -661,7 +695,7 @@ K1_DI void sort_block(PZ8 h8, bool ok) {
             rank[r] = c;
         }
     }
-    __syncthreads();
+    k1_sync();
 #pragma unroll
     for (int r = 0; r < R; r++) {
         if (rank[r] >= 0) {
@@ -770,7 +804,7 @@ K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale
         }
     }
     rad_publish<SZ>(rad, pruned_any);
-    __syncthreads();
+    k1_sync();
     bool ok;
     const PZ8 h8 = dense_emit<SZ>(top, d, &ok);
     if (ok && tid < SZ) {
@@ -790,7 +824,7 @@ K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(r0[e], r1[e]), radt[e]);
         }
     }
-    __syncthreads();
+    k1_sync();
     return h8;
 }
 
@@ -831,7 +865,7 @@ K1_DI PZ8 map_op(int top, int n_in, const u64* keys_in, Fn fn, double* rad_total
 #pragma unroll
         for (int e = 0; e < SZ; e++) S.red[warp * RED_STRIDE + e] = rad[e];
     }
-    __syncthreads();
+    k1_sync();
     int before = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) {
@@ -949,7 +983,7 @@ K1_OP PZ8 op_cross_const(int top, PZ8 x8, const double* v, bool left_const) {
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(a, b), rad[e]);
         }
     }
-    __syncthreads();
+    k1_sync();
     return h8;
 }
 
@@ -1036,7 +1070,7 @@ K1_OP PZ8 op_const_mul(int top, const double* K, double pct_lane1, PZ8 x8) {
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr, __dadd_ru(ra2, ra3)), rad[e]);
         }
     }
-    __syncthreads();
+    k1_sync();
     return h8;
 }
 
@@ -1179,7 +1213,7 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
     }
     rad_publish<SZ>(rad, pruned_any);
     if (outerL) abs_sum_partial<SZ>(R); else abs_sum_partial<9>(L);
-    __syncthreads();
+    k1_sync();
     bool ok;
     const PZ8 h8 = dense_emit<SZ>(top, d, &ok);
     if (ok && tid < SZ) {
@@ -1217,7 +1251,7 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(rr, __dadd_ru(ra2, ra3)), radt[e]);
         }
     }
-    __syncthreads();
+    k1_sync();
     return h8;
 }
 
@@ -1247,7 +1281,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
         u64* z = t.keys;
         const int words = t.cap * 7;
         for (int i = tid; i < words; i += NT) z[i] = 0;
-        __syncthreads();
+        k1_sync();
     }
     const double thr = S.thr;
     const u64* kA = pz_keys(A);
@@ -1265,7 +1299,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
     }
     for (int o = tid; o < nO; o += NT) tab_insert(t, kO[o]);
     if (outerA) abs_sum_partial<3>(B); else abs_sum_partial<3>(A);
-    __syncthreads();
+    k1_sync();
     {
         const double* cc = pz_c(B);
         const double cen[3] = {cc[0], cc[1], cc[2]};
@@ -1277,7 +1311,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
             for (int e = 0; e < 6; e++) t.acc[size_t(slot) * 6 + e] += v[e];
         }
     }
-    __syncthreads();
+    k1_sync();
     {
         const double* cc = pz_c(A);
         const double cen[3] = {cc[0], cc[1], cc[2]};
@@ -1289,7 +1323,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
             for (int e = 0; e < 6; e++) t.acc[size_t(slot) * 6 + e] += v[e];
         }
     }
-    __syncthreads();
+    k1_sync();
     for (int o = 0; o < nO; o++) {
         const u64 ko = kO[o];
         const double* co = (outerA ? cA : cB) + size_t(o) * 3;
@@ -1304,7 +1338,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
 #pragma unroll
             for (int e = 0; e < 6; e++) t.acc[size_t(slot) * 6 + e] += v[e];
         }
-        __syncthreads();
+        k1_sync();
     }
     double rad[3];
     bool ok;
@@ -1361,11 +1395,11 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
             pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(p0, p1), rad[e]);
         }
     }
-    __syncthreads();
+    k1_sync();
     sort_block<3>(h8, ok);  // survivors leave the table in slot order
-    __syncthreads();
+    k1_sync();
     return h8;
 }
 
-}  // namespace k1
+}  // namespace K1_NS
 }  // namespace armour

@@ -11,18 +11,17 @@
 //
 // CTAs are persistent: each takes (problem, interval) units from a global counter, so a batch of
 // worlds x replans fills the 148 SMs without any cross-CTA communication.
-#pragma once
 #ifndef ARMOUR_EMU
 #include "../../include/armour_b200.h"
 #endif
 #include "bezier.cuh"
 #include "device_constants.cuh"
-#include "k1_interval.cuh"
 #include "k1_pz.cuh"
+#include "k1_interval.cuh"
 #include "layout.h"
 
 namespace armour {
-namespace k1 {
+namespace K1_NS {
 
 // fixed shared-memory region for the joint reachable set of the current interval
 constexpr int ROT_WORDS = 27 + 3 + 27;  // 3x3 PZ with at most 3 monomials
@@ -39,7 +38,8 @@ struct K1Params {
     char* gtab;         // [grid][gtab_bytes], all zero between launches
     int gtab_bytes;
     int arena_words;    // shared-memory working arena per CTA (behind the fixed JRS region)
-    int tab_s_bytes;    // shared-memory table pool per CTA
+    int tab_s_bytes;    // shared-memory table pool per group
+    int group_bytes;    // shared memory per group (control block + JRS region + arena + table pool)
     const int* units;   // optional explicit unit list (p*T + t); nullptr = all units of the batch
     int nunits;
     int* stats;         // [4]: max arena words used, tables placed in global memory, failed units, units done
@@ -290,7 +290,7 @@ K1_OP void export_link(PZ8 L8, const Batch& B, int p, int t, int l) {
     }
     double* gens = B.link_gens + idx * 18;
     if (tid < 18) gens[tid] = 0.0;
-    __syncthreads();
+    k1_sync();
     for (int m = tid; m < L.n; m += NT) {
         const u64 key = keys[m];
         const bool konly = key < KEY_K_ONLY;
@@ -317,7 +317,7 @@ K1_OP void export_link(PZ8 L8, const Batch& B, int p, int t, int l) {
     for (int e = 0; e < 3; e++) rad[e] = warp_sum_up(rad[e]);
     if (lane == 0)
         for (int e = 0; e < 3; e++) S.red[warp * RED_STRIDE + e] = rad[e];
-    __syncthreads();
+    k1_sync();
     if (tid < 3) {
         const int e = tid;
         double v = pz_r(L, 0)[e];
@@ -326,7 +326,7 @@ K1_OP void export_link(PZ8 L8, const Batch& B, int p, int t, int l) {
         B.link_c[idx * 3 + e] = pz_c(L)[e];
     }
     if (tid == 0) B.link_n[idx] = nk;
-    __syncthreads();
+    k1_sync();
 }
 
 // u_nom.reduce() (KPR/PZsparse.cu:352-368) + the k-only table of one torque reach set; leaves in S.misc the
@@ -360,7 +360,7 @@ K1_OP void export_torque(PZ8 U8, const Batch& B, int p, int t, int j) {
     }
     rad = warp_sum_up(rad);
     if (lane == 0) S.red[warp * RED_STRIDE] = rad;
-    __syncthreads();
+    k1_sync();
     if (tid == 0) {
         double v = 0.0;
         for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE]);
@@ -372,7 +372,7 @@ K1_OP void export_torque(PZ8 U8, const Batch& B, int p, int t, int j) {
         B.u_c[idx] = pz_c(U)[0];
         B.u_r[idx] = __dmul_ru(reduced, RADIUS_SLACK);
     }
-    __syncthreads();
+    k1_sync();
 }
 
 // ---- one (problem, interval) unit -----------------------------------------------------------------
@@ -380,10 +380,12 @@ K1_OP void export_torque(PZ8 U8, const Batch& B, int p, int t, int j) {
 // allocates exactly one block at `top` and the new top is the end of the block it returns.
 #define K1_OP_DO(h, SZ, ...)      \
     const PZ8 h = (__VA_ARGS__);  \
+    k1_sync_cta();                \
     top = end_of<SZ>(h);          \
     top_max = top > top_max ? top : top_max
 #define K1_OP_VAR(h, SZ, ...) \
     h = (__VA_ARGS__);        \
+    k1_sync_cta();            \
     top = end_of<SZ>(h);      \
     top_max = top > top_max ? top : top_max
 
@@ -415,7 +417,7 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
         }
         S.jrs_n[i] = 0;
     }
-    __syncthreads();
+    k1_sync();
 
     // ---- forward kinematics of the link volumes (KPR/Dynamics.cu:69-81) ----
     {
@@ -428,7 +430,7 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
             if (tid < 27) vptr(FK_R.off)[tid] = (tid < 9 && tid % 4 == 0) ? 1.0 : 0.0;
             if (tid >= 32 && tid < 41) vptr(FK_T.off)[tid - 32] = 0.0;
         }
-        __syncthreads();
+        k1_sync();
         for (int i = 0; i < NJ; i++) {
             K1_OP_DO(t1, 3, op_const_mul<2>(top, &rc.trans[3 * i], 0.0, FK_R));
             PZ8 FK_T2, FK_R2;
@@ -464,10 +466,10 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
                     for (int e = 0; e < 3; e++) bp[9 + n + q * 3 + e] = gg[q][e];
                 S.cnt[0] = n;
             }
-            __syncthreads();
+            k1_sync();
             box.n = ok ? S.cnt[0] : 0;
             top = box.off + pz_words(3, 3);  // the block was sized for three generators
-            __syncthreads();
+            k1_sync();
             K1_OP_DO(l1, 3, op_mul33<1, false>(top, FK_R2, box));
             K1_OP_DO(link, 3, op_add<3>(top, l1, FK_T2));
             export_link(link, B, p, t, i);
@@ -488,7 +490,7 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
     K1_OP_VAR(wa, 3, pz_zero<3>(top));
     K1_OP_VAR(wd, 3, pz_zero<3>(top));
     if (!S.fail && tid == 0) vptr(la.off)[2] = rc.gravity;
-    __syncthreads();
+    k1_sync();
     for (int i = 0; i < NJ; i++) {
         const double* pI = &rc.trans[3 * i];
         const double* cI = &rc.com[3 * i];
@@ -659,21 +661,24 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
             B.torque_radius[size_t(p) * NF * T + size_t(j) * T + t] = __dmul_ru(v, RADIUS_SLACK);
         }
     }
-    __syncthreads();
+    k1_sync();
     return top_max;
 }
 #undef K1_OP_DO
 #undef K1_OP_VAR
 
 // ---- kernel ---------------------------------------------------------------------------------------
-constexpr int K1_FIXED_BYTES = K1S_BYTES + JRS_WORDS * 8;  // control block + joint reachable set region
+constexpr int K1_FIXED_BYTES = K1S_BYTES + JRS_WORDS * 8;  // per group: control block + joint reachable set region
 
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_reachsets(K1Params P) {
+__global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params P) {
+    if (threadIdx.x == 0) *reinterpret_cast<int*>(smem_cta()) = P.group_bytes;
+    __syncthreads();
     K1S& S = k1s();
     const int tid = k1_tid();
+    const int slot = blockIdx.x * GROUPS + k1_group();  // scratch slot of this group
     if (tid == 0) {
-        S.gbase = P.gscr + size_t(blockIdx.x) * P.gscr_words;
-        S.tab_g = P.gtab + size_t(blockIdx.x) * P.gtab_bytes;
+        S.gbase = P.gscr + size_t(slot) * P.gscr_words;
+        S.tab_g = P.gtab + size_t(slot) * P.gtab_bytes;
         S.thr = c_robot.simplify_threshold;
         S.AW = JRS_WORDS + P.arena_words;
         S.GW = P.gscr_words - P.fn_words;
@@ -685,44 +690,48 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_reachsets(K1Params P) {
         S.flip = 0;
     }
     for (int i = tid; i < 2 * MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0u;
-    __syncthreads();
+    k1_sync();
     u64* s_tab = reinterpret_cast<u64*>(tab_s0());
     for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
-    __syncthreads();
+    k1_sync();
 
     const int nunits = P.units ? P.nunits : P.B.nprob * P.B.T;
     int nfail = 0, ndone = 0, top_max = 0;
+    int* cta_unit = reinterpret_cast<int*>(smem_cta()) + 1;
     for (;;) {
-        if (tid == 0) {
-            S.unit = atomicAdd(P.work, 1);
-            S.fail = 0;
-        }
+        // one tile of GROUPS consecutive units per CTA; consecutive units are the SAME interval of consecutive
+        // problems, i.e. equally long, so the groups stay in step
+        if (threadIdx.x == 0) *cta_unit = atomicAdd(P.work, GROUPS);
+        if (tid == 0) S.fail = 0;
         __syncthreads();
-        int unit = S.unit;
+        const int unit0 = *cta_unit;
         __syncthreads();
-        if (unit >= nunits) break;
+        if (unit0 >= nunits) break;
+        int unit = unit0 + k1_group();
+        const bool extra = unit >= nunits;  // a partial last tile: the spare groups redo its last unit (same results)
+        if (extra) unit = nunits - 1;
         int p, t;
         if (P.units) {
             unit = P.units[unit];
             p = unit / P.B.T;
             t = unit % P.B.T;
         } else {
-            p = unit / P.B.T;
-            t = P.B.T - 1 - (unit % P.B.T);  // long intervals first
+            t = P.B.T - 1 - (unit / P.B.nprob);  // long intervals first
+            p = unit % P.B.nprob;
         }
         const int tm = build_unit(P.B, p, t);
         top_max = tm > top_max ? tm : top_max;
-        ndone++;
+        if (!extra) ndone++;
         const int failed = S.fail;
         if (failed) {
-            nfail++;
+            if (!extra) nfail++;
             if (tid == 0) atomicMax(&P.B.status[p], failed);
             // a failed operation may leave a table half-built: restore the all-zero invariant
             for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
             for (int i = tid; i < P.gtab_bytes / 8; i += NT) reinterpret_cast<u64*>(S.tab_g)[i] = 0;
             for (int i = tid; i < 2 * MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0u;
         }
-        __syncthreads();
+        k1_sync();
     }
     if (tid == 0 && P.stats) {
         atomicMax(&P.stats[0], top_max - JRS_WORDS);
@@ -741,7 +750,7 @@ struct K1Scratch {
     char* gtab = nullptr;
     int grid = 0;
     int gscr_words = 0, fn_words = 0, gtab_bytes = 0;
-    int arena_words = 0, tab_s_bytes = 0;
+    int arena_words = 0, tab_s_bytes = 0, group_bytes = 0;
     size_t smem_bytes = 0;
     int h_stats[4] = {0, 0, 0, 0};
 };
@@ -763,11 +772,13 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     // CTAS_PER_SM CTAs per SM: an equal share of the SM's shared memory each (1 KB per CTA is reserved by the system)
     int per_cta = (smem_optin + 1024) / CTAS_PER_SM - 1024;
     per_cta &= ~1023;
-    const int dyn = per_cta - K1_FIXED_BYTES;
+    const int per_group = ((per_cta - 16) / GROUPS) & ~15;
+    const int dyn = per_group - K1_FIXED_BYTES;
     s->tab_s_bytes = (dyn * 5 / 8) & ~1023;
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
-    s->smem_bytes = size_t(K1_FIXED_BYTES) + size_t(s->arena_words) * 8 + s->tab_s_bytes;
-    s->grid = CTAS_PER_SM * sms;
+    s->group_bytes = K1_FIXED_BYTES + s->arena_words * 8 + s->tab_s_bytes;
+    s->smem_bytes = 16 + size_t(GROUPS) * s->group_bytes;
+    s->grid = CTAS_PER_SM * sms;  // CTAs; each holds GROUPS scratch slots
     // per-CTA global scratch: arena spill space, then F_i / N_i of one unit; and the overflow hash-table pool
     const int capw = cfg.cap_work_monomials;
     s->fn_words = 2 * MAXJ * (9 + capw * 2);
@@ -775,9 +786,9 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     s->gtab_bytes = 16 * capw * 8 * 7;  // a cross product table for up to ~10 * capw candidate keys
     if ((e = cudaMalloc(&s->work, sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->stats, 4 * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&s->gscr, size_t(s->grid) * s->gscr_words * 8)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&s->gtab, size_t(s->grid) * s->gtab_bytes)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(s->gtab, 0, size_t(s->grid) * s->gtab_bytes, st)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&s->gscr, size_t(s->grid) * GROUPS * s->gscr_words * 8)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&s->gtab, size_t(s->grid) * GROUPS * s->gtab_bytes)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s->gtab, 0, size_t(s->grid) * GROUPS * s->gtab_bytes, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s->stats, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_reachsets, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->smem_bytes));
 }
@@ -798,22 +809,18 @@ inline cudaError_t launch_reachsets(const Batch& B, K1Scratch& s, cudaStream_t s
     P.gtab_bytes = s.gtab_bytes;
     P.arena_words = s.arena_words;
     P.tab_s_bytes = s.tab_s_bytes;
+    P.group_bytes = s.group_bytes;
     P.stats = s.stats;
     P.units = nullptr;
     P.nunits = 0;
-    const int nunits = B.nprob * B.T;
-    const int grid = nunits < s.grid ? nunits : s.grid;
-    k_reachsets<<<grid, NT, s.smem_bytes, st>>>(P);
+    const int ntiles = (B.nprob * B.T + GROUPS - 1) / GROUPS;
+    const int grid = ntiles < s.grid ? ntiles : s.grid;
+    k_reachsets<<<grid, NT * GROUPS, s.smem_bytes, st>>>(P);
     *nlaunch = 1;
     return cudaGetLastError();
 }
 #endif  // ARMOUR_EMU
 
-}  // namespace k1
-#ifndef ARMOUR_EMU
-using k1::K1Scratch;
-using k1::k1_scratch_create;
-using k1::k1_scratch_destroy;
-using k1::launch_reachsets;
-#endif
+}  // namespace K1_NS
+
 }  // namespace armour
