@@ -35,6 +35,11 @@
 #ifndef K1THR_CTAS
 #define K1THR_CTAS 1
 #endif
+#ifndef K1THR_TAB_EIGHTHS
+#define K1THR_TAB_EIGHTHS 3  // share (in eighths) of a group's dynamic shared memory given to the scratch pool
+#endif
+#undef K1_TAB_EIGHTHS
+#define K1_TAB_EIGHTHS K1THR_TAB_EIGHTHS
 #define K1_NS k1thr
 #define K1_NT K1THR_NT
 #define K1_CTAS K1THR_CTAS

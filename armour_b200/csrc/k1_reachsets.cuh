@@ -743,6 +743,9 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
 
 #ifndef ARMOUR_EMU
 // ---- host side: scratch buffers and launch ----------------------------------------------------------
+#ifndef K1_TAB_EIGHTHS
+#define K1_TAB_EIGHTHS 5
+#endif
 struct K1Scratch {
     int* work = nullptr;
     int* stats = nullptr;
@@ -774,7 +777,7 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     per_cta &= ~1023;
     const int per_group = ((per_cta - 16) / GROUPS) & ~15;
     const int dyn = per_group - K1_FIXED_BYTES;
-    s->tab_s_bytes = (dyn * 5 / 8) & ~1023;
+    s->tab_s_bytes = (dyn * K1_TAB_EIGHTHS / 8) & ~1023;  // scratch of the merge / hash passes; the rest is the PZ arena
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
     s->group_bytes = K1_FIXED_BYTES + s->arena_words * 8 + s->tab_s_bytes;
     s->smem_bytes = 16 + size_t(GROUPS) * s->group_bytes;

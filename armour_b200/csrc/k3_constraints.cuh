@@ -86,75 +86,141 @@ __device__ __forceinline__ void load_row_generators(const double* __restrict__ o
 // offset.  Only the survivors are stored, in scan order, as 32-byte records (s_i C_i, b_i), so that the
 // evaluation kernel returns bit-identical values and gradients while reading ~100 B per row instead
 // of 1440 B.  Rows with more than HP_CAP survivors are flagged and evaluated from the generators.
-__global__ void __launch_bounds__(128) k_hyperplanes(Batch B) {
-    const int tb = blockIdx.x, p = blockIdx.y;
+// One thread per (row, generator pair): HP_ROWS rows per CTA.  Step 1 computes the pair's two half-spaces and
+// their value bounds, step 2 the row's best guaranteed lower bound, step 3 decides per candidate (bound
+// filter + "an earlier candidate with the same normal and a smaller offset dominates"; dominance is
+// transitive, so testing against all earlier candidates that pass the filter equals the sequential rule),
+// step 4 writes the survivors at their scan-order positions.  Bit-identical lists to a sequential scan.
+constexpr int HP_ROWS = 8;
+constexpr int HP_THREADS = HP_ROWS * NCOMB;  // 288
+__global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
+    const int p = blockIdx.y;
     const int NJ = B.NJ, O = B.O, T = B.T;
-    const int per_pair = NJ * TB * O;
-    const double* obs = B.obstacles + size_t(p) * O * 12;
-    const size_t chunk = size_t(p) * (T / TB) + tb;
-    double* cand = B.hp_cand + chunk * B.hp_chunk();
-    unsigned char* cnt = B.hp_cnt + chunk * per_pair;
-
-    for (int x = threadIdx.x; x < per_pair; x += blockDim.x) {
-        const int o = x % O;
-        const int ltt = x / O;
-        const int tt = ltt % TB, l = ltt / TB;
-        const size_t idx = (size_t(p) * T + size_t(tb) * TB + tt) * NJ + l;
-        double G[9][3], oc[3];
-        load_row_generators(obs + o * 12, B.link_gens + idx * 18, G, oc);
+    const int per_pair = NJ * TB * O;          // rows of one (problem, TB intervals) chunk
+    const int rows_total = per_pair * (T / TB);
+    const int lr = threadIdx.x / NCOMB, pi = threadIdx.x % NCOMB;  // local row, pair index
+    const int r = blockIdx.x * HP_ROWS + lr;   // row of the problem, chunk-major
+    __shared__ double s_G[HP_ROWS][9][3], s_oc[HP_ROWS][3], s_c[HP_ROWS][3];
+    __shared__ double s_A[HP_ROWS][NCOMB][3], s_b[HP_ROWS][2 * NCOMB], s_up[HP_ROWS][2 * NCOMB], s_lo[HP_ROWS][NCOMB];
+    __shared__ double s_lomax[HP_ROWS];
+    __shared__ unsigned char s_flag[HP_ROWS][2 * NCOMB], s_pos[HP_ROWS][2 * NCOMB];
+    __shared__ int s_count[HP_ROWS];
+    const bool live = r < rows_total;
+    int tb = 0, x = 0;
+    size_t idx = 0;
+    if (live) {
+        tb = r / per_pair;
+        x = r - tb * per_pair;
+        const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
+        idx = (size_t(p) * T + size_t(tb) * TB + tt) * NJ + l;
+        if (pi < 27) {  // 9 generators x 3 components: 3 of the obstacle, then the 3x6 link matrix (column-major)
+            const int gI = pi / 3, e = pi % 3;
+            s_G[lr][gI][e] = (gI < 3) ? B.obstacles[(size_t(p) * O + o) * 12 + (gI + 1) * 3 + e] : B.link_gens[idx * 18 + e + (gI - 3) * 3];
+        } else if (pi < 30) {
+            s_oc[lr][pi - 27] = B.obstacles[(size_t(p) * O + o) * 12 + (pi - 27)];
+        } else if (pi < 33) {
+            s_c[lr][pi - 30] = B.link_c[idx * 3 + (pi - 30)];
+        }
+    }
+    __syncthreads();
+    bool nz = false;
+    if (live) {  // step 1: same expressions as for_each_plane / the bounds of the sequential version
+        const int a = c_combA[pi], b = c_combB[pi];
+        const double(*G)[3] = s_G[lr];
+        const double cx = G[a][1] * G[b][2] - G[a][2] * G[b][1];
+        const double cy = G[a][2] * G[b][0] - G[a][0] * G[b][2];
+        const double cz = G[a][0] * G[b][1] - G[a][1] * G[b][0];
+        const double nrm = sqrt(cx * cx + cy * cy + cz * cz);
+        double C0 = 0, C1 = 0, C2 = 0;
+        if (nrm > 0) {
+            C0 = cx / nrm;
+            C1 = cy / nrm;
+            C2 = cz / nrm;
+        }
+        const double d = C0 * s_oc[lr][0] + C1 * s_oc[lr][1] + C2 * s_oc[lr][2];
+        double delta = 0.0;
+#pragma unroll 1
+        for (int gI = 0; gI < 9; gI++) delta += fabs(C0 * G[gI][0] + C1 * G[gI][1] + C2 * G[gI][2]);
+        nz = sqrt(C0 * C0 + C1 * C1 + C2 * C2) > 0;  // the test of checkCollisionKernel (:259)
+        const double dot = C0 * s_c[lr][0] + C1 * s_c[lr][1] + C2 * s_c[lr][2];
+        const double vpos = dot - (d + delta);
+        const double vneg = -dot - (-d + delta);
         const int n = B.link_n[idx];
         const double* __restrict__ lg = B.link_g + idx * B.capL * 3;
-        const double c0 = B.link_c[idx * 3 + 0], c1 = B.link_c[idx * 3 + 1], c2 = B.link_c[idx * 3 + 2];
-
-        auto bounds = [&](double C0, double C1, double C2, double d, double delta, double& vpos, double& vneg,
-                          double& rho) {
-            const double dot = C0 * c0 + C1 * c1 + C2 * c2;
-            vpos = dot - (d + delta);
-            vneg = -dot - (-d + delta);
-            double r = 0.0;
-            for (int mI = 0; mI < n; mI++)
-                r += fabs(C0 * lg[mI * 3 + 0] + C1 * lg[mI * 3 + 1] + C2 * lg[mI * 3 + 2]);
-            // |k_j| <= K_DOMAIN, total degree <= 21; plus evaluation round-off (values are O(1))
-            rho = r * HP_RHO_SCALE + (1e-10 + 1e-12 * (fabs(dot) + fabs(d) + delta));
-        };
-
-        // pass 1: the best guaranteed lower bound
+        double rr = 0.0;
+#pragma unroll 1
+        for (int mI = 0; mI < n; mI++) rr += fabs(C0 * lg[mI * 3 + 0] + C1 * lg[mI * 3 + 1] + C2 * lg[mI * 3 + 2]);
+        // |k_j| <= K_DOMAIN, total degree <= 21; plus evaluation round-off (values are O(1))
+        const double rho = rr * HP_RHO_SCALE + (1e-10 + 1e-12 * (fabs(dot) + fabs(d) + delta));
+        s_A[lr][pi][0] = C0;
+        s_A[lr][pi][1] = C1;
+        s_A[lr][pi][2] = C2;
+        s_b[lr][2 * pi] = d + delta;
+        s_b[lr][2 * pi + 1] = -d + delta;
+        s_up[lr][2 * pi] = nz ? vpos + rho : -1e300;
+        s_up[lr][2 * pi + 1] = nz ? vneg + rho : -1e300;
+        s_lo[lr][pi] = nz ? fmax(vpos, vneg) - rho : -1e300;
+    }
+    __syncthreads();
+    if (live && pi == 0) {  // step 2: the best guaranteed lower bound of the row
         double lo_max = -100000000;
-        for_each_plane(G, oc, [&](int, double C0, double C1, double C2, double d, double delta, bool nz) {
-            if (!nz) return;
-            double vpos, vneg, rho;
-            bounds(C0, C1, C2, d, delta, vpos, vneg, rho);
-            lo_max = fmax(lo_max, fmax(vpos, vneg) - rho);
-        });
-        // pass 2: emit the survivors in scan order
+#pragma unroll 1
+        for (int i = 0; i < NCOMB; i++) lo_max = fmax(lo_max, s_lo[lr][i]);
+        s_lomax[lr] = lo_max;
+    }
+    __syncthreads();
+    if (live) {  // step 3: which of my two candidates survive
+        const double lo_max = s_lomax[lr];
+#pragma unroll 1
+        for (int sgn = 0; sgn < 2; sgn++) {
+            const int sI = 2 * pi + sgn;  // position in the scan order pos_0, neg_0, pos_1, ...
+            bool keep = nz && s_up[lr][sI] >= lo_max;
+            if (keep) {
+                const double sg = sgn ? -1.0 : 1.0;
+                const double A0 = sg * s_A[lr][pi][0], A1 = sg * s_A[lr][pi][1], A2 = sg * s_A[lr][pi][2], bb = s_b[lr][sI];
+#pragma unroll 1
+                for (int q = 0; q < sI && keep; q++) {
+                    if (!(s_up[lr][q] >= lo_max)) continue;  // q does not pass the filter (or is a zero normal)
+                    const double sq = (q & 1) ? -1.0 : 1.0;
+                    const int qi = q >> 1;
+                    if (sq * s_A[lr][qi][0] == A0 && sq * s_A[lr][qi][1] == A1 && sq * s_A[lr][qi][2] == A2 && s_b[lr][q] <= bb)
+                        keep = false;
+                }
+            }
+            s_flag[lr][sI] = keep ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (live && pi == 0) {  // positions in scan order
         int count = 0;
-        bool overflow = false;
-        double* row = cand + size_t(x) * 4;
+#pragma unroll 1
+        for (int sI = 0; sI < 2 * NCOMB; sI++) {
+            s_pos[lr][sI] = (unsigned char)(count < 255 ? count : 255);
+            count += s_flag[lr][sI];
+        }
+        s_count[lr] = count;
+    }
+    __syncthreads();
+    if (live) {  // step 4
+        const size_t chunk = size_t(p) * (T / TB) + tb;
+        double* row = B.hp_cand + chunk * B.hp_chunk() + size_t(x) * 4;
         const size_t cstride = size_t(per_pair) * 4;
-        auto emit = [&](double A0, double A1, double A2, double b) {
-            for (int q = 0; q < count; q++) {  // an earlier candidate with the same normal and b_q <= b dominates
-                const double* e = row + q * cstride;
-                if (e[0] == A0 && e[1] == A1 && e[2] == A2 && e[3] <= b) return;
+        const int count = s_count[lr];
+        if (count <= HP_CAP) {
+#pragma unroll 1
+            for (int sgn = 0; sgn < 2; sgn++) {
+                const int sI = 2 * pi + sgn;
+                if (s_flag[lr][sI]) {
+                    const double sg = sgn ? -1.0 : 1.0;
+                    double* e = row + size_t(s_pos[lr][sI]) * cstride;
+                    e[0] = sg * s_A[lr][pi][0];
+                    e[1] = sg * s_A[lr][pi][1];
+                    e[2] = sg * s_A[lr][pi][2];
+                    e[3] = s_b[lr][sI];
+                }
             }
-            if (count == HP_CAP) {
-                overflow = true;
-                return;
-            }
-            double* e = row + count * cstride;
-            e[0] = A0;
-            e[1] = A1;
-            e[2] = A2;
-            e[3] = b;
-            count++;
-        };
-        for_each_plane(G, oc, [&](int, double C0, double C1, double C2, double d, double delta, bool nz) {
-            if (!nz || overflow) return;
-            double vpos, vneg, rho;
-            bounds(C0, C1, C2, d, delta, vpos, vneg, rho);
-            if (vpos + rho >= lo_max) emit(C0, C1, C2, d + delta);
-            if (vneg + rho >= lo_max) emit(-C0, -C1, -C2, -d + delta);
-        });
-        cnt[x] = overflow ? (unsigned char)HP_OVERFLOW : (unsigned char)count;
+        }
+        if (pi == 0) B.hp_cnt[chunk * per_pair + x] = (count > HP_CAP) ? (unsigned char)HP_OVERFLOW : (unsigned char)count;
     }
 }
 
@@ -318,13 +384,25 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             const int n = cnt[x];
             if (n != HP_OVERFLOW && in_domain) {
                 const double2* row = reinterpret_cast<const double2*>(cand) + size_t(x) * 2;
-                for (int q = 0; q < n; q++) {
-                    const double2 u = __ldg(row + q * cstride2);
-                    const double2 w = __ldg(row + q * cstride2 + 1);
-                    const double v = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
-                    if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
-                        max_elt = v;
-                        A0 = -u.x; A1 = -u.y; A2 = -w.x;
+                // four candidate records in flight per thread (the scan itself stays in order)
+                for (int q0 = 0; q0 < n; q0 += 4) {
+                    double2 u[4], w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (q0 + i < n) {
+                            u[i] = __ldg(row + (q0 + i) * cstride2);
+                            w[i] = __ldg(row + (q0 + i) * cstride2 + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (q0 + i < n) {
+                            const double v = (u[i].x * c0 + u[i].y * c1 + w[i].x * c2) - w[i].y;
+                            if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
+                                max_elt = v;
+                                A0 = -u[i].x; A1 = -u[i].y; A2 = -w[i].x;
+                            }
+                        }
                     }
                 }
             } else {
@@ -429,8 +507,9 @@ k_verdict(Batch B, const double* __restrict__ g, int* __restrict__ feasible, int
 // host launchers (called from capi.cu)
 cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
     if (B.O == 0 || B.nprob == 0) return cudaSuccess;
-    dim3 grid(B.T / TB, B.nprob);
-    k_hyperplanes<<<grid, 128, 0, st>>>(B);
+    const int rows = B.NJ * B.T * B.O;
+    dim3 grid((rows + HP_ROWS - 1) / HP_ROWS, B.nprob);
+    k_hyperplanes<<<grid, HP_THREADS, 0, st>>>(B);
     return cudaGetLastError();
 }
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
