@@ -260,36 +260,63 @@ __device__ __noinline__ void row_from_generators(const double* __restrict__ ob, 
 // PZsparse::slice (KPR/PZsparse.cu:404-435) and its gradient overloads (:477-555); a factor with
 // d_j = 0 is 1.0 and is skipped (exact).  D[v] carries coef * prod_{j<v} f_j * f'_v * prod_{v<j} f_j.
 __device__ __forceinline__ void slice_component(const uint16_t* __restrict__ keys, const double* __restrict__ coef,
-                                                int n, int cstride, const double (*kp)[4], const double (*dkp)[4],
-                                                double& value, double (&grad)[NF]) {
-    for (int mI = 0; mI < n; mI++) {
-        const unsigned key = keys[mI];
-        double val = coef[mI * cstride];
-        double D[NF];
+                                                int n, int kstride, int cstride, const double (*kp)[4],
+                                                const double (*dkp)[4], double& value, double (&grad)[NF]) {
+    constexpr int CH = 8;  // monomials fetched together: the loads of a chunk are independent and overlap
+    for (int m0 = 0; m0 < n; m0 += CH) {
+        unsigned kk[CH];
+        double cc[CH];
 #pragma unroll
-        for (int j = 0; j < NF; j++) {
-            const int dg = (key >> (2 * j)) & 3;
-            D[j] = 0.0;
-            if (dg) {
-                const double f = kp[j][dg], df = dkp[j][dg];
-                D[j] = val * df;
-#pragma unroll
-                for (int v = 0; v < j; v++) D[v] *= f;
-                val *= f;
-            }
+        for (int i = 0; i < CH; i++) {
+            const bool on = m0 + i < n;
+            kk[i] = on ? keys[(m0 + i) * kstride] : 0u;
+            cc[i] = on ? coef[(m0 + i) * cstride] : 0.0;
         }
-        value += val;
+#pragma unroll 1
+        for (int i = 0; i < CH; i++) {
+            if (m0 + i >= n) break;
+            // (dynamic index into kk / cc would spill: rotate instead)
+            const unsigned key = kk[0];
+            double val = cc[0];
 #pragma unroll
-        for (int v = 0; v < NF; v++) grad[v] += D[v];
+            for (int q = 0; q + 1 < CH; q++) {
+                kk[q] = kk[q + 1];
+                cc[q] = cc[q + 1];
+            }
+            double D[NF];
+#pragma unroll
+            for (int j = 0; j < NF; j++) {
+                const int dg = (key >> (2 * j)) & 3;
+                D[j] = 0.0;
+                if (dg) {
+                    const double f = kp[j][dg], df = dkp[j][dg];
+                    D[j] = val * df;
+#pragma unroll
+                    for (int v = 0; v < j; v++) D[v] *= f;
+                    val *= f;
+                }
+            }
+            value += val;
+#pragma unroll
+            for (int v = 0; v < NF; v++) grad[v] += D[v];
+        }
     }
 }
 
-constexpr int K3_THREADS = 256;
+// Warp roles: warps [0, 6) slice the link reach sets (one thread per (interval, link, component)), warps
+// [6, 10) slice the torque reach sets, two lanes per (interval, joint) table (the torque tables are ~3x longer).
+// The link warps meet on named barrier 1 and go straight to the collision rows; the torque warps write their
+// rows, then join through barrier 2 (on which the link warps only arrive), so nobody waits for the slowest
+// slice.  Collision rows are handed out in chunks of 32 from a shared counter.
+constexpr int K3_LINK_THREADS = 192;
+constexpr int K3_TORQUE_LANES = 2;
+constexpr int K3_THREADS = 320;
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int K3_TORQUE_T0 = 192;  // first thread of the torque slices (warp aligned; link slices use 0..TB*3*NJ-1)
-static_assert(TB * 3 * MAXJ <= K3_TORQUE_T0 && K3_TORQUE_T0 + TB * NF <= K3_THREADS, "thread map of the slice phase");
+constexpr int K3_TORQUE_T0 = K3_LINK_THREADS;
+static_assert(TB * 3 * MAXJ <= K3_LINK_THREADS && K3_TORQUE_T0 + TB * NF * K3_TORQUE_LANES <= K3_THREADS,
+              "thread map of the slice phase");
 
-__global__ void __launch_bounds__(K3_THREADS, 4)
+__global__ void __launch_bounds__(K3_THREADS, 3)
 k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
     const int tb = blockIdx.x, p = blockIdx.y;
     const int NJ = B.NJ, O = B.O, T = B.T;
@@ -300,11 +327,13 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     __shared__ double s_dlc[TB][MAXJ][NF][3];
     __shared__ double s_stage[K3_WARPS][32 * NF];  // per-warp transpose buffer: Jacobian rows leave coalesced
     __shared__ int s_in_domain;
+    __shared__ int s_next;  // next chunk of 32 collision rows
 
     if (tid == 32) {
         bool in = true;
         for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
         s_in_domain = in ? 1 : 0;
+        s_next = 0;
     }
     if (tid < NF) {
         const double k = kin[size_t(p) * NF + tid];
@@ -322,44 +351,61 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     double* gp = g ? g + size_t(p) * m : nullptr;
     double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
 
-    // ---- phase 1: slices.  Threads [0, TB*NJ*3): link component (tt, l, e); threads [192, 192+TB*NF): torque (tt, j)
-    if (tid < TB * NJ * 3) {
-        const int e = tid % 3;
-        const int l = (tid / 3) % NJ;
-        const int tt = tid / (3 * NJ);
-        const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
-        double value = B.link_c[idx * 3 + e];
-        double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
-        slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 3, kp, dkp, value,
-                        grad);
-        // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
-        const double r = B.link_gens[idx * 18 + e + (3 + e) * 3];
-        const double c = ((value - r) + (value + r)) * 0.5;
-        s_lc[tt][l][e] = c;
-        B.link_sliced[idx * 3 + e] = c;
+    // ---- phase 1: slices
+    if (tid < K3_LINK_THREADS) {
+        if (tid < TB * NJ * 3) {
+            const int e = tid % 3;
+            const int l = (tid / 3) % NJ;
+            const int tt = tid / (3 * NJ);
+            const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+            double value = B.link_c[idx * 3 + e];
+            double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
+            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 1, 3, kp, dkp, value,
+                            grad);
+            // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
+            const double r = B.link_gens[idx * 18 + e + (3 + e) * 3];
+            const double c = ((value - r) + (value + r)) * 0.5;
+            s_lc[tt][l][e] = c;
+            B.link_sliced[idx * 3 + e] = c;
 #pragma unroll
-        for (int v = 0; v < NF; v++) s_dlc[tt][l][v][e] = grad[v];
-    } else if (tid >= K3_TORQUE_T0 && tid < K3_TORQUE_T0 + TB * NF) {
-        const int i = tid - K3_TORQUE_T0;  // tt*NF + j
-        const size_t idx = (size_t(p) * T + tb * TB) * NF + i;
-        double value = B.u_c[idx];
+            for (int v = 0; v < NF; v++) s_dlc[tt][l][v][e] = grad[v];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(K3_LINK_THREADS) : "memory");    // link slices complete
+        asm volatile("bar.arrive 2, %0;" ::"n"(K3_THREADS) : "memory");       // tell the torque warps, do not wait
+    } else {
+        const int tq = tid - K3_TORQUE_T0;
+        const int i = tq / K3_TORQUE_LANES, part = tq % K3_TORQUE_LANES;  // table tt*NF + j, lane of the table
+        double value = 0.0;
         double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
-        slice_component(B.u_key + idx * B.capU, B.u_g + idx * B.capU, B.u_n[idx], 1, kp, dkp, value, grad);
-        const double r = B.u_r[idx];
-        if (gp) gp[tb * TB * NF + i] = ((value - r) + (value + r)) * 0.5;
-        if (jp) {  // rows tb*TB*NF + i, i < 56: 392 contiguous doubles, transposed through the stage of warps 6 and 7
-            double* st = &s_stage[K3_TORQUE_T0 / 32][0];
+        const bool on = i < TB * NF;
+        const size_t idx = (size_t(p) * T + tb * TB) * NF + (on ? i : 0);
+        if (on) {
+            // lane `part` takes the monomials part, part + 2, ...; the two partial sums are added below
+            // (the oracle adds the monomials one after the other: a difference of a few ulp)
+            const int n = B.u_n[idx];
+            const int mine = (n - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
+            slice_component(B.u_key + idx * B.capU + part, B.u_g + idx * B.capU + part, mine > 0 ? mine : 0,
+                            K3_TORQUE_LANES, K3_TORQUE_LANES, kp, dkp, value, grad);
+        }
+        value += __shfl_xor_sync(0xffffffffu, value, 1);
+#pragma unroll
+        for (int v = 0; v < NF; v++) grad[v] += __shfl_xor_sync(0xffffffffu, grad[v], 1);
+        double* st = &s_stage[K3_TORQUE_T0 / 32][0];  // the stages of the four torque warps are contiguous
+        if (on && part == 0) {
+            value = B.u_c[idx] + value;
+            const double r = B.u_r[idx];
+            if (gp) gp[tb * TB * NF + i] = ((value - r) + (value + r)) * 0.5;
 #pragma unroll
             for (int v = 0; v < NF; v++) st[i * NF + v] = grad[v];
         }
+        asm volatile("bar.sync 3, %0;" ::"n"(K3_THREADS - K3_LINK_THREADS) : "memory");
+        if (jp) {  // rows tb*TB*NF + i, i < 56: 392 contiguous doubles
+            double* dst = jp + size_t(tb) * TB * NF * NF;
+            for (int q = tq; q < TB * NF * NF; q += K3_THREADS - K3_TORQUE_T0) dst[q] = st[q];
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(K3_THREADS - K3_LINK_THREADS) : "memory");  // stage free again
+        asm volatile("bar.sync 2, %0;" ::"n"(K3_THREADS) : "memory");                      // link slices are complete
     }
-    __syncthreads();
-    if (jp && tid >= K3_TORQUE_T0) {
-        const double* st = &s_stage[K3_TORQUE_T0 / 32][0];
-        double* dst = jp + size_t(tb) * TB * NF * NF;
-        for (int i = tid - K3_TORQUE_T0; i < TB * NF * NF; i += K3_THREADS - K3_TORQUE_T0) dst[i] = st[i];
-    }
-    __syncthreads();
 
     // ---- phase 2: collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
     const int per_pair = NJ * TB * O;
@@ -369,7 +415,11 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     const size_t cstride2 = size_t(per_pair) * 2;  // candidate stride in double2 units
     const bool in_domain = s_in_domain != 0;
     double* stage = &s_stage[warp][0];
-    for (int x0 = warp * 32; x0 < per_pair; x0 += K3_THREADS) {
+    for (;;) {
+        int x0 = 0;
+        if (lane == 0) x0 = atomicAdd(&s_next, 1) * 32;
+        x0 = __shfl_sync(0xffffffffu, x0, 0);
+        if (x0 >= per_pair) break;
         const int x = x0 + lane;
         const bool active = x < per_pair;
         double max_elt = -100000000;

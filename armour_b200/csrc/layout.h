@@ -11,7 +11,7 @@
 namespace armour {
 
 constexpr int TB = 8;        // time intervals per CTA in the constraint kernels
-constexpr int HP_CAP = 16;         // stored candidate half-spaces per (link, interval, obstacle) row
+constexpr int HP_CAP = 32;         // stored candidate half-spaces per (link, interval, obstacle) row
 constexpr int HP_OVERFLOW = 255;   // row count marker: more than HP_CAP candidates, evaluate from the generators
 constexpr double K_DOMAIN = 1.0 + 1e-6;        // the candidate lists are exact for |k_j| <= K_DOMAIN
 constexpr double HP_RHO_SCALE = 1.0 + 3e-5;    // >= K_DOMAIN^21 (largest total degree of a link monomial)
