@@ -169,6 +169,30 @@ def oracle_run(nthreads, nobs, iters, steps, warmup, seed, seconds=None):
     return build_s, times
 
 
+def reference_build_timing(nobs, seed):
+    """Reach-set build of ONE world by the REFERENCE's own sources (oracle/_ref: KPR PZsparse / Trajectory / Dynamics
+    compiled against stand-in Eigen / Boost headers, OpenMP over the 128 intervals like the reference).  None if the
+    library did not travel to this box."""
+    try:
+        from oracle import pyref
+        if not os.path.exists(pyref.LIB_PATH):
+            return None
+        from armour_b200 import worlds
+        q0, qd0, qdd0, _, _ = worlds.random_problems(2, max(nobs, 1), seed=seed)
+        cores = os.cpu_count() or 1
+        best = None
+        for p in range(2):
+            t0 = time.perf_counter()
+            pyref.ReferenceProblem(q0[p], qd0[p], qdd0[p], nthreads=cores)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return {"build_s_per_world": best, "threads": cores, "worlds_per_s": 1.0 / best,
+                "kind": "reference sources (KPR/PZsparse.cu, Trajectory.cu, Dynamics.cu) + stand-in Eigen/Boost headers, "
+                        "OpenMP over intervals; sections II.A-II.C of main() without the CUDA hyper-plane stage"}
+    except Exception as exc:  # the baseline must never take the bench down
+        return {"error": repr(exc)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -189,7 +213,8 @@ def run_reference(args):
                    "time_intervals": T, "obstacles": args.nobs, "k_iterates_per_step": args.iters},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "m1": {"build_s_per_world_1thread": build_s, "builds_per_s_all_cores": cores / build_s},
+        "m1": {"build_s_per_world_1thread": build_s, "builds_per_s_all_cores": cores / build_s,
+               "reference_build": reference_build_timing(args.nobs, 20261017)},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -386,7 +411,8 @@ def run_b200(args):
         cpu = {"value": cores * iters * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{cores} worlds of the same generator (one per host thread) x {iters} k-iterates x "
                          f"{len(times)} repetitions ({sum(times):.1f} s); oracle = C++ restatement of the reference",
-               "build_s_per_world_1thread": build_s}
+               "build_s_per_world_1thread": build_s, "builds_per_s_all_cores": cores / build_s,
+               "reference_build": reference_build_timing(nobs, 20261017)}
         if m1 is not None:
             # FP64 roofline of the build kernel: flops counted by the oracle on one problem of this batch
             from oracle.pyoracle import OracleProblem
