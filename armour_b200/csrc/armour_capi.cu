@@ -17,9 +17,19 @@
 //   k1lat: one unit per CTA, 256 threads, 2 CTAs per SM  -> lowest latency for one planning problem
 //   k1thr: 8 units per CTA in lock step, 64 threads each -> highest throughput for batches (instruction fetch,
 //          the resource that bounds this kernel, is shared by the 8 units)
+#ifdef K1_PROFILE
+constexpr int K1_PROF_SITES = 512;
+__device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
+#endif
+#ifndef K1LAT_NT
+#define K1LAT_NT 256
+#endif
+#ifndef K1LAT_CTAS
+#define K1LAT_CTAS 2
+#endif
 #define K1_NS k1lat
-#define K1_NT 256
-#define K1_CTAS 2
+#define K1_NT K1LAT_NT
+#define K1_CTAS K1LAT_CTAS
 #define K1_GROUPS 1
 #include "k1_reachsets.cuh"
 #undef K1_NS
@@ -451,6 +461,20 @@ int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, in
     CU(cudaStreamSynchronize(ctx->stream));
     return ARMOUR_OK;
 }
+
+#ifdef K1_PROFILE
+// developer builds only: per-(interval, operation site) cycle counts of the last single-problem builds
+extern "C" int armour_debug_k1_profile(long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (out && cudaMemcpyFromSymbol(out, g_k1prof, sizeof(long long) * 128 * K1_PROF_SITES * 2) != cudaSuccess) return ARMOUR_ERR_CUDA;
+    if (reset) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_k1prof) != cudaSuccess) return ARMOUR_ERR_CUDA;
+        if (cudaMemset(p, 0, sizeof(long long) * 128 * K1_PROF_SITES * 2) != cudaSuccess) return ARMOUR_ERR_CUDA;
+    }
+    return ARMOUR_OK;
+}
+#endif
 
 int armour_measure_fp64_peak(armour_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return ARMOUR_ERR_ARG;

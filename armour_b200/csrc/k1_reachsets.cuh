@@ -378,13 +378,36 @@ K1_OP void export_torque(PZ8 U8, const Batch& B, int p, int t, int j) {
 // ---- one (problem, interval) unit -----------------------------------------------------------------
 // `top` (the arena top, a CTA-uniform register) is threaded through the operations: every operation
 // allocates exactly one block at `top` and the new top is the end of the block it returns.
+// K1_PROFILE (developer builds only, tools/k1_profile.py): thread 0 of a unit accumulates the cycles of every
+// operation site into g_k1prof[interval][site] = {cycles, source line}
+#ifdef K1_PROFILE
+#define K1_PROF_T0 const long long _pt0 = clock64()
+#define K1_PROF_T1                                                               \
+    if (k1_tid() == 0) {                                                         \
+        long long* _pp = g_k1prof + (size_t(t) * K1_PROF_SITES + (__COUNTER__ % K1_PROF_SITES)) * 2; \
+        _pp[0] += clock64() - _pt0;                                              \
+        _pp[1] = __LINE__;                                                       \
+    }
+#else
+#define K1_PROF_T0
+#define K1_PROF_T1
+#endif
 #define K1_OP_DO(h, SZ, ...)      \
-    const PZ8 h = (__VA_ARGS__);  \
+    PZ8 h;                        \
+    {                             \
+        K1_PROF_T0;               \
+        h = (__VA_ARGS__);        \
+        K1_PROF_T1                \
+    }                             \
     k1_sync_cta();                \
     top = end_of<SZ>(h);          \
     top_max = top > top_max ? top : top_max
 #define K1_OP_VAR(h, SZ, ...) \
-    h = (__VA_ARGS__);        \
+    {                         \
+        K1_PROF_T0;           \
+        h = (__VA_ARGS__);    \
+        K1_PROF_T1            \
+    }                         \
     k1_sync_cta();            \
     top = end_of<SZ>(h);      \
     top_max = top > top_max ? top : top_max
@@ -719,7 +742,16 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
             t = P.B.T - 1 - (unit / P.B.nprob);  // long intervals first
             p = unit % P.B.nprob;
         }
+#ifdef K1_PROFILE
+        const long long _u0 = clock64();
+#endif
         const int tm = build_unit(P.B, p, t);
+#ifdef K1_PROFILE
+        if (tid == 0) {
+            g_k1prof[(size_t(t) * K1_PROF_SITES + K1_PROF_SITES - 1) * 2] += clock64() - _u0;
+            g_k1prof[(size_t(t) * K1_PROF_SITES + K1_PROF_SITES - 1) * 2 + 1] = 0;
+        }
+#endif
         top_max = tm > top_max ? tm : top_max;
         if (!extra) ndone++;
         const int failed = S.fail;
