@@ -21,21 +21,35 @@
 constexpr int K1_PROF_SITES = 512;
 __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
 #endif
+// Latency configuration: MG mode, K1LAT_GROUPS groups of K1LAT_NT threads build ONE unit together (one CTA per SM)
 #ifndef K1LAT_NT
-#define K1LAT_NT 256
+#define K1LAT_NT 128
 #endif
 #ifndef K1LAT_CTAS
-#define K1LAT_CTAS 2
+#define K1LAT_CTAS 1
 #endif
+#ifndef K1LAT_GROUPS
+#define K1LAT_GROUPS 3
+#endif
+#ifndef K1LAT_MG
+#define K1LAT_MG 1
+#endif
+#ifndef K1LAT_TAB_EIGHTHS
+#define K1LAT_TAB_EIGHTHS 5
+#endif
+#define K1_TAB_EIGHTHS K1LAT_TAB_EIGHTHS
 #define K1_NS k1lat
 #define K1_NT K1LAT_NT
 #define K1_CTAS K1LAT_CTAS
-#define K1_GROUPS 1
+#define K1_GROUPS K1LAT_GROUPS
+#define K1_MG K1LAT_MG
 #include "k1_reachsets.cuh"
 #undef K1_NS
 #undef K1_NT
 #undef K1_CTAS
 #undef K1_GROUPS
+#undef K1_MG
+#define K1_MG 0
 #ifndef K1THR_NT
 #define K1THR_NT 64
 #endif

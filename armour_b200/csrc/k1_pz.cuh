@@ -53,9 +53,17 @@ typedef unsigned long long u64;
 #ifndef K1_GROUPS
 #define K1_GROUPS 1
 #endif
+#ifndef K1_MG
+#define K1_MG 0
+#endif
 constexpr int NT = K1_NT;    // threads working on one (problem, interval) unit
 constexpr int GROUPS = K1_GROUPS;  // units built side by side by one CTA (CTA = GROUPS * NT threads), op by op in
                                    // step, so that the instruction stream of an operation is fetched once for all
+// MG ("multi-group") mode: the GROUPS groups of a CTA work on the SAME unit.  The unit is cut into tasks (a few
+// PZ operations each) whose operands travel through a per-CTA mailbox in global memory; every group claims the
+// next task of a fixed priority list, waits for its inputs, runs it in its own arena and publishes the results
+// (k1_reachsets.cuh, build_unit_mg).  Without MG the groups build different units in lock step.
+constexpr bool MG = K1_MG != 0;
 constexpr int CTAS_PER_SM = K1_CTAS;  // resident CTAs per SM (shared memory is split evenly)
 constexpr int NW = NT / 32;  // warps per CTA
 constexpr int RED_STRIDE = 12;
@@ -106,7 +114,8 @@ struct Tab {
 struct K1S {
     double* gbase;   // global continuation of the virtual arena: [spill space GW words | F/N scratch FW words]
     char* tab_g;     // global-memory pool for the rare hash table that does not fit (all zero between operations)
-    double thr;
+    double thr;      // simplify threshold (KPR/PZsparse.cu:321)
+    double thr2;     // largest double x with sqrt(x) <= thr: the prune test on the sum of squares, without the root
     int AW;          // words of the shared-memory part of the virtual arena (JRS region + working arena)
     int GW, FW;
     int tab_s_bytes, tab_g_bytes;
@@ -119,12 +128,33 @@ struct K1S {
     double red[NW * RED_STRIDE];   // partial sums (prune amounts)
     double red2[NW * RED_STRIDE];  // partial sums (|coefficient| sums)
     double misc[16];               // [0..7) u_nom radius, [8..15) disturbance radius
+    int nsurv;                     // survivor counter of op_cross (list path)
     int flip;                      // which survivor-mask buffer the next merge operation uses
     unsigned mask[2][MASK_WORDS];  // survivor bits of a merge operation, by merged position (double-buffered)
 };
 constexpr int K1S_BYTES = (int(sizeof(K1S)) + 15) & ~15;
 
-// Dynamic shared memory of a CTA: [16-byte CTA header: bytes per group][group 0][group 1]...; every group has
+// CTA-shared exchange block of the MG mode (lives in the CTA header)
+constexpr int MB_SLOTS = 20 * (MAXJ + 1);
+constexpr int MG_MAX_TASKS = 16 * (MAXJ + 1);
+struct K1X {
+    int group_bytes;          // (first two words: the layout of the plain header)
+    int unit;
+    int seq;                  // sequence number of the unit this CTA is building: the value of a signalled event
+    int next;                 // next unclaimed task
+    int ntasks;
+    int bump;                 // words of the mailbox handed out
+    int mbox_words;
+    int pad0;
+    double* mbox;             // this CTA's mailbox
+    double misc[16];          // [0..7) u_nom radius, [8..15) disturbance radius (written by the torque tasks)
+    int ev[MB_SLOTS];         // ev[slot] == seq: the block (or plain event) `slot` of this unit is published
+    PZ8 mb[MB_SLOTS];         // mailbox offset (words; -1 = failed) and monomial count of a published block
+    unsigned short tasks[MG_MAX_TASKS];  // kind << 8 | joint, in claim order
+};
+constexpr int K1_HDR_BYTES = MG ? ((int(sizeof(K1X)) + 15) & ~15) : 16;
+
+// Dynamic shared memory of a CTA: [CTA header: bytes per group, ...][group 0][group 1]...; every group has
 // its own control block, arena and table pool, and its own named barrier.
 #ifndef ARMOUR_EMU
 K1_DI unsigned char* smem_cta() {
@@ -134,8 +164,8 @@ K1_DI unsigned char* smem_cta() {
 K1_DI int k1_tid() { return GROUPS == 1 ? int(threadIdx.x) : int(threadIdx.x) % NT; }
 K1_DI int k1_group() { return GROUPS == 1 ? 0 : int(threadIdx.x) / NT; }
 K1_DI unsigned char* smem_base() {
-    if (GROUPS == 1) return smem_cta() + 16;
-    return smem_cta() + 16 + size_t(k1_group()) * size_t(*reinterpret_cast<const int*>(smem_cta()));
+    if (GROUPS == 1) return smem_cta() + K1_HDR_BYTES;
+    return smem_cta() + K1_HDR_BYTES + size_t(k1_group()) * size_t(*reinterpret_cast<const int*>(smem_cta()));
 }
 // barrier over the NT threads of one unit
 K1_DI void k1_sync() {
@@ -147,15 +177,17 @@ K1_DI void k1_sync() {
 }
 // barrier over the whole CTA: keeps the groups in step between operations
 K1_DI void k1_sync_cta() {
-    if (GROUPS > 1) __syncthreads();
+    if (GROUPS > 1 && !MG) __syncthreads();
 }
+K1_DI K1X& k1x() { return *reinterpret_cast<K1X*>(smem_cta()); }
 #else
 inline unsigned char* smem_cta() { return reinterpret_cast<unsigned char*>(emu::S().dyn_smem); }
 inline int k1_tid() { return int(threadIdx.x); }
 inline int k1_group() { return 0; }
-inline unsigned char* smem_base() { return smem_cta() + 16; }
+inline unsigned char* smem_base() { return smem_cta() + K1_HDR_BYTES; }
 inline void k1_sync() { __syncthreads(); }
 inline void k1_sync_cta() {}
+inline K1X& k1x() { return *reinterpret_cast<K1X*>(smem_cta()); }
 #endif
 K1_DI K1S& k1s() { return *reinterpret_cast<K1S*>(smem_base()); }
 K1_DI double* arena0() { return reinterpret_cast<double*>(smem_base() + K1S_BYTES); }
@@ -228,9 +260,20 @@ K1_DI double sumsqN(const double* v) {  // the argument of the square root in fr
     for (int i = 0; i < N; i++) s += v[i] * v[i];
     return s;
 }
-// sqrt(ss) <= thr, the prune test of simplify() (KPR/PZsparse.cu:321), out of line so that the square-root
-// expansion exists once in the kernel
-K1_OP bool norm_le(double ss, double thr) { return sqrt(ss) <= thr; }
+// The prune test of simplify() (KPR/PZsparse.cu:321) is sqrt(ss) <= thr.  The IEEE square root is correctly
+// rounded and monotone, so the test equals ss <= thr2 with thr2 = max{x : sqrt(x) <= thr} (threshold_sq below,
+// computed once per kernel): same decisions bit for bit, one comparison instead of a square root.
+K1_DI bool norm_le(double ss, double thr2) { return ss <= thr2; }
+K1_DI double threshold_sq(double thr) {
+    double x = thr * thr;
+    while (sqrt(x) > thr) x = nextafter(x, 0.0);
+    for (;;) {
+        const double y = nextafter(x, 1e300);
+        if (!(sqrt(y) <= thr)) break;
+        x = y;
+    }
+    return x;
+}
 // C(3 x P) = A(3x3) * B(3 x P), column-major, inner index ascending, no FMA (Eigen-like: KPR/PZsparse.cu:864-994)
 template <int P, bool TRANS>
 K1_DI void matmul3(const double* A, const double* B, double* C) {
@@ -764,7 +807,7 @@ K1_OP PZ8 op_lin2(int top, PZ8 a8, int a_sz, int a_in, int a_out, double a_scale
     const int na = s0.h.n, nb = s1.h.n;
     Dense d;
     if (!dense_select(na + nb, SZ, d)) return dummy;
-    const double thr = S.thr;
+    const double thr = S.thr2;  // squared-threshold constant of norm_le
     double rad[SZ];
 #pragma unroll
     for (int e = 0; e < SZ; e++) rad[e] = 0.0;
@@ -953,7 +996,7 @@ K1_OP PZ8 op_cross_const(int top, PZ8 x8, const double* v, bool left_const) {
     if (S.fail) return dummy;
     const int tid = k1_tid();
     const PZH x = view<3>(x8);
-    const double thr = S.thr;
+    const double thr = S.thr2;  // squared-threshold constant of norm_le
     const double* cf = pz_coef(x);
     const double v0 = v[0], v1 = v[1], v2 = v[2];
     double rad[3];
@@ -1000,7 +1043,7 @@ K1_OP PZ8 op_const_mul(int top, const double* K, double pct_lane1, PZ8 x8) {
     const int tid = k1_tid();
     constexpr int XS = (KIND == 2) ? 9 : 3;
     const PZH x = view<XS>(x8);
-    const double thr = S.thr;
+    const double thr = S.thr2;  // squared-threshold constant of norm_le
     const double* cf = pz_coef(x);
     double kk[9];
 #pragma unroll
@@ -1103,7 +1146,7 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
     const int M = nI * (nO + 1) + nO;
     Dense d;
     if (!dense_select(M, SZ, d)) return dummy;
-    const double thr = S.thr;
+    const double thr = S.thr2;  // squared-threshold constant of norm_le
     const u64* kL = pz_keys(L);
     const u64* kR = pz_keys(R);
     const double* cL = pz_coef(L);
@@ -1268,6 +1311,260 @@ K1_DI void cross_six(const double* a, const double* b, double* v) {
     v[4] = a[0] * b[1];
     v[5] = a[1] * b[0];
 }
+// simplify() chain of one key of cross(PZ, PZ): the six scalar products, the three differences, the stack
+K1_DI bool cross_fin(double thr, const double* a, double* out, double* r) {
+    double p[6];
+    bool have[6];
+#pragma unroll
+    for (int x = 0; x < 6; x++) {  // simplify() of each scalar product
+        have[x] = !norm_le(a[x] * a[x], thr);
+        p[x] = have[x] ? a[x] : 0.0;
+        if (!have[x]) r[x >> 1] = __dadd_ru(r[x >> 1], fabs(a[x]));
+    }
+    bool any = false;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {  // simplify() of P_{2e} - P_{2e+1}
+        out[e] = 0.0;
+        if (have[2 * e] || have[2 * e + 1]) {
+            const double d = p[2 * e] + (-p[2 * e + 1]);
+            if (norm_le(d * d, thr)) {
+                r[e] = __dadd_ru(r[e], fabs(d));
+            } else {
+                out[e] = d;
+                any = true;
+            }
+        }
+    }
+    if (!any) return false;
+    return prune_or_keep<3>(out, thr, r);  // simplify() of the stack
+}
+// centre and radii of cross(A, B) written by threads 0..2 (rad = pruned amounts of the whole operation)
+K1_DI void cross_header(PZ8 h8, const PZH& A, const PZH& B, bool outerA, const double* rad) {
+    const int tid = k1_tid();
+    if (tid < 3) {
+        const PZH h = view<3>(h8);
+        const int e = tid;
+        const int e1 = (e + 1) % 3, e2 = (e + 2) % 3;
+        const double aA1 = outerA ? abs_serial_entry(A, e1) : abs_collect_entry(A, e1);
+        const double aA2 = outerA ? abs_serial_entry(A, e2) : abs_collect_entry(A, e2);
+        const double aB1 = outerA ? abs_collect_entry(B, e1) : abs_serial_entry(B, e1);
+        const double aB2 = outerA ? abs_collect_entry(B, e2) : abs_serial_entry(B, e2);
+        const double* ca = pz_c(A);
+        const double* cb = pz_c(B);
+        // r_e = a_{e1} b_{e2} - a_{e2} b_{e1}
+        pz_c(h)[e] = ca[e1] * cb[e2] - ca[e2] * cb[e1];
+#pragma unroll 1
+        for (int lane = 0; lane < 2; lane++) {
+            const double* ra = pz_r(A, lane);
+            const double* rb = pz_r(B, lane);
+            // radius of a scalar product x*y: rx*ry + (|x|*ry + rx*|y|)   (KPR/PZsparse.cu:944-989)
+            const double p0 = __dadd_ru(__dmul_ru(ra[e1], rb[e2]),
+                                        __dadd_ru(__dmul_ru(aA1, rb[e2]), __dmul_ru(ra[e1], aB2)));
+            const double p1 = __dadd_ru(__dmul_ru(ra[e2], rb[e1]),
+                                        __dadd_ru(__dmul_ru(aA2, rb[e1]), __dmul_ru(ra[e2], aB1)));
+            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(p0, p1), rad[e]);
+        }
+    }
+}
+
+// List path of cross(PZ, PZ): everything in shared memory, no accumulators in the table.  The hash table holds
+// only the key set; a counting sort groups the contributing terms ("pairs") by slot; the owner thread of a slot
+// adds its terms up in registers in the fixed order [A_i x centre(B)], [centre(A) x B_j], pairs by ascending
+// outer index — the order of the table path below, so both paths give bit-identical results — and runs the
+// simplify chain.  The few survivors are parked as (key, coef) records and written out ranked by key.
+// Pool layout: keys[cap] u64 | cnt[cap] u32 | list[P] u32 | survivor records (4 words each).
+// Returns false (nothing written) when the pool is too small for this operand pair: the caller takes the table path.
+K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
+    K1S& S = k1s();
+    const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
+    const int nA = A.n, nB = B.n;
+    const bool outerA = nA <= nB;
+    const int nO = outerA ? nA : nB, nI = outerA ? nB : nA;
+    const long long Pll = (long long)nA + nB + (long long)nA * nB;
+    if (Pll > (1 << 20) || nO > 65000 || nI > 65535) return false;
+    const int P = int(Pll);
+    int cap = 64, lg = 6;
+    while (cap * 2 < P * 3) {
+        cap <<= 1;
+        lg++;
+    }
+    const size_t fixed = (size_t(cap) * 12 + size_t(P) * 4 + 7) & ~size_t(7);
+    if (fixed + 32 * 32 > size_t(S.tab_s_bytes)) return false;
+    const int surv_max = int((size_t(S.tab_s_bytes) - fixed) / 32);
+    char* base = tab_s0();
+    Tab t;
+    t.keys = reinterpret_cast<u64*>(base);
+    t.acc = nullptr;
+    t.cap = cap;
+    t.shift = 64 - lg;
+    unsigned* cnt = reinterpret_cast<unsigned*>(base + size_t(cap) * 8);
+    unsigned* list = cnt + cap;
+    double* surv = reinterpret_cast<double*>(base + fixed);
+    {
+        unsigned* z = reinterpret_cast<unsigned*>(base);
+        for (int i = tid; i < cap * 3; i += NT) z[i] = 0u;
+        if (tid == 0) S.nsurv = 0;
+    }
+    k1_sync();
+    const double thr = S.thr2;  // squared-threshold constant of norm_le
+    const u64* kA = pz_keys(A);
+    const u64* kB = pz_keys(B);
+    const double* cA = pz_coef(A);
+    const double* cB = pz_coef(B);
+    const u64* kO = outerA ? kA : kB;
+    const u64* kI = outerA ? kB : kA;
+    // the key set
+    for (int q = tid; q < P; q += NT) {
+        u64 key;
+        if (q < nA) {
+            key = kA[q];
+        } else if (q < nA + nB) {
+            key = kB[q - nA];
+        } else {
+            const int r = q - nA - nB, o = r / nI, j = r - o * nI;
+            key = kO[o] + kI[j];
+        }
+        tab_insert(t, key);
+    }
+    if (outerA) abs_sum_partial<3>(B); else abs_sum_partial<3>(A);
+    k1_sync();
+    // terms per slot
+    for (int q = tid; q < P; q += NT) {
+        u64 key;
+        if (q < nA) {
+            key = kA[q];
+        } else if (q < nA + nB) {
+            key = kB[q - nA];
+        } else {
+            const int r = q - nA - nB, o = r / nI, j = r - o * nI;
+            key = kO[o] + kI[j];
+        }
+        atomicAdd(&cnt[tab_find(t, key)], 1u);
+    }
+    k1_sync();
+    // exclusive prefix sum of cnt[0..cap): contiguous chunk per thread, warp scan, warp totals through S.cnt
+    {
+        const int chunk = (cap + NT - 1) / NT;
+        const int c0 = tid * chunk;
+        const int c1 = (c0 + chunk) < cap ? (c0 + chunk) : cap;
+        int sum = 0;
+        for (int i = c0; i < c1; i++) sum += int(cnt[i]);
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) S.cnt[warp] = incl;
+        k1_sync();
+        int before = incl - sum;
+        for (int w = 0; w < warp; w++) before += S.cnt[w];
+        for (int i = c0; i < c1; i++) {
+            const int v = int(cnt[i]);
+            cnt[i] = unsigned(before);
+            before += v;
+        }
+    }
+    k1_sync();
+    // fill the term lists: id = tag << 16 | index, tag 0: A_i x centre(B), 1: centre(A) x B_j, 2 + o: outer o x inner j
+    for (int q = tid; q < P; q += NT) {
+        u64 key;
+        unsigned id;
+        if (q < nA) {
+            key = kA[q];
+            id = unsigned(q);
+        } else if (q < nA + nB) {
+            key = kB[q - nA];
+            id = (1u << 16) | unsigned(q - nA);
+        } else {
+            const int r = q - nA - nB, o = r / nI, j = r - o * nI;
+            key = kO[o] + kI[j];
+            id = (unsigned(2 + o) << 16) | unsigned(j);
+        }
+        const unsigned pos = atomicAdd(&cnt[tab_find(t, key)], 1u);  // cnt[s] ends as the END of slot s's list
+        list[pos] = id;
+    }
+    k1_sync();
+    // owner pass, slots distributed like tab_finalize (same order of the pruned-amount sums)
+    double rad[3] = {0.0, 0.0, 0.0};
+    {
+        const double* ccA = pz_c(A);
+        const double* ccB = pz_c(B);
+        const double cenA[3] = {ccA[0], ccA[1], ccA[2]};
+        const double cenB[3] = {ccB[0], ccB[1], ccB[2]};
+        const int seg = (cap / NW) < 32 ? 32 : (cap / NW);
+        const int s0 = warp * seg;
+        const int s1 = (s0 + seg) < cap ? (s0 + seg) : cap;
+        for (int s = s0 + lane; s < s1; s += 32) {
+            const u64 key = t.keys[s];
+            if (key == 0) continue;
+            const int b = s ? int(cnt[s - 1]) : 0, e = int(cnt[s]);
+            double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            long long last = -1;
+            for (int c = b; c < e; c++) {
+                unsigned best = 0xffffffffu;  // next id in ascending order (ids of a slot are distinct)
+                for (int x = b; x < e; x++) {
+                    const unsigned u = list[x];
+                    if ((long long)u > last && u < best) best = u;
+                }
+                last = (long long)best;
+                const int tag = int(best >> 16), idx = int(best & 0xffffu);
+                double v[6];
+                if (tag == 0) {
+                    cross_six(cA + size_t(idx) * 3, cenB, v);
+                } else if (tag == 1) {
+                    cross_six(cenA, cB + size_t(idx) * 3, v);
+                } else if (outerA) {
+                    cross_six(cA + size_t(tag - 2) * 3, cB + size_t(idx) * 3, v);
+                } else {
+                    cross_six(cA + size_t(idx) * 3, cB + size_t(tag - 2) * 3, v);
+                }
+#pragma unroll
+                for (int x = 0; x < 6; x++) a[x] += v[x];
+            }
+            double out[3];
+            if (cross_fin(thr, a, out, rad)) {
+                const int i = atomicAdd(&S.nsurv, 1);
+                if (i < surv_max) {
+                    reinterpret_cast<u64*>(surv)[size_t(i) * 4] = key;
+                    surv[size_t(i) * 4 + 1] = out[0];
+                    surv[size_t(i) * 4 + 2] = out[1];
+                    surv[size_t(i) * 4 + 3] = out[2];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 3; e++) rad[e] = warp_sum_up(rad[e]);
+    if (lane == 0)
+#pragma unroll
+        for (int e = 0; e < 3; e++) S.red[warp * RED_STRIDE + e] = rad[e];
+    k1_sync();
+    const int n = S.nsurv;
+    if (n > surv_max) return false;  // uniform; nothing of the output exists yet
+    double radt[3];
+    rad_collect<3>(radt);
+    bool ok;
+    const PZ8 h8 = pz_alloc<3>(top, n, &ok);
+    if (ok) {
+        const PZH h = view<3>(h8);
+        u64* okk = pz_keys(h);
+        double* oc = pz_coef(h);
+        for (int r = tid; r < n; r += NT) {  // survivors ranked by key (the records are in arrival order)
+            const u64 key = reinterpret_cast<const u64*>(surv)[size_t(r) * 4];
+            int rank = 0;
+            for (int x = 0; x < n; x++) rank += (reinterpret_cast<const u64*>(surv)[size_t(x) * 4] < key);
+            okk[rank] = key;
+#pragma unroll
+            for (int e = 0; e < 3; e++) oc[size_t(rank) * 3 + e] = surv[size_t(r) * 4 + 1 + e];
+        }
+        cross_header(h8, A, B, outerA, radt);
+    }
+    k1_sync();
+    *out_h = h8;
+    return true;
+}
+
 K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
     const PZ8 dummy = {0, 0};
     K1S& S = k1s();
@@ -1275,6 +1572,11 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
     const int tid = k1_tid();
     const PZH A = view<3>(A8), B = view<3>(B8);
     const int nA = A.n, nB = B.n;
+    {
+        PZ8 h8;
+        if (cross_list_path(top, A, B, &h8)) return h8;
+        if (S.fail) return dummy;
+    }
     Tab t;
     if (!tab_select(nA + nB + nA * nB, 6, t)) return dummy;
     if (reinterpret_cast<char*>(t.keys) == tab_s0()) {  // merge operations leave the shared pool dirty
@@ -1283,7 +1585,7 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
         for (int i = tid; i < words; i += NT) z[i] = 0;
         k1_sync();
     }
-    const double thr = S.thr;
+    const double thr = S.thr2;  // squared-threshold constant of norm_le
     const u64* kA = pz_keys(A);
     const u64* kB = pz_keys(B);
     const double* cA = pz_coef(A);
@@ -1343,58 +1645,8 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
     double rad[3];
     bool ok;
     const PZ8 h8 = tab_finalize<6, 3>(
-        top, t,
-        [thr](const double* a, double* out, double* r) {
-            double p[6];
-            bool have[6];
-#pragma unroll
-            for (int x = 0; x < 6; x++) {  // simplify() of each scalar product
-                have[x] = !norm_le(a[x] * a[x], thr);
-                p[x] = have[x] ? a[x] : 0.0;
-                if (!have[x]) r[x >> 1] = __dadd_ru(r[x >> 1], fabs(a[x]));
-            }
-            bool any = false;
-#pragma unroll
-            for (int e = 0; e < 3; e++) {  // simplify() of P_{2e} - P_{2e+1}
-                out[e] = 0.0;
-                if (have[2 * e] || have[2 * e + 1]) {
-                    const double d = p[2 * e] + (-p[2 * e + 1]);
-                    if (norm_le(d * d, thr)) {
-                        r[e] = __dadd_ru(r[e], fabs(d));
-                    } else {
-                        out[e] = d;
-                        any = true;
-                    }
-                }
-            }
-            if (!any) return false;
-            return prune_or_keep<3>(out, thr, r);  // simplify() of the stack
-        },
-        rad, &ok);
-    if (ok && tid < 3) {
-        const PZH h = view<3>(h8);
-        const int e = tid;
-        const int e1 = (e + 1) % 3, e2 = (e + 2) % 3;
-        const double aA1 = outerA ? abs_serial_entry(A, e1) : abs_collect_entry(A, e1);
-        const double aA2 = outerA ? abs_serial_entry(A, e2) : abs_collect_entry(A, e2);
-        const double aB1 = outerA ? abs_collect_entry(B, e1) : abs_serial_entry(B, e1);
-        const double aB2 = outerA ? abs_collect_entry(B, e2) : abs_serial_entry(B, e2);
-        const double* ca = pz_c(A);
-        const double* cb = pz_c(B);
-        // r_e = a_{e1} b_{e2} - a_{e2} b_{e1}
-        pz_c(h)[e] = ca[e1] * cb[e2] - ca[e2] * cb[e1];
-#pragma unroll 1
-        for (int lane = 0; lane < 2; lane++) {
-            const double* ra = pz_r(A, lane);
-            const double* rb = pz_r(B, lane);
-            // radius of a scalar product x*y: rx*ry + (|x|*ry + rx*|y|)   (KPR/PZsparse.cu:944-989)
-            const double p0 = __dadd_ru(__dmul_ru(ra[e1], rb[e2]),
-                                        __dadd_ru(__dmul_ru(aA1, rb[e2]), __dmul_ru(ra[e1], aB2)));
-            const double p1 = __dadd_ru(__dmul_ru(ra[e2], rb[e1]),
-                                        __dadd_ru(__dmul_ru(aA2, rb[e1]), __dmul_ru(ra[e2], aB1)));
-            pz_r(h, lane)[e] = __dadd_ru(__dadd_ru(p0, p1), rad[e]);
-        }
-    }
+        top, t, [thr](const double* a, double* out, double* r) { return cross_fin(thr, a, out, r); }, rad, &ok);
+    if (ok) cross_header(h8, A, B, outerA, rad);
     k1_sync();
     sort_block<3>(h8, ok);  // survivors leave the table in slot order
     k1_sync();

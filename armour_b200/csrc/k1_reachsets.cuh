@@ -43,6 +43,8 @@ struct K1Params {
     const int* units;   // optional explicit unit list (p*T + t); nullptr = all units of the batch
     int nunits;
     int* stats;         // [4]: max arena words used, tables placed in global memory, failed units, units done
+    double* mbox;       // MG mode: [grid][mbox_words] mailboxes
+    int mbox_words;
 };
 
 // handles of the joint reachable set blocks (fixed places at the bottom of the virtual arena)
@@ -366,8 +368,9 @@ K1_OP void export_torque(PZ8 U8, const Batch& B, int p, int t, int j) {
         for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE]);
         const double r_nom = pz_r(U, 0)[0], r_int = pz_r(U, 1)[0];
         const double reduced = __dadd_ru(r_nom, v);
-        S.misc[j] = reduced;
-        S.misc[8 + j] = __dadd_ru(r_int, r_nom);
+        double* misc = MG ? k1x().misc : S.misc;  // MG: the torque tasks of a unit run on different groups
+        misc[j] = reduced;
+        misc[8 + j] = __dadd_ru(r_int, r_nom);
         B.u_n[idx] = nk;
         B.u_c[idx] = pz_c(U)[0];
         B.u_r[idx] = __dmul_ru(reduced, RADIUS_SLACK);
@@ -375,53 +378,13 @@ K1_OP void export_torque(PZ8 U8, const Batch& B, int p, int t, int j) {
     k1_sync();
 }
 
-// ---- one (problem, interval) unit -----------------------------------------------------------------
-// `top` (the arena top, a CTA-uniform register) is threaded through the operations: every operation
-// allocates exactly one block at `top` and the new top is the end of the block it returns.
-// K1_PROFILE (developer builds only, tools/k1_profile.py): thread 0 of a unit accumulates the cycles of every
-// operation site into g_k1prof[interval][site] = {cycles, source line}
-#ifdef K1_PROFILE
-#define K1_PROF_T0 const long long _pt0 = clock64()
-#define K1_PROF_T1                                                               \
-    if (k1_tid() == 0) {                                                         \
-        long long* _pp = g_k1prof + (size_t(t) * K1_PROF_SITES + (__COUNTER__ % K1_PROF_SITES)) * 2; \
-        _pp[0] += clock64() - _pt0;                                              \
-        _pp[1] = __LINE__;                                                       \
-    }
-#else
-#define K1_PROF_T0
-#define K1_PROF_T1
-#endif
-#define K1_OP_DO(h, SZ, ...)      \
-    PZ8 h;                        \
-    {                             \
-        K1_PROF_T0;               \
-        h = (__VA_ARGS__);        \
-        K1_PROF_T1                \
-    }                             \
-    k1_sync_cta();                \
-    top = end_of<SZ>(h);          \
-    top_max = top > top_max ? top : top_max
-#define K1_OP_VAR(h, SZ, ...) \
-    {                         \
-        K1_PROF_T0;           \
-        h = (__VA_ARGS__);    \
-        K1_PROF_T1            \
-    }                         \
-    k1_sync_cta();            \
-    top = end_of<SZ>(h);      \
-    top_max = top > top_max ? top : top_max
-
-K1_DI int build_unit(const Batch& B, int p, int t) {
+// ---- K2: joint reachable set of interval t into the fixed region at the bottom of the arena ----
+K1_DI void build_jrs(const Batch& B, int p, int t) {
     const RobotConstants& rc = c_robot;
     K1S& S = k1s();
     const int tid = k1_tid();
     const int NJ = B.NJ, T = B.T;
     const double thr = S.thr;
-    constexpr int B0 = JRS_WORDS;  // bottom of the working arena
-    int top = B0, top_max = B0, gtop = 0;
-
-    // ---- K2: joint reachable set ----
     double* rot_mem = arena0();
     double* scl_mem = arena0() + (MAXJ + 1) * ROT_WORDS;
     if (tid < NF) {
@@ -442,6 +405,98 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
     }
     k1_sync();
 
+}
+
+// link box zonotope of joint i as a 3x1 PZ at `top`: centre + diag(generators) on the x / y / z generator
+// variables, which reuse the hash slots of qde_0 / qdae_0 / qddae_0 (KPR/Dynamics.cu:51-66)
+K1_DI PZ8 make_link_box(int top, int i) {
+    const RobotConstants& rc = c_robot;
+    K1S& S = k1s();
+    const int tid = k1_tid();
+    const double thr = S.thr;
+    bool ok;
+    PZ8 box = pz_alloc<3>(top, 3, &ok);
+    if (ok && tid == 0) {
+        double* bp = vptr(box.off);
+        double rad[3] = {0, 0, 0};
+        int n = 0;
+        u64 kk[3];
+        double gg[3][3];
+        for (int jx = 0; jx < 3; jx++) {
+            const double g = rc.link_zonotope_generators[i * 3 + jx];
+            if (sqrt(g * g) <= thr) {
+                rad[jx] = fabs(g);
+            } else {
+                kk[n] = 1ull << (14 + 7 * jx);
+                for (int e = 0; e < 3; e++) gg[n][e] = (e == jx) ? g : 0.0;
+                n++;
+            }
+        }
+        for (int e = 0; e < 3; e++) {
+            bp[e] = rc.link_zonotope_center[i * 3 + e];
+            bp[3 + e] = rad[e];
+            bp[6 + e] = rad[e];
+        }
+        u64* pk = reinterpret_cast<u64*>(bp + 9);
+        for (int q = 0; q < n; q++) pk[q] = kk[q];
+        for (int q = 0; q < n; q++)
+            for (int e = 0; e < 3; e++) bp[9 + n + q * 3 + e] = gg[q][e];
+        S.cnt[0] = n;
+    }
+    k1_sync();
+    box.n = ok ? S.cnt[0] : 0;
+    k1_sync();
+    return box;
+}
+
+// ---- one (problem, interval) unit -----------------------------------------------------------------
+// `top` (the arena top, a CTA-uniform register) is threaded through the operations: every operation
+// allocates exactly one block at `top` and the new top is the end of the block it returns.
+// K1_PROFILE (developer builds only, tools/k1_profile.py): thread 0 of a unit accumulates the cycles of every
+// operation site into g_k1prof[interval][site] = {cycles, source line}
+#ifdef K1_PROFILE
+#define K1_PROF_T0 const long long _pt0 = clock64()
+#define K1_PROF_T1(_h)                                                           \
+    if (k1_tid() == 0) {                                                         \
+        long long* _pp = g_k1prof + (size_t(t) * K1_PROF_SITES + (__COUNTER__ % K1_PROF_SITES)) * 2; \
+        _pp[0] += clock64() - _pt0;                                              \
+        const long long _n = (_pp[1] >> 32) > _h.n ? (_pp[1] >> 32) : _h.n;      \
+        _pp[1] = __LINE__ | (_n << 32);                                          \
+    }
+#else
+#define K1_PROF_T0
+#define K1_PROF_T1(_h)
+#endif
+#define K1_OP_DO(h, SZ, ...)      \
+    PZ8 h;                        \
+    {                             \
+        K1_PROF_T0;               \
+        h = (__VA_ARGS__);        \
+        K1_PROF_T1(h)             \
+    }                             \
+    k1_sync_cta();                \
+    top = end_of<SZ>(h);          \
+    top_max = top > top_max ? top : top_max
+#define K1_OP_VAR(h, SZ, ...) \
+    {                         \
+        K1_PROF_T0;           \
+        h = (__VA_ARGS__);    \
+        K1_PROF_T1(h)         \
+    }                         \
+    k1_sync_cta();            \
+    top = end_of<SZ>(h);      \
+    top_max = top > top_max ? top : top_max
+
+K1_DI int build_unit(const Batch& B, int p, int t) {
+    const RobotConstants& rc = c_robot;
+    K1S& S = k1s();
+    const int tid = k1_tid();
+    const int NJ = B.NJ, T = B.T;
+    constexpr int B0 = JRS_WORDS;  // bottom of the working arena
+    int top = B0, top_max = B0, gtop = 0;
+
+    build_jrs(B, p, t);
+
     // ---- forward kinematics of the link volumes (KPR/Dynamics.cu:69-81) ----
     {
         bool ok;
@@ -459,40 +514,8 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
             PZ8 FK_T2, FK_R2;
             K1_OP_VAR(FK_T2, 3, op_add<3>(top, FK_T, t1));
             K1_OP_VAR(FK_R2, 9, op_mul33<3, false>(top, FK_R, jrs_R(i)));
-            // link box zonotope: centre + diag(generators) on the x / y / z generator variables, which
-            // reuse the hash slots of qde_0 / qdae_0 / qddae_0 (KPR/Dynamics.cu:51-66)
-            PZ8 box = pz_alloc<3>(top, 3, &ok);
-            if (ok && tid == 0) {
-                double* bp = vptr(box.off);
-                double rad[3] = {0, 0, 0};
-                int n = 0;
-                u64 kk[3];
-                double gg[3][3];
-                for (int jx = 0; jx < 3; jx++) {
-                    const double g = rc.link_zonotope_generators[i * 3 + jx];
-                    if (sqrt(g * g) <= thr) {
-                        rad[jx] = fabs(g);
-                    } else {
-                        kk[n] = 1ull << (14 + 7 * jx);
-                        for (int e = 0; e < 3; e++) gg[n][e] = (e == jx) ? g : 0.0;
-                        n++;
-                    }
-                }
-                for (int e = 0; e < 3; e++) {
-                    bp[e] = rc.link_zonotope_center[i * 3 + e];
-                    bp[3 + e] = rad[e];
-                    bp[6 + e] = rad[e];
-                }
-                u64* pk = reinterpret_cast<u64*>(bp + 9);
-                for (int q = 0; q < n; q++) pk[q] = kk[q];
-                for (int q = 0; q < n; q++)
-                    for (int e = 0; e < 3; e++) bp[9 + n + q * 3 + e] = gg[q][e];
-                S.cnt[0] = n;
-            }
-            k1_sync();
-            box.n = ok ? S.cnt[0] : 0;
+            const PZ8 box = make_link_box(top, i);
             top = box.off + pz_words(3, 3);  // the block was sized for three generators
-            k1_sync();
             K1_OP_DO(l1, 3, op_mul33<1, false>(top, FK_R2, box));
             K1_OP_DO(link, 3, op_add<3>(top, l1, FK_T2));
             export_link(link, B, p, t, i);
@@ -690,11 +713,320 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
 #undef K1_OP_DO
 #undef K1_OP_VAR
 
+
+#if K1_MG
+// ---- MG mode: one unit built by all groups of the CTA ------------------------------------------------
+// The unit is a list of tasks; operands and results travel through the CTA's mailbox (global memory, written
+// once per unit, L2-resident), so a task is a pure function mailbox -> mailbox and any group can run it.
+// Operation order inside every chain of the recursion and every simplify() point are those of build_unit().
+enum {
+    MB_W, MB_WA1, MB_WA2, MB_WD, MB_T4, MB_LA, MB_T10, MB_F, MB_A3, MB_N, MB_FKR, MB_FKT, MB_A6, MB_F2, MB_N2,
+    EV_FKL, EV_U, MB_KINDS
+};
+static_assert(MB_KINDS * (MAXJ + 1) <= MB_SLOTS, "mailbox slots");
+enum { TK_W, TK_WA, TK_WD, TK_T4, TK_LA, TK_T10, TK_TF, TK_TN, TK_FKC, TK_FKL, TK_FB, TK_NB, TK_U, TK_EPI };
+K1_DI int mb_slot(int kind, int i) { return kind * (MAXJ + 1) + i; }
+
+K1_DI void ev_signal(int slot) {  // called by all threads of the group after a barrier that follows the writes
+    if (k1_tid() == 0) {
+        K1X& X = k1x();
+        __threadfence_block();
+        reinterpret_cast<volatile int*>(X.ev)[slot] = X.seq;
+    }
+}
+K1_DI void ev_wait(int slot) {
+    if (k1_tid() == 0) {
+        K1X& X = k1x();
+        const int seq = X.seq;
+        while (reinterpret_cast<volatile int*>(X.ev)[slot] != seq) __nanosleep(40);
+        __threadfence_block();
+    }
+    k1_sync();
+}
+// copy block h into the mailbox and announce it under `slot`
+template <int SZ>
+K1_DI void mb_publish(int slot, PZ8 h) {
+    K1S& S = k1s();
+    K1X& X = k1x();
+    const int tid = k1_tid();
+    const int w = pz_words(h.n, SZ);
+    if (tid == 0) S.cnt[0] = atomicAdd(&X.bump, w);
+    k1_sync();
+    const int off = S.cnt[0];
+    const bool ok = !S.fail && off + w <= X.mbox_words;
+    if (ok) {
+        const double* src = vptr(h.off);
+        double* dst = X.mbox + off;
+        for (int i = tid; i < w; i += NT) dst[i] = src[i];
+    } else {
+        set_fail(FAIL_SCRATCH);
+    }
+    k1_sync();
+    if (tid == 0) {
+        PZ8 m;
+        m.off = ok ? off : -1;
+        m.n = ok ? h.n : 0;
+        X.mb[slot] = m;
+    }
+    ev_signal(slot);
+}
+// wait for block `slot` and copy it into the arena at `top`
+template <int SZ>
+K1_DI PZ8 mb_import(int slot, int top) {
+    K1X& X = k1x();
+    const int tid = k1_tid();
+    ev_wait(slot);
+    const PZ8 m = X.mb[slot];
+    if (m.off < 0) set_fail(FAIL_SCRATCH);  // the producer failed
+    bool ok;
+    const PZ8 h = pz_alloc<SZ>(top, m.off < 0 ? 0 : m.n, &ok);
+    if (ok) {
+        const int w = pz_words(h.n, SZ);
+        const double* src = X.mbox + m.off;
+        double* dst = vptr(h.off);
+        for (int i = tid; i < w; i += NT) dst[i] = src[i];
+    }
+    k1_sync();
+    return h;
+}
+// the block of joint i - 1, or the recursion's zero start value for the first joint
+template <int SZ>
+K1_DI PZ8 mb_prev(int kind, int i, int top) {
+    if (i == 0) return pz_zero<SZ>(top);
+    return mb_import<SZ>(mb_slot(kind, i - 1), top);
+}
+
+#define MG_DO(h, SZ, ...)        \
+    const PZ8 h = (__VA_ARGS__); \
+    top = end_of<SZ>(h);         \
+    top_max = top > top_max ? top : top_max
+
+K1_DI int run_task(const Batch& B, int p, int t, int kind, int i) {
+    const RobotConstants& rc = c_robot;
+    K1S& S = k1s();
+    const int tid = k1_tid();
+    const int NJ = B.NJ;
+    constexpr int B0 = JRS_WORDS;
+    int top = B0, top_max = B0;
+    const int ax = (kind != TK_EPI && rc.axes[i] != 0) ? abs(rc.axes[i]) - 1 : -1;  // -1: fixed joint
+    switch (kind) {
+    case TK_W: {  // w_i = R_i^T w_{i-1} + qd_i e_axis   (KPR/Dynamics.cu:95-103)
+        MG_DO(w, 3, mb_prev<3>(MB_W, i, top));
+        MG_DO(w1, 3, op_mul33<1, true>(top, jrs_R(i), w));
+        if (ax >= 0) {
+            MG_DO(w2, 3, op_add_one_dim(top, w1, jrs_scalar(0, i), ax));
+            mb_publish<3>(mb_slot(MB_W, i), w2);
+        } else {
+            mb_publish<3>(mb_slot(MB_W, i), w1);
+        }
+    } break;
+    case TK_WA: {  // auxiliary angular velocity
+        MG_DO(wa, 3, mb_prev<3>(MB_WA2, i, top));
+        MG_DO(wa1, 3, op_mul33<1, true>(top, jrs_R(i), wa));
+        if (ax >= 0) {
+            mb_publish<3>(mb_slot(MB_WA1, i), wa1);
+            MG_DO(wa2, 3, op_add_one_dim(top, wa1, jrs_scalar(1, i), ax));
+            mb_publish<3>(mb_slot(MB_WA2, i), wa2);
+        } else {
+            mb_publish<3>(mb_slot(MB_WA2, i), wa1);
+        }
+    } break;
+    case TK_WD: {  // angular acceleration
+        MG_DO(wd, 3, mb_prev<3>(MB_WD, i, top));
+        MG_DO(wd1, 3, op_mul33<1, true>(top, jrs_R(i), wd));
+        if (ax >= 0) {
+            MG_DO(wa1, 3, mb_import<3>(mb_slot(MB_WA1, i), top));
+            MG_DO(zero3, 3, pz_zero<3>(top));
+            MG_DO(tmp, 3, op_add_one_dim(top, zero3, jrs_scalar(0, i), ax));
+            MG_DO(t6, 3, op_cross(top, wa1, tmp));
+            MG_DO(wd2, 3, op_add<3>(top, wd1, t6));
+            MG_DO(wd3, 3, op_add_one_dim(top, wd2, jrs_scalar(2, i), ax));
+            mb_publish<3>(mb_slot(MB_WD, i), wd3);
+        } else {
+            mb_publish<3>(mb_slot(MB_WD, i), wd1);
+        }
+    } break;
+    case TK_T4: {  // w_{i-1} x (wa_{i-1} x p_i)
+        MG_DO(wa, 3, mb_prev<3>(MB_WA2, i, top));
+        MG_DO(t3, 3, op_cross_const(top, wa, &rc.trans[3 * i], false));
+        MG_DO(w, 3, mb_prev<3>(MB_W, i, top));
+        MG_DO(t4, 3, op_cross(top, w, t3));
+        mb_publish<3>(mb_slot(MB_T4, i), t4);
+    } break;
+    case TK_LA: {  // linear acceleration of the joint frame
+        PZ8 la;
+        if (i == 0) {
+            la = pz_zero<3>(top);
+            if (!S.fail && tid == 0) vptr(la.off)[2] = rc.gravity;
+            k1_sync();
+        } else {
+            la = mb_import<3>(mb_slot(MB_LA, i - 1), top);
+        }
+        top = end_of<3>(la);
+        MG_DO(wd, 3, mb_prev<3>(MB_WD, i, top));
+        MG_DO(t1, 3, op_cross_const(top, wd, &rc.trans[3 * i], false));
+        MG_DO(t2, 3, op_add<3>(top, la, t1));
+        MG_DO(t4, 3, mb_import<3>(mb_slot(MB_T4, i), top));
+        MG_DO(t5, 3, op_add<3>(top, t2, t4));
+        MG_DO(la2, 3, op_mul33<1, true>(top, jrs_R(i), t5));
+        mb_publish<3>(mb_slot(MB_LA, i), la2);
+    } break;
+    case TK_T10: {  // w_i x (wa_i x c_i)
+        MG_DO(wa2, 3, mb_import<3>(mb_slot(MB_WA2, i), top));
+        MG_DO(t9, 3, op_cross_const(top, wa2, &rc.com[3 * i], false));
+        MG_DO(w2, 3, mb_import<3>(mb_slot(MB_W, i), top));
+        MG_DO(t10, 3, op_cross(top, w2, t9));
+        mb_publish<3>(mb_slot(MB_T10, i), t10);
+    } break;
+    case TK_TF: {  // F_i = m_i (la_i + wd_i x c_i + w_i x (wa_i x c_i)), and c_i x F_i for the backward pass
+        MG_DO(wd3, 3, mb_import<3>(mb_slot(MB_WD, i), top));
+        MG_DO(t7, 3, op_cross_const(top, wd3, &rc.com[3 * i], false));
+        MG_DO(la2, 3, mb_import<3>(mb_slot(MB_LA, i), top));
+        MG_DO(t8, 3, op_add<3>(top, la2, t7));
+        MG_DO(t10, 3, mb_import<3>(mb_slot(MB_T10, i), top));
+        MG_DO(t11, 3, op_add<3>(top, t8, t10));
+        MG_DO(F, 3, op_const_mul<0>(top, &rc.mass[i], rc.mass_uncertainty, t11));
+        mb_publish<3>(mb_slot(MB_F, i), F);
+        MG_DO(a3, 3, op_cross_const(top, F, &rc.com[3 * i], true));
+        mb_publish<3>(mb_slot(MB_A3, i), a3);
+    } break;
+    case TK_TN: {  // N_i = I_i wd_i + wa_i x (I_i w_i)
+        MG_DO(wd3, 3, mb_import<3>(mb_slot(MB_WD, i), top));
+        MG_DO(t12, 3, op_const_mul<1>(top, &rc.inertia[i * 9], rc.inertia_uncertainty, wd3));
+        MG_DO(w2, 3, mb_import<3>(mb_slot(MB_W, i), top));
+        MG_DO(t13, 3, op_const_mul<1>(top, &rc.inertia[i * 9], rc.inertia_uncertainty, w2));
+        MG_DO(wa2, 3, mb_import<3>(mb_slot(MB_WA2, i), top));
+        MG_DO(t14, 3, op_cross(top, wa2, t13));
+        MG_DO(N, 3, op_add<3>(top, t12, t14));
+        mb_publish<3>(mb_slot(MB_N, i), N);
+    } break;
+    case TK_FKC: {  // forward-kinematics chain (KPR/Dynamics.cu:69-81)
+        bool ok;
+        PZ8 FK_R, FK_T;
+        if (i == 0) {
+            FK_R = pz_alloc<9>(top, 0, &ok);
+            top = end_of<9>(FK_R);
+            FK_T = pz_alloc<3>(top, 0, &ok);
+            top = end_of<3>(FK_T);
+            if (ok) {
+                if (tid < 27) vptr(FK_R.off)[tid] = (tid < 9 && tid % 4 == 0) ? 1.0 : 0.0;
+                if (tid >= 32 && tid < 41) vptr(FK_T.off)[tid - 32] = 0.0;
+            }
+            k1_sync();
+        } else {
+            FK_R = mb_import<9>(mb_slot(MB_FKR, i - 1), top);
+            top = end_of<9>(FK_R);
+            FK_T = mb_import<3>(mb_slot(MB_FKT, i - 1), top);
+            top = end_of<3>(FK_T);
+        }
+        top_max = top > top_max ? top : top_max;
+        MG_DO(t1, 3, op_const_mul<2>(top, &rc.trans[3 * i], 0.0, FK_R));
+        MG_DO(FK_T2, 3, op_add<3>(top, FK_T, t1));
+        mb_publish<3>(mb_slot(MB_FKT, i), FK_T2);
+        MG_DO(FK_R2, 9, op_mul33<3, false>(top, FK_R, jrs_R(i)));
+        mb_publish<9>(mb_slot(MB_FKR, i), FK_R2);
+    } break;
+    case TK_FKL: {  // link volume i: FK_R box + FK_T, reduce_link_PZ
+        MG_DO(FK_R2, 9, mb_import<9>(mb_slot(MB_FKR, i), top));
+        MG_DO(FK_T2, 3, mb_import<3>(mb_slot(MB_FKT, i), top));
+        MG_DO(box, 3, make_link_box(top, i));
+        MG_DO(l1, 3, op_mul33<1, false>(top, FK_R2, box));
+        MG_DO(link, 3, op_add<3>(top, l1, FK_T2));
+        export_link(link, B, p, t, i);
+    } break;
+    case TK_FB: {  // backward pass, force chain: f_i = R_{i+1} f_{i+1} + F_i; also p_{i+1} x (R_{i+1} f_{i+1})
+        PZ8 f;
+        if (i == NJ - 1) f = pz_zero<3>(top); else f = mb_import<3>(mb_slot(MB_F2, i + 1), top);
+        top = end_of<3>(f);
+        MG_DO(a5, 3, op_mul33<1, false>(top, jrs_R(i + 1), f));
+        MG_DO(a6, 3, op_cross_const(top, a5, &rc.trans[3 * (i + 1)], true));
+        mb_publish<3>(mb_slot(MB_A6, i), a6);
+        MG_DO(Fi, 3, mb_import<3>(mb_slot(MB_F, i), top));
+        MG_DO(f2, 3, op_add<3>(top, a5, Fi));
+        mb_publish<3>(mb_slot(MB_F2, i), f2);
+    } break;
+    case TK_NB: {  // backward pass, moment chain: n_i = ((N_i + R_{i+1} n_{i+1}) + c_i x F_i) + p_{i+1} x (R f)
+        PZ8 n;
+        if (i == NJ - 1) n = pz_zero<3>(top); else n = mb_import<3>(mb_slot(MB_N2, i + 1), top);
+        top = end_of<3>(n);
+        MG_DO(a1, 3, op_mul33<1, false>(top, jrs_R(i + 1), n));
+        MG_DO(Ni, 3, mb_import<3>(mb_slot(MB_N, i), top));
+        MG_DO(a2, 3, op_add<3>(top, Ni, a1));
+        MG_DO(a3, 3, mb_import<3>(mb_slot(MB_A3, i), top));
+        MG_DO(a4, 3, op_add<3>(top, a2, a3));
+        MG_DO(a6, 3, mb_import<3>(mb_slot(MB_A6, i), top));
+        MG_DO(n2, 3, op_add<3>(top, a4, a6));
+        mb_publish<3>(mb_slot(MB_N2, i), n2);
+    } break;
+    case TK_U: {  // joint torque u_i = n_i[axis] + armature qdda + damping qd, its k-only table
+        if (ax >= 0) {
+            MG_DO(n, 3, mb_import<3>(mb_slot(MB_N2, i), top));
+            MG_DO(u1, 1, op_lin2<1>(top, n, 3, ax, 0, 1.0, jrs_scalar(2, i), 1, 0, 0, rc.armature[i]));
+            MG_DO(u2, 1, op_lin2<1>(top, u1, 1, 0, 0, 1.0, jrs_scalar(0, i), 1, 0, 0, rc.damping[i]));
+            export_torque(u2, B, p, t, i);
+        }
+        k1_sync();
+        ev_signal(mb_slot(EV_U, i));
+    } break;
+    case TK_EPI: {  // robust-input radius (KPR/armour_main.cu:172-201), after every torque task
+        for (int j = 0; j < NJ; j++) ev_wait(mb_slot(EV_U, j));
+        bool any_fail = S.fail != 0;
+        if (tid == 0) {
+            const K1X& X = k1x();
+            const double* s_unom_r = X.misc;
+            const double* s_dist = X.misc + 8;
+            double rho = 0.0;
+            for (int j = 0; j < NF; j++) rho = __dadd_ru(rho, __dmul_ru(s_dist[j], s_dist[j]));
+            const double nrm = __dsqrt_ru(rho);
+            for (int j = 0; j < NF && !any_fail; j++) {
+                double v = __dadd_ru(__dmul_ru(__dmul_ru(rc.alpha, rc.M_max - rc.M_min), rc.eps), 0.5 * s_dist[j]);
+                v = __dadd_ru(v, 0.5 * nrm);
+                v = __dadd_ru(v, s_unom_r[j]);
+                v = __dadd_ru(v, rc.friction[j]);
+                B.torque_radius[size_t(p) * NF * B.T + size_t(j) * B.T + t] = __dmul_ru(v, RADIUS_SLACK);
+            }
+        }
+        k1_sync();
+    } break;
+    }
+    return top_max;
+}
+#undef MG_DO
+
+// claim order of the tasks of one unit (a topological order; see DESIGN.md for the schedule it produces)
+K1_DI int mg_task_list(unsigned short* tasks, int NJ) {
+    int n = 0;
+    const int fwd[10] = {TK_W, TK_WA, TK_T4, TK_WD, TK_FKC, TK_LA, TK_T10, TK_TN, TK_TF, TK_FKL};
+    for (int i = 0; i < NJ; i++)
+        for (int q = 0; q < 10; q++) tasks[n++] = (unsigned short)((fwd[q] << 8) | i);
+    // backward: the force chain runs one joint ahead of the moment chain
+    for (int i = NJ - 1; i >= -2; i--) {
+        if (i >= 0) tasks[n++] = (unsigned short)((TK_FB << 8) | i);
+        if (i + 1 >= 0 && i + 1 < NJ) tasks[n++] = (unsigned short)((TK_NB << 8) | (i + 1));
+        if (i + 2 >= 0 && i + 2 < NJ) tasks[n++] = (unsigned short)((TK_U << 8) | (i + 2));
+    }
+    tasks[n++] = (unsigned short)(TK_EPI << 8);
+    return n;
+}
+#endif  // K1_MG
+
 // ---- kernel ---------------------------------------------------------------------------------------
 constexpr int K1_FIXED_BYTES = K1S_BYTES + JRS_WORDS * 8;  // per group: control block + joint reachable set region
 
 __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params P) {
+#if K1_MG
+    if (threadIdx.x == 0) {
+        K1X& X0 = k1x();
+        X0.group_bytes = P.group_bytes;
+        X0.seq = 0;
+        X0.mbox = P.mbox + size_t(blockIdx.x) * P.mbox_words;
+        X0.mbox_words = P.mbox_words;
+        X0.ntasks = mg_task_list(X0.tasks, P.B.NJ);
+    }
+    for (int i = threadIdx.x; i < MB_SLOTS; i += NT * GROUPS) k1x().ev[i] = 0;
+#else
     if (threadIdx.x == 0) *reinterpret_cast<int*>(smem_cta()) = P.group_bytes;
+#endif
     __syncthreads();
     K1S& S = k1s();
     const int tid = k1_tid();
@@ -703,6 +1035,7 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
         S.gbase = P.gscr + size_t(slot) * P.gscr_words;
         S.tab_g = P.gtab + size_t(slot) * P.gtab_bytes;
         S.thr = c_robot.simplify_threshold;
+        S.thr2 = threshold_sq(S.thr);
         S.AW = JRS_WORDS + P.arena_words;
         S.GW = P.gscr_words - P.fn_words;
         S.FW = P.fn_words;
@@ -722,6 +1055,54 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
     int nfail = 0, ndone = 0, top_max = 0;
     int* cta_unit = reinterpret_cast<int*>(smem_cta()) + 1;
     for (;;) {
+#if K1_MG
+        // one unit per CTA, built by all groups: claim it, reset the mailbox and the task cursor
+        if (threadIdx.x == 0) {
+            K1X& X0 = k1x();
+            *cta_unit = atomicAdd(P.work, 1);
+            X0.seq++;
+            X0.next = 0;
+            X0.bump = 0;
+        }
+        if (tid == 0) S.fail = 0;
+        __syncthreads();
+        int unit = *cta_unit;
+        if (unit >= nunits) break;
+        const bool extra = false;
+        int p, t;
+        if (P.units) {
+            unit = P.units[unit];
+            p = unit / P.B.T;
+            t = unit % P.B.T;
+        } else {
+            t = P.B.T - 1 - (unit / P.B.nprob);  // long intervals first
+            p = unit % P.B.nprob;
+        }
+        // joint reachable set: group 0 computes, the others copy its fixed region
+        if (k1_group() == 0) build_jrs(P.B, p, t);
+        __syncthreads();
+        if (k1_group() != 0) {
+            const unsigned char* g0 = smem_cta() + K1_HDR_BYTES;
+            const K1S* S0 = reinterpret_cast<const K1S*>(g0);
+            const double* a0 = reinterpret_cast<const double*>(g0 + K1S_BYTES);
+            for (int i = tid; i < JRS_WORDS; i += NT) arena0()[i] = a0[i];
+            for (int i = tid; i < 40; i += NT) S.jrs_n[i] = S0->jrs_n[i];
+        }
+        k1_sync();
+        int tm = 0;
+        for (;;) {
+            if (tid == 0) S.cnt[0] = atomicAdd(&k1x().next, 1);
+            k1_sync();
+            const int k = S.cnt[0];
+            k1_sync();
+            if (k >= k1x().ntasks) break;
+            const int code = k1x().tasks[k];
+            const int tk = run_task(P.B, p, t, code >> 8, code & 255);
+            tm = tk > tm ? tk : tm;
+        }
+        top_max = tm > top_max ? tm : top_max;
+        if (k1_group() == 0) ndone++;
+#else
         // one tile of GROUPS consecutive units per CTA; consecutive units are the SAME interval of consecutive
         // problems, i.e. equally long, so the groups stay in step
         if (threadIdx.x == 0) *cta_unit = atomicAdd(P.work, GROUPS);
@@ -754,9 +1135,10 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
 #endif
         top_max = tm > top_max ? tm : top_max;
         if (!extra) ndone++;
+#endif
         const int failed = S.fail;
         if (failed) {
-            if (!extra) nfail++;
+            if (!extra && (!MG || k1_group() == 0)) nfail++;
             if (tid == 0) atomicMax(&P.B.status[p], failed);
             // a failed operation may leave a table half-built: restore the all-zero invariant
             for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
@@ -764,6 +1146,7 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
             for (int i = tid; i < 2 * MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0u;
         }
         k1_sync();
+        if (MG) __syncthreads();  // the unit is complete in every group before the mailbox is reused
     }
     if (tid == 0 && P.stats) {
         atomicMax(&P.stats[0], top_max - JRS_WORDS);
@@ -787,6 +1170,8 @@ struct K1Scratch {
     int gscr_words = 0, fn_words = 0, gtab_bytes = 0;
     int arena_words = 0, tab_s_bytes = 0, group_bytes = 0;
     size_t smem_bytes = 0;
+    double* mbox = nullptr;
+    int mbox_words = 0;
     int h_stats[4] = {0, 0, 0, 0};
 };
 
@@ -795,6 +1180,7 @@ inline void k1_scratch_destroy(K1Scratch* s) {
     if (s->stats) cudaFree(s->stats);
     if (s->gscr) cudaFree(s->gscr);
     if (s->gtab) cudaFree(s->gtab);
+    if (s->mbox) cudaFree(s->mbox);
     *s = K1Scratch();
 }
 
@@ -807,12 +1193,12 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     // CTAS_PER_SM CTAs per SM: an equal share of the SM's shared memory each (1 KB per CTA is reserved by the system)
     int per_cta = (smem_optin + 1024) / CTAS_PER_SM - 1024;
     per_cta &= ~1023;
-    const int per_group = ((per_cta - 16) / GROUPS) & ~15;
+    const int per_group = ((per_cta - K1_HDR_BYTES) / GROUPS) & ~15;
     const int dyn = per_group - K1_FIXED_BYTES;
     s->tab_s_bytes = (dyn * K1_TAB_EIGHTHS / 8) & ~1023;  // scratch of the merge / hash passes; the rest is the PZ arena
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
     s->group_bytes = K1_FIXED_BYTES + s->arena_words * 8 + s->tab_s_bytes;
-    s->smem_bytes = 16 + size_t(GROUPS) * s->group_bytes;
+    s->smem_bytes = K1_HDR_BYTES + size_t(GROUPS) * s->group_bytes;
     s->grid = CTAS_PER_SM * sms;  // CTAs; each holds GROUPS scratch slots
     // per-CTA global scratch: arena spill space, then F_i / N_i of one unit; and the overflow hash-table pool
     const int capw = cfg.cap_work_monomials;
@@ -824,6 +1210,10 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     if ((e = cudaMalloc(&s->gscr, size_t(s->grid) * GROUPS * s->gscr_words * 8)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->gtab, size_t(s->grid) * GROUPS * s->gtab_bytes)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s->gtab, 0, size_t(s->grid) * GROUPS * s->gtab_bytes, st)) != cudaSuccess) return e;
+    if (MG) {  // mailbox of a CTA: every block a unit publishes (about 14 per joint), bump-allocated
+        s->mbox_words = 12 * (MAXJ + 1) * (9 + 4 * capw);
+        if ((e = cudaMalloc(&s->mbox, size_t(s->grid) * s->mbox_words * 8)) != cudaSuccess) return e;
+    }
     if ((e = cudaMemsetAsync(s->stats, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_reachsets, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->smem_bytes));
 }
@@ -846,9 +1236,11 @@ inline cudaError_t launch_reachsets(const Batch& B, K1Scratch& s, cudaStream_t s
     P.tab_s_bytes = s.tab_s_bytes;
     P.group_bytes = s.group_bytes;
     P.stats = s.stats;
+    P.mbox = s.mbox;
+    P.mbox_words = s.mbox_words;
     P.units = nullptr;
     P.nunits = 0;
-    const int ntiles = (B.nprob * B.T + GROUPS - 1) / GROUPS;
+    const int ntiles = MG ? B.nprob * B.T : (B.nprob * B.T + GROUPS - 1) / GROUPS;
     const int grid = ntiles < s.grid ? ntiles : s.grid;
     k_reachsets<<<grid, NT * GROUPS, s.smem_bytes, st>>>(P);
     *nlaunch = 1;

@@ -63,6 +63,8 @@ extern "C" int emu_k1_build(int model_id, int T, double thr, const double* k_ran
     P.units = units;
     P.nunits = nunits;
     P.stats = stats;
+    P.mbox = nullptr;
+    P.mbox_words = 0;
     P.group_bytes = k1::K1_FIXED_BYTES + arena_words * 8 + tab_s_bytes;
     const size_t smem = 16 + size_t(P.group_bytes);
     emu::launch(dim3(1), dim3(k1::NT), smem, [&]() { k1::k_reachsets(P); });

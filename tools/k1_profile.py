@@ -27,7 +27,8 @@ eng.synchronize()
 buf = np.zeros((128, SITES, 2), dtype=np.int64)
 lib.armour_debug_k1_profile(buf.ctypes.data_as(ctypes.c_void_p), 0)
 cyc = buf[:, :, 0] / REPS
-line = buf[:, :, 1]
+line = buf[:, :, 1] & 0xffffffff
+nmax = buf[:, :, 1] >> 32
 unit = cyc[:, SITES - 1]
 print("unit cycles: min %.0f  median %.0f  max %.0f (t=%d)  sum/128 %.0f" % (unit.min(), np.median(unit), unit.max(), unit.argmax(), unit.mean()))
 print("per-interval:", " ".join("%d" % (u / 1000) for u in unit), "(kcycles)")
@@ -35,10 +36,11 @@ t = int(unit.argmax())
 ops = cyc[t, :SITES - 1]
 tot_ops = ops.sum()
 print(f"slowest interval t={t}: unit {unit[t]:.0f} cycles, operation sites {tot_ops:.0f} ({100*tot_ops/unit[t]:.1f}%)")
-by_line = {}
+by_line, n_line = {}, {}
 for s in range(SITES - 1):
     if ops[s] > 0:
         by_line[int(line[t, s])] = by_line.get(int(line[t, s]), 0) + ops[s]
+        n_line[int(line[t, s])] = max(n_line.get(int(line[t, s]), 0), int(nmax[t, s]))
 src = open(os.path.join(ROOT, "armour_b200", "csrc", "k1_reachsets.cuh")).read().split("\n")
 for ln, c in sorted(by_line.items(), key=lambda kv: -kv[1]):
-    print(f"  {100*c/unit[t]:5.1f}%  {c:9.0f}  L{ln}: {src[ln-1].strip()[:100]}")
+    print(f"  {100*c/unit[t]:5.1f}%  {c:9.0f}  nmax {n_line[ln]:4d}  L{ln}: {src[ln-1].strip()[:100]}")
