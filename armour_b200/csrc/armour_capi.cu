@@ -20,6 +20,7 @@
 #ifdef K1_PROFILE
 constexpr int K1_PROF_SITES = 512;
 __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
+__device__ int g_k1spill[4];  // arena blocks in global memory, all arena blocks, scratch pools in global memory
 #endif
 // Latency configuration: MG mode, K1LAT_GROUPS groups of K1LAT_NT threads build ONE unit together (one CTA per SM)
 #ifndef K1LAT_NT
@@ -34,10 +35,10 @@ __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
 #ifndef K1LAT_MG
 #define K1LAT_MG 1
 #endif
-#ifndef K1LAT_TAB_EIGHTHS
-#define K1LAT_TAB_EIGHTHS 5
+#ifndef K1LAT_TAB_16THS
+#define K1LAT_TAB_16THS 11  // share (in sixteenths) of a group's dynamic shared memory given to the scratch pool
 #endif
-#define K1_TAB_EIGHTHS K1LAT_TAB_EIGHTHS
+#define K1_TAB_16THS K1LAT_TAB_16THS
 #define K1_NS k1lat
 #define K1_NT K1LAT_NT
 #define K1_CTAS K1LAT_CTAS
@@ -49,6 +50,7 @@ __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
 #undef K1_CTAS
 #undef K1_GROUPS
 #undef K1_MG
+#undef K1_TAB_16THS
 #define K1_MG 0
 #ifndef K1THR_NT
 #define K1THR_NT 64
@@ -64,6 +66,7 @@ __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
 #endif
 #undef K1_TAB_EIGHTHS
 #define K1_TAB_EIGHTHS K1THR_TAB_EIGHTHS
+#define K1_TAB_16THS (2 * K1THR_TAB_EIGHTHS)
 #define K1_NS k1thr
 #define K1_NT K1THR_NT
 #define K1_CTAS K1THR_CTAS
@@ -480,6 +483,11 @@ int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, in
 // developer builds only: per-(interval, operation site) cycle counts of the last single-problem builds
 extern "C" int armour_debug_k1_profile(long long* out, int reset) {
     cudaDeviceSynchronize();
+    if (out) {
+        int sp[4];
+        if (cudaMemcpyFromSymbol(sp, g_k1spill, sizeof(sp)) == cudaSuccess)
+            std::printf("k1 profile: %d of %d arena blocks in global memory, %d scratch pools in global memory\n", sp[0], sp[1], sp[2]);
+    }
     if (out && cudaMemcpyFromSymbol(out, g_k1prof, sizeof(long long) * 128 * K1_PROF_SITES * 2) != cudaSuccess) return ARMOUR_ERR_CUDA;
     if (reset) {
         void* p = nullptr;

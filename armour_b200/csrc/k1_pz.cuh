@@ -234,6 +234,10 @@ K1_DI PZ8 pz_alloc(int top, int n, bool* ok) {
         *ok = false;
         return h;
     }
+#ifdef K1_PROFILE
+    if (k1_tid() == 0 && at >= S.AW) atomicAdd(&g_k1spill[0], 1);
+    if (k1_tid() == 0) atomicAdd(&g_k1spill[1], 1);
+#endif
     h.off = at;
     h.n = n;
     *ok = true;
@@ -348,6 +352,9 @@ K1_DI bool tab_select(int nterms, int na, Tab& t) {
     } else if (cap * slot_bytes <= S.tab_g_bytes) {
         base = S.tab_g;
         if (k1_tid() == 0) S.n_tab_global++;
+#ifdef K1_PROFILE
+        if (k1_tid() == 0) atomicAdd(&g_k1spill[2], 1);
+#endif
     } else {
         set_fail(FAIL_TABLE);
         return false;
@@ -578,6 +585,9 @@ K1_DI bool dense_select(int M, int sz, Dense& d) {
         base = S.tab_g;
         d.global = true;
         if (k1_tid() == 0) S.n_tab_global++;
+#ifdef K1_PROFILE
+        if (k1_tid() == 0) atomicAdd(&g_k1spill[2], 1);
+#endif
     } else {
         set_fail(FAIL_TABLE);
         return false;
@@ -1179,19 +1189,45 @@ K1_OP PZ8 op_mul33(int top, PZ8 L8, PZ8 R8) {
         const u64 ko_a = (a == 1) ? ko[0] : ((a == 2) ? ko[1] : ko[2]);
         const u64 ko_j = (j == 0) ? ko[0] : ((j == 1) ? ko[1] : ko[2]);
         const u64 key = (a == 0) ? kI[j] : ((a <= nO) ? kI[j] + ko_a : ko_j);
-        // rank and hit of `key` in every list
+        // rank and hit of `key` in every list: list b holds kI[.] + (b ? ko[b-1] : 0), so the rank of `key` there
+        // is the rank of key - ko[b-1] in kI.  The four binary searches run over the same array with the same step
+        // sequence: one loop, four independent probes per step (the latency of one search instead of four); the
+        // search in the candidate's own list is known without looking (rank j, hit).
         int lb[MUL_MAX_OUTER + 1];
         bool hit[MUL_MAX_OUTER + 1];
-        lb[0] = lower_bound(kI, nI, key);
-        hit[0] = lb[0] < nI && kI[lb[0]] == key;
+        {
+            u64 tg[MUL_MAX_OUTER + 1];
+            bool on[MUL_MAX_OUTER + 1];
+            tg[0] = key;
+            on[0] = (a != 0);
 #pragma unroll
-        for (int o = 0; o < MUL_MAX_OUTER; o++) {
-            lb[o + 1] = 0;
-            hit[o + 1] = false;
-            if (o < nO && key >= ko[o]) {
-                const u64 target = key - ko[o];
-                lb[o + 1] = lower_bound(kI, nI, target);
-                hit[o + 1] = lb[o + 1] < nI && kI[lb[o + 1]] == target;
+            for (int o = 0; o < MUL_MAX_OUTER; o++) {
+                on[o + 1] = o < nO && key >= ko[o] && a != o + 1;
+                tg[o + 1] = key - ((o < nO) ? ko[o] : 0ull);
+            }
+#pragma unroll
+            for (int b = 0; b <= MUL_MAX_OUTER; b++) lb[b] = 0;
+            int step = 1;
+            while (step < nI) step <<= 1;
+            for (; step > 0; step >>= 1) {
+#pragma unroll
+                for (int b = 0; b <= MUL_MAX_OUTER; b++) {
+                    const int probe = lb[b] + step;
+                    if (on[b] && probe <= nI && kI[probe - 1] < tg[b]) lb[b] = probe;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b <= MUL_MAX_OUTER; b++) {
+                hit[b] = on[b] && lb[b] < nI && kI[lb[b]] == tg[b];
+                if (!on[b]) lb[b] = 0;
+            }
+            if (a <= nO) {  // own list: element j itself
+#pragma unroll
+                for (int b = 0; b <= MUL_MAX_OUTER; b++)
+                    if (b == a) {
+                        lb[b] = j;
+                        hit[b] = true;
+                    }
             }
         }
         int lbH = 0, hitH = -1;
@@ -1383,10 +1419,16 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
     const long long Pll = (long long)nA + nB + (long long)nA * nB;
     if (Pll > (1 << 20) || nO > 65000 || nI > 65535) return false;
     const int P = int(Pll);
+    // the table holds keys only and equal keys share a slot: sized for a load of at most 0.94 if every term had
+    // its own key (about half of them do), 2/3 when that still fits the pool
     int cap = 64, lg = 6;
     while (cap * 2 < P * 3) {
         cap <<= 1;
         lg++;
+    }
+    if (size_t(cap) * 12 + size_t(P) * 4 + 2048 > size_t(S.tab_s_bytes) && (cap >> 1) >= P + (P >> 4)) {
+        cap >>= 1;
+        lg--;
     }
     const size_t fixed = (size_t(cap) * 12 + size_t(P) * 4 + 7) & ~size_t(7);
     if (fixed + 32 * 32 > size_t(S.tab_s_bytes)) return false;

@@ -738,8 +738,14 @@ K1_DI void ev_wait(int slot) {
     if (k1_tid() == 0) {
         K1X& X = k1x();
         const int seq = X.seq;
+#ifdef K1_PROFILE
+        const long long _w0 = clock64();
+#endif
         while (reinterpret_cast<volatile int*>(X.ev)[slot] != seq) __nanosleep(40);
         __threadfence_block();
+#ifdef K1_PROFILE
+        k1s().red2[NW * RED_STRIDE - 1] += double(clock64() - _w0);  // (thread 0 only; last word is otherwise unused)
+#endif
     }
     k1_sync();
 }
@@ -750,24 +756,21 @@ K1_DI void mb_publish(int slot, PZ8 h) {
     K1X& X = k1x();
     const int tid = k1_tid();
     const int w = pz_words(h.n, SZ);
-    if (tid == 0) S.cnt[0] = atomicAdd(&X.bump, w);
-    k1_sync();
-    const int off = S.cnt[0];
-    const bool ok = !S.fail && off + w <= X.mbox_words;
+    const bool ok = !S.fail && w <= X.mbox_words;  // mbox_words: words of ONE slot
     if (ok) {
         const double* src = vptr(h.off);
-        double* dst = X.mbox + off;
+        double* dst = X.mbox + size_t(slot) * X.mbox_words;
         for (int i = tid; i < w; i += NT) dst[i] = src[i];
     } else {
         set_fail(FAIL_SCRATCH);
     }
-    k1_sync();
     if (tid == 0) {
         PZ8 m;
-        m.off = ok ? off : -1;
+        m.off = ok ? 0 : -1;
         m.n = ok ? h.n : 0;
         X.mb[slot] = m;
     }
+    k1_sync();
     ev_signal(slot);
 }
 // wait for block `slot` and copy it into the arena at `top`
@@ -782,7 +785,7 @@ K1_DI PZ8 mb_import(int slot, int top) {
     const PZ8 h = pz_alloc<SZ>(top, m.off < 0 ? 0 : m.n, &ok);
     if (ok) {
         const int w = pz_words(h.n, SZ);
-        const double* src = X.mbox + m.off;
+        const double* src = X.mbox + size_t(slot) * X.mbox_words;
         double* dst = vptr(h.off);
         for (int i = tid; i < w; i += NT) dst[i] = src[i];
     }
@@ -935,24 +938,24 @@ K1_DI int run_task(const Batch& B, int p, int t, int kind, int i) {
         export_link(link, B, p, t, i);
     } break;
     case TK_FB: {  // backward pass, force chain: f_i = R_{i+1} f_{i+1} + F_i; also p_{i+1} x (R_{i+1} f_{i+1})
+        MG_DO(Fi, 3, mb_import<3>(mb_slot(MB_F, i), top));  // published long ago: fetched while the chain value is awaited
         PZ8 f;
         if (i == NJ - 1) f = pz_zero<3>(top); else f = mb_import<3>(mb_slot(MB_F2, i + 1), top);
         top = end_of<3>(f);
         MG_DO(a5, 3, op_mul33<1, false>(top, jrs_R(i + 1), f));
+        MG_DO(f2, 3, op_add<3>(top, a5, Fi));
+        mb_publish<3>(mb_slot(MB_F2, i), f2);  // the chain moves on before the side product is made
         MG_DO(a6, 3, op_cross_const(top, a5, &rc.trans[3 * (i + 1)], true));
         mb_publish<3>(mb_slot(MB_A6, i), a6);
-        MG_DO(Fi, 3, mb_import<3>(mb_slot(MB_F, i), top));
-        MG_DO(f2, 3, op_add<3>(top, a5, Fi));
-        mb_publish<3>(mb_slot(MB_F2, i), f2);
     } break;
     case TK_NB: {  // backward pass, moment chain: n_i = ((N_i + R_{i+1} n_{i+1}) + c_i x F_i) + p_{i+1} x (R f)
+        MG_DO(Ni, 3, mb_import<3>(mb_slot(MB_N, i), top));
+        MG_DO(a3, 3, mb_import<3>(mb_slot(MB_A3, i), top));
         PZ8 n;
         if (i == NJ - 1) n = pz_zero<3>(top); else n = mb_import<3>(mb_slot(MB_N2, i + 1), top);
         top = end_of<3>(n);
         MG_DO(a1, 3, op_mul33<1, false>(top, jrs_R(i + 1), n));
-        MG_DO(Ni, 3, mb_import<3>(mb_slot(MB_N, i), top));
         MG_DO(a2, 3, op_add<3>(top, Ni, a1));
-        MG_DO(a3, 3, mb_import<3>(mb_slot(MB_A3, i), top));
         MG_DO(a4, 3, op_add<3>(top, a2, a3));
         MG_DO(a6, 3, mb_import<3>(mb_slot(MB_A6, i), top));
         MG_DO(n2, 3, op_add<3>(top, a4, a6));
@@ -1019,7 +1022,7 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
         K1X& X0 = k1x();
         X0.group_bytes = P.group_bytes;
         X0.seq = 0;
-        X0.mbox = P.mbox + size_t(blockIdx.x) * P.mbox_words;
+        X0.mbox = P.mbox + size_t(blockIdx.x) * MB_SLOTS * P.mbox_words;
         X0.mbox_words = P.mbox_words;
         X0.ntasks = mg_task_list(X0.tasks, P.B.NJ);
     }
@@ -1078,6 +1081,9 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
             t = P.B.T - 1 - (unit / P.B.nprob);  // long intervals first
             p = unit % P.B.nprob;
         }
+#ifdef K1_PROFILE
+        const long long _u0 = clock64();
+#endif
         // joint reachable set: group 0 computes, the others copy its fixed region
         if (k1_group() == 0) build_jrs(P.B, p, t);
         __syncthreads();
@@ -1097,7 +1103,20 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
             k1_sync();
             if (k >= k1x().ntasks) break;
             const int code = k1x().tasks[k];
+#ifdef K1_PROFILE
+            const long long _c0 = clock64();
+            if (tid == 0) S.red2[NW * RED_STRIDE - 1] = 0.0;
+#endif
             const int tk = run_task(P.B, p, t, code >> 8, code & 255);
+#ifdef K1_PROFILE
+            if (tid == 0 && k < 255) {
+                long long* pp = g_k1prof + (size_t(t) * K1_PROF_SITES * 2) + size_t(k) * 4;
+                pp[0] = _c0 - _u0;
+                pp[1] = clock64() - _u0;
+                pp[2] = (long long)S.red2[NW * RED_STRIDE - 1];
+                pp[3] = code | (k1_group() << 16);
+            }
+#endif
             tm = tk > tm ? tk : tm;
         }
         top_max = tm > top_max ? tm : top_max;
@@ -1147,6 +1166,9 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
         }
         k1_sync();
         if (MG) __syncthreads();  // the unit is complete in every group before the mailbox is reused
+#if defined(K1_PROFILE) && K1_MG
+        if (threadIdx.x == 0) g_k1prof[(size_t(t) * 256 + 255) * 4] = clock64() - _u0;
+#endif
     }
     if (tid == 0 && P.stats) {
         atomicMax(&P.stats[0], top_max - JRS_WORDS);
@@ -1160,6 +1182,9 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
 // ---- host side: scratch buffers and launch ----------------------------------------------------------
 #ifndef K1_TAB_EIGHTHS
 #define K1_TAB_EIGHTHS 5
+#endif
+#ifndef K1_TAB_16THS
+#define K1_TAB_16THS (2 * K1_TAB_EIGHTHS)
 #endif
 struct K1Scratch {
     int* work = nullptr;
@@ -1195,7 +1220,7 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     per_cta &= ~1023;
     const int per_group = ((per_cta - K1_HDR_BYTES) / GROUPS) & ~15;
     const int dyn = per_group - K1_FIXED_BYTES;
-    s->tab_s_bytes = (dyn * K1_TAB_EIGHTHS / 8) & ~1023;  // scratch of the merge / hash passes; the rest is the PZ arena
+    s->tab_s_bytes = (dyn * K1_TAB_16THS / 16) & ~1023;  // scratch of the merge / hash passes; the rest is the PZ arena
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
     s->group_bytes = K1_FIXED_BYTES + s->arena_words * 8 + s->tab_s_bytes;
     s->smem_bytes = K1_HDR_BYTES + size_t(GROUPS) * s->group_bytes;
@@ -1210,9 +1235,9 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     if ((e = cudaMalloc(&s->gscr, size_t(s->grid) * GROUPS * s->gscr_words * 8)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->gtab, size_t(s->grid) * GROUPS * s->gtab_bytes)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s->gtab, 0, size_t(s->grid) * GROUPS * s->gtab_bytes, st)) != cudaSuccess) return e;
-    if (MG) {  // mailbox of a CTA: every block a unit publishes (about 14 per joint), bump-allocated
-        s->mbox_words = 12 * (MAXJ + 1) * (9 + 4 * capw);
-        if ((e = cudaMalloc(&s->mbox, size_t(s->grid) * s->mbox_words * 8)) != cudaSuccess) return e;
+    if (MG) {  // mailbox of a CTA: one fixed slot per published block
+        s->mbox_words = 27 + 4 * capw;
+        if ((e = cudaMalloc(&s->mbox, size_t(s->grid) * MB_SLOTS * s->mbox_words * 8)) != cudaSuccess) return e;
     }
     if ((e = cudaMemsetAsync(s->stats, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_reachsets, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->smem_bytes));

@@ -1,6 +1,6 @@
-"""Developer tool: per-operation-site cycle profile of the reach-set kernel for ONE planning problem.
-Needs a library built with -DK1_PROFILE (exp/lib_prof.so); prints, for the slowest interval, the cycles per
-operation site (source line of k1_reachsets.cuh) and the distribution of unit times over the 128 intervals."""
+"""Developer tool: task timeline of the reach-set kernel (MG latency configuration) for ONE planning problem.
+Needs a library built with -DK1_PROFILE (exp/lib_prof.so).  Prints the per-interval unit times and, for the slowest
+interval, every task with its claim time, end time, cycles spent waiting for inputs and the group that ran it."""
 import ctypes
 import os
 import sys
@@ -12,35 +12,34 @@ import numpy as np  # noqa: E402
 
 from armour_b200 import ReachSetEngine, worlds  # noqa: E402
 
-SITES = 512
+KINDS = ["W", "WA", "WD", "T4", "LA", "T10", "TF", "TN", "FKC", "FKL", "FB", "NB", "U", "EPI"]
 q0, qd0, qdd0, _, obs = worlds.config1_problem(os.path.join(ROOT, "tests", "golden", "worlds", "scene_016_006.csv"))
 eng = ReachSetEngine(max_problems=1, max_obstacles=obs.shape[0])
 lib = eng.lib
 lib.armour_debug_k1_profile.argtypes = [ctypes.c_void_p, ctypes.c_int]
-eng.build(q0, qd0, qdd0, obs)
-eng.synchronize()
-lib.armour_debug_k1_profile(None, 1)
-REPS = 5
-for _ in range(REPS):
+for _ in range(3):
     eng.build(q0, qd0, qdd0, obs)
 eng.synchronize()
-buf = np.zeros((128, SITES, 2), dtype=np.int64)
+buf = np.zeros((128, 256, 4), dtype=np.int64)
 lib.armour_debug_k1_profile(buf.ctypes.data_as(ctypes.c_void_p), 0)
-cyc = buf[:, :, 0] / REPS
-line = buf[:, :, 1] & 0xffffffff
-nmax = buf[:, :, 1] >> 32
-unit = cyc[:, SITES - 1]
-print("unit cycles: min %.0f  median %.0f  max %.0f (t=%d)  sum/128 %.0f" % (unit.min(), np.median(unit), unit.max(), unit.argmax(), unit.mean()))
-print("per-interval:", " ".join("%d" % (u / 1000) for u in unit), "(kcycles)")
+unit = buf[:, 255, 0]
+print("unit cycles: min %d median %d max %d (t=%d)" % (unit.min(), np.median(unit), unit.max(), unit.argmax()))
 t = int(unit.argmax())
-ops = cyc[t, :SITES - 1]
-tot_ops = ops.sum()
-print(f"slowest interval t={t}: unit {unit[t]:.0f} cycles, operation sites {tot_ops:.0f} ({100*tot_ops/unit[t]:.1f}%)")
-by_line, n_line = {}, {}
-for s in range(SITES - 1):
-    if ops[s] > 0:
-        by_line[int(line[t, s])] = by_line.get(int(line[t, s]), 0) + ops[s]
-        n_line[int(line[t, s])] = max(n_line.get(int(line[t, s]), 0), int(nmax[t, s]))
-src = open(os.path.join(ROOT, "armour_b200", "csrc", "k1_reachsets.cuh")).read().split("\n")
-for ln, c in sorted(by_line.items(), key=lambda kv: -kv[1]):
-    print(f"  {100*c/unit[t]:5.1f}%  {c:9.0f}  nmax {n_line[ln]:4d}  L{ln}: {src[ln-1].strip()[:100]}")
+rows = buf[t]
+busy = {}
+print(f"interval t={t}: task  group  claim  end  run  wait")
+for k in range(255):
+    c0, c1, w, code = rows[k]
+    if c1 == 0:
+        continue
+    g, kind, i = code >> 16, (code >> 8) & 255, code & 255
+    busy[g] = busy.get(g, 0) + (c1 - c0 - w)
+    print(f"  {k:3d} {KINDS[kind]:4s}({i}) g{g}  {c0:8d} {c1:8d}  run {c1-c0-w:7d}  wait {w:7d}")
+print("busy cycles per group:", busy, " unit:", unit[t])
+bykind = {}
+for k in range(255):
+    c0, c1, w, code = rows[k]
+    if c1:
+        kind = KINDS[(code >> 8) & 255]
+        bykind[kind] = bykind.get(kind, 0) + (c1 - c0 - w)
+print("run cycles per task kind:", bykind)
