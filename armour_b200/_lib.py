@@ -80,6 +80,7 @@ SIGNATURES = {
     "armour_batch_get_bounds": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
     "armour_batch_get_build_status": (C.c_int, [C.c_void_p, C.c_int, ip]),
     "armour_batch_get_monomial_counts": (C.c_int, [C.c_void_p, C.c_int, ip, ip]),
+    "armour_batch_get_candidate_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "armour_measure_fp64_peak": (C.c_int, [C.c_void_p, dp]),
     "armour_export_reachsets": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ReachsetTables)]),
     "armour_import_reachsets": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ReachsetTables), dp, dp, dp, dp,

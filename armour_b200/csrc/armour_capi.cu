@@ -479,6 +479,14 @@ int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, in
     return ARMOUR_OK;
 }
 
+int armour_batch_get_candidate_counts(armour_ctx* ctx, int nprob, unsigned char* out) {
+    if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
+    const size_t rows = size_t(ctx->B.NJ) * ctx->B.T * ctx->B.O;
+    if (rows) CU(cudaMemcpyAsync(out, ctx->B.hp_cnt, nprob * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+
 #ifdef K1_PROFILE
 // developer builds only: per-(interval, operation site) cycle counts of the last single-problem builds
 extern "C" int armour_debug_k1_profile(long long* out, int reset) {

@@ -92,6 +92,7 @@ __device__ __forceinline__ void load_row_generators(const double* __restrict__ o
 // transitive, so testing against all earlier candidates that pass the filter equals the sequential rule),
 // step 4 writes the survivors at their scan-order positions.  Bit-identical lists to a sequential scan.
 constexpr int HP_ROWS = 8;
+constexpr int HP_STAGE = 32;  // link monomials staged in shared memory per row (longer tables are read from global)
 constexpr int HP_THREADS = HP_ROWS * NCOMB;  // 288
 __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
     const int p = blockIdx.y;
@@ -103,6 +104,9 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
     __shared__ double s_G[HP_ROWS][9][3], s_oc[HP_ROWS][3], s_c[HP_ROWS][3];
     __shared__ double s_A[HP_ROWS][NCOMB][3], s_b[HP_ROWS][2 * NCOMB], s_up[HP_ROWS][2 * NCOMB], s_lo[HP_ROWS][NCOMB];
     __shared__ double s_lomax[HP_ROWS];
+    __shared__ double s_vc[HP_ROWS][2 * NCOMB];           // value of each signed half-space at the centre of the k box
+    __shared__ double s_gm[HP_ROWS][HP_STAGE][3];        // monomial coefficients of the row's link reach set
+    __shared__ int s_best[HP_ROWS];                        // signed half-space with the best guaranteed lower bound
     __shared__ unsigned char s_flag[HP_ROWS][2 * NCOMB], s_pos[HP_ROWS][2 * NCOMB];
     __shared__ int s_count[HP_ROWS];
     const bool live = r < rows_total;
@@ -121,6 +125,9 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
         } else if (pi < 33) {
             s_c[lr][pi - 30] = B.link_c[idx * 3 + (pi - 30)];
         }
+        const int n = B.link_n[idx];
+        const int ns = n < HP_STAGE ? n : HP_STAGE;
+        for (int q = pi; q < ns * 3; q += NCOMB) s_gm[lr][q / 3][q % 3] = B.link_g[idx * B.capL * 3 + q];
     }
     __syncthreads();
     bool nz = false;
@@ -146,10 +153,13 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
         const double vpos = dot - (d + delta);
         const double vneg = -dot - (-d + delta);
         const int n = B.link_n[idx];
+        const int ns = n < HP_STAGE ? n : HP_STAGE;
         const double* __restrict__ lg = B.link_g + idx * B.capL * 3;
         double rr = 0.0;
 #pragma unroll 1
-        for (int mI = 0; mI < n; mI++) rr += fabs(C0 * lg[mI * 3 + 0] + C1 * lg[mI * 3 + 1] + C2 * lg[mI * 3 + 2]);
+        for (int mI = 0; mI < ns; mI++) rr += fabs(C0 * s_gm[lr][mI][0] + C1 * s_gm[lr][mI][1] + C2 * s_gm[lr][mI][2]);
+#pragma unroll 1
+        for (int mI = ns; mI < n; mI++) rr += fabs(C0 * lg[mI * 3 + 0] + C1 * lg[mI * 3 + 1] + C2 * lg[mI * 3 + 2]);
         // |k_j| <= K_DOMAIN, total degree <= 21; plus evaluation round-off (values are O(1))
         const double rho = rr * HP_RHO_SCALE + (1e-10 + 1e-12 * (fabs(dot) + fabs(d) + delta));
         s_A[lr][pi][0] = C0;
@@ -160,13 +170,58 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
         s_up[lr][2 * pi] = nz ? vpos + rho : -1e300;
         s_up[lr][2 * pi + 1] = nz ? vneg + rho : -1e300;
         s_lo[lr][pi] = nz ? fmax(vpos, vneg) - rho : -1e300;
+        s_vc[lr][2 * pi] = vpos;
+        s_vc[lr][2 * pi + 1] = vneg;
     }
     __syncthreads();
-    if (live && pi == 0) {  // step 2: the best guaranteed lower bound of the row
+    if (live && pi == 0) {  // step 2: the best guaranteed lower bound of the row, and who holds it
         double lo_max = -100000000;
+        int best = -1;
 #pragma unroll 1
-        for (int i = 0; i < NCOMB; i++) lo_max = fmax(lo_max, s_lo[lr][i]);
+        for (int i = 0; i < NCOMB; i++) {
+            if (s_lo[lr][i] > lo_max) {
+                lo_max = s_lo[lr][i];
+                best = 2 * i + (s_vc[lr][2 * i + 1] > s_vc[lr][2 * i] ? 1 : 0);
+            }
+        }
         s_lomax[lr] = lo_max;
+        s_best[lr] = best;
+    }
+    __syncthreads();
+    // step 2b: pairwise test against that half-space j.  v_j(k) - v_i(k) = (vc_j - vc_i) + (A_j - A_i) . sum_m g_m mono_m(k)
+    // >= (vc_j - vc_i) - sum_m |(A_j - A_i) . g_m| for every k of the box: the variation the two half-spaces share
+    // cancels, so this removes the half-spaces that are nearly parallel to j but further out, which the separate
+    // bounds of step 1 cannot.  i is dropped only when the difference is positive by a margin (never on a tie), so
+    // the maximum over the survivors and its first attaining index are those of the full scan.
+    bool drop[2] = {false, false};
+    if (live && nz && s_best[lr] >= 0) {
+        const int jb = s_best[lr];
+        const double sj = (jb & 1) ? -1.0 : 1.0;
+        const double J0 = sj * s_A[lr][jb >> 1][0], J1 = sj * s_A[lr][jb >> 1][1], J2 = sj * s_A[lr][jb >> 1][2];
+        const double vj = s_vc[lr][jb];
+        const int n = B.link_n[idx];
+        const int ns = n < HP_STAGE ? n : HP_STAGE;
+        const double* __restrict__ lg = B.link_g + idx * B.capL * 3;
+#pragma unroll 1
+        for (int sgn = 0; sgn < 2; sgn++) {
+            const int sI = 2 * pi + sgn;
+            if (sI == jb || !(s_up[lr][sI] >= s_lomax[lr])) continue;
+            const double sg = sgn ? -1.0 : 1.0;
+            const double D0 = J0 - sg * s_A[lr][pi][0], D1 = J1 - sg * s_A[lr][pi][1], D2 = J2 - sg * s_A[lr][pi][2];
+            double rd = 0.0;
+#pragma unroll 1
+            for (int mI = 0; mI < ns; mI++) rd += fabs(D0 * s_gm[lr][mI][0] + D1 * s_gm[lr][mI][1] + D2 * s_gm[lr][mI][2]);
+#pragma unroll 1
+            for (int mI = ns; mI < n; mI++) rd += fabs(D0 * lg[mI * 3 + 0] + D1 * lg[mI * 3 + 1] + D2 * lg[mI * 3 + 2]);
+            const double vi = s_vc[lr][sI];
+            const double margin = rd * HP_RHO_SCALE + (1e-10 + 1e-12 * (fabs(vi) + fabs(vj) + fabs(s_b[lr][sI]) + fabs(s_b[lr][jb])));
+            drop[sgn] = (vj - vi) > margin;
+        }
+    }
+    __syncthreads();
+    if (live) {
+        if (drop[0]) s_up[lr][2 * pi] = -1e300;
+        if (drop[1]) s_up[lr][2 * pi + 1] = -1e300;
     }
     __syncthreads();
     if (live) {  // step 3: which of my two candidates survive

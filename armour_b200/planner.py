@@ -117,6 +117,14 @@ class ReachSetEngine:
                                                               un.ctypes.data_as(_lib.ip)))
         return ln, un
 
+    def candidate_counts(self):
+        """Stored collision half-space candidates per row, uint8 [nprob, T/8, NJ, 8, O] (255: evaluated from the
+        generators)."""
+        out = np.zeros((self.nprob, self.T // 8, self.NJ, 8, max(self.nobs, 0)), np.uint8)
+        if out.size:
+            self._check(self.lib.armour_batch_get_candidate_counts(self._h, self.nprob, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def measure_fp64_peak(self):
         """Sustained non-tensor FP64 rate of the device in TFLOP/s (FMA probe kernel in the library)."""
         v = C.c_double(0)

@@ -135,6 +135,11 @@ int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out);
 /* Stored k-only monomial counts of the built reach sets: link_n[nprob*T*NJ], u_n[nprob*T*NF] (either may
  * be NULL).  bench.py derives the algorithmic bytes of one evaluation from them (SURVEY.md 8d B_eval). */
 int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, int* u_n);
+/* Stored collision half-space candidates per (link, interval, obstacle) row, out[nprob][T/8][NJ][8][O] bytes in
+ * the kernel's chunk order (255 = row evaluated from the generators).  bench.py reports the candidate bytes one
+ * evaluation streams; there is no counterpart in the reference, which stores all 72 half-spaces per row
+ * (KPR/CollisionChecking.cu:169-228). */
+int armour_batch_get_candidate_counts(armour_ctx* ctx, int nprob, unsigned char* out);
 /* Measurement aid: runs a dependent-chain-free FP64 FMA kernel on the context's device and returns the
  * sustained non-tensor FP64 rate in TFLOP/s (the FP64 roofline denominator). */
 int armour_measure_fp64_peak(armour_ctx* ctx, double* tflops);

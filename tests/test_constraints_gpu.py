@@ -120,3 +120,29 @@ def test_error_paths(built):
     with pytest.raises(ArmourError) as ei:  # too many obstacles (reference throws, CollisionChecking.cu:10-13)
         eng.build(np.zeros(7), np.zeros(7), np.zeros(7), np.zeros((3, 12)))
     assert ei.value.code == -3
+
+
+def test_candidate_lists_are_exact_over_the_whole_box(built):
+    """The build keeps only the half-spaces that can attain a row's maximum somewhere in the k box (interval
+    bound + pairwise test against the best one).  Dropping a half-space that wins anywhere would change g or
+    its gradient there: compare with the oracle's full 72-half-space scan on a dense sample of the box, its
+    corners and points on its faces."""
+    from armour_b200 import ReachSetEngine, worlds
+    from oracle.pyoracle import OracleProblem
+    rng = np.random.default_rng(12)
+    for pi in (0, 3):
+        q0, qd0, qdd0, q_des, obs = _problems()[pi]
+        ref = OracleProblem().build(q0, qd0, qdd0, obs)
+        eng = ReachSetEngine(max_problems=1, max_obstacles=obs.shape[0])
+        eng.import_reachsets(0, 1, ref.tables(), q0, qd0, qdd0, obs)
+        cnt = eng.candidate_counts()
+        assert cnt.max() != 255 and cnt.min() >= 1
+        assert cnt.mean() < 6.0, cnt.mean()   # the point of the lists: a few half-spaces per row instead of 72
+        corners = rng.choice([-1.0, 1.0], size=(24, 7))
+        faces = rng.uniform(-1, 1, size=(24, 7))
+        faces[np.arange(24), rng.integers(0, 7, 24)] = rng.choice([-1.0, 1.0], 24)
+        ks = np.vstack([worlds.halton_k(48, skip=3), corners, faces])
+        for k in ks:
+            g, jac = eng.eval(k)
+            assert np.max(np.abs(g[0] - ref.eval_g(k))) <= TOL
+            assert np.max(np.abs(jac[0] - ref.eval_jac_g(k))) <= TOL
