@@ -315,8 +315,8 @@ __device__ __noinline__ void row_from_generators(const double* __restrict__ ob, 
 // PZsparse::slice (KPR/PZsparse.cu:404-435) and its gradient overloads (:477-555); a factor with
 // d_j = 0 is 1.0 and is skipped (exact).  D[v] carries coef * prod_{j<v} f_j * f'_v * prod_{v<j} f_j.
 __device__ __forceinline__ void slice_component(const uint16_t* __restrict__ keys, const double* __restrict__ coef,
-                                                int n, int kstride, int cstride, const double (*kp)[4],
-                                                const double (*dkp)[4], double& value, double (&grad)[NF]) {
+                                                int n, int kstride, int cstride, const double2 (*kpd)[4], double& value,
+                                                double (&grad)[NF]) {
     constexpr int CH = 8;  // monomials fetched together: the loads of a chunk are independent and overlap
     for (int m0 = 0; m0 < n; m0 += CH) {
         unsigned kk[CH];
@@ -338,18 +338,16 @@ __device__ __forceinline__ void slice_component(const uint16_t* __restrict__ key
                 kk[q] = kk[q + 1];
                 cc[q] = cc[q + 1];
             }
+            // No branch on the degree: kpd[j][0] = {1, 0}, and x * 1.0 is exact, val * 0.0 adds a zero to the
+            // gradient: the same values as skipping the factor, without seven divergent branches per monomial.
             double D[NF];
 #pragma unroll
             for (int j = 0; j < NF; j++) {
-                const int dg = (key >> (2 * j)) & 3;
-                D[j] = 0.0;
-                if (dg) {
-                    const double f = kp[j][dg], df = dkp[j][dg];
-                    D[j] = val * df;
+                const double2 fd = kpd[j][(key >> (2 * j)) & 3];
+                D[j] = val * fd.y;
 #pragma unroll
-                    for (int v = 0; v < j; v++) D[v] *= f;
-                    val *= f;
-                }
+                for (int v = 0; v < j; v++) D[v] *= fd.x;
+                val *= fd.x;
             }
             value += val;
 #pragma unroll
@@ -366,6 +364,7 @@ __device__ __forceinline__ void slice_component(const uint16_t* __restrict__ key
 constexpr int K3_LINK_THREADS = 192;
 constexpr int K3_TORQUE_LANES = 2;
 constexpr int K3_THREADS = 320;
+constexpr int K3_CNT_SMEM = 2048;  // rows per CTA whose candidate counts are staged in shared memory
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_TORQUE_T0 = K3_LINK_THREADS;
 static_assert(TB * 3 * MAXJ <= K3_LINK_THREADS && K3_TORQUE_T0 + TB * NF * K3_TORQUE_LANES <= K3_THREADS,
@@ -377,7 +376,8 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int m = B.m();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ double kp[NF][4], dkp[NF][4];
+    __shared__ double2 kpd[NF][4];  // {k_j^d, d/dk_j k_j^d} for d = 0..3
+    __shared__ __align__(4) unsigned char s_cnt[K3_CNT_SMEM];  // candidate counts of this CTA's rows
     __shared__ double s_lc[TB][MAXJ][3];
     __shared__ double s_dlc[TB][MAXJ][NF][3];
     __shared__ double s_stage[K3_WARPS][32 * NF];  // per-warp transpose buffer: Jacobian rows leave coalesced
@@ -392,15 +392,14 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     }
     if (tid < NF) {
         const double k = kin[size_t(p) * NF + tid];
-        kp[tid][0] = 1.0;
-        kp[tid][1] = k;
-        kp[tid][2] = k * k;
-        kp[tid][3] = k * k * k;
-        dkp[tid][0] = 0.0;
-        dkp[tid][1] = 1.0;
-        dkp[tid][2] = 2.0 * k;
-        dkp[tid][3] = 3.0 * (k * k);
+        kpd[tid][0] = make_double2(1.0, 0.0);
+        kpd[tid][1] = make_double2(k, 1.0);
+        kpd[tid][2] = make_double2(k * k, 2.0 * k);
+        kpd[tid][3] = make_double2(k * k * k, 3.0 * (k * k));
     }
+    const int per_pair = NJ * TB * O;
+    const size_t chunk = size_t(p) * (T / TB) + tb;
+    const bool cnt_in_smem = per_pair <= K3_CNT_SMEM;
     __syncthreads();
 
     double* gp = g ? g + size_t(p) * m : nullptr;
@@ -408,6 +407,15 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 
     // ---- phase 1: slices
     if (tid < K3_LINK_THREADS) {
+        // candidate counts of the CTA's rows: fetched now, parked in shared memory after the slice (the loads are in
+        // flight meanwhile), visible to everybody through barriers 1 and 2.  per_pair is a multiple of 8: whole words
+        constexpr int CW = (K3_CNT_SMEM / 4 + K3_LINK_THREADS - 1) / K3_LINK_THREADS;
+        unsigned cw[CW];
+        if (cnt_in_smem) {
+            const unsigned* src = reinterpret_cast<const unsigned*>(B.hp_cnt + chunk * per_pair);
+#pragma unroll
+            for (int q = 0; q < CW; q++) cw[q] = (tid + q * K3_LINK_THREADS < per_pair / 4) ? __ldg(src + tid + q * K3_LINK_THREADS) : 0u;
+        }
         if (tid < TB * NJ * 3) {
             const int e = tid % 3;
             const int l = (tid / 3) % NJ;
@@ -415,8 +423,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
             double value = B.link_c[idx * 3 + e];
             double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
-            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 1, 3, kp, dkp, value,
-                            grad);
+            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 1, 3, kpd, value, grad);
             // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
             const double r = B.link_gens[idx * 18 + e + (3 + e) * 3];
             const double c = ((value - r) + (value + r)) * 0.5;
@@ -424,6 +431,11 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             B.link_sliced[idx * 3 + e] = c;
 #pragma unroll
             for (int v = 0; v < NF; v++) s_dlc[tt][l][v][e] = grad[v];
+        }
+        if (cnt_in_smem) {
+#pragma unroll
+            for (int q = 0; q < CW; q++)
+                if (tid + q * K3_LINK_THREADS < per_pair / 4) reinterpret_cast<unsigned*>(s_cnt)[tid + q * K3_LINK_THREADS] = cw[q];
         }
         asm volatile("bar.sync 1, %0;" ::"n"(K3_LINK_THREADS) : "memory");    // link slices complete
         asm volatile("bar.arrive 2, %0;" ::"n"(K3_THREADS) : "memory");       // tell the torque warps, do not wait
@@ -440,7 +452,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             const int n = B.u_n[idx];
             const int mine = (n - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
             slice_component(B.u_key + idx * B.capU + part, B.u_g + idx * B.capU + part, mine > 0 ? mine : 0,
-                            K3_TORQUE_LANES, K3_TORQUE_LANES, kp, dkp, value, grad);
+                            K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
         }
         value += __shfl_xor_sync(0xffffffffu, value, 1);
 #pragma unroll
@@ -463,8 +475,6 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     }
 
     // ---- phase 2: collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
-    const int per_pair = NJ * TB * O;
-    const size_t chunk = size_t(p) * (T / TB) + tb;
     const double* cand = B.hp_cand + chunk * B.hp_chunk();
     const unsigned char* cnt = B.hp_cnt + chunk * per_pair;
     const size_t cstride2 = size_t(per_pair) * 2;  // candidate stride in double2 units
@@ -486,7 +496,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             tt = ltt % TB;
             l = ltt / TB;
             const double c0 = s_lc[tt][l][0], c1 = s_lc[tt][l][1], c2 = s_lc[tt][l][2];
-            const int n = cnt[x];
+            const int n = cnt_in_smem ? s_cnt[x] : cnt[x];
             if (n != HP_OVERFLOW && in_domain) {
                 const double2* row = reinterpret_cast<const double2*>(cand) + size_t(x) * 2;
                 // four candidate records in flight per thread (the scan itself stays in order)
