@@ -24,6 +24,17 @@
 
 namespace armour {
 
+// tuning knobs of k_constraints (see the sweep quoted at the kernel)
+#ifndef K3_CH
+#define K3_CH 2   // monomials of a table fetched together by a slicing thread
+#endif
+#ifndef K3_CQ
+#define K3_CQ 2   // candidate records in flight per collision row (2.05 stored per row on average)
+#endif
+#ifndef K3_MINB
+#define K3_MINB 4 // resident CTAs per SM the register budget is sized for (48 registers per thread)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Collision half-spaces of one (link, interval, obstacle) row.
 //
@@ -317,7 +328,7 @@ __device__ __noinline__ void row_from_generators(const double* __restrict__ ob, 
 __device__ __forceinline__ void slice_component(const uint16_t* __restrict__ keys, const double* __restrict__ coef,
                                                 int n, int kstride, int cstride, const double2 (*kpd)[4], double& value,
                                                 double (&grad)[NF]) {
-    constexpr int CH = 8;  // monomials fetched together: the loads of a chunk are independent and overlap
+    constexpr int CH = K3_CH;  // monomials fetched together: the loads of a chunk are independent and overlap
     for (int m0 = 0; m0 < n; m0 += CH) {
         unsigned kk[CH];
         double cc[CH];
@@ -370,7 +381,11 @@ constexpr int K3_TORQUE_T0 = K3_LINK_THREADS;
 static_assert(TB * 3 * MAXJ <= K3_LINK_THREADS && K3_TORQUE_T0 + TB * NF * K3_TORQUE_LANES <= K3_THREADS,
               "thread map of the slice phase");
 
-__global__ void __launch_bounds__(K3_THREADS, 3)
+// Register budget (round-1 sweep on B200, 1 024 worlds, ms per launch): 64 registers / 3 CTAs per SM with 8 monomials and
+// 4 candidate records in flight per thread 0.81; the same at 96 registers / 2 CTAs 0.98, at 48 / 4 CTAs 1.68 (spills);
+// 2 monomials + 2 records in flight at 64 / 3 CTAs 0.73, at 48 / 4 CTAs 0.66, at 40 / 5 CTAs 0.81.  The kernel lives
+// on resident warps, not on loads in flight per warp: anything that spills or costs a CTA per SM loses.
+__global__ void __launch_bounds__(K3_THREADS, K3_MINB)
 k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
     const int tb = blockIdx.x, p = blockIdx.y;
     const int NJ = B.NJ, O = B.O, T = B.T;
@@ -499,18 +514,18 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             const int n = cnt_in_smem ? s_cnt[x] : cnt[x];
             if (n != HP_OVERFLOW && in_domain) {
                 const double2* row = reinterpret_cast<const double2*>(cand) + size_t(x) * 2;
-                // four candidate records in flight per thread (the scan itself stays in order)
-                for (int q0 = 0; q0 < n; q0 += 4) {
-                    double2 u[4], w[4];
+                // K3_CQ candidate records in flight per thread (the scan itself stays in order)
+                for (int q0 = 0; q0 < n; q0 += K3_CQ) {
+                    double2 u[K3_CQ], w[K3_CQ];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < K3_CQ; i++) {
                         if (q0 + i < n) {
                             u[i] = __ldg(row + (q0 + i) * cstride2);
                             w[i] = __ldg(row + (q0 + i) * cstride2 + 1);
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < K3_CQ; i++) {
                         if (q0 + i < n) {
                             const double v = (u[i].x * c0 + u[i].y * c1 + w[i].x * c2) - w[i].y;
                             if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
