@@ -15,8 +15,9 @@
 #include "device_constants.cuh"
 // The reach-set kernel is compiled twice (see k1_pz.cuh):
 //   k1lat: one unit per CTA, 256 threads, 2 CTAs per SM  -> lowest latency for one planning problem
-//   k1thr: 8 units per CTA in lock step, 64 threads each -> highest throughput for batches (instruction fetch,
-//          the resource that bounds this kernel, is shared by the 8 units)
+//   k1thr: 12 units per CTA in lock step, 64 threads each -> highest throughput for batches (instruction fetch,
+//          the resource that bounds this kernel, is shared by the 12 units; round-1 sweep on 1 024 problems:
+//          8 groups 535 us per problem, 10: 519, 12: 503, 14: 497, pool share 3/8..5/8 within 2 %)
 #ifdef K1_PROFILE
 constexpr int K1_PROF_SITES = 512;
 __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
@@ -56,13 +57,13 @@ __device__ int g_k1spill[4];  // arena blocks in global memory, all arena blocks
 #define K1THR_NT 64
 #endif
 #ifndef K1THR_GROUPS
-#define K1THR_GROUPS 8
+#define K1THR_GROUPS 12
 #endif
 #ifndef K1THR_CTAS
 #define K1THR_CTAS 1
 #endif
 #ifndef K1THR_TAB_EIGHTHS
-#define K1THR_TAB_EIGHTHS 3  // share (in eighths) of a group's dynamic shared memory given to the scratch pool
+#define K1THR_TAB_EIGHTHS 4  // share (in eighths) of a group's dynamic shared memory given to the scratch pool
 #endif
 #undef K1_TAB_EIGHTHS
 #define K1_TAB_EIGHTHS K1THR_TAB_EIGHTHS
