@@ -996,17 +996,21 @@ K1_DI int run_task(const Batch& B, int p, int t, int kind, int i) {
 }
 #undef MG_DO
 
-// claim order of the tasks of one unit (a topological order; see DESIGN.md for the schedule it produces)
+// Claim order of the tasks of one unit (a topological order).  The forward Newton-Euler pass keeps the three groups
+// busy on its own; the backward pass is a chain (FB, one group) with a follower (NB, U), so the kinematics tasks -
+// which nothing inside the kernel consumes - are dealt out there: round r of the backward pass offers FB(NJ-1-r),
+// FKC(r), FKL(r-1), NB(NJ-r), U(NJ+1-r), all of which depend only on results of round r-1.
 K1_DI int mg_task_list(unsigned short* tasks, int NJ) {
     int n = 0;
-    const int fwd[10] = {TK_W, TK_WA, TK_T4, TK_WD, TK_FKC, TK_LA, TK_T10, TK_TN, TK_TF, TK_FKL};
+    const int fwd[8] = {TK_W, TK_WA, TK_T4, TK_WD, TK_LA, TK_T10, TK_TN, TK_TF};
     for (int i = 0; i < NJ; i++)
-        for (int q = 0; q < 10; q++) tasks[n++] = (unsigned short)((fwd[q] << 8) | i);
-    // backward: the force chain runs one joint ahead of the moment chain
-    for (int i = NJ - 1; i >= -2; i--) {
-        if (i >= 0) tasks[n++] = (unsigned short)((TK_FB << 8) | i);
-        if (i + 1 >= 0 && i + 1 < NJ) tasks[n++] = (unsigned short)((TK_NB << 8) | (i + 1));
-        if (i + 2 >= 0 && i + 2 < NJ) tasks[n++] = (unsigned short)((TK_U << 8) | (i + 2));
+        for (int q = 0; q < 8; q++) tasks[n++] = (unsigned short)((fwd[q] << 8) | i);
+    for (int r = 0; r <= NJ + 1; r++) {
+        if (NJ - 1 - r >= 0) tasks[n++] = (unsigned short)((TK_FB << 8) | (NJ - 1 - r));
+        if (r < NJ) tasks[n++] = (unsigned short)((TK_FKC << 8) | r);
+        if (r >= 1 && r <= NJ) tasks[n++] = (unsigned short)((TK_FKL << 8) | (r - 1));
+        if (NJ - r >= 0 && NJ - r < NJ) tasks[n++] = (unsigned short)((TK_NB << 8) | (NJ - r));
+        if (NJ + 1 - r >= 0 && NJ + 1 - r < NJ) tasks[n++] = (unsigned short)((TK_U << 8) | (NJ + 1 - r));
     }
     tasks[n++] = (unsigned short)(TK_EPI << 8);
     return n;
