@@ -21,7 +21,7 @@
 #ifdef K1_PROFILE
 constexpr int K1_PROF_SITES = 512;
 __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
-__device__ int g_k1spill[4];  // arena blocks in global memory, all arena blocks, scratch pools in global memory
+__device__ int g_k1spill[8];  // arena blocks in global memory, all arena blocks, scratch pools in global memory
 #endif
 // Latency configuration: MG mode, K1LAT_GROUPS groups of K1LAT_NT threads build ONE unit together (one CTA per SM)
 #ifndef K1LAT_NT
@@ -493,9 +493,10 @@ int armour_batch_get_candidate_counts(armour_ctx* ctx, int nprob, unsigned char*
 extern "C" int armour_debug_k1_profile(long long* out, int reset) {
     cudaDeviceSynchronize();
     if (out) {
-        int sp[4];
+        int sp[8];
         if (cudaMemcpyFromSymbol(sp, g_k1spill, sizeof(sp)) == cudaSuccess)
-            std::printf("k1 profile: %d of %d arena blocks in global memory, %d scratch pools in global memory\n", sp[0], sp[1], sp[2]);
+            std::printf("k1 profile: %d of %d arena blocks in global memory, %d scratch pools in global memory, %d cross products on "
+                        "the table path (largest term count %d)\n", sp[0], sp[1], sp[2], sp[3], sp[4]);
     }
     if (out && cudaMemcpyFromSymbol(out, g_k1prof, sizeof(long long) * 128 * K1_PROF_SITES * 2) != cudaSuccess) return ARMOUR_ERR_CUDA;
     if (reset) {

@@ -1417,30 +1417,48 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
     const bool outerA = nA <= nB;
     const int nO = outerA ? nA : nB, nI = outerA ? nB : nA;
     const long long Pll = (long long)nA + nB + (long long)nA * nB;
-    if (Pll > (1 << 20) || nO > 65000 || nI > 65535) return false;
+    if (Pll > 65535) return false;  // terms are listed by their 16-bit number
     const int P = int(Pll);
+    // Scratch: the group's pool, extended downwards into whatever the arena has free above `top` (the operands lie
+    // below `top`; the output block goes AT `top`, after the table is dead - OUT_RESERVE words are kept clear of the
+    // table for it, and a larger output may run into the dead keys but never into the survivor records, see n_cap).
+    constexpr int OUT_RESERVE = 9 + 4 * 64;
+    char* base = tab_s0();
+    size_t pool_bytes = size_t(S.tab_s_bytes);
+    bool borrowed = false;
+    {
+        const int base_words = (top + OUT_RESERVE + 1) & ~1;
+        if (base_words < S.AW) {
+            base = reinterpret_cast<char*>(arena0() + base_words);
+            pool_bytes += size_t(S.AW - base_words) * 8;
+            borrowed = true;
+        }
+    }
     // the table holds keys only and equal keys share a slot: sized for a load of at most 0.94 if every term had
-    // its own key (about half of them do), 2/3 when that still fits the pool
+    // its own key (about half of them do), 2/3 when that still fits
     int cap = 64, lg = 6;
     while (cap * 2 < P * 3) {
         cap <<= 1;
         lg++;
     }
-    if (size_t(cap) * 12 + size_t(P) * 4 + 2048 > size_t(S.tab_s_bytes) && (cap >> 1) >= P + (P >> 4)) {
+    if (size_t(cap) * 12 + size_t(P) * 2 + 2048 > pool_bytes && (cap >> 1) >= P + (P >> 4)) {
         cap >>= 1;
         lg--;
     }
-    const size_t fixed = (size_t(cap) * 12 + size_t(P) * 4 + 7) & ~size_t(7);
-    if (fixed + 32 * 32 > size_t(S.tab_s_bytes)) return false;
-    const int surv_max = int((size_t(S.tab_s_bytes) - fixed) / 32);
-    char* base = tab_s0();
+    const size_t fixed = (size_t(cap) * 12 + size_t(P) * 2 + 7) & ~size_t(7);
+    if (fixed + 32 * 32 > pool_bytes) return false;
+    int surv_max = int((pool_bytes - fixed) / 32);
+    if (borrowed) {
+        const int n_cap = 64 + cap / 4 - 4;  // output of n monomials = 9 + 4n words <= OUT_RESERVE + the key array
+        surv_max = surv_max < n_cap ? surv_max : n_cap;
+    }
     Tab t;
     t.keys = reinterpret_cast<u64*>(base);
     t.acc = nullptr;
     t.cap = cap;
     t.shift = 64 - lg;
     unsigned* cnt = reinterpret_cast<unsigned*>(base + size_t(cap) * 8);
-    unsigned* list = cnt + cap;
+    unsigned short* list = reinterpret_cast<unsigned short*>(cnt + cap);
     double* surv = reinterpret_cast<double*>(base + fixed);
     {
         unsigned* z = reinterpret_cast<unsigned*>(base);
@@ -1508,23 +1526,20 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
         }
     }
     k1_sync();
-    // fill the term lists: id = tag << 16 | index, tag 0: A_i x centre(B), 1: centre(A) x B_j, 2 + o: outer o x inner j
+    // fill the term lists with the term numbers q: [0, nA) A_i x centre(B), [nA, nA + nB) centre(A) x B_j, then
+    // outer o x inner j at nA + nB + o * nI + j (ascending q = the fixed order of the sums)
     for (int q = tid; q < P; q += NT) {
         u64 key;
-        unsigned id;
         if (q < nA) {
             key = kA[q];
-            id = unsigned(q);
         } else if (q < nA + nB) {
             key = kB[q - nA];
-            id = (1u << 16) | unsigned(q - nA);
         } else {
             const int r = q - nA - nB, o = r / nI, j = r - o * nI;
             key = kO[o] + kI[j];
-            id = (unsigned(2 + o) << 16) | unsigned(j);
         }
         const unsigned pos = atomicAdd(&cnt[tab_find(t, key)], 1u);  // cnt[s] ends as the END of slot s's list
-        list[pos] = id;
+        list[pos] = (unsigned short)q;
     }
     k1_sync();
     // owner pass, slots distributed like tab_finalize (same order of the pruned-amount sums)
@@ -1542,24 +1557,25 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
             if (key == 0) continue;
             const int b = s ? int(cnt[s - 1]) : 0, e = int(cnt[s]);
             double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            long long last = -1;
+            int last = -1;
             for (int c = b; c < e; c++) {
-                unsigned best = 0xffffffffu;  // next id in ascending order (ids of a slot are distinct)
+                int best = 0x7fffffff;  // next term in ascending order (the terms of a slot are distinct)
                 for (int x = b; x < e; x++) {
-                    const unsigned u = list[x];
-                    if ((long long)u > last && u < best) best = u;
+                    const int u = list[x];
+                    if (u > last && u < best) best = u;
                 }
-                last = (long long)best;
-                const int tag = int(best >> 16), idx = int(best & 0xffffu);
+                last = best;
                 double v[6];
-                if (tag == 0) {
-                    cross_six(cA + size_t(idx) * 3, cenB, v);
-                } else if (tag == 1) {
-                    cross_six(cenA, cB + size_t(idx) * 3, v);
-                } else if (outerA) {
-                    cross_six(cA + size_t(tag - 2) * 3, cB + size_t(idx) * 3, v);
+                if (best < nA) {
+                    cross_six(cA + size_t(best) * 3, cenB, v);
+                } else if (best < nA + nB) {
+                    cross_six(cenA, cB + size_t(best - nA) * 3, v);
                 } else {
-                    cross_six(cA + size_t(idx) * 3, cB + size_t(tag - 2) * 3, v);
+                    const int r = best - nA - nB, o = r / nI, j = r - o * nI;
+                    if (outerA)
+                        cross_six(cA + size_t(o) * 3, cB + size_t(j) * 3, v);
+                    else
+                        cross_six(cA + size_t(j) * 3, cB + size_t(o) * 3, v);
                 }
 #pragma unroll
                 for (int x = 0; x < 6; x++) a[x] += v[x];
@@ -1619,6 +1635,12 @@ K1_OP PZ8 op_cross(int top, PZ8 A8, PZ8 B8) {
         if (cross_list_path(top, A, B, &h8)) return h8;
         if (S.fail) return dummy;
     }
+#ifdef K1_PROFILE
+    if (tid == 0) {
+        atomicAdd(&g_k1spill[3], 1);
+        atomicMax(&g_k1spill[4], nA + nB + nA * nB);
+    }
+#endif
     Tab t;
     if (!tab_select(nA + nB + nA * nB, 6, t)) return dummy;
     if (reinterpret_cast<char*>(t.keys) == tab_s0()) {  // merge operations leave the shared pool dirty
