@@ -1415,7 +1415,7 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
     const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
     const int nA = A.n, nB = B.n;
     const bool outerA = nA <= nB;
-    const int nO = outerA ? nA : nB, nI = outerA ? nB : nA;
+    const int nI = outerA ? nB : nA;
     const long long Pll = (long long)nA + nB + (long long)nA * nB;
     if (Pll > 65535) return false;  // terms are listed by their 16-bit number
     const int P = int(Pll);

@@ -103,7 +103,7 @@ __device__ __forceinline__ void load_row_generators(const double* __restrict__ o
 // transitive, so testing against all earlier candidates that pass the filter equals the sequential rule),
 // step 4 writes the survivors at their scan-order positions.  Bit-identical lists to a sequential scan.
 constexpr int HP_ROWS = 8;
-constexpr int HP_STAGE = 32;  // link monomials staged in shared memory per row (longer tables are read from global)
+constexpr int HP_STAGE = 24;  // link monomials staged in shared memory per row (longer tables are read from global)
 constexpr int HP_THREADS = HP_ROWS * NCOMB;  // 288
 __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
     const int p = blockIdx.y;
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
     __shared__ double s_vc[HP_ROWS][2 * NCOMB];           // value of each signed half-space at the centre of the k box
     __shared__ double s_gm[HP_ROWS][HP_STAGE][3];        // monomial coefficients of the row's link reach set
     __shared__ int s_best[HP_ROWS];                        // signed half-space with the best guaranteed lower bound
-    __shared__ unsigned char s_flag[HP_ROWS][2 * NCOMB], s_pos[HP_ROWS][2 * NCOMB];
-    __shared__ int s_count[HP_ROWS];
+    __shared__ unsigned char s_flag[HP_ROWS][2 * NCOMB], s_list[HP_ROWS][2 * NCOMB];
+    __shared__ int s_nlist[HP_ROWS];
     const bool live = r < rows_total;
     int tb = 0, x = 0;
     size_t idx = 0;
@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
             s_oc[lr][pi - 27] = B.obstacles[(size_t(p) * O + o) * 12 + (pi - 27)];
         } else if (pi < 33) {
             s_c[lr][pi - 30] = B.link_c[idx * 3 + (pi - 30)];
+        } else if (pi == 33) {
+            s_nlist[lr] = 0;
         }
         const int n = B.link_n[idx];
         const int ns = n < HP_STAGE ? n : HP_STAGE;
@@ -235,58 +237,77 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
         if (drop[1]) s_up[lr][2 * pi + 1] = -1e300;
     }
     __syncthreads();
-    if (live) {  // step 3: which of my two candidates survive
+    // step 3: the candidates that pass the filters enter a short list per row (a handful of the 72; arrival order,
+    // the tests below do not depend on it)
+    if (live) {
         const double lo_max = s_lomax[lr];
 #pragma unroll 1
         for (int sgn = 0; sgn < 2; sgn++) {
             const int sI = 2 * pi + sgn;  // position in the scan order pos_0, neg_0, pos_1, ...
-            bool keep = nz && s_up[lr][sI] >= lo_max;
-            if (keep) {
+            if (nz && s_up[lr][sI] >= lo_max) s_list[lr][atomicAdd(&s_nlist[lr], 1)] = (unsigned char)sI;
+        }
+    }
+    __syncthreads();
+    // step 3b: a listed candidate is dropped when a listed candidate EARLIER in the scan order has the same normal and
+    // a smaller or equal offset (it can never win the strict '>' scan).  Dominance is transitive, so testing against
+    // all earlier listed candidates equals the sequential rule.
+    bool keep[2] = {false, false};
+    if (live) {
+        const double lo_max = s_lomax[lr];
+        const int nl = s_nlist[lr];
+#pragma unroll 1
+        for (int sgn = 0; sgn < 2; sgn++) {
+            const int sI = 2 * pi + sgn;
+            bool k = nz && s_up[lr][sI] >= lo_max;
+            if (k) {
                 const double sg = sgn ? -1.0 : 1.0;
                 const double A0 = sg * s_A[lr][pi][0], A1 = sg * s_A[lr][pi][1], A2 = sg * s_A[lr][pi][2], bb = s_b[lr][sI];
 #pragma unroll 1
-                for (int q = 0; q < sI && keep; q++) {
-                    if (!(s_up[lr][q] >= lo_max)) continue;  // q does not pass the filter (or is a zero normal)
+                for (int c = 0; c < nl && k; c++) {
+                    const int q = s_list[lr][c];
+                    if (q >= sI) continue;
                     const double sq = (q & 1) ? -1.0 : 1.0;
                     const int qi = q >> 1;
                     if (sq * s_A[lr][qi][0] == A0 && sq * s_A[lr][qi][1] == A1 && sq * s_A[lr][qi][2] == A2 && s_b[lr][q] <= bb)
-                        keep = false;
+                        k = false;
                 }
             }
-            s_flag[lr][sI] = keep ? 1 : 0;
+            keep[sgn] = k;
+            s_flag[lr][sI] = k ? 1 : 0;
         }
     }
     __syncthreads();
-    if (live && pi == 0) {  // positions in scan order
-        int count = 0;
-#pragma unroll 1
-        for (int sI = 0; sI < 2 * NCOMB; sI++) {
-            s_pos[lr][sI] = (unsigned char)(count < 255 ? count : 255);
-            count += s_flag[lr][sI];
-        }
-        s_count[lr] = count;
-    }
-    __syncthreads();
-    if (live) {  // step 4
+    if (live) {  // step 4: survivors to their scan-order positions (counted over the short list)
         const size_t chunk = size_t(p) * (T / TB) + tb;
         double* row = B.hp_cand + chunk * B.hp_chunk() + size_t(x) * 4;
         const size_t cstride = size_t(per_pair) * 4;
-        const int count = s_count[lr];
-        if (count <= HP_CAP) {
+        const int nl = s_nlist[lr];
+        if (keep[0] || keep[1] || pi == 0) {
+            int count = 0, before[2] = {0, 0};
 #pragma unroll 1
-            for (int sgn = 0; sgn < 2; sgn++) {
-                const int sI = 2 * pi + sgn;
-                if (s_flag[lr][sI]) {
-                    const double sg = sgn ? -1.0 : 1.0;
-                    double* e = row + size_t(s_pos[lr][sI]) * cstride;
-                    e[0] = sg * s_A[lr][pi][0];
-                    e[1] = sg * s_A[lr][pi][1];
-                    e[2] = sg * s_A[lr][pi][2];
-                    e[3] = s_b[lr][sI];
+            for (int c = 0; c < nl; c++) {
+                const int q = s_list[lr][c];
+                if (s_flag[lr][q]) {
+                    count++;
+                    before[0] += (q < 2 * pi);
+                    before[1] += (q < 2 * pi + 1);
                 }
             }
+            if (count <= HP_CAP) {
+#pragma unroll 1
+                for (int sgn = 0; sgn < 2; sgn++) {
+                    if (keep[sgn]) {
+                        const double sg = sgn ? -1.0 : 1.0;
+                        double* e = row + size_t(before[sgn]) * cstride;
+                        e[0] = sg * s_A[lr][pi][0];
+                        e[1] = sg * s_A[lr][pi][1];
+                        e[2] = sg * s_A[lr][pi][2];
+                        e[3] = s_b[lr][2 * pi + sgn];
+                    }
+                }
+            }
+            if (pi == 0) B.hp_cnt[chunk * per_pair + x] = (count > HP_CAP) ? (unsigned char)HP_OVERFLOW : (unsigned char)count;
         }
-        if (pi == 0) B.hp_cnt[chunk * per_pair + x] = (count > HP_CAP) ? (unsigned char)HP_OVERFLOW : (unsigned char)count;
     }
 }
 
