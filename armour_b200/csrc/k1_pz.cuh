@@ -1445,13 +1445,31 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
         cap >>= 1;
         lg--;
     }
-    const size_t fixed = (size_t(cap) * 12 + size_t(P) * 2 + 7) & ~size_t(7);
-    if (fixed + 32 * 32 > pool_bytes) return false;
+    size_t fixed = (size_t(cap) * 12 + size_t(P) * 2 + 7) & ~size_t(7);
+    bool in_global = false;
+    if (fixed + 32 * 32 > pool_bytes) {
+        // Shared memory is too small (the lock-step throughput configuration leaves a group ~10 KB): the same lists
+        // in the group's global pool (L2-resident).  Still far less traffic than the accumulator table - one atomic
+        // per term instead of six read-modify-writes, sums in registers.  The pool is all zero between operations.
+        cap = 64, lg = 6;
+        while (cap * 2 < P * 3) {
+            cap <<= 1;
+            lg++;
+        }
+        fixed = (size_t(cap) * 12 + size_t(P) * 2 + 7) & ~size_t(7);
+        if (fixed + 32 * 128 > size_t(S.tab_g_bytes)) return false;
+        base = S.tab_g;
+        pool_bytes = size_t(S.tab_g_bytes);
+        borrowed = false;
+        in_global = true;
+        if (tid == 0) S.n_tab_global++;
+    }
     int surv_max = int((pool_bytes - fixed) / 32);
     if (borrowed) {
         const int n_cap = 64 + cap / 4 - 4;  // output of n monomials = 9 + 4n words <= OUT_RESERVE + the key array
         surv_max = surv_max < n_cap ? surv_max : n_cap;
     }
+    if (in_global && surv_max > 2048) surv_max = 2048;
     Tab t;
     t.keys = reinterpret_cast<u64*>(base);
     t.acc = nullptr;
@@ -1462,7 +1480,8 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
     double* surv = reinterpret_cast<double*>(base + fixed);
     {
         unsigned* z = reinterpret_cast<unsigned*>(base);
-        for (int i = tid; i < cap * 3; i += NT) z[i] = 0u;
+        if (!in_global)
+            for (int i = tid; i < cap * 3; i += NT) z[i] = 0u;
         if (tid == 0) S.nsurv = 0;
     }
     k1_sync();
@@ -1599,7 +1618,16 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
         for (int e = 0; e < 3; e++) S.red[warp * RED_STRIDE + e] = rad[e];
     k1_sync();
     const int n = S.nsurv;
-    if (n > surv_max) return false;  // uniform; nothing of the output exists yet
+    if (n > surv_max) {  // uniform; nothing of the output exists yet
+        if (in_global) {
+            k1_sync();
+            unsigned* z = reinterpret_cast<unsigned*>(base);
+            const int words = int((fixed + size_t(surv_max) * 32) / 4);
+            for (int i = tid; i < words; i += NT) z[i] = 0u;
+            k1_sync();
+        }
+        return false;
+    }
     double radt[3];
     rad_collect<3>(radt);
     bool ok;
@@ -1619,6 +1647,12 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
         cross_header(h8, A, B, outerA, radt);
     }
     k1_sync();
+    if (in_global) {  // hand the pool back all zero
+        unsigned* z = reinterpret_cast<unsigned*>(base);
+        const int words = int((fixed + size_t(n) * 32) / 4);
+        for (int i = tid; i < words; i += NT) z[i] = 0u;
+        k1_sync();
+    }
     *out_h = h8;
     return true;
 }
