@@ -1000,15 +1000,30 @@ K1_DI int run_task(const Batch& B, int p, int t, int kind, int i) {
 // busy on its own; the backward pass is a chain (FB, one group) with a follower (NB, U), so the kinematics tasks -
 // which nothing inside the kernel consumes - are dealt out there: round r of the backward pass offers FB(NJ-1-r),
 // FKC(r), FKL(r-1), NB(NJ-r), U(NJ+1-r), all of which depend only on results of round r-1.
+#ifndef K1_FK_EARLY
+#define K1_FK_EARLY 3
+#endif
 K1_DI int mg_task_list(unsigned short* tasks, int NJ) {
     int n = 0;
     const int fwd[8] = {TK_W, TK_WA, TK_T4, TK_WD, TK_LA, TK_T10, TK_TN, TK_TF};
+    // the forward pass ends in a chain (T10 -> TF of the last joint, the biggest cross product of the unit) on which
+    // two groups would wait: the kinematics of the first K1_FK_EARLY joints is offered there
+    const int early = K1_FK_EARLY < NJ ? K1_FK_EARLY : NJ;
     for (int i = 0; i < NJ; i++)
-        for (int q = 0; q < 8; q++) tasks[n++] = (unsigned short)((fwd[q] << 8) | i);
+        for (int q = 0; q < 8; q++) {
+            if (i == NJ - 1 && fwd[q] == TK_TF)
+                for (int r = 0; r < early; r++) {
+                    tasks[n++] = (unsigned short)((TK_FKC << 8) | r);
+                    tasks[n++] = (unsigned short)((TK_FKL << 8) | r);
+                }
+            tasks[n++] = (unsigned short)((fwd[q] << 8) | i);
+        }
+    // backward rounds; the remaining kinematics joints are spread over them
     for (int r = 0; r <= NJ + 1; r++) {
+        const int fk = early + r;  // FKC(fk) and FKL(fk - 1) in round r
         if (NJ - 1 - r >= 0) tasks[n++] = (unsigned short)((TK_FB << 8) | (NJ - 1 - r));
-        if (r < NJ) tasks[n++] = (unsigned short)((TK_FKC << 8) | r);
-        if (r >= 1 && r <= NJ) tasks[n++] = (unsigned short)((TK_FKL << 8) | (r - 1));
+        if (fk < NJ) tasks[n++] = (unsigned short)((TK_FKC << 8) | fk);
+        if (fk - 1 >= early && fk - 1 < NJ) tasks[n++] = (unsigned short)((TK_FKL << 8) | (fk - 1));
         if (NJ - r >= 0 && NJ - r < NJ) tasks[n++] = (unsigned short)((TK_NB << 8) | (NJ - r));
         if (NJ + 1 - r >= 0 && NJ + 1 - r < NJ) tasks[n++] = (unsigned short)((TK_U << 8) | (NJ + 1 - r));
     }
