@@ -714,17 +714,54 @@ K1_DI int build_unit(const Batch& B, int p, int t) {
 #undef K1_OP_VAR
 
 
-#if K1_MG
-// ---- MG mode: one unit built by all groups of the CTA ------------------------------------------------
-// The unit is a list of tasks; operands and results travel through the CTA's mailbox (global memory, written
-// once per unit, L2-resident), so a task is a pure function mailbox -> mailbox and any group can run it.
-// Operation order inside every chain of the recursion and every simplify() point are those of build_unit().
+// ---- MG mode, host-checkable part: mailbox slots, task kinds and the claim order (pure integer code; the CPU
+// suite checks through tests/emu that the order is topological for the dependencies of run_task) ----
 enum {
     MB_W, MB_WA1, MB_WA2, MB_WD, MB_T4, MB_LA, MB_T10, MB_F, MB_A3, MB_N, MB_FKR, MB_FKT, MB_A6, MB_F2, MB_N2,
     EV_FKL, EV_U, MB_KINDS
 };
 static_assert(MB_KINDS * (MAXJ + 1) <= MB_SLOTS, "mailbox slots");
 enum { TK_W, TK_WA, TK_WD, TK_T4, TK_LA, TK_T10, TK_TF, TK_TN, TK_FKC, TK_FKL, TK_FB, TK_NB, TK_U, TK_EPI };
+// Claim order of the tasks of one unit (a topological order).  The forward Newton-Euler pass keeps the three groups
+// busy on its own; the backward pass is a chain (FB, one group) with a follower (NB, U), so the kinematics tasks -
+// which nothing inside the kernel consumes - are dealt out there: round r of the backward pass offers FB(NJ-1-r),
+// FKC(r), FKL(r-1), NB(NJ-r), U(NJ+1-r), all of which depend only on results of round r-1.
+#ifndef K1_FK_EARLY
+#define K1_FK_EARLY 3
+#endif
+K1_DI int mg_task_list(unsigned short* tasks, int NJ) {
+    int n = 0;
+    const int fwd[8] = {TK_W, TK_WA, TK_T4, TK_WD, TK_LA, TK_T10, TK_TN, TK_TF};
+    // the forward pass ends in a chain (T10 -> TF of the last joint, the biggest cross product of the unit) on which
+    // two groups would wait: the kinematics of the first K1_FK_EARLY joints is offered there
+    const int early = K1_FK_EARLY < NJ ? K1_FK_EARLY : NJ;
+    for (int i = 0; i < NJ; i++)
+        for (int q = 0; q < 8; q++) {
+            if (i == NJ - 1 && fwd[q] == TK_TF)
+                for (int r = 0; r < early; r++) {
+                    tasks[n++] = (unsigned short)((TK_FKC << 8) | r);
+                    tasks[n++] = (unsigned short)((TK_FKL << 8) | r);
+                }
+            tasks[n++] = (unsigned short)((fwd[q] << 8) | i);
+        }
+    // backward rounds; the remaining kinematics joints are spread over them
+    for (int r = 0; r <= NJ + 1; r++) {
+        const int fk = early + r;  // FKC(fk) and FKL(fk - 1) in round r
+        if (NJ - 1 - r >= 0) tasks[n++] = (unsigned short)((TK_FB << 8) | (NJ - 1 - r));
+        if (fk < NJ) tasks[n++] = (unsigned short)((TK_FKC << 8) | fk);
+        if (fk - 1 >= early && fk - 1 < NJ) tasks[n++] = (unsigned short)((TK_FKL << 8) | (fk - 1));
+        if (NJ - r >= 0 && NJ - r < NJ) tasks[n++] = (unsigned short)((TK_NB << 8) | (NJ - r));
+        if (NJ + 1 - r >= 0 && NJ + 1 - r < NJ) tasks[n++] = (unsigned short)((TK_U << 8) | (NJ + 1 - r));
+    }
+    tasks[n++] = (unsigned short)(TK_EPI << 8);
+    return n;
+}
+
+#if K1_MG
+// ---- MG mode: one unit built by all groups of the CTA ------------------------------------------------
+// The unit is a list of tasks; operands and results travel through the CTA's mailbox (global memory, written
+// once per unit, L2-resident), so a task is a pure function mailbox -> mailbox and any group can run it.
+// Operation order inside every chain of the recursion and every simplify() point are those of build_unit().
 K1_DI int mb_slot(int kind, int i) { return kind * (MAXJ + 1) + i; }
 
 K1_DI void ev_signal(int slot) {  // called by all threads of the group after a barrier that follows the writes
@@ -996,40 +1033,6 @@ K1_DI int run_task(const Batch& B, int p, int t, int kind, int i) {
 }
 #undef MG_DO
 
-// Claim order of the tasks of one unit (a topological order).  The forward Newton-Euler pass keeps the three groups
-// busy on its own; the backward pass is a chain (FB, one group) with a follower (NB, U), so the kinematics tasks -
-// which nothing inside the kernel consumes - are dealt out there: round r of the backward pass offers FB(NJ-1-r),
-// FKC(r), FKL(r-1), NB(NJ-r), U(NJ+1-r), all of which depend only on results of round r-1.
-#ifndef K1_FK_EARLY
-#define K1_FK_EARLY 3
-#endif
-K1_DI int mg_task_list(unsigned short* tasks, int NJ) {
-    int n = 0;
-    const int fwd[8] = {TK_W, TK_WA, TK_T4, TK_WD, TK_LA, TK_T10, TK_TN, TK_TF};
-    // the forward pass ends in a chain (T10 -> TF of the last joint, the biggest cross product of the unit) on which
-    // two groups would wait: the kinematics of the first K1_FK_EARLY joints is offered there
-    const int early = K1_FK_EARLY < NJ ? K1_FK_EARLY : NJ;
-    for (int i = 0; i < NJ; i++)
-        for (int q = 0; q < 8; q++) {
-            if (i == NJ - 1 && fwd[q] == TK_TF)
-                for (int r = 0; r < early; r++) {
-                    tasks[n++] = (unsigned short)((TK_FKC << 8) | r);
-                    tasks[n++] = (unsigned short)((TK_FKL << 8) | r);
-                }
-            tasks[n++] = (unsigned short)((fwd[q] << 8) | i);
-        }
-    // backward rounds; the remaining kinematics joints are spread over them
-    for (int r = 0; r <= NJ + 1; r++) {
-        const int fk = early + r;  // FKC(fk) and FKL(fk - 1) in round r
-        if (NJ - 1 - r >= 0) tasks[n++] = (unsigned short)((TK_FB << 8) | (NJ - 1 - r));
-        if (fk < NJ) tasks[n++] = (unsigned short)((TK_FKC << 8) | fk);
-        if (fk - 1 >= early && fk - 1 < NJ) tasks[n++] = (unsigned short)((TK_FKL << 8) | (fk - 1));
-        if (NJ - r >= 0 && NJ - r < NJ) tasks[n++] = (unsigned short)((TK_NB << 8) | (NJ - r));
-        if (NJ + 1 - r >= 0 && NJ + 1 - r < NJ) tasks[n++] = (unsigned short)((TK_U << 8) | (NJ + 1 - r));
-    }
-    tasks[n++] = (unsigned short)(TK_EPI << 8);
-    return n;
-}
 #endif  // K1_MG
 
 // ---- kernel ---------------------------------------------------------------------------------------

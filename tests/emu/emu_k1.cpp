@@ -72,3 +72,7 @@ extern "C" int emu_k1_build(int model_id, int T, double thr, const double* k_ran
         if (ch) return -100;  // the global table pool must be left all-zero
     return status;
 }
+
+// claim order of the MG latency configuration (armour_b200/csrc/k1_reachsets.cuh: mg_task_list), for the CPU check
+// that it is a topological order: out[i] = kind << 8 | joint, returns the number of tasks
+extern "C" int emu_mg_task_list(int NJ, unsigned short* out) { return k1::mg_task_list(out, NJ); }

@@ -122,3 +122,34 @@ def test_small_shared_memory_spills_to_global_with_identical_results(emu):
     assert b["stats"][1] > 0, "expected hash tables in the global pool"
     for key in ("nl", "cl", "hl", "gl", "nu", "cu", "ru", "hu", "gu", "torque_radius", "link_gens"):
         assert np.array_equal(a[key], b[key]), key
+
+
+def test_mg_task_list_is_a_topological_order(emu):
+    """The latency configuration builds one unit as a list of tasks claimed in a fixed order by three groups; a
+    group waits for the inputs of the task it claimed, so the order must be topological (no deadlock) and hold every
+    task exactly once.  The dependencies below are the mailbox imports of run_task (k1_reachsets.cuh)."""
+    KINDS = ["W", "WA", "WD", "T4", "LA", "T10", "TF", "TN", "FKC", "FKL", "FB", "NB", "U", "EPI"]
+    emu.emu_mg_task_list.argtypes = [C.c_int, C.POINTER(C.c_ushort)]
+    emu.emu_mg_task_list.restype = C.c_int
+    for NJ in (7, 8):
+        buf = (C.c_ushort * 256)()
+        n = emu.emu_mg_task_list(NJ, buf)
+        tasks = [(KINDS[buf[i] >> 8], buf[i] & 255) for i in range(n)]
+        assert len(tasks) == len(set(tasks)) == 13 * NJ + 1
+        pos = {t: i for i, t in enumerate(tasks)}
+
+        def deps(kind, i):
+            prev = i - 1
+            d = {
+                "W": [("W", prev)], "WA": [("WA", prev)], "WD": [("WD", prev), ("WA", i)],
+                "T4": [("WA", prev), ("W", prev)], "LA": [("LA", prev), ("WD", prev), ("T4", i)],
+                "T10": [("WA", i), ("W", i)], "TF": [("WD", i), ("LA", i), ("T10", i)],
+                "TN": [("WD", i), ("W", i), ("WA", i)], "FKC": [("FKC", prev)], "FKL": [("FKC", i)],
+                "FB": [("FB", i + 1), ("TF", i)], "NB": [("NB", i + 1), ("TN", i), ("TF", i), ("FB", i)],
+                "U": [("NB", i)], "EPI": [("U", j) for j in range(NJ)],
+            }[kind]
+            return [(k, j) for k, j in d if 0 <= j < NJ]
+
+        for t in tasks:
+            for dep in deps(*t):
+                assert pos[dep] < pos[t], (NJ, t, dep)
