@@ -7,6 +7,7 @@
 //
 // usage: armour_main [buffer_dir]      buffer_dir defaults to $ARMOUR_BUFFER_PATH or ./buffer/
 //        armour_main --selftest        host-logic self test (parser / writers / local solver), no GPU needed
+//        armour_main --serve           persistent server: one buffer directory per stdin line (see main)
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -182,13 +183,13 @@ int selftest() {
     return bad ? 1 : 0;
 }
 
-}  // namespace
 
-int main(int argc, char** argv) {
-    if (argc > 1 && std::strcmp(argv[1], "--selftest") == 0) return selftest();
-    std::string dir = (argc > 1) ? argv[1] : (std::getenv("ARMOUR_BUFFER_PATH") ? std::getenv("ARMOUR_BUFFER_PATH") : "buffer/");
+
+// One planning iteration on a live context: armour.in -> reach sets -> NLP -> the five output files of the reference
+// (KPR/armour_main.cu:36-78, 86-372).  Returns the process exit code the reference would give (0 = ran, even if no
+// feasible plan was found; -1 = error, with a single -1 in armour.out).
+int plan_once(armour_ctx* ctx, const armour_config& cfg, std::string dir) {
     if (!dir.empty() && dir.back() != '/') dir += '/';
-
     std::ofstream out1(dir + "armour.out");  // declared first so that there is always a new output (reference :36)
     auto fail_early = [&](const char* msg) {
         std::fprintf(stderr, "        CUDA & C++: %s\n", msg);
@@ -196,26 +197,19 @@ int main(int argc, char** argv) {
         out1.close();
         return -1;
     };
-
-    armour_config cfg;
-    armour_config_default(&cfg);  // NUM_TIME_STEPS 128, SIMPLIFY_THRESHOLD 5e-4, k_range pi/48, MAX_OBSTACLE_NUM 40
     PlannerInput in;
     const int prc = parse_input(dir + "armour.in", cfg.max_obstacles, &in);
     if (prc == -1) return fail_early("Error reading input files !");
     if (prc == -2) return fail_early("Number of obstacles larger than MAX_OBSTACLE_NUM !");
+    if (!ctx) return fail_early("cannot create the CUDA context (a GPU is required; there is no CPU path)");
     const double t_plan = 0.5;  // reference :80
-
-    armour_ctx* ctx = nullptr;
-    int rc = armour_ctx_create(&cfg, &ctx);
-    if (rc != ARMOUR_OK) return fail_early("cannot create the CUDA context (a GPU is required; there is no CPU path)");
 
     armour_ctx_reserve(ctx, 1, in.num_obstacles);  // device buffers, like the Obstacles constructor before the timer (:86-88)
 
     const auto start1 = std::chrono::high_resolution_clock::now();
-    rc = armour_reachsets_build(ctx, in.q0, in.qd0, in.qdd0, in.obstacles.data(), in.num_obstacles);  // sections II.A-II.D
+    int rc = armour_reachsets_build(ctx, in.q0, in.qd0, in.qdd0, in.obstacles.data(), in.num_obstacles);  // sections II.A-II.D
     if (rc != ARMOUR_OK) {
         std::fprintf(stderr, "        CUDA & C++: %s\n", armour_last_error(ctx));
-        armour_ctx_destroy(ctx);
         return fail_early("Error computing link PZs and nominal torque PZs!");
     }
     const int T = armour_num_time_steps(ctx), NJ = armour_num_joints(ctx);
@@ -230,11 +224,9 @@ int main(int argc, char** argv) {
     std::cout << "        CUDA & C++: Time allocated for the optimiser: " << time_for_optimization * 1000.0 << " milliseconds\n";
 
     const auto start2 = std::chrono::high_resolution_clock::now();
+    const long long launches0 = armour_kernel_launches(ctx);
     armtd_NLP nlp;
-    if (!nlp.set_parameters(in.q_des, t_plan, ctx, in.num_obstacles)) {
-        armour_ctx_destroy(ctx);
-        return fail_early("Error initializing the NLP!");
-    }
+    if (!nlp.set_parameters(in.q_des, t_plan, ctx, in.num_obstacles)) return fail_early("Error initializing the NLP!");
     LocalSolverOptions opt;
     opt.tol = 1e-4;  // IPOPT_OPTIMIZATION_TOLERANCE
     opt.max_wall_time = time_for_optimization;
@@ -245,10 +237,50 @@ int main(int argc, char** argv) {
     if (status == CPUTIME_EXCEEDED) std::cout << "        CUDA & C++: optimiser wall time exceeded!\n";
     std::cout << (nlp.feasible ? "        CUDA & C++: Found a feasible solution!\n" : "        CUDA & C++: Did not find a feasible solution!\n");
     std::cout << "        CUDA & C++: Time taken by the optimiser: " << ms2 << " milliseconds (" << st.iterations
-              << " iterations, " << st.evals << " constraint evaluations, " << armour_kernel_launches(ctx) << " kernel launches)\n";
+              << " iterations, " << st.evals << " constraint evaluations, " << (armour_kernel_launches(ctx) - launches0)
+              << " kernel launches)\n";
 
     out1.close();
     write_outputs(dir, nlp, T, NJ, gens, torque_radius, ms1 + ms2);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc > 1 && std::strcmp(argv[1], "--selftest") == 0) return selftest();
+    const bool serve = argc > 1 && std::strcmp(argv[1], "--serve") == 0;
+    const char* env = std::getenv("ARMOUR_BUFFER_PATH");
+    const std::string default_dir = env ? env : "buffer/";
+
+    armour_config cfg;
+    armour_config_default(&cfg);  // NUM_TIME_STEPS 128, SIMPLIFY_THRESHOLD 5e-4, k_range pi/48, MAX_OBSTACLE_NUM 40
+    armour_ctx* ctx = nullptr;
+    if (armour_ctx_create(&cfg, &ctx) != ARMOUR_OK) ctx = nullptr;  // reported per request, with -1 in armour.out
+
+    if (!serve) {
+        const int rc = plan_once(ctx, cfg, argc > 1 ? argv[1] : default_dir);
+        if (ctx) armour_ctx_destroy(ctx);
+        return rc;
+    }
+    // Server mode: the process - CUDA context, device buffers, loaded kernels - stays alive between
+    // replans; the reference pays process start + context + 10 cudaMallocs on every planning iteration
+    // (uarmtd_planner.m:187-208 runs the executable once per replan).  Protocol on stdin / stdout, one request per
+    // line: a buffer directory (empty line = the default directory) -> the five output files are written there and
+    // the line "done <exit code>" is printed; "quit" or end of input ends the server.
+    if (!ctx) {
+        std::fprintf(stderr, "        CUDA & C++: cannot create the CUDA context (a GPU is required; there is no CPU path)\n");
+        return -1;
+    }
+    armour_ctx_reserve(ctx, 1, cfg.max_obstacles);
+    std::cout << "ready" << std::endl;
+    std::string line;
+    while (std::getline(std::cin, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+        if (line == "quit") break;
+        const int rc = plan_once(ctx, cfg, line.empty() ? default_dir : line);
+        std::cout << "done " << rc << std::endl;
+    }
     armour_ctx_destroy(ctx);
     return 0;
 }

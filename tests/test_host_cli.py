@@ -79,3 +79,38 @@ def test_cli_end_to_end_matches_oracle(built, tmp_path, scene):
     assert np.max(np.abs(rad.T - tr) / tr) <= 1e-9
     gens = np.loadtxt(tmp_path / "armour_joint_position_radius.out").reshape(T, NJ, 3, 6)
     assert np.max(np.abs(gens - ref.link_gens())) <= 1e-9
+
+
+def test_server_mode_needs_a_gpu(built):
+    """--serve without a device ends at once with an error (no CPU path behind the server either)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    res = subprocess.run([CLI, "--serve"], input="quit\n", capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0 and "ready" not in res.stdout
+
+
+@pytest.mark.gpu
+def test_server_mode_matches_one_shot_runs(built, tmp_path):
+    """Persistent server: two replans through one live context write the same files as two separate
+    processes (the total time at the end of armour.out aside)."""
+    from armour_b200 import worlds
+    dirs = []
+    for scene in ("scene_016_006.csv", "scene_013_001.csv"):
+        for mode in ("oneshot", "served"):
+            d = tmp_path / f"{mode}_{scene[:-4]}"
+            d.mkdir()
+            q0, qd0, qdd0, q_des, obs = worlds.config1_problem(os.path.join(WORLDS, scene))
+            worlds.write_armour_in(d / "armour.in", q0, qd0, qdd0, q_des, obs)
+            dirs.append(d)
+    for d in dirs[0::2]:
+        assert subprocess.run([CLI, str(d)], capture_output=True, text=True, timeout=120).returncode == 0
+    req = "".join(f"{d}\n" for d in dirs[1::2]) + "quit\n"
+    res = subprocess.run([CLI, "--serve"], input=req, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("done 0") == 2 and "ready" in res.stdout
+    for one, served in zip(dirs[0::2], dirs[1::2]):
+        for f in K_FILES[1:]:
+            assert (one / f).read_text() == (served / f).read_text(), f
+        a, b = (one / "armour.out").read_text().split(), (served / "armour.out").read_text().split()
+        assert a[:-1] == b[:-1]  # k_opt (or -1); the last entry is the elapsed time
