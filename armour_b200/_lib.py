@@ -82,10 +82,19 @@ SIGNATURES = {
     "armour_batch_get_monomial_counts": (C.c_int, [C.c_void_p, C.c_int, ip, ip]),
     "armour_batch_get_candidate_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "armour_measure_fp64_peak": (C.c_int, [C.c_void_p, dp]),
+    "armour_solver_options_default": (None, [C.c_void_p]),
+    "armour_batch_solve_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
+    "armour_batch_solve": (C.c_int, [C.c_void_p, C.c_int, dp, C.c_void_p, dp, ip, ip, ip]),
     "armour_export_reachsets": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ReachsetTables)]),
     "armour_import_reachsets": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ReachsetTables), dp, dp, dp, dp,
                                           C.c_int]),
 }
+
+class SolverOptions(C.Structure):
+    """armour_solver_options (include/armour_b200.h)."""
+    _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("torque_tol", C.c_double), ("collision_tol", C.c_double)]
+
 
 _LIB = None
 

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -78,6 +79,7 @@ __device__ int g_k1spill[8];  // arena blocks in global memory, all arena blocks
 #undef K1_CTAS
 #undef K1_GROUPS
 #include "k3_constraints.cuh"
+#include "k4_solver.cuh"
 #include "layout.h"
 
 using namespace armour;
@@ -98,6 +100,11 @@ struct armour_ctx {
     double* d_jac = nullptr;
     size_t g_capacity = 0, jac_capacity = 0;
     int* d_verdict = nullptr;  // [2][max_problems]
+    // batched device solver (allocated on first use)
+    double* d_solver = nullptr;   // state arrays + second g buffer + linearised rows
+    int* d_solver_i = nullptr;    // have_best, status, iters, evals, running counter
+    double* d_solver_io = nullptr;  // q_des, k_opt staging of the host-pointer call
+    int solver_cap = 0;
     k1lat::K1Scratch k1_lat;  // scratch of the latency configuration of k_reachsets
     k1thr::K1Scratch k1_thr;  // scratch of the throughput configuration (allocated on first use)
     bool k1_thr_ready = false;
@@ -346,7 +353,8 @@ int armour_ctx_destroy(armour_ctx* ctx) {
     if (!ctx) return ARMOUR_OK;
     cudaSetDevice(ctx->cfg.device);
     Batch& B = ctx->B;
-    void* ptrs[] = {ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
+    void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io,
+                    ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
                     B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.hp_cand, B.hp_cnt,
                     B.link_sliced, B.status};
     for (void* p : ptrs)
@@ -582,6 +590,140 @@ int armour_batch_verdict_device(armour_ctx* ctx, int nprob, const double* d_g, i
     B.nprob = nprob;
     CU(launch_verdict(B, d_g, d_feasible, d_first, ctx->stream));
     ctx->launches += 1;
+    return ARMOUR_OK;
+}
+
+// ---- batched device solver -------------------------------------------------------------
+void armour_solver_options_default(armour_solver_options* opt) {
+    if (!opt) return;
+    opt->max_iter = 60;
+    opt->tol = 1e-4;
+    opt->torque_tol = 1e-2;
+    opt->collision_tol = 1e-4;
+}
+
+int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des, const armour_solver_options* opt_in,
+                              double* d_k_opt, int* d_feasible, int* d_first, int* d_iters) {
+    if (!ctx || !d_q_des || !d_k_opt || !d_feasible || !d_first) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "solve before build");
+    armour_solver_options opt;
+    armour_solver_options_default(&opt);
+    if (opt_in) opt = *opt_in;
+    if (opt.max_iter < 1 || !(opt.tol > 0)) return fail(ctx, ARMOUR_ERR_ARG, "solver options");
+    CU(cudaSetDevice(ctx->cfg.device));
+    Batch B = ctx->B;
+    B.nprob = nprob;
+    const size_t m = size_t(B.m());
+    int rc = ensure_eval_buffers(ctx, nprob, true, true);
+    if (rc) return rc;
+    if (ctx->solver_cap < nprob) {
+        if (ctx->d_solver) cudaFree(ctx->d_solver);
+        if (ctx->d_solver_i) cudaFree(ctx->d_solver_i);
+        ctx->d_solver = nullptr;
+        ctx->d_solver_i = nullptr;
+        ctx->solver_cap = 0;
+        const size_t P = size_t(nprob);
+        CU(dalloc(&ctx->d_solver, P * (3 * NF + 4) + P * m + P * SOLVER_ROWCAP * SOLVER_ROWW));
+        CU(dalloc(&ctx->d_solver_i, 7 * P + 1));
+        ctx->solver_cap = nprob;
+    }
+    const size_t P = size_t(ctx->solver_cap);
+    SolverState S;
+    double* w = ctx->d_solver;
+    S.x = w; w += P * NF;
+    S.xt = w; w += P * NF;
+    S.best = w; w += P * NF;
+    S.f = w; w += P;
+    S.viol = w; w += P;
+    S.fbest = w; w += P;
+    S.delta = w; w += P;
+    double* d_gt = w; w += P * m;
+    S.rows = w;
+    S.have_best = ctx->d_solver_i;
+    S.status = S.have_best + P;
+    S.iters = S.status + P;
+    S.evals = S.iters + P;
+    S.dbg = S.evals + P;
+    int* d_running = S.dbg + 3 * P;
+    S.q_des = d_q_des;
+    S.tol = opt.tol;
+    S.torque_tol = opt.torque_tol;
+    S.collision_tol = opt.collision_tol;
+    S.max_iter = opt.max_iter;
+    cudaStream_t st = ctx->stream;
+    static int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        CU(cudaFuncSetAttribute(k_solver_step, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SOLVER_ROWCAP * sizeof(double))));
+        attr_dev = dev;
+    }
+    // x = 0 (armtd_NLP::get_starting_point), g(0)
+    CU(cudaMemsetAsync(S.x, 0, size_t(nprob) * NF * sizeof(double), st));
+    CU(cudaMemsetAsync(S.xt, 0, size_t(nprob) * NF * sizeof(double), st));
+    CU(launch_constraints(B, S.x, ctx->d_g, nullptr, st));
+    k_solver_start<<<nprob, SOLVER_THREADS, 0, st>>>(B, S, ctx->d_g);
+    ctx->launches += 2;
+    for (int it = 0; it < opt.max_iter; it++) {
+        CU(launch_constraints(B, S.x, ctx->d_g, ctx->d_jac, st));
+        k_solver_step<<<nprob, SOLVER_THREADS, SOLVER_ROWCAP * sizeof(double), st>>>(B, S, ctx->d_g, ctx->d_jac, it);
+        CU(launch_constraints(B, S.xt, d_gt, nullptr, st));
+        k_solver_accept<<<nprob, SOLVER_THREADS, 0, st>>>(B, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
+        ctx->launches += 4;
+        if ((it & 3) == 3 && it + 1 < opt.max_iter) {  // every fourth iteration: is anybody still running?
+            int running = 0;
+            CU(cudaMemsetAsync(d_running, 0, sizeof(int), st));
+            k_solver_count_running<<<(nprob + 255) / 256, 256, 0, st>>>(S, nprob, d_running);
+            CU(cudaMemcpyAsync(&running, d_running, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            ctx->launches += 1;
+            if (running == 0) break;
+        }
+    }
+    k_solver_final<<<(nprob + 255) / 256, 256, 0, st>>>(S, nprob, d_k_opt, nullptr);
+    CU(launch_constraints(B, d_k_opt, ctx->d_g, nullptr, st));
+    CU(launch_verdict(B, ctx->d_g, d_feasible, d_first, st));
+    if (d_iters) CU(cudaMemcpyAsync(d_iters, S.iters, size_t(nprob) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (std::getenv("ARMOUR_SOLVER_DEBUG")) {  // developer aid: row / sweep / update counts of the last step per problem
+        std::vector<int> dbg(size_t(nprob) * 3);
+        CU(cudaMemcpyAsync(dbg.data(), S.dbg, dbg.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        long long r = 0, sw = 0, mv = 0;
+        int rmax = 0, mvmax = 0;
+        for (int p = 0; p < nprob; p++) {
+            r += dbg[p * 3];
+            sw += dbg[p * 3 + 1];
+            mv += dbg[p * 3 + 2];
+            rmax = std::max(rmax, dbg[p * 3]);
+            mvmax = std::max(mvmax, dbg[p * 3 + 2]);
+        }
+        std::printf("solver debug: last step per problem: rows mean %.0f max %d, sweeps mean %.1f, row updates mean %.0f max %d\n",
+                    double(r) / nprob, rmax, double(sw) / nprob, double(mv) / nprob, mvmax);
+    }
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return ARMOUR_OK;
+}
+
+int armour_batch_solve(armour_ctx* ctx, int nprob, const double* q_des, const armour_solver_options* opt, double* k_opt,
+                       int* feasible, int* first_violation, int* iterations) {
+    if (!ctx || !q_des || !k_opt || !feasible) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "solve before build");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->d_solver_io) CU(dalloc(&ctx->d_solver_io, size_t(ctx->cfg.max_problems) * (2 * NF + 2)));
+    const size_t P = size_t(ctx->cfg.max_problems);
+    double* d_q = ctx->d_solver_io;
+    double* d_ko = d_q + P * NF;
+    int* d_i = reinterpret_cast<int*>(d_ko + P * NF);  // feasible, first, iterations: 3 * P ints in 2 * P doubles
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_q, q_des, size_t(nprob) * NF * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = armour_batch_solve_device(ctx, nprob, d_q, opt, d_ko, d_i, d_i + P, d_i + 2 * P);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(k_opt, d_ko, size_t(nprob) * NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(feasible, d_i, size_t(nprob) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (first_violation) CU(cudaMemcpyAsync(first_violation, d_i + P, size_t(nprob) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iterations) CU(cudaMemcpyAsync(iterations, d_i + 2 * P, size_t(nprob) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return ARMOUR_OK;
 }
 

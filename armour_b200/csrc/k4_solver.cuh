@@ -1,0 +1,388 @@
+// K4: batched trust-region SQP on the device — the caller of the hot path.
+//
+// The reference hands ONE armtd_NLP to Ipopt (KPR/armour_main.cu:237-278); every iteration crosses PCIe twice
+// (eval_g, eval_jac_g) and Ipopt is serial.  With the constraint kernel at ~0.65 us per evaluation the solver loop
+// is what bounds "planning iterations per second", so the loop itself runs on the device for a whole batch: one
+// CTA per planning problem, thousands in step, only k_opt and the verdict leave the GPU.
+//
+// The algorithm is the one of armour_b200/host/local_solver.cpp (the stand-in for Ipopt of the C++ host side),
+// statement for statement, so that both give the same iterates: the planner's cost is an exactly spherical
+// quadratic in k (KPR/NLPclass.cu:207-268), each iteration solves
+//     min 1/2 h |d|^2 + grad_f . d   s.t.  g_l <= g + J d <= g_u,  -1 <= x + d <= 1,  |d|_inf <= Delta
+// by Hildreth's dual coordinate ascent over the rows that can become active inside the trust region (Gauss-Seidel
+// in row order: one thread), then accepts / rejects on (violation, cost).  Per iteration: k_constraints (g, J at x),
+// k_solver_step, k_constraints (g at the trial point), k_solver_accept.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bezier.cuh"
+#include "device_constants.cuh"
+#include "layout.h"
+
+namespace armour {
+
+constexpr int SOLVER_THREADS = 256;
+constexpr int SOLVER_ROWCAP = 2048;   // linearised rows kept per problem; more -> status ROW_OVERFLOW
+constexpr int SOLVER_ROWW = 17;       // doubles per row: a[7], b, |a|^2 / h, a[7] / h, sqrt(|a|^2 / h * h)
+enum { SOLVER_RUNNING = 0, SOLVER_SUCCESS = 1, SOLVER_MAXITER = 2, SOLVER_TINY_STEP = 3, SOLVER_INFEASIBLE = 4,
+       SOLVER_ROW_OVERFLOW = 5 };
+
+struct SolverState {   // structure of arrays, [nprob] or [nprob][NF]
+    double* x;         // current iterate
+    double* xt;        // trial point
+    double* best;      // best accepted feasible point
+    double* f;         // cost at x
+    double* viol;      // violation at x (<= 0: finalize_solution would accept)
+    double* fbest;
+    double* delta;     // trust-region radius
+    int* have_best;
+    int* status;       // SOLVER_*
+    int* iters;
+    int* evals;
+    int* dbg;          // [nprob][3]: rows, sweeps, row updates of the last step (diagnostics)
+    double* rows;      // [nprob][SOLVER_ROWCAP][SOLVER_ROWW]
+    const double* q_des;  // [nprob][NF]
+    double tol, torque_tol, collision_tol;
+    int max_iter;
+};
+
+// cost and gradient of one problem (KPR/NLPclass.cu:207-268; same expressions as armour_cost in armour_capi.cu)
+__device__ __forceinline__ double solver_wrap(double a) {
+    while (a < -M_PI) a += 2 * M_PI;
+    while (a > M_PI) a -= 2 * M_PI;
+    return a;
+}
+__device__ inline double solver_cost(const Batch& B, int p, const double* q_des, const double* k, double* grad) {
+    const RobotConstants& R = c_robot;
+    const double tp = R.t_plan, D = R.duration;
+    double qp[NF];
+    for (int i = 0; i < NF; i++)
+        qp[i] = bez_q(B.q0[size_t(p) * NF + i], B.qd0[size_t(p) * NF + i] * D, B.qdd0[size_t(p) * NF + i] * D * D,
+                      R.k_range[i] * k[i], tp);
+    const double v = pw2(solver_wrap(q_des[0] - qp[0])) + pw2(solver_wrap(q_des[2] - qp[2])) + pw2(solver_wrap(q_des[4] - qp[4])) +
+                     pw2(solver_wrap(q_des[6] - qp[6])) + pw2(q_des[1] - qp[1]) + pw2(q_des[3] - qp[3]) + pw2(q_des[5] - qp[5]);
+    if (grad) {
+        for (int i = 0; i < NF; i++) {
+            const double dk = pw3(tp) * (6 * pw2(tp) - 15 * tp + 10) * R.k_range[i];
+            grad[i] = (i % 2 == 0) ? (2 * solver_wrap(qp[i] - q_des[i]) * dk) : (2 * (qp[i] - q_des[i]) * dk);
+            grad[i] *= R.cost_scale;
+        }
+    }
+    return v * R.cost_scale;
+}
+
+// bounds of row i (armour_batch_get_bounds / KPR/NLPclass.cu:116-165) and the acceptance tolerance of its class
+__device__ __forceinline__ void solver_row_bounds(const Batch& B, int p, int i, double ttol, double ctol, double* gl,
+                                                  double* gu, double* tol) {
+    const RobotConstants& R = c_robot;
+    const int T = B.T, NJ = B.NJ, O = B.O;
+    if (i < NF * T) {
+        const int t = i / NF, j = i % NF;
+        const double tr = B.torque_radius[size_t(p) * NF * T + size_t(j) * T + t];
+        *gl = -R.torque_limits[j] + tr;
+        *gu = R.torque_limits[j] - tr;
+        *tol = ttol;
+    } else if (i < NF * T + NJ * T * O) {
+        *gl = -1e19;
+        *gu = 0;
+        *tol = ctol;
+    } else {
+        const int q = i - (NF * T + NJ * T * O), j = q % NF;
+        if (q < 2 * NF) {
+            *gl = R.state_limits_lb[j] + R.qe;
+            *gu = R.state_limits_ub[j] - R.qe;
+        } else {
+            *gl = -R.speed_limits[j] + R.qde;
+            *gu = R.speed_limits[j] - R.qde;
+        }
+        *tol = 0.0;
+    }
+}
+
+// block-wide maximum (all threads get it)
+__device__ inline double solver_block_max(double v, double* s_red) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = s_red[0];
+    for (int w = 1; w < SOLVER_THREADS / 32; w++) r = fmax(r, s_red[w]);
+    return r;
+}
+// violation with the verdict's tolerances folded in: <= 0 means "finalize_solution would accept"
+__device__ inline double solver_violation(const Batch& B, int p, const double* g, double ttol, double ctol, double* s_red) {
+    const int m = B.m();
+    double v = -1e300;
+    for (int i = threadIdx.x; i < m; i += SOLVER_THREADS) {
+        double gl, gu, tol;
+        solver_row_bounds(B, p, i, ttol, ctol, &gl, &gu, &tol);
+        v = fmax(v, g[i] - gu - tol);
+        if (gl > -1e18) v = fmax(v, gl - g[i] - tol);
+    }
+    return solver_block_max(v, s_red);
+}
+
+// start: x = 0 (armtd_NLP::get_starting_point), cost and violation there from g(0)
+__global__ void __launch_bounds__(SOLVER_THREADS) k_solver_start(Batch B, SolverState S, const double* __restrict__ g) {
+    const int p = blockIdx.x;
+    __shared__ double s_red[SOLVER_THREADS / 32];
+    const double viol = solver_violation(B, p, g + size_t(p) * B.m(), S.torque_tol, S.collision_tol, s_red);
+    if (threadIdx.x == 0) {
+        double x[NF];
+        for (int j = 0; j < NF; j++) x[j] = S.x[size_t(p) * NF + j];
+        const double f = solver_cost(B, p, S.q_des + size_t(p) * NF, x, nullptr);
+        S.f[p] = f;
+        S.viol[p] = viol;
+        S.have_best[p] = viol <= 0;
+        S.fbest[p] = f;
+        if (viol <= 0)
+            for (int j = 0; j < NF; j++) S.best[size_t(p) * NF + j] = x[j];
+        S.delta[p] = 0.5;
+        S.status[p] = SOLVER_RUNNING;
+        S.iters[p] = 0;
+        S.evals[p] = 1;
+    }
+}
+
+// one SQP step from (g, J) at x: writes the trial point xt, or ends the problem (step below tolerance)
+__global__ void __launch_bounds__(SOLVER_THREADS)
+k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const double* __restrict__ jac_all, int it) {
+    const int p = blockIdx.x, tid = threadIdx.x;
+    if (S.status[p] != SOLVER_RUNNING) return;  // uniform per CTA
+    const int m = B.m();
+    const double* g = g_all + size_t(p) * m;
+    const double* J = jac_all + size_t(p) * m * NF;
+    __shared__ double s_x[NF], s_gf[NF], s_h, s_delta;
+    __shared__ int s_cnt[SOLVER_THREADS], s_total;
+    if (tid == 0) {
+        double x[NF], gf[NF], xt[NF];
+        for (int j = 0; j < NF; j++) x[j] = S.x[size_t(p) * NF + j];
+        const double* qd = S.q_des + size_t(p) * NF;
+        solver_cost(B, p, qd, x, gf);
+        // curvature of the cost along the gradient from one extra evaluation (exact for the planner's quadratic cost)
+        double h = 1.0, gn2 = 0;
+        for (int j = 0; j < NF; j++) gn2 += gf[j] * gf[j];
+        if (gn2 > 0) {
+            const double eps = 1e-3 / sqrt(gn2);
+            for (int j = 0; j < NF; j++) xt[j] = x[j] - eps * gf[j];
+            const double f2 = solver_cost(B, p, qd, xt, nullptr);
+            const double curv = 2.0 * (f2 - S.f[p] + eps * gn2) / (eps * eps * gn2);
+            if (curv > 1e-8) h = curv;
+        }
+        for (int j = 0; j < NF; j++) {
+            s_x[j] = x[j];
+            s_gf[j] = gf[j];
+        }
+        s_h = h;
+        s_delta = S.delta[p];
+        S.iters[p] = it + 1;
+    }
+    __syncthreads();
+    const double h = s_h, delta = s_delta;
+    // rows that can be reached inside the trust region, linearised, in row order (upper side, then lower side)
+    const int per = (m + SOLVER_THREADS - 1) / SOLVER_THREADS;
+    const int i0 = tid * per, i1 = (i0 + per) < m ? (i0 + per) : m;
+    double* rows = S.rows + size_t(p) * SOLVER_ROWCAP * SOLVER_ROWW;
+    for (int pass = 0; pass < 2; pass++) {
+        int n = 0;
+        int at = 0;
+        if (pass == 1) {
+            for (int q = 0; q < tid; q++) at += s_cnt[q];  // (256 short sums; the scan is not what costs here)
+        }
+        for (int i = i0; i < i1; i++) {
+            double gl, gu, tol;
+            solver_row_bounds(B, p, i, S.torque_tol, S.collision_tol, &gl, &gu, &tol);
+            tol *= 0.5;  // aim inside the acceptance band
+            double a[NF], aa = 0, l1 = 0;
+            for (int j = 0; j < NF; j++) {
+                a[j] = J[size_t(i) * NF + j];
+                aa += a[j] * a[j];
+                l1 += fabs(a[j]);
+            }
+            const double bu = gu + tol - g[i];
+            const double bl = g[i] - (gl - tol);
+            const bool pu = !(bu > l1 * delta);
+            const bool pl = gl > -1e18 && !(bl > l1 * delta);
+            if (pass == 1) {
+                if (pu && at + n < SOLVER_ROWCAP) {
+                    double* r = rows + size_t(at + n) * SOLVER_ROWW;
+                    for (int j = 0; j < NF; j++) r[j] = 1.0 * a[j];
+                    r[7] = bu;
+                    r[8] = aa / h;
+                    for (int j = 0; j < NF; j++) r[9 + j] = r[j] / h;
+                    r[16] = sqrt(r[8] * h);
+                }
+                if (pl && at + n + (pu ? 1 : 0) < SOLVER_ROWCAP) {
+                    double* r = rows + size_t(at + n + (pu ? 1 : 0)) * SOLVER_ROWW;
+                    for (int j = 0; j < NF; j++) r[j] = -1.0 * a[j];
+                    r[7] = bl;
+                    r[8] = aa / h;
+                    for (int j = 0; j < NF; j++) r[9 + j] = r[j] / h;
+                    r[16] = sqrt(r[8] * h);
+                }
+            }
+            n += (pu ? 1 : 0) + (pl ? 1 : 0);
+        }
+        if (pass == 0) {
+            s_cnt[tid] = n;
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int q = 0; q < SOLVER_THREADS; q++) tot += s_cnt[q];
+                s_total = tot;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    __shared__ int s_nrows;
+    if (tid == 0) {
+        int nrows = s_total;
+        if (nrows + 2 * NF > SOLVER_ROWCAP) {
+            S.status[p] = SOLVER_ROW_OVERFLOW;
+            nrows = -1;
+        } else {
+            // variable bounds and trust region: e_j . d <= min(delta, xu - x), -e_j . d <= min(delta, x - xl)
+            for (int j = 0; j < NF; j++) {
+                for (int sgn = 0; sgn < 2; sgn++) {
+                    const double b = sgn == 0 ? fmin(delta, 1.0 - s_x[j]) : fmin(delta, s_x[j] - (-1.0));
+                    if (b > 1.0 * delta) continue;  // push(): l1 = 1, the row is kept unless b > delta
+                    double* r = rows + size_t(nrows) * SOLVER_ROWW;
+                    for (int q = 0; q < NF; q++) r[q] = 0.0;
+                    r[j] = sgn == 0 ? 1.0 : -1.0;
+                    r[7] = b;
+                    r[8] = 1.0 / h;
+                    for (int q = 0; q < NF; q++) r[9 + q] = r[q] / h;
+                    r[16] = sqrt(r[8] * h);
+                    nrows++;
+                }
+            }
+        }
+        s_nrows = nrows;
+    }
+    __syncthreads();
+    const int nrows = s_nrows;
+    if (nrows < 0 || tid >= 32) return;
+    // Hildreth's method on the dual (lambda >= 0), d(lambda) = -(c + sum lambda_i a_i) / h: Gauss-Seidel over the rows in
+    // order.  A row whose multiplier stays put (lambda = 0 and satisfied: almost all of them) leaves d unchanged, so
+    // one warp tests 32 consecutive rows against the current d at once, applies the update of the FIRST row that moves,
+    // re-tests the rows behind it, and so on: the arithmetic and its order are those of the sequential loop of the host
+    // solver, the cost is ~rows/32 + (rows that move) steps per sweep.  The multipliers live in dynamic shared memory.
+    extern __shared__ double s_lam[];
+    const int lane = tid;
+    for (int i = lane; i < nrows; i += 32) s_lam[i] = 0.0;
+    __syncwarp();
+    double d[NF];
+    for (int j = 0; j < NF; j++) d[j] = -s_gf[j] / h;
+    int n_sweeps = 0, n_moves = 0;
+    for (int s = 0; s < 200; s++) {
+        double moved = 0.0;
+        n_sweeps++;
+        for (int base = 0; base < nrows; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < nrows;
+            double a[NF], ah[NF], b = 0, raa = 0, sq = 0, lam = 0;
+            for (int j = 0; j < NF; j++) a[j] = ah[j] = 0;
+            if (valid) {
+                const double* r = rows + size_t(i) * SOLVER_ROWW;
+                for (int j = 0; j < NF; j++) a[j] = r[j];
+                b = r[7];
+                raa = r[8];
+                for (int j = 0; j < NF; j++) ah[j] = r[9 + j];
+                sq = r[16];
+                lam = s_lam[i];
+            }
+            int from = 0;  // lanes below `from` are done for this sweep
+            for (;;) {
+                double nl = 0, dl = 0;
+                bool moves = false;
+                if (valid && lane >= from && raa > 0) {
+                    double viol = -b;
+                    for (int j = 0; j < NF; j++) viol += a[j] * d[j];
+                    nl = lam + viol / raa;  // exact coordinate maximisation
+                    if (nl < 0) nl = 0;
+                    dl = nl - lam;
+                    moves = dl != 0.0;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, moves);
+                if (mask == 0) break;
+                const int first = __ffs(mask) - 1;
+                const double bdl = __shfl_sync(0xffffffffu, dl, first);
+                const double bsq = __shfl_sync(0xffffffffu, sq, first);
+                for (int j = 0; j < NF; j++) d[j] -= bdl * __shfl_sync(0xffffffffu, ah[j], first);
+                if (lane == first) {
+                    lam = nl;
+                    s_lam[i] = nl;
+                }
+                moved = fmax(moved, fabs(bdl) * bsq);
+                from = first + 1;
+                n_moves++;
+            }
+        }
+        if (moved < 1e-12) break;
+    }
+    if (lane == 0) {
+        S.dbg[p * 3 + 0] = nrows;
+        S.dbg[p * 3 + 1] = n_sweeps;
+        S.dbg[p * 3 + 2] = n_moves;
+        double dn = 0;
+        for (int j = 0; j < NF; j++) {
+            d[j] = fmax(-delta, fmin(delta, d[j]));
+            const double xt = fmax(-1.0, fmin(1.0, s_x[j] + d[j]));
+            S.xt[size_t(p) * NF + j] = xt;
+            dn = fmax(dn, fabs(xt - s_x[j]));
+        }
+        if (dn < S.tol) {
+            S.status[p] = (S.viol[p] <= 0) ? SOLVER_SUCCESS : SOLVER_INFEASIBLE;
+            for (int j = 0; j < NF; j++) S.xt[size_t(p) * NF + j] = s_x[j];
+        }
+    }
+}
+
+// acceptance test of the trial point from g(xt): filter-style — feasible points must lower the cost, infeasible ones
+// must lower the violation
+__global__ void __launch_bounds__(SOLVER_THREADS) k_solver_accept(Batch B, SolverState S, const double* __restrict__ gt_all, int last) {
+    const int p = blockIdx.x;
+    if (S.status[p] != SOLVER_RUNNING) return;
+    __shared__ double s_red[SOLVER_THREADS / 32];
+    const double vt = solver_violation(B, p, gt_all + size_t(p) * B.m(), S.torque_tol, S.collision_tol, s_red);
+    if (threadIdx.x == 0) {
+        double xt[NF];
+        for (int j = 0; j < NF; j++) xt[j] = S.xt[size_t(p) * NF + j];
+        const double ft = solver_cost(B, p, S.q_des + size_t(p) * NF, xt, nullptr);
+        S.evals[p] += 1;
+        const double f = S.f[p], viol = S.viol[p];
+        const bool accept = (vt <= 0 && (viol > 0 || ft < f - 1e-12)) || (vt > 0 && viol > 0 && vt < viol - 1e-12);
+        if (accept) {
+            for (int j = 0; j < NF; j++) S.x[size_t(p) * NF + j] = xt[j];
+            S.f[p] = ft;
+            S.viol[p] = vt;
+            S.delta[p] = fmin(1.0, S.delta[p] * 1.5);
+            if (vt <= 0 && (!S.have_best[p] || ft < S.fbest[p])) {
+                S.have_best[p] = 1;
+                S.fbest[p] = ft;
+                for (int j = 0; j < NF; j++) S.best[size_t(p) * NF + j] = xt[j];
+            }
+        } else {
+            const double nd = S.delta[p] * 0.4;
+            S.delta[p] = nd;
+            if (nd < S.tol) S.status[p] = (viol <= 0) ? SOLVER_TINY_STEP : SOLVER_INFEASIBLE;
+        }
+        if (last && S.status[p] == SOLVER_RUNNING) S.status[p] = SOLVER_MAXITER;
+    }
+}
+
+// the point handed to finalize_solution: the best accepted feasible point if there is one, else the last iterate
+__global__ void k_solver_final(SolverState S, int nprob, double* __restrict__ k_opt, int* __restrict__ running) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nprob) return;
+    const bool hb = S.have_best[p] != 0;
+    for (int j = 0; j < NF; j++) k_opt[size_t(p) * NF + j] = hb ? S.best[size_t(p) * NF + j] : S.x[size_t(p) * NF + j];
+    if (running && S.status[p] == SOLVER_RUNNING) atomicAdd(running, 1);
+}
+__global__ void k_solver_count_running(SolverState S, int nprob, int* __restrict__ running) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nprob && S.status[p] == SOLVER_RUNNING) atomicAdd(running, 1);
+}
+
+}  // namespace armour

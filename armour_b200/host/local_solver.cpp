@@ -12,7 +12,9 @@ namespace {
 struct Lin {  // one linearised inequality  a . d <= b
     double a[16];
     double b;
-    double aa;  // |a|^2 / h
+    double aa;      // |a|^2 / h
+    double ah[16];  // a / h: the primal step of a unit multiplier change (computed once per row, not per update)
+    double sq;      // sqrt(aa * h) = |a|: scale of the progress measure
 };
 
 // min 1/2 h |d|^2 + c . d  s.t.  a_i . d <= b_i : Hildreth's method on the dual (lambda >= 0).
@@ -31,9 +33,9 @@ void hildreth(int n, double h, const double* c, std::vector<Lin>& rows, double* 
             if (nl < 0) nl = 0;
             const double dl = nl - lam[i];
             if (dl != 0.0) {
-                for (int j = 0; j < n; j++) d[j] -= dl * r.a[j] / h;
+                for (int j = 0; j < n; j++) d[j] -= dl * r.ah[j];
                 lam[i] = nl;
-                moved = std::max(moved, std::fabs(dl) * std::sqrt(r.aa * h));
+                moved = std::max(moved, std::fabs(dl) * r.sq);
             }
         }
         if (moved < 1e-12) break;
@@ -119,6 +121,8 @@ SolverReturn local_solve(TNLP& nlp, const LocalSolverOptions& opt, LocalSolverSt
             if (b > l1 * delta) return;  // cannot become active within |d|_inf <= delta
             r.b = b;
             r.aa = aa / h;
+            for (Index j = 0; j < n; j++) r.ah[j] = r.a[j] / h;
+            r.sq = std::sqrt(r.aa * h);
             rows.push_back(r);
         };
         for (Index i = 0; i < m; i++) {

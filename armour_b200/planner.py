@@ -125,6 +125,26 @@ class ReachSetEngine:
             self._check(self.lib.armour_batch_get_candidate_counts(self._h, self.nprob, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def solve(self, q_des, max_iter=None, tol=None):
+        """Batched planning on the device (armour_batch_solve): the trust-region SQP of the C++ host solver run on the
+        GPU for every built problem, from k = 0.  Returns (k_opt [nprob, 7], feasible [nprob] bool, first violated row
+        [nprob], iterations [nprob])."""
+        q_des = np.ascontiguousarray(np.asarray(q_des, dtype=np.float64).reshape(self.nprob, NF))
+        opt = _lib.SolverOptions()
+        self.lib.armour_solver_options_default(C.byref(opt))
+        if max_iter is not None:
+            opt.max_iter = int(max_iter)
+        if tol is not None:
+            opt.tol = float(tol)
+        k = np.empty((self.nprob, NF))
+        ok = np.zeros(self.nprob, np.int32)
+        first = np.zeros(self.nprob, np.int32)
+        iters = np.zeros(self.nprob, np.int32)
+        self._check(self.lib.armour_batch_solve(self._h, self.nprob, _dp(q_des), C.byref(opt), _dp(k),
+                                                ok.ctypes.data_as(_lib.ip), first.ctypes.data_as(_lib.ip),
+                                                iters.ctypes.data_as(_lib.ip)))
+        return k, ok.astype(bool), first, iters
+
     def measure_fp64_peak(self):
         """Sustained non-tensor FP64 rate of the device in TFLOP/s (FMA probe kernel in the library)."""
         v = C.c_double(0)

@@ -130,6 +130,23 @@ int armour_batch_verdict_device(armour_ctx* ctx, int nprob, const double* d_g, i
 int armour_batch_get_torque_radius(armour_ctx* ctx, int nprob, double* out /* [nprob][NF*T] */);
 int armour_batch_get_link_independent_generators(armour_ctx* ctx, int nprob, double* out /* [nprob][T*NJ*18] */);
 int armour_batch_get_bounds(armour_ctx* ctx, int nprob, double* g_l, double* g_u);
+/* Batched planning on the device (replaces, for a batch, the IpoptApplication::OptimizeTNLP call of
+ * KPR/armour_main.cu:237-278 and the PCIe round trips of its eval_g / eval_jac_g callbacks): every problem of the
+ * batch runs the trust-region SQP of armour_b200/host/local_solver.cpp on the GPU, in step, from k = 0.  Outputs (device
+ * pointers in the _device variant): k_opt[nprob*7] = the point finalize_solution would receive, feasible[nprob] and
+ * first_violation[nprob] = its verdict (KPR/NLPclass.cu:449-537), iterations[nprob] (may be NULL).  q_des[nprob*7].
+ * No wall-clock limit (the reference's max_wall_time makes results machine dependent); max_iter bounds the work. */
+typedef struct armour_solver_options {
+    int max_iter;          /* 60, as the host solver */
+    double tol;            /* 1e-4 = IPOPT_OPTIMIZATION_TOLERANCE (KPR/Parameters.h:51): step-size stopping test */
+    double torque_tol;     /* 1e-2 N m, the verdict's tolerances (KPR/Parameters.h:40-43) */
+    double collision_tol;  /* 1e-4 m */
+} armour_solver_options;
+void armour_solver_options_default(armour_solver_options* opt);
+int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des, const armour_solver_options* opt,
+                              double* d_k_opt, int* d_feasible, int* d_first_violation, int* d_iterations);
+int armour_batch_solve(armour_ctx* ctx, int nprob, const double* q_des, const armour_solver_options* opt, double* k_opt,
+                       int* feasible, int* first_violation, int* iterations);
 /* Status of the last build per problem (ARMOUR_OK or ARMOUR_ERR_CAPACITY), out[nprob]. */
 int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out);
 /* Stored k-only monomial counts of the built reach sets: link_n[nprob*T*NJ], u_n[nprob*T*NF] (either may
