@@ -93,7 +93,8 @@ SIGNATURES = {
 
 class SolverOptions(C.Structure):
     """armour_solver_options (include/armour_b200.h)."""
-    _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("torque_tol", C.c_double), ("collision_tol", C.c_double)]
+    _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("torque_tol", C.c_double), ("collision_tol", C.c_double),
+                ("qp_sweeps", C.c_int)]
 
 
 _LIB = None

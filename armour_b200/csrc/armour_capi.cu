@@ -600,6 +600,7 @@ void armour_solver_options_default(armour_solver_options* opt) {
     opt->tol = 1e-4;
     opt->torque_tol = 1e-2;
     opt->collision_tol = 1e-4;
+    opt->qp_sweeps = 200;
 }
 
 int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des, const armour_solver_options* opt_in,
@@ -609,7 +610,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     armour_solver_options opt;
     armour_solver_options_default(&opt);
     if (opt_in) opt = *opt_in;
-    if (opt.max_iter < 1 || !(opt.tol > 0)) return fail(ctx, ARMOUR_ERR_ARG, "solver options");
+    if (opt.max_iter < 1 || !(opt.tol > 0) || opt.qp_sweeps < 1) return fail(ctx, ARMOUR_ERR_ARG, "solver options");
     CU(cudaSetDevice(ctx->cfg.device));
     Batch B = ctx->B;
     B.nprob = nprob;
@@ -650,6 +651,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     S.torque_tol = opt.torque_tol;
     S.collision_tol = opt.collision_tol;
     S.max_iter = opt.max_iter;
+    S.qp_sweeps = opt.qp_sweeps;
     cudaStream_t st = ctx->stream;
     static int attr_dev = -1;
     int dev = 0;

@@ -44,6 +44,7 @@ struct SolverState {   // structure of arrays, [nprob] or [nprob][NF]
     const double* q_des;  // [nprob][NF]
     double tol, torque_tol, collision_tol;
     int max_iter;
+    int qp_sweeps;
 };
 
 // cost and gradient of one problem (KPR/NLPclass.cu:207-268; same expressions as armour_cost in armour_capi.cu)
@@ -275,7 +276,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
     double d[NF];
     for (int j = 0; j < NF; j++) d[j] = -s_gf[j] / h;
     int n_sweeps = 0, n_moves = 0;
-    for (int s = 0; s < 200; s++) {
+    for (int s = 0; s < S.qp_sweeps; s++) {
         double moved = 0.0;
         n_sweeps++;
         for (int base = 0; base < nrows; base += 32) {

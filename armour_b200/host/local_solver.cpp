@@ -139,7 +139,7 @@ SolverReturn local_solve(TNLP& nlp, const LocalSolverOptions& opt, LocalSolverSt
             push(e.data(), -1.0, std::min(delta, x[j] - xl[j]));
         }
         std::vector<double> d(n);
-        hildreth(n, h, gf.data(), rows, d.data(), 200);
+        hildreth(n, h, gf.data(), rows, d.data(), opt.qp_sweeps);
         double dn = 0;
         for (Index j = 0; j < n; j++) {
             d[j] = std::max(-delta, std::min(delta, d[j]));

@@ -16,6 +16,7 @@ struct LocalSolverOptions {
     double tol = 1e-4;          // IPOPT_OPTIMIZATION_TOLERANCE (KPR/Parameters.h:51): step-size stopping test
     double max_wall_time = 0.45;  // seconds
     int max_iter = 60;
+    int qp_sweeps = 200;        // cap on the Hildreth sweeps of one QP
     double torque_tol = 1e-2, collision_tol = 1e-4;  // acceptance tolerances = the verdict's (KPR/Parameters.h:40-43)
 };
 struct LocalSolverStats {

@@ -141,6 +141,7 @@ typedef struct armour_solver_options {
     double tol;            /* 1e-4 = IPOPT_OPTIMIZATION_TOLERANCE (KPR/Parameters.h:51): step-size stopping test */
     double torque_tol;     /* 1e-2 N m, the verdict's tolerances (KPR/Parameters.h:40-43) */
     double collision_tol;  /* 1e-4 m */
+    int qp_sweeps;         /* 200: cap on the Hildreth sweeps of one QP (most QPs run into it; cost scales with it) */
 } armour_solver_options;
 void armour_solver_options_default(armour_solver_options* opt);
 int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des, const armour_solver_options* opt,
