@@ -94,7 +94,7 @@ SIGNATURES = {
 class SolverOptions(C.Structure):
     """armour_solver_options (include/armour_b200.h)."""
     _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("torque_tol", C.c_double), ("collision_tol", C.c_double),
-                ("qp_sweeps", C.c_int)]
+                ("qp_sweeps", C.c_int), ("qp_update_budget", C.c_int)]
 
 
 _LIB = None

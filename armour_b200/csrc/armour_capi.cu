@@ -601,6 +601,7 @@ void armour_solver_options_default(armour_solver_options* opt) {
     opt->torque_tol = 1e-2;
     opt->collision_tol = 1e-4;
     opt->qp_sweeps = 200;
+    opt->qp_update_budget = 32768;
 }
 
 int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des, const armour_solver_options* opt_in,
@@ -652,6 +653,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     S.collision_tol = opt.collision_tol;
     S.max_iter = opt.max_iter;
     S.qp_sweeps = opt.qp_sweeps;
+    S.qp_update_budget = opt.qp_update_budget;
     cudaStream_t st = ctx->stream;
     static int attr_dev = -1;
     int dev = 0;

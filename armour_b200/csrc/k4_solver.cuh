@@ -45,6 +45,7 @@ struct SolverState {   // structure of arrays, [nprob] or [nprob][NF]
     double tol, torque_tol, collision_tol;
     int max_iter;
     int qp_sweeps;
+    int qp_update_budget;
 };
 
 // cost and gradient of one problem (KPR/NLPclass.cu:207-268; same expressions as armour_cost in armour_capi.cu)
@@ -321,6 +322,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
             }
         }
         if (moved < 1e-12) break;
+        if (S.qp_update_budget > 0 && n_moves >= S.qp_update_budget) break;
     }
     if (lane == 0) {
         S.dbg[p * 3 + 0] = nrows;

@@ -19,9 +19,10 @@ struct Lin {  // one linearised inequality  a . d <= b
 
 // min 1/2 h |d|^2 + c . d  s.t.  a_i . d <= b_i : Hildreth's method on the dual (lambda >= 0).
 // d(lambda) = -(c + sum lambda_i a_i) / h.  Returns the primal step.
-void hildreth(int n, double h, const double* c, std::vector<Lin>& rows, double* d, int sweeps) {
+void hildreth(int n, double h, const double* c, std::vector<Lin>& rows, double* d, int sweeps, int update_budget) {
     std::vector<double> lam(rows.size(), 0.0);
     for (int j = 0; j < n; j++) d[j] = -c[j] / h;
+    long long updates = 0;
     for (int s = 0; s < sweeps; s++) {
         double moved = 0.0;
         for (size_t i = 0; i < rows.size(); i++) {
@@ -36,9 +37,11 @@ void hildreth(int n, double h, const double* c, std::vector<Lin>& rows, double* 
                 for (int j = 0; j < n; j++) d[j] -= dl * r.ah[j];
                 lam[i] = nl;
                 moved = std::max(moved, std::fabs(dl) * r.sq);
+                updates++;
             }
         }
         if (moved < 1e-12) break;
+        if (update_budget > 0 && updates >= update_budget) break;  // diverging multipliers: an infeasible QP
     }
 }
 
@@ -139,7 +142,7 @@ SolverReturn local_solve(TNLP& nlp, const LocalSolverOptions& opt, LocalSolverSt
             push(e.data(), -1.0, std::min(delta, x[j] - xl[j]));
         }
         std::vector<double> d(n);
-        hildreth(n, h, gf.data(), rows, d.data(), opt.qp_sweeps);
+        hildreth(n, h, gf.data(), rows, d.data(), opt.qp_sweeps, opt.qp_update_budget);
         double dn = 0;
         for (Index j = 0; j < n; j++) {
             d[j] = std::max(-delta, std::min(delta, d[j]));

@@ -125,7 +125,7 @@ class ReachSetEngine:
             self._check(self.lib.armour_batch_get_candidate_counts(self._h, self.nprob, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def solve(self, q_des, max_iter=None, tol=None, qp_sweeps=None):
+    def solve(self, q_des, max_iter=None, tol=None, qp_sweeps=None, qp_update_budget=None):
         """Batched planning on the device (armour_batch_solve): the trust-region SQP of the C++ host solver run on the
         GPU for every built problem, from k = 0.  Returns (k_opt [nprob, 7], feasible [nprob] bool, first violated row
         [nprob], iterations [nprob])."""
@@ -138,6 +138,8 @@ class ReachSetEngine:
             opt.tol = float(tol)
         if qp_sweeps is not None:
             opt.qp_sweeps = int(qp_sweeps)
+        if qp_update_budget is not None:
+            opt.qp_update_budget = int(qp_update_budget)
         k = np.empty((self.nprob, NF))
         ok = np.zeros(self.nprob, np.int32)
         first = np.zeros(self.nprob, np.int32)
