@@ -559,9 +559,16 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             } else {
                 // all 72 half-spaces from the generators: rows with more than HP_CAP candidates, or k outside
                 // the box the candidate lists were built for
+                // (results through temporaries: taking the address of max_elt / A0..A2 themselves would move them
+                // to local memory for the streaming path as well)
                 const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+                double r_max, r_a0, r_a1, r_a2;
                 row_from_generators(B.obstacles + (size_t(p) * O + o) * 12, B.link_gens + idx * 18, c0, c1, c2,
-                                    &max_elt, &A0, &A1, &A2);
+                                    &r_max, &r_a0, &r_a1, &r_a2);
+                max_elt = r_max;
+                A0 = r_a0;
+                A1 = r_a1;
+                A2 = r_a2;
             }
         }
         const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
