@@ -1404,11 +1404,11 @@ K1_DI void cross_header(PZ8 h8, const PZH& A, const PZH& B, bool outerA, const d
 }
 
 // List path of cross(PZ, PZ): everything in shared memory, no accumulators in the table.  The hash table holds
-// only the key set; a counting sort groups the contributing terms ("pairs") by slot; the owner thread of a slot
+// only the key set; linked lists group the contributing terms ("pairs") by slot; the owner thread of a slot
 // adds its terms up in registers in the fixed order [A_i x centre(B)], [centre(A) x B_j], pairs by ascending
 // outer index — the order of the table path below, so both paths give bit-identical results — and runs the
 // simplify chain.  The few survivors are parked as (key, coef) records and written out ranked by key.
-// Pool layout: keys[cap] u64 | cnt[cap] u32 | list[P] u32 | survivor records (4 words each).
+// Pool layout: keys[cap] u64 | list heads[cap] u32 | links[P] u16 | survivor records (4 words each).
 // Returns false (nothing written) when the pool is too small for this operand pair: the caller takes the table path.
 K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
     K1S& S = k1s();
@@ -1507,7 +1507,10 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
     }
     if (outerA) abs_sum_partial<3>(B); else abs_sum_partial<3>(A);
     k1_sync();
-    // terms per slot
+    // terms per slot as linked lists: head[s] = 1 + the last term that arrived, next[q] = 1 + the one before it (0 ends
+    // the list).  One pass with one atomic exchange per term; the arrival order does not matter, the owner visits
+    // the terms in ascending term number.  Term numbers q: [0, nA) A_i x centre(B), [nA, nA + nB) centre(A) x B_j,
+    // then outer o x inner j at nA + nB + o * nI + j (ascending q = the fixed order of the sums).
     for (int q = tid; q < P; q += NT) {
         u64 key;
         if (q < nA) {
@@ -1518,47 +1521,7 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
             const int r = q - nA - nB, o = r / nI, j = r - o * nI;
             key = kO[o] + kI[j];
         }
-        atomicAdd(&cnt[tab_find(t, key)], 1u);
-    }
-    k1_sync();
-    // exclusive prefix sum of cnt[0..cap): contiguous chunk per thread, warp scan, warp totals through S.cnt
-    {
-        const int chunk = (cap + NT - 1) / NT;
-        const int c0 = tid * chunk;
-        const int c1 = (c0 + chunk) < cap ? (c0 + chunk) : cap;
-        int sum = 0;
-        for (int i = c0; i < c1; i++) sum += int(cnt[i]);
-        int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
-        }
-        if (lane == 31) S.cnt[warp] = incl;
-        k1_sync();
-        int before = incl - sum;
-        for (int w = 0; w < warp; w++) before += S.cnt[w];
-        for (int i = c0; i < c1; i++) {
-            const int v = int(cnt[i]);
-            cnt[i] = unsigned(before);
-            before += v;
-        }
-    }
-    k1_sync();
-    // fill the term lists with the term numbers q: [0, nA) A_i x centre(B), [nA, nA + nB) centre(A) x B_j, then
-    // outer o x inner j at nA + nB + o * nI + j (ascending q = the fixed order of the sums)
-    for (int q = tid; q < P; q += NT) {
-        u64 key;
-        if (q < nA) {
-            key = kA[q];
-        } else if (q < nA + nB) {
-            key = kB[q - nA];
-        } else {
-            const int r = q - nA - nB, o = r / nI, j = r - o * nI;
-            key = kO[o] + kI[j];
-        }
-        const unsigned pos = atomicAdd(&cnt[tab_find(t, key)], 1u);  // cnt[s] ends as the END of slot s's list
-        list[pos] = (unsigned short)q;
+        list[q] = (unsigned short)atomicExch(&cnt[tab_find(t, key)], unsigned(q + 1));
     }
     k1_sync();
     // owner pass, slots distributed like tab_finalize (same order of the pruned-amount sums)
@@ -1574,15 +1537,16 @@ K1_DI bool cross_list_path(int top, const PZH& A, const PZH& B, PZ8* out_h) {
         for (int s = s0 + lane; s < s1; s += 32) {
             const u64 key = t.keys[s];
             if (key == 0) continue;
-            const int b = s ? int(cnt[s - 1]) : 0, e = int(cnt[s]);
+            const unsigned head = cnt[s];
             double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             int last = -1;
-            for (int c = b; c < e; c++) {
+            for (;;) {
                 int best = 0x7fffffff;  // next term in ascending order (the terms of a slot are distinct)
-                for (int x = b; x < e; x++) {
-                    const int u = list[x];
+                for (unsigned x = head; x != 0u; x = list[x - 1]) {
+                    const int u = int(x) - 1;
                     if (u > last && u < best) best = u;
                 }
+                if (best == 0x7fffffff) break;
                 last = best;
                 double v[6];
                 if (best < nA) {

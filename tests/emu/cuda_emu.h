@@ -205,6 +205,8 @@ template <class T>
 inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 template <class T>
 inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T>
+inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
 
 inline double __dadd_ru(double a, double b) { return orc::rnd::add_up(a, b); }
 inline double __dadd_rd(double a, double b) { return orc::rnd::add_dn(a, b); }
