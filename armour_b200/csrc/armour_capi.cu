@@ -601,7 +601,7 @@ void armour_solver_options_default(armour_solver_options* opt) {
     opt->torque_tol = 1e-2;
     opt->collision_tol = 1e-4;
     opt->qp_sweeps = 200;
-    opt->qp_update_budget = 32768;
+    opt->qp_update_budget = 16384;
 }
 
 int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des, const armour_solver_options* opt_in,

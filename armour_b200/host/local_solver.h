@@ -17,7 +17,7 @@ struct LocalSolverOptions {
     double max_wall_time = 0.45;  // seconds
     int max_iter = 60;
     int qp_sweeps = 200;        // cap on the Hildreth sweeps of one QP
-    int qp_update_budget = 32768;  // no further sweep once this many multiplier updates were made (0 = no limit)
+    int qp_update_budget = 16384;  // no further sweep once this many multiplier updates were made (0 = no limit)
     double torque_tol = 1e-2, collision_tol = 1e-4;  // acceptance tolerances = the verdict's (KPR/Parameters.h:40-43)
 };
 struct LocalSolverStats {

@@ -142,7 +142,7 @@ typedef struct armour_solver_options {
     double torque_tol;     /* 1e-2 N m, the verdict's tolerances (KPR/Parameters.h:40-43) */
     double collision_tol;  /* 1e-4 m */
     int qp_sweeps;         /* 200: cap on the Hildreth sweeps of one QP (most QPs run into it; cost scales with it) */
-    int qp_update_budget;  /* 32768: no further sweep once this many multiplier updates were made in a QP (0 = no limit);
+    int qp_update_budget;  /* 16384: no further sweep once this many multiplier updates were made in a QP (0 = no limit);
                               only near-infeasible QPs, whose multipliers diverge, get there */
 } armour_solver_options;
 void armour_solver_options_default(armour_solver_options* opt);

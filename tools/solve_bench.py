@@ -24,7 +24,7 @@ print("iterations histogram:", np.bincount(iters, minlength=61).tolist())
 def total_cost(kk, okk):
     # cost of the feasible plans (sum), through the oracle-free host formula of the library: use the engine per problem
     return float(np.sum([(np.linalg.norm(kk[p] - k[p])) for p in np.flatnonzero(okk & ok)]))
-for sw in (0, 65536, 32768, 8192):
+for sw in (32768, 16384, 12288, 8192):
     t0 = time.perf_counter()
     k2, ok2, _, it2 = eng.solve(q_des, qp_update_budget=sw)
     dt2 = time.perf_counter() - t0
