@@ -23,7 +23,7 @@ namespace armour {
 
 constexpr int SOLVER_THREADS = 256;
 constexpr int SOLVER_ROWCAP = 2048;   // linearised rows kept per problem; more -> status ROW_OVERFLOW
-constexpr int SOLVER_ROWW = 17;       // doubles per row: a[7], b, |a|^2 / h, a[7] / h, sqrt(|a|^2 / h * h)
+constexpr int SOLVER_ROWW = 18;       // doubles per row: a[7], b, |a|^2 / h, a[7] / h, sqrt(|a|^2 / h * h), h / |a|^2
 enum { SOLVER_RUNNING = 0, SOLVER_SUCCESS = 1, SOLVER_MAXITER = 2, SOLVER_TINY_STEP = 3, SOLVER_INFEASIBLE = 4,
        SOLVER_ROW_OVERFLOW = 5 };
 
@@ -213,6 +213,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                     r[8] = aa / h;
                     for (int j = 0; j < NF; j++) r[9 + j] = r[j] / h;
                     r[16] = sqrt(r[8] * h);
+                    r[17] = r[8] > 0 ? 1.0 / r[8] : 0.0;
                 }
                 if (pl && at + n + (pu ? 1 : 0) < SOLVER_ROWCAP) {
                     double* r = rows + size_t(at + n + (pu ? 1 : 0)) * SOLVER_ROWW;
@@ -221,6 +222,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                     r[8] = aa / h;
                     for (int j = 0; j < NF; j++) r[9 + j] = r[j] / h;
                     r[16] = sqrt(r[8] * h);
+                    r[17] = r[8] > 0 ? 1.0 / r[8] : 0.0;
                 }
             }
             n += (pu ? 1 : 0) + (pl ? 1 : 0);
@@ -256,6 +258,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                     r[8] = 1.0 / h;
                     for (int q = 0; q < NF; q++) r[9 + q] = r[q] / h;
                     r[16] = sqrt(r[8] * h);
+                    r[17] = r[8] > 0 ? 1.0 / r[8] : 0.0;
                     nrows++;
                 }
             }
@@ -283,7 +286,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
         for (int base = 0; base < nrows; base += 32) {
             const int i = base + lane;
             const bool valid = i < nrows;
-            double a[NF], ah[NF], b = 0, raa = 0, sq = 0, lam = 0;
+            double a[NF], ah[NF], b = 0, raa = 0, sq = 0, inv = 0, lam = 0;
             for (int j = 0; j < NF; j++) a[j] = ah[j] = 0;
             if (valid) {
                 const double* r = rows + size_t(i) * SOLVER_ROWW;
@@ -292,6 +295,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                 raa = r[8];
                 for (int j = 0; j < NF; j++) ah[j] = r[9 + j];
                 sq = r[16];
+                inv = r[17];
                 lam = s_lam[i];
             }
             int from = 0;  // lanes below `from` are done for this sweep
@@ -301,7 +305,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                 if (valid && lane >= from && raa > 0) {
                     double viol = -b;
                     for (int j = 0; j < NF; j++) viol += a[j] * d[j];
-                    nl = lam + viol / raa;  // exact coordinate maximisation
+                    nl = lam + viol * inv;  // exact coordinate maximisation
                     if (nl < 0) nl = 0;
                     dl = nl - lam;
                     moves = dl != 0.0;

@@ -15,6 +15,7 @@ struct Lin {  // one linearised inequality  a . d <= b
     double aa;      // |a|^2 / h
     double ah[16];  // a / h: the primal step of a unit multiplier change (computed once per row, not per update)
     double sq;      // sqrt(aa * h) = |a|: scale of the progress measure
+    double inv;     // 1 / aa: the coordinate step is viol * inv (one division per row instead of one per visit)
 };
 
 // min 1/2 h |d|^2 + c . d  s.t.  a_i . d <= b_i : Hildreth's method on the dual (lambda >= 0).
@@ -30,7 +31,7 @@ void hildreth(int n, double h, const double* c, std::vector<Lin>& rows, double* 
             if (r.aa <= 0) continue;
             double viol = -r.b;
             for (int j = 0; j < n; j++) viol += r.a[j] * d[j];
-            double nl = lam[i] + viol / r.aa;  // exact coordinate maximisation
+            double nl = lam[i] + viol * r.inv;  // exact coordinate maximisation
             if (nl < 0) nl = 0;
             const double dl = nl - lam[i];
             if (dl != 0.0) {
@@ -126,6 +127,7 @@ SolverReturn local_solve(TNLP& nlp, const LocalSolverOptions& opt, LocalSolverSt
             r.aa = aa / h;
             for (Index j = 0; j < n; j++) r.ah[j] = r.a[j] / h;
             r.sq = std::sqrt(r.aa * h);
+            r.inv = r.aa > 0 ? 1.0 / r.aa : 0.0;
             rows.push_back(r);
         };
         for (Index i = 0; i < m; i++) {
