@@ -626,7 +626,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
         ctx->solver_cap = 0;
         const size_t P = size_t(nprob);
         CU(dalloc(&ctx->d_solver, P * (3 * NF + 4) + P * m + P * SOLVER_ROWCAP * SOLVER_ROWW));
-        CU(dalloc(&ctx->d_solver_i, 7 * P + 1));
+        CU(dalloc(&ctx->d_solver_i, 8 * P + 1));
         ctx->solver_cap = nprob;
     }
     const size_t P = size_t(ctx->solver_cap);
@@ -647,6 +647,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     S.evals = S.iters + P;
     S.dbg = S.evals + P;
     int* d_running = S.dbg + 3 * P;
+    int* d_list = d_running + 1;  // [P] problems still running
     S.q_des = d_q_des;
     S.tol = opt.tol;
     S.torque_tol = opt.torque_tol;
@@ -668,20 +669,22 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     CU(launch_constraints(B, S.x, ctx->d_g, nullptr, st));
     k_solver_start<<<nprob, SOLVER_THREADS, 0, st>>>(B, S, ctx->d_g);
     ctx->launches += 2;
-    for (int it = 0; it < opt.max_iter; it++) {
-        CU(launch_constraints(B, S.x, ctx->d_g, ctx->d_jac, st));
-        k_solver_step<<<nprob, SOLVER_THREADS, SOLVER_ROWCAP * sizeof(double), st>>>(B, S, ctx->d_g, ctx->d_jac, it);
-        CU(launch_constraints(B, S.xt, d_gt, nullptr, st));
-        k_solver_accept<<<nprob, SOLVER_THREADS, 0, st>>>(B, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
+    Batch Ba = B;      // launches over the problems still running (all of them at first)
+    int nactive = nprob;
+    for (int it = 0; it < opt.max_iter && nactive > 0; it++) {
+        Ba.nprob = nactive;
+        CU(launch_constraints(Ba, S.x, ctx->d_g, ctx->d_jac, st));
+        k_solver_step<<<nactive, SOLVER_THREADS, SOLVER_ROWCAP * sizeof(double), st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
+        CU(launch_constraints(Ba, S.xt, d_gt, nullptr, st));
+        k_solver_accept<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
         ctx->launches += 4;
-        if ((it & 3) == 3 && it + 1 < opt.max_iter) {  // every fourth iteration: is anybody still running?
-            int running = 0;
+        if ((it & 3) == 3 && it + 1 < opt.max_iter) {  // every fourth iteration: who is still running?
             CU(cudaMemsetAsync(d_running, 0, sizeof(int), st));
-            k_solver_count_running<<<(nprob + 255) / 256, 256, 0, st>>>(S, nprob, d_running);
-            CU(cudaMemcpyAsync(&running, d_running, sizeof(int), cudaMemcpyDeviceToHost, st));
+            k_solver_compact<<<(nprob + 255) / 256, 256, 0, st>>>(S, nprob, d_running, d_list);
+            CU(cudaMemcpyAsync(&nactive, d_running, sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             ctx->launches += 1;
-            if (running == 0) break;
+            Ba.plist = d_list;
         }
     }
     k_solver_final<<<(nprob + 255) / 256, 256, 0, st>>>(S, nprob, d_k_opt, nullptr);

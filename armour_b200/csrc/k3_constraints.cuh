@@ -408,7 +408,7 @@ static_assert(TB * 3 * MAXJ <= K3_LINK_THREADS && K3_TORQUE_T0 + TB * NF * K3_TO
 // on resident warps, not on loads in flight per warp: anything that spills or costs a CTA per SM loses.
 __global__ void __launch_bounds__(K3_THREADS, K3_MINB)
 k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
-    const int tb = blockIdx.x, p = blockIdx.y;
+    const int tb = blockIdx.x, p = B.plist ? B.plist[blockIdx.y] : int(blockIdx.y);
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int m = B.m();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) k_solver_start(Batch B, Solver
 // one SQP step from (g, J) at x: writes the trial point xt, or ends the problem (step below tolerance)
 __global__ void __launch_bounds__(SOLVER_THREADS)
 k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const double* __restrict__ jac_all, int it) {
-    const int p = blockIdx.x, tid = threadIdx.x;
+    const int p = B.plist ? B.plist[blockIdx.x] : int(blockIdx.x), tid = threadIdx.x;
     if (S.status[p] != SOLVER_RUNNING) return;  // uniform per CTA
     const int m = B.m();
     const double* g = g_all + size_t(p) * m;
@@ -349,7 +349,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
 // acceptance test of the trial point from g(xt): filter-style — feasible points must lower the cost, infeasible ones
 // must lower the violation
 __global__ void __launch_bounds__(SOLVER_THREADS) k_solver_accept(Batch B, SolverState S, const double* __restrict__ gt_all, int last) {
-    const int p = blockIdx.x;
+    const int p = B.plist ? B.plist[blockIdx.x] : int(blockIdx.x);
     if (S.status[p] != SOLVER_RUNNING) return;
     __shared__ double s_red[SOLVER_THREADS / 32];
     const double vt = solver_violation(B, p, gt_all + size_t(p) * B.m(), S.torque_tol, S.collision_tol, s_red);
@@ -387,9 +387,10 @@ __global__ void k_solver_final(SolverState S, int nprob, double* __restrict__ k_
     for (int j = 0; j < NF; j++) k_opt[size_t(p) * NF + j] = hb ? S.best[size_t(p) * NF + j] : S.x[size_t(p) * NF + j];
     if (running && S.status[p] == SOLVER_RUNNING) atomicAdd(running, 1);
 }
-__global__ void k_solver_count_running(SolverState S, int nprob, int* __restrict__ running) {
+// the problems still running, as a list for the next launches (any order: the problems are independent)
+__global__ void k_solver_compact(SolverState S, int nprob, int* __restrict__ running, int* __restrict__ list) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < nprob && S.status[p] == SOLVER_RUNNING) atomicAdd(running, 1);
+    if (p < nprob && S.status[p] == SOLVER_RUNNING) list[atomicAdd(running, 1)] = p;
 }
 
 }  // namespace armour

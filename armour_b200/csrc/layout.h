@@ -47,6 +47,9 @@ struct Batch {
     // outputs of the last evaluation
     double* link_sliced;      // [p][t][NJ][3]
     int* status;              // [p]
+    // optional indirection for launches over a subset of the problems (the batched solver's still-running list):
+    // CTA row y works on problem plist[y]; nullptr = identity
+    const int* plist;
 
     __host__ __device__ size_t hp_chunk() const { return size_t(HP_CAP) * 4 * NJ * TB * O; }
     __host__ __device__ int m() const { return NF * T + NJ * T * O + 4 * NF; }
