@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned for the reach-set build, slices and Bezier rows (oracle/_ref, tests/test_oracle_pinned.py); the collision rows (KPR/CollisionChecking.cu, CUDA) are restated only: parity unpinned for those rows.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own sources: reach-set build, slices and Bezier rows through oracle/_ref/libarmour_ref.so (tests/test_oracle_pinned.py); collision rows, bounds, cost and verdict through the reference's CUDA kernels and armtd_NLP compiled by nvcc (oracle/_ref/libarmour_ref_cuda.so, run on a B200, frozen as tests/golden/refcuda/, tests/test_refcuda_golden.py).
 // Plain C entry points over orc::Problem so tests / bench.py can drive the oracle with ctypes.
 #include <cstring>
 

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned (see oracle/README.md).
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Constants checked through every pinned quantity (see planner.h).
 //
 // Robot and planner constants of the ARMOUR Kinova Gen3 planner, restated as a
 // runtime struct so that the same oracle binary can serve the 7-joint model
