@@ -81,6 +81,7 @@ SIGNATURES = {
     "armour_batch_get_build_status": (C.c_int, [C.c_void_p, C.c_int, ip]),
     "armour_batch_get_monomial_counts": (C.c_int, [C.c_void_p, C.c_int, ip, ip]),
     "armour_batch_get_candidate_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "armour_chunk_intervals": (C.c_int, []),
     "armour_measure_fp64_peak": (C.c_int, [C.c_void_p, dp]),
     "armour_solver_options_default": (None, [C.c_void_p]),
     "armour_batch_solve_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

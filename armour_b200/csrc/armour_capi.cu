@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -92,6 +93,7 @@ struct armour_ctx {
     Batch B;                 // device pointers + dimensions of the current batch
     int built_nprob = 0;     // problems with valid reach sets
     size_t hp_capacity = 0;  // doubles allocated for B.hp_cand
+    int hp_nprob = 0;        // problems the candidate buffers were sized for
     size_t obs_capacity = 0;
     double* d_in = nullptr;  // [3][max_problems][NF] q0, qd0, qdd0
     double* d_obs = nullptr;
@@ -104,7 +106,7 @@ struct armour_ctx {
     double* d_solver = nullptr;   // state arrays + second g buffer + linearised rows
     int* d_solver_i = nullptr;    // have_best, status, iters, evals, running counter
     double* d_solver_io = nullptr;  // q_des, k_opt staging of the host-pointer call
-    int solver_cap = 0;
+    size_t solver_doubles = 0, solver_ints = 0;  // elements allocated for d_solver / d_solver_i
     k1lat::K1Scratch k1_lat;  // scratch of the latency configuration of k_reachsets
     k1thr::K1Scratch k1_thr;  // scratch of the throughput configuration (allocated on first use)
     bool k1_thr_ready = false;
@@ -176,16 +178,25 @@ int ensure_obstacle_buffers(armour_ctx* ctx, int nprob, int nobs) {
     Batch& B = ctx->B;
     B.O = nobs;
     B.nprob = nprob;
-    const size_t need_hp = size_t(nprob) * (B.T / TB) * B.hp_chunk();
-    if (ctx->hp_capacity < need_hp) {
+    const size_t chunks = size_t(nprob) * (B.T / TB);
+    const size_t need_hp = chunks * B.hp_chunk_records() * 4;  // doubles
+    if (ctx->hp_capacity < need_hp || ctx->hp_nprob < nprob) {
+        // (the candidate lists of the current batch go with the old buffers: whatever was built must be rebuilt)
         if (B.hp_cand) cudaFree(B.hp_cand);
-        if (B.hp_cnt) cudaFree(B.hp_cnt);
+        if (B.hp_meta) cudaFree(B.hp_meta);
+        if (B.hp_total) cudaFree(B.hp_total);
         B.hp_cand = nullptr;
-        B.hp_cnt = nullptr;
+        B.hp_meta = nullptr;
+        B.hp_total = nullptr;
         ctx->hp_capacity = 0;
+        ctx->hp_nprob = 0;
+        ctx->built_nprob = 0;
         CU(dalloc(&B.hp_cand, need_hp));
-        CU(dalloc(&B.hp_cnt, need_hp / (HP_CAP * 4)));
+        CU(dalloc(&B.hp_meta, chunks * size_t(B.chunk_rows())));
+        CU(dalloc(&B.hp_total, size_t(nprob) * (B.T / TB + 1)));
+        CU(cudaMemsetAsync(B.hp_total, 0, size_t(nprob) * (B.T / TB + 1) * sizeof(int), ctx->stream));
         ctx->hp_capacity = need_hp;
+        ctx->hp_nprob = nprob;
     }
     B.obstacles = ctx->d_obs;
     return ARMOUR_OK;
@@ -205,6 +216,31 @@ int launch_build(armour_ctx* ctx, int* nl) {
     } else {
         CU(k1lat::launch_reachsets(ctx->B, ctx->k1_lat, ctx->stream, nl));
     }
+    return ARMOUR_OK;
+}
+
+// The robot / planner constants live in ONE __constant__ block per device, shared by every context of the process.
+// Before a context launches anything it makes sure the block holds ITS constants: contexts with identical
+// configurations share the block freely; switching between contexts that differ (gripper model, threshold, k_range,
+// uncertainties ...) waits for the device to drain and uploads again, so no kernel ever runs on another context's
+// constants.  (Correct, not fast: interleave differing contexts on one device sparingly.)
+std::mutex g_const_mutex;
+struct ConstOwner {
+    bool valid = false;
+    RobotConstants rc;
+};
+ConstOwner g_const_owner[64];
+
+int ensure_constants(armour_ctx* ctx) {
+    const int dev = ctx->cfg.device;
+    if (dev < 0 || dev >= 64) return fail(ctx, ARMOUR_ERR_ARG, "device ordinal");
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    ConstOwner& o = g_const_owner[dev];
+    if (o.valid && std::memcmp(&o.rc, &ctx->rc, sizeof(RobotConstants)) == 0) return ARMOUR_OK;
+    CU(cudaDeviceSynchronize());  // kernels of the previous owner may still read the block
+    CU(upload_constants(ctx->rc, ctx->stream));
+    o.rc = ctx->rc;
+    o.valid = true;
     return ARMOUR_OK;
 }
 
@@ -276,6 +312,9 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     if (cfg->robot_model < 0 || cfg->robot_model > 1) return ARMOUR_ERR_ARG;
     if (cfg->cap_link_monomials < 1 || cfg->cap_torque_monomials < 1 || cfg->cap_work_monomials < 64)
         return ARMOUR_ERR_ARG;
+    // the stored tables are fetched with 16-byte bulk copies (keys are 2 bytes): capacities in multiples of 8
+    if (cfg->cap_link_monomials % 8 != 0 || cfg->cap_torque_monomials % 8 != 0) return ARMOUR_ERR_ARG;
+    if (cfg->max_problems > 65535) return ARMOUR_ERR_ARG;  // the problem index is gridDim.y of the constraint kernels
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) return ARMOUR_ERR_CUDA;
     armour_ctx* ctx = new (std::nothrow) armour_ctx();
@@ -298,7 +337,7 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail("cudaStreamCreate", e);
     ctx->stream = ctx->own_stream;
-    if ((e = upload_constants(ctx->rc, ctx->stream)) != cudaSuccess) return bail("upload_constants", e);
+    if (ensure_constants(ctx) != ARMOUR_OK) return bail("upload_constants", cudaGetLastError());
 
     Batch& B = ctx->B;
     std::memset(&B, 0, sizeof(B));
@@ -321,6 +360,7 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     ALLOC(B.u_g, P * T * NF * B.capU);
     ALLOC(B.torque_radius, P * NF * T);
     ALLOC(B.link_gens, P * T * NJ * 18);
+    ALLOC(B.link_r, P * T * NJ * 3);
     ALLOC(B.link_sliced, P * T * NJ * 3);
     ALLOC(B.status, P);
     ALLOC(ctx->d_k, P * NF);
@@ -330,6 +370,9 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     B.qd0 = ctx->d_in + P * NF;
     B.qdd0 = ctx->d_in + 2 * P * NF;
     if ((e = cudaMemsetAsync(B.status, 0, P * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
+    // no table may ever be read with an uninitialised count (a failed build leaves its tables untouched)
+    if ((e = cudaMemsetAsync(B.link_n, 0, P * T * NJ * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = cudaMemsetAsync(B.u_n, 0, P * T * NF * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
     if ((e = k1lat::k1_scratch_create(&ctx->k1_lat, ctx->cfg, ctx->rc, ctx->stream)) != cudaSuccess) return bail("k1 scratch", e);
     if ((long long)cfg->max_problems * B.T > 2LL * ctx->k1_lat.grid) {  // this context can see batches: set up the throughput kernel too
         if ((e = k1thr::k1_scratch_create(&ctx->k1_thr, ctx->cfg, ctx->rc, ctx->stream)) != cudaSuccess) return bail("k1 throughput scratch", e);
@@ -342,6 +385,9 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
         if ((e = cudaFuncGetAttributes(&fa, k1lat::k_reachsets)) != cudaSuccess) return bail("load k_reachsets", e);
         if ((e = cudaFuncGetAttributes(&fa, k_hyperplanes)) != cudaSuccess) return bail("load k_hyperplanes", e);
         if ((e = cudaFuncGetAttributes(&fa, k_constraints)) != cudaSuccess) return bail("load k_constraints", e);
+        if ((e = cudaFuncSetAttribute(k_constraints, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_MAX)) != cudaSuccess)
+            return bail("k_constraints shared memory", e);
+        if ((e = cudaFuncGetAttributes(&fa, k_constraints_slow)) != cudaSuccess) return bail("load k_constraints_slow", e);
         if ((e = cudaFuncGetAttributes(&fa, k_verdict)) != cudaSuccess) return bail("load k_verdict", e);
     }
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("sync", e);
@@ -355,7 +401,7 @@ int armour_ctx_destroy(armour_ctx* ctx) {
     Batch& B = ctx->B;
     void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io,
                     ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
-                    B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.hp_cand, B.hp_cnt,
+                    B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.link_r, B.hp_cand, B.hp_meta, B.hp_total,
                     B.link_sliced, B.status};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -389,6 +435,7 @@ int armour_ctx_reserve(armour_ctx* ctx, int nprob, int nobs) {
     int rc = check_batch(ctx, nprob, nobs);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     const int O = ctx->B.O, np = ctx->B.nprob;
     rc = ensure_obstacle_buffers(ctx, nprob, nobs);
     ctx->B.O = O;  // reserving does not change the current batch
@@ -407,6 +454,7 @@ int armour_batch_reachsets_build_device(armour_ctx* ctx, int nprob, const double
     if (rc) return rc;
     if (!d_q0 || !d_qd0 || !d_qdd0 || (nobs > 0 && !d_obstacles)) return fail(ctx, ARMOUR_ERR_ARG, "null input");
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     rc = ensure_obstacle_buffers(ctx, nprob, nobs);
     if (rc) return rc;
     const size_t P = size_t(ctx->cfg.max_problems);
@@ -434,6 +482,7 @@ int armour_batch_reachsets_build(armour_ctx* ctx, int nprob, const double* q0, c
     if (rc) return rc;
     if (!q0 || !qd0 || !qdd0 || (nobs > 0 && !obstacles)) return fail(ctx, ARMOUR_ERR_ARG, "null input");
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     rc = ensure_obstacle_buffers(ctx, nprob, nobs);
     if (rc) return rc;
     const size_t P = size_t(ctx->cfg.max_problems);
@@ -491,10 +540,16 @@ int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, in
 int armour_batch_get_candidate_counts(armour_ctx* ctx, int nprob, unsigned char* out) {
     if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
     const size_t rows = size_t(ctx->B.NJ) * ctx->B.T * ctx->B.O;
-    if (rows) CU(cudaMemcpyAsync(out, ctx->B.hp_cnt, nprob * rows, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (rows) {
+        std::vector<unsigned> meta(nprob * rows);
+        CU(cudaMemcpyAsync(meta.data(), ctx->B.hp_meta, meta.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < meta.size(); i++) out[i] = (unsigned char)(meta[i] & 255u);
+    }
     return ARMOUR_OK;
 }
+
+int armour_chunk_intervals(void) { return TB; }
 
 #ifdef K1_PROFILE
 // developer builds only: per-(interval, operation site) cycle counts of the last single-problem builds
@@ -519,6 +574,7 @@ extern "C" int armour_debug_k1_profile(long long* out, int reset) {
 int armour_measure_fp64_peak(armour_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return ARMOUR_ERR_ARG;
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
     double* d_out = nullptr;
@@ -551,10 +607,11 @@ int armour_batch_eval_device(armour_ctx* ctx, int nprob, const double* d_k, doub
     if (!ctx || !d_k) return ARMOUR_ERR_ARG;
     if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "evaluate before build");
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     Batch B = ctx->B;
     B.nprob = nprob;
     CU(launch_constraints(B, d_k, d_g, d_values, ctx->stream));
-    ctx->launches += 1;
+    ctx->launches += 1 + (B.O > 0);
     return ARMOUR_OK;
 }
 
@@ -562,6 +619,7 @@ int armour_batch_eval(armour_ctx* ctx, int nprob, const double* k, double* g, do
     if (!ctx || !k) return ARMOUR_ERR_ARG;
     if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "evaluate before build");
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     int rc = ensure_eval_buffers(ctx, nprob, g != nullptr, values != nullptr);
     if (rc) return rc;
     const size_t m = size_t(ctx->B.m());
@@ -586,6 +644,8 @@ int armour_eval_g_jac(armour_ctx* ctx, const double* k, double* g, double* value
 int armour_batch_verdict_device(armour_ctx* ctx, int nprob, const double* d_g, int* d_feasible, int* d_first) {
     if (!ctx || !d_g || !d_feasible || !d_first) return ARMOUR_ERR_ARG;
     if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "verdict before build");
+    CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     Batch B = ctx->B;
     B.nprob = nprob;
     CU(launch_verdict(B, d_g, d_feasible, d_first, ctx->stream));
@@ -613,23 +673,31 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     if (opt_in) opt = *opt_in;
     if (opt.max_iter < 1 || !(opt.tol > 0) || opt.qp_sweeps < 1) return fail(ctx, ARMOUR_ERR_ARG, "solver options");
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     Batch B = ctx->B;
     B.nprob = nprob;
     const size_t m = size_t(B.m());
     int rc = ensure_eval_buffers(ctx, nprob, true, true);
     if (rc) return rc;
-    if (ctx->solver_cap < nprob) {
+    // scratch: state arrays + second g buffer + linearised rows.  Its size depends on nprob AND on m (obstacle count of
+    // the current batch): capacity is tracked in elements and the layout below always uses this call's nprob.
+    const size_t P = size_t(nprob);
+    const size_t need_d = P * (3 * NF + 4) + P * m + P * SOLVER_ROWCAP * SOLVER_ROWW;
+    const size_t need_i = 8 * P + 1;
+    if (ctx->solver_doubles < need_d) {
         if (ctx->d_solver) cudaFree(ctx->d_solver);
-        if (ctx->d_solver_i) cudaFree(ctx->d_solver_i);
         ctx->d_solver = nullptr;
-        ctx->d_solver_i = nullptr;
-        ctx->solver_cap = 0;
-        const size_t P = size_t(nprob);
-        CU(dalloc(&ctx->d_solver, P * (3 * NF + 4) + P * m + P * SOLVER_ROWCAP * SOLVER_ROWW));
-        CU(dalloc(&ctx->d_solver_i, 8 * P + 1));
-        ctx->solver_cap = nprob;
+        ctx->solver_doubles = 0;
+        CU(dalloc(&ctx->d_solver, need_d));
+        ctx->solver_doubles = need_d;
     }
-    const size_t P = size_t(ctx->solver_cap);
+    if (ctx->solver_ints < need_i) {
+        if (ctx->d_solver_i) cudaFree(ctx->d_solver_i);
+        ctx->d_solver_i = nullptr;
+        ctx->solver_ints = 0;
+        CU(dalloc(&ctx->d_solver_i, need_i));
+        ctx->solver_ints = need_i;
+    }
     SolverState S;
     double* w = ctx->d_solver;
     S.x = w; w += P * NF;
@@ -717,6 +785,7 @@ int armour_batch_solve(armour_ctx* ctx, int nprob, const double* q_des, const ar
     if (!ctx || !q_des || !k_opt || !feasible) return ARMOUR_ERR_ARG;
     if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "solve before build");
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     if (!ctx->d_solver_io) CU(dalloc(&ctx->d_solver_io, size_t(ctx->cfg.max_problems) * (2 * NF + 2)));
     const size_t P = size_t(ctx->cfg.max_problems);
     double* d_q = ctx->d_solver_io;
@@ -908,6 +977,7 @@ int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const ar
         prob >= nprob_total)
         return ARMOUR_ERR_ARG;
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
     if (prob == 0 || ctx->B.O != nobs || ctx->B.nprob != nprob_total) {
         rc = ensure_obstacle_buffers(ctx, nprob_total, nobs);
         if (rc) return rc;
@@ -942,6 +1012,10 @@ int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const ar
     H2D(B.u_g + prob * T * NF * B.capU, ug.data(), ug.size() * sizeof(double));
     H2D(B.torque_radius + prob * NF * T, in->torque_radius, NF * T * sizeof(double));
     H2D(B.link_gens + prob * T * NJ * 18, in->link_gens, T * NJ * 18 * sizeof(double));
+    std::vector<double> lr(T * NJ * 3);
+    for (size_t i = 0; i < T * NJ; i++)
+        for (int e = 0; e < 3; e++) lr[i * 3 + e] = in->link_gens[i * 18 + e + (3 + e) * 3];
+    H2D(B.link_r + prob * T * NJ * 3, lr.data(), lr.size() * sizeof(double));
     H2D(B.u_r + prob * T * NF, in->u_radius, T * NF * sizeof(double));
     H2D(ctx->d_in + prob * NF, q0, NF * sizeof(double));
     H2D(ctx->d_in + P * NF + prob * NF, qd0, NF * sizeof(double));

@@ -325,6 +325,7 @@ K1_OP void export_link(PZ8 L8, const Batch& B, int p, int t, int l) {
         double v = pz_r(L, 0)[e];
         for (int w = 0; w < NW; w++) v = __dadd_ru(v, S.red[w * RED_STRIDE + e]);
         gens[e + (3 + e) * 3] = __dmul_ru(v, RADIUS_SLACK);
+        B.link_r[idx * 3 + e] = gens[e + (3 + e) * 3];  // the diagonal alone, contiguous: what k_constraints streams
         B.link_c[idx * 3 + e] = pz_c(L)[e];
     }
     if (tid == 0) B.link_n[idx] = nk;

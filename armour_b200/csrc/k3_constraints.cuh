@@ -277,36 +277,47 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
         }
     }
     __syncthreads();
-    if (live) {  // step 4: survivors to their scan-order positions (counted over the short list)
-        const size_t chunk = size_t(p) * (T / TB) + tb;
-        double* row = B.hp_cand + chunk * B.hp_chunk() + size_t(x) * 4;
-        const size_t cstride = size_t(per_pair) * 4;
+    // step 4: the row's list is packed behind the lists already placed in its chunk (one atomic per row: the order
+    // of the rows inside a chunk is arrival order and differs run to run, the content of every list does not), so
+    // that an evaluation fetches exactly the records in use with one bulk copy.  Survivors keep their scan order.
+    __shared__ int s_off[HP_ROWS];
+    int count = 0, before[2] = {0, 0};
+    if (live && (keep[0] || keep[1] || pi == 0)) {
         const int nl = s_nlist[lr];
-        if (keep[0] || keep[1] || pi == 0) {
-            int count = 0, before[2] = {0, 0};
 #pragma unroll 1
-            for (int c = 0; c < nl; c++) {
-                const int q = s_list[lr][c];
-                if (s_flag[lr][q]) {
-                    count++;
-                    before[0] += (q < 2 * pi);
-                    before[1] += (q < 2 * pi + 1);
-                }
+        for (int c = 0; c < nl; c++) {
+            const int q = s_list[lr][c];
+            if (s_flag[lr][q]) {
+                count++;
+                before[0] += (q < 2 * pi);
+                before[1] += (q < 2 * pi + 1);
             }
-            if (count <= HP_CAP) {
+        }
+    }
+    const size_t chunk = size_t(p) * (T / TB) + tb;
+    if (live && pi == 0) {
+        int off = -1;
+        if (count <= HP_CAP) {
+            off = atomicAdd(B.hp_total_of(p, tb), count);
+            if (size_t(off) + count > B.hp_chunk_records()) off = -1;  // chunk full: the row goes to the slow path
+        }
+        s_off[lr] = off;
+        if (off < 0) atomicAdd(B.hp_slow_of(p), 1);
+        B.hp_meta[chunk * per_pair + x] = off < 0 ? unsigned(HP_OVERFLOW) : ((unsigned(off) << 8) | unsigned(count));
+    }
+    __syncthreads();
+    if (live && s_off[lr] >= 0) {
+        double* row = B.hp_cand + (chunk * B.hp_chunk_records() + size_t(s_off[lr])) * 4;
 #pragma unroll 1
-                for (int sgn = 0; sgn < 2; sgn++) {
-                    if (keep[sgn]) {
-                        const double sg = sgn ? -1.0 : 1.0;
-                        double* e = row + size_t(before[sgn]) * cstride;
-                        e[0] = sg * s_A[lr][pi][0];
-                        e[1] = sg * s_A[lr][pi][1];
-                        e[2] = sg * s_A[lr][pi][2];
-                        e[3] = s_b[lr][2 * pi + sgn];
-                    }
-                }
+        for (int sgn = 0; sgn < 2; sgn++) {
+            if (keep[sgn]) {
+                const double sg = sgn ? -1.0 : 1.0;
+                double* e = row + size_t(before[sgn]) * 4;
+                e[0] = sg * s_A[lr][pi][0];
+                e[1] = sg * s_A[lr][pi][1];
+                e[2] = sg * s_A[lr][pi][2];
+                e[3] = s_b[lr][2 * pi + sgn];
             }
-            if (pi == 0) B.hp_cnt[chunk * per_pair + x] = (count > HP_CAP) ? (unsigned char)HP_OVERFLOW : (unsigned char)count;
         }
     }
 }
@@ -314,8 +325,7 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
 // ---------------------------------------------------------------------------------------------------
 // K3
 // Slow path of one collision row: scan all 72 half-spaces computed from the generators
-// (checkCollisionKernel, KPR/CollisionChecking.cu:230-299).  Kept out of line so that the streaming
-// path of k_constraints keeps its register budget.
+// (checkCollisionKernel, KPR/CollisionChecking.cu:230-299).  Only k_constraints_slow calls it.
 __device__ __noinline__ void row_from_generators(const double* __restrict__ ob, const double* __restrict__ LG,
                                                  double c0, double c1, double c2, double* max_out, double* A0o,
                                                  double* A1o, double* A2o) {
@@ -342,255 +352,397 @@ __device__ __noinline__ void row_from_generators(const double* __restrict__ ob, 
     *A2o = A2;
 }
 
-// One component of one reach set sliced at k: value and all seven d/dk in a single pass over the
-// monomials.  Per monomial the factors k_j^{d_j} are applied in ascending j exactly like
-// PZsparse::slice (KPR/PZsparse.cu:404-435) and its gradient overloads (:477-555); a factor with
-// d_j = 0 is 1.0 and is skipped (exact).  D[v] carries coef * prod_{j<v} f_j * f'_v * prod_{v<j} f_j.
-__device__ __forceinline__ void slice_component(const uint16_t* __restrict__ keys, const double* __restrict__ coef,
-                                                int n, int kstride, int cstride, const double2 (*kpd)[4], double& value,
-                                                double (&grad)[NF]) {
-    constexpr int CH = K3_CH;  // monomials fetched together: the loads of a chunk are independent and overlap
-    for (int m0 = 0; m0 < n; m0 += CH) {
-        unsigned kk[CH];
-        double cc[CH];
-#pragma unroll
-        for (int i = 0; i < CH; i++) {
-            const bool on = m0 + i < n;
-            kk[i] = on ? keys[(m0 + i) * kstride] : 0u;
-            cc[i] = on ? coef[(m0 + i) * cstride] : 0.0;
-        }
-#pragma unroll 1
-        for (int i = 0; i < CH; i++) {
-            if (m0 + i >= n) break;
-            // (dynamic index into kk / cc would spill: rotate instead)
-            const unsigned key = kk[0];
-            double val = cc[0];
-#pragma unroll
-            for (int q = 0; q + 1 < CH; q++) {
-                kk[q] = kk[q + 1];
-                cc[q] = cc[q + 1];
-            }
-            // No branch on the degree: kpd[j][0] = {1, 0}, and x * 1.0 is exact, val * 0.0 adds a zero to the
-            // gradient: the same values as skipping the factor, without seven divergent branches per monomial.
-            double D[NF];
-#pragma unroll
-            for (int j = 0; j < NF; j++) {
-                const double2 fd = kpd[j][(key >> (2 * j)) & 3];
-                D[j] = val * fd.y;
-#pragma unroll
-                for (int v = 0; v < j; v++) D[v] *= fd.x;
-                val *= fd.x;
-            }
-            value += val;
-#pragma unroll
-            for (int v = 0; v < NF; v++) grad[v] += D[v];
-        }
-    }
+// ---- TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier) ---------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ unsigned r16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
-// Warp roles: warps [0, 6) slice the link reach sets (one thread per (interval, link, component)), warps
-// [6, 10) slice the torque reach sets, two lanes per (interval, joint) table (the torque tables are ~3x longer).
-// The link warps meet on named barrier 1 and go straight to the collision rows; the torque warps write their
-// rows, then join through barrier 2 (on which the link warps only arrive), so nobody waits for the slowest
-// slice.  Collision rows are handed out in chunks of 32 from a shared counter.
-constexpr int K3_LINK_THREADS = 192;
-constexpr int K3_TORQUE_LANES = 2;
-constexpr int K3_THREADS = 320;
-constexpr int K3_CNT_SMEM = 2048;  // rows per CTA whose candidate counts are staged in shared memory
+// k_constraints: one CTA per chunk = (problem, TB intervals), K3_THREADS threads.
+//
+// Everything the chunk needs comes in two rounds of TMA bulk copies into shared memory, so a CTA pays two DRAM
+// latencies, not one per monomial fetched:
+//   round 1 (fixed sizes): monomial counts, centres and radii of its TB*(NJ+NF) reach-set tables, the (first
+//            record, count) word of its NJ*TB*O collision rows;
+//   round 2 (sizes known from round 1): every table, exactly its n monomials (16-bit keys, coefficients), and the
+//            candidate half-space records in use of the chunk: one contiguous run.
+// Slices: eight lanes per table, lane v owns output v (the value, or d/dk_{v-1}); a warp walks the tables of
+// four consecutive intervals of one link / one joint together (similar lengths).  The power products of a monomial come
+// from three small tables in shared memory, k0 k1 k2 | k3 k4 | k5 k6, whose entry (index, v) already is the factor lane v
+// needs (the derivative for its own variable, the plain product otherwise): term_v = coeff * A[.][v] * (B[.][v] *
+// C[.][v]).  Keys are sorted, so the B*C factor is reloaded only when the upper key bits change.  (The reference
+// applies the factors one variable after the other, KPR/PZsparse.cu:404-555: same value up to a few ulp.)
+// Rows: one lane per collision row, records read from the staged run (or from global memory for the part of a chunk that
+// does not fit), g and the Jacobian rows leave transposed through shared memory, coalesced.
+constexpr int K3_THREADS = 256;
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int K3_TORQUE_T0 = K3_LINK_THREADS;
-static_assert(TB * 3 * MAXJ <= K3_LINK_THREADS && K3_TORQUE_T0 + TB * NF * K3_TORQUE_LANES <= K3_THREADS,
-              "thread map of the slice phase");
+constexpr int K3_TABLE_ARENA = 16384;          // bytes of staged tables; later the transposition buffers of the warps
+constexpr int K3_NTAB = TB * (MAXJ + NF);      // tables of a chunk (upper bound)
+static_assert(TB % 4 == 0, "a warp slices four intervals of a link / joint together");
+static_assert(K3_NTAB <= 64, "one warp issues the table copies, two tables per lane");
+static_assert(K3_WARPS * 32 * NF * 8 <= K3_TABLE_ARENA, "transposition buffers reuse the table arena");
 
-// Register budget (round-1 sweep on B200, 1 024 worlds, ms per launch): 64 registers / 3 CTAs per SM with 8 monomials and
-// 4 candidate records in flight per thread 0.81; the same at 96 registers / 2 CTAs 0.98, at 48 / 4 CTAs 1.68 (spills);
-// 2 monomials + 2 records in flight at 64 / 3 CTAs 0.73, at 48 / 4 CTAs 0.66, at 40 / 5 CTAs 0.81.  The kernel lives
-// on resident warps, not on loads in flight per warp: anything that spills or costs a CTA per SM loses.
-__global__ void __launch_bounds__(K3_THREADS, K3_MINB)
-k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
+struct K3Smem {  // fixed part of the dynamic shared memory; the row words and the candidate arena follow
+    unsigned long long bar[4];
+    double pw[96][8];                      // power-product tables A (64 entries), B (16), C (16), 8 lanes each
+    double lc[TB][MAXJ][3];                // sliced link centres
+    double dlc[TB][MAXJ][NF][3];           // and their d/dk
+    double cen_l[TB * MAXJ * 3], rad_l[TB * MAXJ * 3], cen_u[TB * NF + 4], rad_u[TB * NF + 4];
+    double tg[TB * NF + 4];                // torque rows of g
+    double tj[TB * NF * NF + 4];           // torque rows of the Jacobian
+    double k[8];
+    int nl[TB * MAXJ], nu[TB * NF + 4];
+    int toff[K3_NTAB];                     // byte offset of a staged table in the arena, -1: read it from global memory
+    int total, task, rownext, in_domain;
+    __align__(16) unsigned char arena[K3_TABLE_ARENA];
+};
+
+__global__ void __launch_bounds__(K3_THREADS, 3)
+k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac, int cand_arena) {
+    extern __shared__ __align__(16) unsigned char k3_raw[];
+    K3Smem& S = *reinterpret_cast<K3Smem*>(k3_raw);
     const int tb = blockIdx.x, p = B.plist ? B.plist[blockIdx.y] : int(blockIdx.y);
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int m = B.m();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ double2 kpd[NF][4];  // {k_j^d, d/dk_j k_j^d} for d = 0..3
-    __shared__ __align__(4) unsigned char s_cnt[K3_CNT_SMEM];  // candidate counts of this CTA's rows
-    __shared__ double s_lc[TB][MAXJ][3];
-    __shared__ double s_dlc[TB][MAXJ][NF][3];
-    __shared__ double s_stage[K3_WARPS][32 * NF];  // per-warp transpose buffer: Jacobian rows leave coalesced
-    __shared__ int s_in_domain;
-    __shared__ int s_next;  // next chunk of 32 collision rows
-
-    if (tid == 32) {
-        bool in = true;
-        for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
-        s_in_domain = in ? 1 : 0;
-        s_next = 0;
-    }
-    if (tid < NF) {
-        const double k = kin[size_t(p) * NF + tid];
-        kpd[tid][0] = make_double2(1.0, 0.0);
-        kpd[tid][1] = make_double2(k, 1.0);
-        kpd[tid][2] = make_double2(k * k, 2.0 * k);
-        kpd[tid][3] = make_double2(k * k * k, 3.0 * (k * k));
-    }
-    const int per_pair = NJ * TB * O;
+    const int rows = NJ * TB * O;
+    unsigned* s_meta = reinterpret_cast<unsigned*>(k3_raw + sizeof(K3Smem));
+    double* s_cand = reinterpret_cast<double*>(k3_raw + sizeof(K3Smem) + r16(unsigned(rows) * 4u));
     const size_t chunk = size_t(p) * (T / TB) + tb;
-    const bool cnt_in_smem = per_pair <= K3_CNT_SMEM;
-    __syncthreads();
-
+    const size_t t0 = size_t(p) * T + size_t(tb) * TB;  // first (problem, interval) of the chunk
     double* gp = g ? g + size_t(p) * m : nullptr;
     double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
 
-    // ---- phase 1: slices
-    if (tid < K3_LINK_THREADS) {
-        // candidate counts of the CTA's rows: fetched now, parked in shared memory after the slice (the loads are in
-        // flight meanwhile), visible to everybody through barriers 1 and 2.  per_pair is a multiple of 8: whole words
-        constexpr int CW = (K3_CNT_SMEM / 4 + K3_LINK_THREADS - 1) / K3_LINK_THREADS;
-        unsigned cw[CW];
-        if (cnt_in_smem) {
-            const unsigned* src = reinterpret_cast<const unsigned*>(B.hp_cnt + chunk * per_pair);
-#pragma unroll
-            for (int q = 0; q < CW; q++) cw[q] = (tid + q * K3_LINK_THREADS < per_pair / 4) ? __ldg(src + tid + q * K3_LINK_THREADS) : 0u;
+    if (B.status[p] != 0) {
+        // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe rows:
+        // every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
+        for (int i = tid; i < TB * NF; i += K3_THREADS) {
+            if (gp) gp[size_t(tb) * TB * NF + i] = 1e300;
+            if (jp)
+                for (int v = 0; v < NF; v++) jp[(size_t(tb) * TB * NF + i) * NF + v] = 0.0;
         }
-        if (tid < TB * NJ * 3) {
-            const int e = tid % 3;
-            const int l = (tid / 3) % NJ;
-            const int tt = tid / (3 * NJ);
-            const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
-            double value = B.link_c[idx * 3 + e];
-            double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
-            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 1, 3, kpd, value, grad);
-            // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
-            const double r = B.link_gens[idx * 18 + e + (3 + e) * 3];
-            const double c = ((value - r) + (value + r)) * 0.5;
-            s_lc[tt][l][e] = c;
-            B.link_sliced[idx * 3 + e] = c;
-#pragma unroll
-            for (int v = 0; v < NF; v++) s_dlc[tt][l][v][e] = grad[v];
+        for (int x = tid; x < rows; x += K3_THREADS) {
+            const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
+            const size_t r = size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o;
+            if (gp) gp[r] = 1e300;
+            if (jp)
+                for (int v = 0; v < NF; v++) jp[r * NF + v] = 0.0;
         }
-        if (cnt_in_smem) {
-#pragma unroll
-            for (int q = 0; q < CW; q++)
-                if (tid + q * K3_LINK_THREADS < per_pair / 4) reinterpret_cast<unsigned*>(s_cnt)[tid + q * K3_LINK_THREADS] = cw[q];
+        if (tb == 0 && tid < 4 * NF) {
+            const size_t r = size_t(NF) * T + size_t(NJ) * T * O + tid;
+            if (gp) gp[r] = 0.0;
+            if (jp)
+                for (int v = 0; v < NF; v++) jp[r * NF + v] = 0.0;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(K3_LINK_THREADS) : "memory");    // link slices complete
-        asm volatile("bar.arrive 2, %0;" ::"n"(K3_THREADS) : "memory");       // tell the torque warps, do not wait
-    } else {
-        const int tq = tid - K3_TORQUE_T0;
-        const int i = tq / K3_TORQUE_LANES, part = tq % K3_TORQUE_LANES;  // table tt*NF + j, lane of the table
-        double value = 0.0;
-        double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
-        const bool on = i < TB * NF;
-        const size_t idx = (size_t(p) * T + tb * TB) * NF + (on ? i : 0);
-        if (on) {
-            // lane `part` takes the monomials part, part + 2, ...; the two partial sums are added below
-            // (the oracle adds the monomials one after the other: a difference of a few ulp)
-            const int n = B.u_n[idx];
-            const int mine = (n - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
-            slice_component(B.u_key + idx * B.capU + part, B.u_g + idx * B.capU + part, mine > 0 ? mine : 0,
-                            K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
-        }
-        value += __shfl_xor_sync(0xffffffffu, value, 1);
-#pragma unroll
-        for (int v = 0; v < NF; v++) grad[v] += __shfl_xor_sync(0xffffffffu, grad[v], 1);
-        double* st = &s_stage[K3_TORQUE_T0 / 32][0];  // the stages of the four torque warps are contiguous
-        if (on && part == 0) {
-            value = B.u_c[idx] + value;
-            const double r = B.u_r[idx];
-            if (gp) gp[tb * TB * NF + i] = ((value - r) + (value + r)) * 0.5;
-#pragma unroll
-            for (int v = 0; v < NF; v++) st[i * NF + v] = grad[v];
-        }
-        asm volatile("bar.sync 3, %0;" ::"n"(K3_THREADS - K3_LINK_THREADS) : "memory");
-        if (jp) {  // rows tb*TB*NF + i, i < 56: 392 contiguous doubles
-            double* dst = jp + size_t(tb) * TB * NF * NF;
-            for (int q = tq; q < TB * NF * NF; q += K3_THREADS - K3_TORQUE_T0) dst[q] = st[q];
-        }
-        asm volatile("bar.sync 3, %0;" ::"n"(K3_THREADS - K3_LINK_THREADS) : "memory");  // stage free again
-        asm volatile("bar.sync 2, %0;" ::"n"(K3_THREADS) : "memory");                      // link slices are complete
+        return;
     }
 
-    // ---- phase 2: collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
-    const double* cand = B.hp_cand + chunk * B.hp_chunk();
-    const unsigned char* cnt = B.hp_cnt + chunk * per_pair;
-    const size_t cstride2 = size_t(per_pair) * 2;  // candidate stride in double2 units
-    const bool in_domain = s_in_domain != 0;
-    double* stage = &s_stage[warp][0];
-    for (;;) {
-        int x0 = 0;
-        if (lane == 0) x0 = atomicAdd(&s_next, 1) * 32;
-        x0 = __shfl_sync(0xffffffffu, x0, 0);
-        if (x0 >= per_pair) break;
-        const int x = x0 + lane;
-        const bool active = x < per_pair;
-        double max_elt = -100000000;
-        double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
-        int l = 0, tt = 0, o = 0;
-        if (active) {
-            o = x % O;
-            const int ltt = x / O;
-            tt = ltt % TB;
-            l = ltt / TB;
-            const double c0 = s_lc[tt][l][0], c1 = s_lc[tt][l][1], c2 = s_lc[tt][l][2];
-            const int n = cnt_in_smem ? s_cnt[x] : cnt[x];
-            if (n != HP_OVERFLOW && in_domain) {
-                const double2* row = reinterpret_cast<const double2*>(cand) + size_t(x) * 2;
-                // K3_CQ candidate records in flight per thread (the scan itself stays in order)
-                for (int q0 = 0; q0 < n; q0 += K3_CQ) {
-                    double2 u[K3_CQ], w[K3_CQ];
+    // ---- round 1
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 32);
+        mbar_init(&S.bar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.task = 0;
+        S.rownext = 0;
+        bool in = true;
+        for (int j = 0; j < NF; j++) {
+            const double k = kin[size_t(p) * NF + j];
+            S.k[j] = k;
+            in = in && (fabs(k) <= K_DOMAIN);
+        }
+        S.in_domain = in ? 1 : 0;
+        int tot = O > 0 ? *B.hp_total_of(p, tb) : 0;
+        const int cap = int(B.hp_chunk_records());
+        S.total = tot < cap ? tot : cap;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned b_nl = unsigned(TB * NJ) * 4u, b_nu = unsigned(TB * NF) * 4u, b_l = unsigned(TB * NJ) * 24u,
+                       b_u = unsigned(TB * NF) * 8u, b_meta = unsigned(rows) * 4u;
+        mbar_arrive_expect_tx(&S.bar[0], b_nl + b_nu + 2 * b_l + 2 * b_u + b_meta);
+        bulk_g2s(S.nl, B.link_n + t0 * NJ, b_nl, &S.bar[0]);
+        bulk_g2s(S.nu, B.u_n + t0 * NF, b_nu, &S.bar[0]);
+        bulk_g2s(S.cen_l, B.link_c + t0 * NJ * 3, b_l, &S.bar[0]);
+        bulk_g2s(S.rad_l, B.link_r + t0 * NJ * 3, b_l, &S.bar[0]);
+        bulk_g2s(S.cen_u, B.u_c + t0 * NF, b_u, &S.bar[0]);
+        bulk_g2s(S.rad_u, B.u_r + t0 * NF, b_u, &S.bar[0]);
+        if (b_meta) bulk_g2s(s_meta, B.hp_meta + chunk * rows, b_meta, &S.bar[0]);
+    }
+    // power-product tables (while round 1 is in flight): entry e of table A / B / C, all eight lane variants
+    if (tid < 96) {
+        const int tab = tid < 64 ? 0 : (tid < 80 ? 1 : 2);
+        const int e = tid < 64 ? tid : (tid < 80 ? tid - 64 : tid - 80);
+        const int j0 = tab == 0 ? 0 : (tab == 1 ? 3 : 5), nv = tab == 0 ? 3 : 2;
+        double f[3] = {1.0, 1.0, 1.0}, d[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-                    for (int i = 0; i < K3_CQ; i++) {
-                        if (q0 + i < n) {
-                            u[i] = __ldg(row + (q0 + i) * cstride2);
-                            w[i] = __ldg(row + (q0 + i) * cstride2 + 1);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < K3_CQ; i++) {
-                        if (q0 + i < n) {
-                            const double v = (u[i].x * c0 + u[i].y * c1 + w[i].x * c2) - w[i].y;
-                            if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
-                                max_elt = v;
-                                A0 = -u[i].x; A1 = -u[i].y; A2 = -w[i].x;
-                            }
-                        }
-                    }
-                }
-            } else {
-                // all 72 half-spaces from the generators: rows with more than HP_CAP candidates, or k outside
-                // the box the candidate lists were built for
-                // (results through temporaries: taking the address of max_elt / A0..A2 themselves would move them
-                // to local memory for the streaming path as well)
-                const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
-                double r_max, r_a0, r_a1, r_a2;
-                row_from_generators(B.obstacles + (size_t(p) * O + o) * 12, B.link_gens + idx * 18, c0, c1, c2,
-                                    &r_max, &r_a0, &r_a1, &r_a2);
-                max_elt = r_max;
-                A0 = r_a0;
-                A1 = r_a1;
-                A2 = r_a2;
+        for (int q = 0; q < 3; q++) {
+            if (q < nv) {
+                const double k = S.k[j0 + q];
+                const int dg = (e >> (2 * q)) & 3;
+                f[q] = dg == 0 ? 1.0 : (dg == 1 ? k : (dg == 2 ? k * k : k * k * k));
+                d[q] = dg == 0 ? 0.0 : (dg == 1 ? 1.0 : (dg == 2 ? 2.0 * k : 3.0 * (k * k)));
             }
         }
-        const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
-        if (gp && active) gp[row_i] = -max_elt;
-        if (jp) {
-            if (active) {
+        const double plain = f[0] * f[1] * f[2];
+        double* row = S.pw[tid];
 #pragma unroll
-                for (int v = 0; v < NF; v++) {
-                    const double* dk = s_dlc[tt][l][v];
-                    // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
-                    stage[lane * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+        for (int v = 0; v < 8; v++) row[v] = plain;
+        // lane v = 1 + j owns d/dk_j
+        row[1 + j0] = d[0] * f[1] * f[2];
+        row[2 + j0] = f[0] * d[1] * f[2];
+        if (nv == 3) row[3 + j0] = f[0] * f[1] * d[2];
+    }
+    __syncthreads();
+    mbar_wait(&S.bar[0], 0);
+
+    // ---- round 2: warp 0 places and fetches the tables (task-major: q = task*TB + tt, tasks = 7 joints, then NJ links),
+    // thread 32 fetches the candidate records in use
+    const int ntab = TB * (NF + NJ);
+    if (warp == 0) {
+        unsigned kb[2], cb[2], bytes[2];
+        const uint16_t* ksrc[2];
+        const double* csrc[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int q = lane + 32 * h;
+            kb[h] = cb[h] = 0;
+            ksrc[h] = nullptr;
+            csrc[h] = nullptr;
+            if (q < ntab) {
+                const int task = q / TB, tt = q % TB;
+                if (task < NF) {
+                    const int n = S.nu[tt * NF + task];
+                    const size_t idx = (t0 + tt) * NF + task;
+                    kb[h] = r16(unsigned(n) * 2u);
+                    cb[h] = r16(unsigned(n) * 8u);
+                    ksrc[h] = B.u_key + idx * B.capU;
+                    csrc[h] = B.u_g + idx * B.capU;
+                } else {
+                    const int l = task - NF;
+                    const int n = S.nl[tt * NJ + l];
+                    const size_t idx = (t0 + tt) * NJ + l;
+                    kb[h] = r16(unsigned(n) * 2u);
+                    cb[h] = r16(unsigned(n) * 24u);
+                    ksrc[h] = B.link_key + idx * B.capL;
+                    csrc[h] = B.link_g + idx * B.capL * 3;
                 }
             }
-            __syncwarp();
+            bytes[h] = kb[h] + cb[h];
+        }
+        // exclusive prefix over the 64 slots
+        unsigned inc0 = bytes[0], inc1 = bytes[1];
 #pragma unroll
-            for (int q = 0; q < NF; q++) {
-                const int e = q * 32 + lane;
-                const int r = e / NF;
-                const long long rr = __shfl_sync(0xffffffffu, row_i, r);
-                if (rr >= 0) jp[rr * NF + (e - r * NF)] = stage[e];
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned a0 = __shfl_up_sync(0xffffffffu, inc0, d), a1 = __shfl_up_sync(0xffffffffu, inc1, d);
+            if (lane >= d) {
+                inc0 += a0;
+                inc1 += a1;
             }
-            __syncwarp();
+        }
+        const unsigned tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+        unsigned off[2] = {inc0 - bytes[0], tot0 + inc1 - bytes[1]};
+        unsigned tx = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int q = lane + 32 * h;
+            if (q < ntab) {
+                const bool staged = off[h] + bytes[h] <= unsigned(K3_TABLE_ARENA);
+                S.toff[q] = staged ? int(off[h]) : -1;
+                if (staged) tx += bytes[h];
+                else bytes[h] = 0;
+            } else {
+                bytes[h] = 0;
+            }
+        }
+        mbar_arrive_expect_tx(&S.bar[1], tx);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (bytes[h]) {  // keys first, then the coefficients (both 16-byte aligned)
+                bulk_g2s(S.arena + off[h], ksrc[h], kb[h], &S.bar[1]);
+                bulk_g2s(S.arena + off[h] + kb[h], csrc[h], cb[h], &S.bar[1]);
+            }
+        }
+    } else if (tid == 32) {
+        const int nrec = S.total < cand_arena ? S.total : cand_arena;
+        mbar_arrive_expect_tx(&S.bar[2], unsigned(nrec) * 32u);
+        if (nrec > 0) bulk_g2s(s_cand, B.hp_cand + chunk * B.hp_chunk_records() * 4, unsigned(nrec) * 32u, &S.bar[2]);
+    }
+    __syncthreads();  // S.toff
+    mbar_wait(&S.bar[1], 0);
+
+    // ---- slices
+    {
+        const int grp = lane >> 3, v = lane & 7;
+        const double* pwA = &S.pw[0][v];
+        const double* pwB = &S.pw[64][v];
+        const double* pwC = &S.pw[80][v];
+        const int ntask = (NF + NJ) * (TB / 4);
+        for (;;) {
+            int task = 0;
+            if (lane == 0) task = atomicAdd(&S.task, 1);
+            task = __shfl_sync(0xffffffffu, task, 0);
+            if (task >= ntask) break;
+            const int sub = task % (TB / 4), which = task / (TB / 4);  // longest tables (torques) first
+            const int tt = sub * 4 + grp;
+            const bool torque = which < NF;
+            const int l = which - NF;
+            const int q = which * TB + tt;
+            const int n = torque ? S.nu[tt * NF + which] : S.nl[tt * NJ + l];
+            const int cs = torque ? 1 : 3;
+            const uint16_t* keys;
+            const double* coef;
+            const int to = S.toff[q];
+            if (to >= 0) {
+                keys = reinterpret_cast<const uint16_t*>(S.arena + to);
+                coef = reinterpret_cast<const double*>(S.arena + to + r16(unsigned(n) * 2u));
+            } else if (torque) {
+                const size_t idx = (t0 + tt) * NF + which;
+                keys = B.u_key + idx * B.capU;
+                coef = B.u_g + idx * B.capU;
+            } else {
+                const size_t idx = (t0 + tt) * NJ + l;
+                keys = B.link_key + idx * B.capL;
+                coef = B.link_g + idx * B.capL * 3;
+            }
+            int nmax = n;
+            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
+            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, pbc = 1.0;
+            unsigned last_hi = 0xffffffffu;
+            for (int mI = 0; mI < nmax; mI++) {
+                const bool on = mI < n;
+                const unsigned key = on ? keys[mI] : 0u;
+                const unsigned hi = key >> 6;
+                if (hi != last_hi) {
+                    pbc = pwB[(hi & 15u) * 8] * pwC[(hi >> 4) * 8];
+                    last_hi = hi;
+                }
+                const double f = pwA[(key & 63u) * 8] * pbc;
+                if (on) {
+                    a0 = __fma_rn(coef[mI * cs], f, a0);
+                    if (!torque) {
+                        a1 = __fma_rn(coef[mI * cs + 1], f, a1);
+                        a2 = __fma_rn(coef[mI * cs + 2], f, a2);
+                    }
+                }
+            }
+            if (torque) {
+                const int i = tt * NF + which;
+                if (v == 0) {
+                    const double value = S.cen_u[i] + a0;
+                    const double r = S.rad_u[i];
+                    S.tg[i] = ((value - r) + (value + r)) * 0.5;  // centre of Interval(c - r, c + r) (KPR/NLPclass.cu:306)
+                } else {
+                    S.tj[i * NF + (v - 1)] = a0;
+                }
+            } else {
+                const int i = tt * NJ + l;
+                if (v == 0) {
+                    const double acc[3] = {a0, a1, a2};
+#pragma unroll
+                    for (int e = 0; e < 3; e++) {
+                        const double value = S.cen_l[i * 3 + e] + acc[e];
+                        const double r = S.rad_l[i * 3 + e];
+                        S.lc[tt][l][e] = ((value - r) + (value + r)) * 0.5;  // getCenter(slice()) (KPR/NLPclass.cu:313)
+                    }
+                } else {
+                    S.dlc[tt][l][v - 1][0] = a0;
+                    S.dlc[tt][l][v - 1][1] = a1;
+                    S.dlc[tt][l][v - 1][2] = a2;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // torque rows tb*TB*NF + i, i < TB*NF: contiguous runs of g and of the Jacobian
+    if (gp)
+        for (int i = tid; i < TB * NF; i += K3_THREADS) gp[size_t(tb) * TB * NF + i] = S.tg[i];
+    if (jp)
+        for (int i = tid; i < TB * NF * NF; i += K3_THREADS) jp[size_t(tb) * TB * NF * NF + i] = S.tj[i];
+    if (p == 0 && B.link_sliced)
+        for (int i = tid; i < TB * NJ * 3; i += K3_THREADS)
+            B.link_sliced[(size_t(tb) * TB * NJ) * 3 + i] = S.lc[i / (NJ * 3)][(i / 3) % NJ][i % 3];
+
+    // ---- collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
+    mbar_wait(&S.bar[2], 0);  // (also when the rows are skipped: no bulk copy may be in flight when the CTA exits)
+    if (O > 0 && S.in_domain) {
+        const double* gcand = B.hp_cand + chunk * B.hp_chunk_records() * 4;
+        const int staged = S.total < cand_arena ? S.total : cand_arena;
+        double* stage = reinterpret_cast<double*>(S.arena) + warp * (32 * NF);
+        for (;;) {
+            int x0 = 0;
+            if (lane == 0) x0 = atomicAdd(&S.rownext, 1) * 32;
+            x0 = __shfl_sync(0xffffffffu, x0, 0);
+            if (x0 >= rows) break;
+            const int x = x0 + lane;
+            bool active = x < rows;
+            double max_elt = -100000000;
+            double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
+            int l = 0, tt = 0, o = 0;
+            if (active) {
+                o = x % O;
+                const int ltt = x / O;
+                tt = ltt % TB;
+                l = ltt / TB;
+                const unsigned meta = s_meta[x];
+                const int n = int(meta & 255u), off = int(meta >> 8);
+                if (n == HP_OVERFLOW) {
+                    active = false;  // no stored list: k_constraints_slow writes this row
+                } else {
+                    const double c0 = S.lc[tt][l][0], c1 = S.lc[tt][l][1], c2 = S.lc[tt][l][2];
+                    const double2* rec = reinterpret_cast<const double2*>(off + n <= staged ? s_cand + size_t(off) * 4
+                                                                                             : gcand + size_t(off) * 4);
+                    for (int q = 0; q < n; q++) {
+                        const double2 u = rec[2 * q], w = rec[2 * q + 1];
+                        const double val = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
+                        if (val > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
+                            max_elt = val;
+                            A0 = -u.x; A1 = -u.y; A2 = -w.x;
+                        }
+                    }
+                }
+            }
+            const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
+            if (gp && active) gp[row_i] = -max_elt;
+            if (jp) {
+                if (active) {
+#pragma unroll
+                    for (int v = 0; v < NF; v++) {
+                        const double* dk = S.dlc[tt][l][v];
+                        // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
+                        stage[lane * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < NF; q++) {
+                    const int e = q * 32 + lane;
+                    const int r = e / NF;
+                    const long long rr = __shfl_sync(0xffffffffu, row_i, r);
+                    if (rr >= 0) jp[rr * NF + (e - r * NF)] = stage[e];
+                }
+                __syncwarp();
+            }
         }
     }
 
@@ -618,6 +770,73 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                 }
             }
         }
+    }
+}
+
+// k_constraints_slow: the collision rows k_constraints leaves out — rows without a stored candidate list (more than HP_CAP
+// survivors, or no room left in the chunk) and every row of a problem whose k lies outside the box the lists were built
+// for.  One CTA per problem, which returns at once in the usual case (no such row); otherwise one thread per row slices
+// the link reach set in the reference's factor order (KPR/PZsparse.cu:404-555) and scans all 72 half-spaces computed from
+// the generators (KPR/CollisionChecking.cu:169-299).
+__global__ void __launch_bounds__(128)
+k_constraints_slow(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
+    const int p = B.plist ? B.plist[blockIdx.x] : int(blockIdx.x);
+    const int NJ = B.NJ, O = B.O, T = B.T;
+    if (O == 0 || B.status[p] != 0) return;
+    __shared__ double2 kpd[NF][4];  // {k_j^d, d/dk_j k_j^d} for d = 0..3
+    bool in = true;
+    for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
+    if (in && *B.hp_slow_of(p) == 0) return;
+    if (threadIdx.x < NF) {
+        const double k = kin[size_t(p) * NF + threadIdx.x];
+        kpd[threadIdx.x][0] = make_double2(1.0, 0.0);
+        kpd[threadIdx.x][1] = make_double2(k, 1.0);
+        kpd[threadIdx.x][2] = make_double2(k * k, 2.0 * k);
+        kpd[threadIdx.x][3] = make_double2(k * k * k, 3.0 * (k * k));
+    }
+    __syncthreads();
+    const int m = B.m();
+    const int per_chunk = NJ * TB * O;
+    double* gp = g ? g + size_t(p) * m : nullptr;
+    double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
+    for (int r = threadIdx.x; r < per_chunk * (T / TB); r += blockDim.x) {
+        const int tb = r / per_chunk, x = r - tb * per_chunk;
+        const size_t chunk = size_t(p) * (T / TB) + tb;
+        if (in && (B.hp_meta[chunk * per_chunk + x] & 255u) != HP_OVERFLOW) continue;
+        const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
+        const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+        double c[3], dk[NF][3];
+        const int n = B.link_n[idx];
+        for (int e = 0; e < 3; e++) {
+            double value = B.link_c[idx * 3 + e];
+            double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
+            for (int mI = 0; mI < n; mI++) {
+                const unsigned key = B.link_key[idx * B.capL + mI];
+                double val = B.link_g[(idx * B.capL + mI) * 3 + e];
+                double D[NF];
+#pragma unroll
+                for (int j = 0; j < NF; j++) {
+                    const double2 fd = kpd[j][(key >> (2 * j)) & 3];
+                    D[j] = val * fd.y;
+#pragma unroll
+                    for (int v = 0; v < j; v++) D[v] *= fd.x;
+                    val *= fd.x;
+                }
+                value += val;
+#pragma unroll
+                for (int v = 0; v < NF; v++) grad[v] += D[v];
+            }
+            const double rr = B.link_r[idx * 3 + e];
+            c[e] = ((value - rr) + (value + rr)) * 0.5;
+#pragma unroll
+            for (int v = 0; v < NF; v++) dk[v][e] = grad[v];
+        }
+        double r_max, A0, A1, A2;
+        row_from_generators(B.obstacles + (size_t(p) * O + o) * 12, B.link_gens + idx * 18, c[0], c[1], c[2], &r_max, &A0, &A1, &A2);
+        const size_t row = size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o;
+        if (gp) gp[row] = -r_max;
+        if (jp)
+            for (int v = 0; v < NF; v++) jp[row * NF + v] = A0 * dk[v][0] + A1 * dk[v][1] + A2 * dk[v][2];
     }
 }
 
@@ -665,15 +884,42 @@ k_verdict(Batch B, const double* __restrict__ g, int* __restrict__ feasible, int
 // host launchers (called from capi.cu)
 cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
     if (B.O == 0 || B.nprob == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(B.hp_total, 0, size_t(B.nprob) * (B.T / TB + 1) * sizeof(int), st);
+    if (e != cudaSuccess) return e;
     const int rows = B.NJ * B.T * B.O;
     dim3 grid((rows + HP_ROWS - 1) / HP_ROWS, B.nprob);
     k_hyperplanes<<<grid, HP_THREADS, 0, st>>>(B);
     return cudaGetLastError();
 }
+
+// Shared memory of one k_constraints CTA: the fixed part, the row words and as many candidate records as keep three
+// (else two, else one) CTAs per SM resident while covering the chunk's expected 2.5 records per row.
+constexpr int K3_SMEM_MAX = 200 * 1024;
+inline void k3_smem_plan(const Batch& B, int* smem_bytes, int* cand_arena) {
+    const int rows = B.chunk_rows();
+    const int fixed = int(sizeof(K3Smem)) + int((size_t(rows) * 4 + 15) & ~size_t(15));
+    const int want = rows * 5 / 2 + 32;
+    const int budgets[3] = {74 * 1024, 110 * 1024, K3_SMEM_MAX};
+    int rec = 0;
+    for (int b = 0; b < 3; b++) {
+        rec = (budgets[b] - fixed) / 32;
+        if (rec >= want) break;
+    }
+    if (rec < 0) rec = 0;
+    if (rec > want) rec = want > int(B.hp_chunk_records()) ? int(B.hp_chunk_records()) : want;
+    *cand_arena = rec;
+    *smem_bytes = fixed + rec * 32;
+}
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
+    int smem = 0, arena = 0;
+    k3_smem_plan(B, &smem, &arena);
+    if (smem > K3_SMEM_MAX) return cudaErrorInvalidValue;  // (armour_ctx_create bounds max_obstacles accordingly)
     dim3 grid(B.T / TB, B.nprob);
-    k_constraints<<<grid, K3_THREADS, 0, st>>>(B, d_k, d_g, d_jac);
+    k_constraints<<<grid, K3_THREADS, smem, st>>>(B, d_k, d_g, d_jac, arena);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || B.O == 0) return e;
+    k_constraints_slow<<<B.nprob, 128, 0, st>>>(B, d_k, d_g, d_jac);
     return cudaGetLastError();
 }
 cudaError_t launch_verdict(const Batch& B, const double* d_g, int* d_feasible, int* d_first, cudaStream_t st) {

@@ -118,9 +118,10 @@ class ReachSetEngine:
         return ln, un
 
     def candidate_counts(self):
-        """Stored collision half-space candidates per row, uint8 [nprob, T/8, NJ, 8, O] (255: evaluated from the
-        generators)."""
-        out = np.zeros((self.nprob, self.T // 8, self.NJ, 8, max(self.nobs, 0)), np.uint8)
+        """Stored collision half-space candidates per row, uint8 [nprob, T/C, NJ, C, O] with C intervals per kernel
+        chunk (255: evaluated from the generators)."""
+        C_ = self.lib.armour_chunk_intervals()
+        out = np.zeros((self.nprob, self.T // C_, self.NJ, C_, max(self.nobs, 0)), np.uint8)
         if out.size:
             self._check(self.lib.armour_batch_get_candidate_counts(self._h, self.nprob, out.ctypes.data_as(C.c_void_p)))
         return out

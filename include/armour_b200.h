@@ -10,7 +10,11 @@
  *   - the caller owns all host buffers; the context owns all device memory;
  *   - one context = one CUDA device + one stream; thread-compatible, not thread-safe (Ipopt calls
  *     eval_g / eval_jac_g serially from one thread);
- *   - there is NO CPU fallback: without a CUDA device armour_ctx_create fails with ARMOUR_ERR_CUDA.
+ *   - there is NO CPU fallback: without a CUDA device armour_ctx_create fails with ARMOUR_ERR_CUDA;
+ *   - several contexts may live on one device.  Contexts of identical configuration run side by side; switching
+ *     between contexts whose configuration differs drains the device first (their constants share one block);
+ *   - a problem whose build returned / recorded ARMOUR_ERR_CAPACITY has no valid reach sets: every evaluation of it
+ *     returns fail-safe rows (torque and collision rows 1e300, zero Jacobian), so its verdict is always infeasible.
  *
  * Index conventions (T = num_time_steps = 128, NJ = links, NF = 7, O = obstacles of the problem):
  *   constraint rows m = NF*T + NJ*T*O + 4*NF            (KPR/NLPclass.cu:45-57)
@@ -51,9 +55,9 @@ typedef struct armour_config {
     int robot_model;            /* 0: Kinova Gen3 without gripper (NUM_JOINTS 7); 1: with fixed gripper link (8) */
     int num_time_steps;         /* NUM_TIME_STEPS, even, <= 128 */
     int max_obstacles;          /* per problem (reference MAX_OBSTACLE_NUM = 40) */
-    int max_problems;           /* batch capacity of this context */
-    int cap_link_monomials;     /* capacity of the stored k-only table of one link reach set */
-    int cap_torque_monomials;   /* capacity of the stored k-only table of one torque reach set */
+    int max_problems;           /* batch capacity of this context (<= 65535) */
+    int cap_link_monomials;     /* capacity of the stored k-only table of one link reach set (multiple of 8) */
+    int cap_torque_monomials;   /* capacity of the stored k-only table of one torque reach set (multiple of 8) */
     int cap_work_monomials;     /* capacity of one intermediate PZ during reach-set construction */
     double simplify_threshold;  /* SIMPLIFY_THRESHOLD */
     double k_range[ARMOUR_NF];  /* k_range */
@@ -65,7 +69,8 @@ int armour_config_default(armour_config* cfg);
 int armour_ctx_create(const armour_config* cfg, armour_ctx** out);
 int armour_ctx_destroy(armour_ctx* ctx);
 /* Allocate now everything a batch of nprob problems with nobs obstacles will need (obstacle / half-space /
- * staging buffers), so that the first build is not charged for cudaMalloc.  The reference allocates in the
+ * staging buffers), so that the first build is not charged for cudaMalloc.  If the reservation has to grow the
+ * half-space buffers the current batch is dropped (build again before evaluating).  The reference allocates in the
  * Obstacles constructor, before its reach-set timer starts (KPR/armour_main.cu:86-88, CollisionChecking.cu:6-55). */
 int armour_ctx_reserve(armour_ctx* ctx, int nprob, int nobs);
 /* Launch everything on this cudaStream_t (default: a stream owned by the context). */
@@ -155,11 +160,12 @@ int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out);
 /* Stored k-only monomial counts of the built reach sets: link_n[nprob*T*NJ], u_n[nprob*T*NF] (either may
  * be NULL).  bench.py derives the algorithmic bytes of one evaluation from them (SURVEY.md 8d B_eval). */
 int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, int* u_n);
-/* Stored collision half-space candidates per (link, interval, obstacle) row, out[nprob][T/8][NJ][8][O] bytes in
- * the kernel's chunk order (255 = row evaluated from the generators).  bench.py reports the candidate bytes one
- * evaluation streams; there is no counterpart in the reference, which stores all 72 half-spaces per row
- * (KPR/CollisionChecking.cu:169-228). */
+/* Stored collision half-space candidates per (link, interval, obstacle) row, out[nprob][T/C][NJ][C][O] bytes in
+ * the kernel's chunk order, C = armour_chunk_intervals() (255 = row evaluated from the generators).  bench.py reports
+ * the candidate bytes one evaluation streams; there is no counterpart in the reference, which stores all 72
+ * half-spaces per row (KPR/CollisionChecking.cu:169-228). */
 int armour_batch_get_candidate_counts(armour_ctx* ctx, int nprob, unsigned char* out);
+int armour_chunk_intervals(void);
 /* Measurement aid: runs a dependent-chain-free FP64 FMA kernel on the context's device and returns the
  * sustained non-tensor FP64 rate in TFLOP/s (the FP64 roofline denominator). */
 int armour_measure_fp64_peak(armour_ctx* ctx, double* tflops);

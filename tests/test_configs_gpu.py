@@ -46,10 +46,26 @@ def test_config4_100_obstacles_lower_threshold(built, thr):
 
 
 def test_too_small_capacity_is_reported_not_truncated(built):
-    """A monomial table that does not fit its configured capacity fails the build with ARMOUR_ERR_CAPACITY."""
+    """A monomial table that does not fit its configured capacity fails the build with ARMOUR_ERR_CAPACITY, and the
+    problem can never be taken for feasible afterwards: evaluations return fail-safe rows."""
     from armour_b200 import ArmourError, ReachSetEngine, worlds
-    q0, qd0, qdd0, _, obs = worlds.random_problems(1, 2, seed=8)
-    eng = ReachSetEngine(max_problems=1, max_obstacles=2, cap_link=2, cap_torque=4)
+    q0, qd0, qdd0, q_des, obs = worlds.random_problems(1, 2, seed=8)
+    eng = ReachSetEngine(max_problems=1, max_obstacles=2, cap_link=8, cap_torque=8)
     with pytest.raises(ArmourError) as ei:
         eng.build(q0[0], qd0[0], qdd0[0], obs[0])
     assert ei.value.code == -4
+    eng.nprob, eng.nobs = 1, 2  # (the Python mirror only records a successful build)
+    assert eng.build_status()[0] != 0
+    g, jac = eng.eval(np.zeros(7))
+    assert np.all(np.isfinite(jac)) and np.all(g[0][:7 * 128 + 7 * 128 * 2] >= 1e299)
+    assert eng.finalize_solution(g[0]) == (False, 0)
+    k, ok, first, _ = eng.solve(q_des)
+    assert not ok[0]
+
+
+def test_capacities_must_be_multiples_of_eight(built):
+    from armour_b200 import ArmourError, ReachSetEngine
+    with pytest.raises(ArmourError):
+        ReachSetEngine(max_problems=1, max_obstacles=2, cap_link=2, cap_torque=4)
+    with pytest.raises(ArmourError):
+        ReachSetEngine(max_problems=70000, max_obstacles=2)
