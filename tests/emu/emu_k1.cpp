@@ -44,6 +44,8 @@ extern "C" int emu_k1_build(int model_id, int T, double thr, const double* k_ran
     B.u_g = u_g;
     B.torque_radius = torque_radius;
     B.link_gens = link_gens;
+    std::vector<double> link_r(size_t(T) * MAXJ * 3);
+    B.link_r = link_r.data();
     int status = 0, work = 0;
     B.status = &status;
     k1::K1Params P;
