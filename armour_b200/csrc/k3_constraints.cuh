@@ -376,150 +376,130 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 __device__ __forceinline__ unsigned r16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
-// k_constraints: one CTA per chunk = (problem, TB intervals), K3_THREADS threads.
+// k_constraints: persistent CTAs (two per SM), each walks a contiguous range of chunks = (problem, TB intervals) through a
+// two-stage TMA pipeline, so the DRAM latency of a chunk is paid while the previous chunk computes.
 //
-// Everything the chunk needs comes in two rounds of TMA bulk copies into shared memory, so a CTA pays two DRAM
-// latencies, not one per monomial fetched:
+// Everything a chunk needs comes in two rounds of bulk copies into shared memory:
 //   round 1 (fixed sizes): monomial counts, centres and radii of its TB*(NJ+NF) reach-set tables, the (first
 //            record, count) word of its NJ*TB*O collision rows;
 //   round 2 (sizes known from round 1): every table, exactly its n monomials (16-bit keys, coefficients), and the
 //            candidate half-space records in use of the chunk: one contiguous run.
-// Slices: eight lanes per table, lane v owns output v (the value, or d/dk_{v-1}); a warp walks the tables of
-// four consecutive intervals of one link / one joint together (similar lengths).  The power products of a monomial come
-// from three small tables in shared memory, k0 k1 k2 | k3 k4 | k5 k6, whose entry (index, v) already is the factor lane v
-// needs (the derivative for its own variable, the plain product otherwise): term_v = coeff * A[.][v] * (B[.][v] *
-// C[.][v]).  Keys are sorted, so the B*C factor is reloaded only when the upper key bits change.  (The reference
-// applies the factors one variable after the other, KPR/PZsparse.cu:404-555: same value up to a few ulp.)
+// Schedule of iteration i (stage s = i & 1):  issue round 1 of chunk i+1  |  wait tables(i), slice  |  warp 0: place and
+// issue round 2 of chunk i+1  |  torque rows, collision rows of chunk i  |  barrier.
+// Slices: eight lanes per table, lane v owns output v (the value, or d/dk_{v-1}); a warp walks the tables of four
+// consecutive intervals of one link / one joint together (similar lengths), branch-free, operands in shared memory.
+// The power product of a monomial comes from two tables in shared memory, k0..k3 (256 entries) and k4..k6 (64), whose
+// columns hold the plain product and its derivatives: term_v = coeff * A[key & 255][colA(v)] * B[key >> 8][colB(v)].
+// They depend on k only, i.e. on the problem: a CTA rebuilds them when its chunk range crosses into the next problem.
+// (The reference applies the factors one variable after the other, KPR/PZsparse.cu:404-555: same value up to a few ulp.)
 // Rows: one lane per collision row, records read from the staged run (or from global memory for the part of a chunk that
 // does not fit), g and the Jacobian rows leave transposed through shared memory, coalesced.
-constexpr int K3_THREADS = 256;
+#ifndef K3_THREADS_N
+#define K3_THREADS_N 256
+#endif
+#ifndef K3_TRANSPOSE
+#define K3_TRANSPOSE 0   // 1: Jacobian rows leave through a shared-memory transposition (coalesced), 0: 56 B per lane
+#endif
+constexpr int K3_THREADS = K3_THREADS_N;
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int K3_TABLE_ARENA = 16384;          // bytes of staged tables; later the transposition buffers of the warps
-constexpr int K3_NTAB = TB * (MAXJ + NF);      // tables of a chunk (upper bound)
+constexpr int K3_TABLE_ARENA = 14336;  // bytes of staged tables per stage (later the warps' transposition buffers)
+static_assert(!K3_TRANSPOSE || K3_WARPS * 32 * NF * 8 <= K3_TABLE_ARENA, "transposition buffers reuse the table arena");
+constexpr int K3_NTAB = TB * (MAXJ + NF);               // tables of a chunk (upper bound)
 static_assert(TB % 4 == 0, "a warp slices four intervals of a link / joint together");
 static_assert(K3_NTAB <= 64, "one warp issues the table copies, two tables per lane");
-static_assert(K3_WARPS * 32 * NF * 8 <= K3_TABLE_ARENA, "transposition buffers reuse the table arena");
 
-struct K3Smem {  // fixed part of the dynamic shared memory; the row words and the candidate arena follow
-    unsigned long long bar[4];
-    double pw[96][8];                      // power-product tables A (64 entries), B (16), C (16), 8 lanes each
-    double lc[TB][MAXJ][3];                // sliced link centres
-    double dlc[TB][MAXJ][NF][3];           // and their d/dk
-    double cen_l[TB * MAXJ * 3], rad_l[TB * MAXJ * 3], cen_u[TB * NF + 4], rad_u[TB * NF + 4];
-    double tg[TB * NF + 4];                // torque rows of g
-    double tj[TB * NF * NF + 4];           // torque rows of the Jacobian
-    double k[8];
+struct K3Stage {
     int nl[TB * MAXJ], nu[TB * NF + 4];
-    int toff[K3_NTAB];                     // byte offset of a staged table in the arena, -1: read it from global memory
-    int total, task, rownext, in_domain;
+    double cen_l[TB * MAXJ * 3], rad_l[TB * MAXJ * 3], cen_u[TB * NF + 4], rad_u[TB * NF + 4];
+    int toff[K3_NTAB];  // byte offset of a staged table in the arena, -1: read it from global memory
+    int staged;         // candidate records staged
+    int pad[3];
     __align__(16) unsigned char arena[K3_TABLE_ARENA];
 };
+struct K3Smem {  // fixed part of the dynamic shared memory; 2 x row words and 2 x candidate arena follow
+    unsigned long long bar_r1[2], bar_tab[2], bar_cand[2];
+    double pwA[256][5];            // k0..k3: plain product, d/dk0 .. d/dk3
+    double pwB[64][4];             // k4..k6: plain product, d/dk4 .. d/dk6
+    double lc[TB][MAXJ][4];        // sliced link centres
+    double dlc[TB][MAXJ][NF][4];   // and their d/dk
+    double tg[TB * NF + 4];        // torque rows of g
+    double tj[TB * NF * NF + 4];   // torque rows of the Jacobian
+    double k[8];
+    double zero_d[4];              // operands of an empty table
+    unsigned short zero_k[8];
+    int task, rownext, in_domain, pad;
+    K3Stage st[2];
+};
 
-__global__ void __launch_bounds__(K3_THREADS, 3)
+// one table sliced by an 8-lane group, operands in shared memory.  n >= 0 own monomials, nmax = longest of the warp's
+// four tables (lanes past their own n re-read their last monomial with a zero factor: no branch, no garbage)
+template <bool TORQUE>
+__device__ __forceinline__ void slice_group(const unsigned short* __restrict__ kp, const double* __restrict__ cp, int n,
+                                            int nmax, const double* __restrict__ pa, const double* __restrict__ pb,
+                                            double& a0, double& a1, double& a2) {
+    const int nlast = n > 0 ? n - 1 : 0;
+#pragma unroll 4
+    for (int mI = 0; mI < nmax; mI++) {
+        const int mm = mI < nlast ? mI : nlast;
+        const unsigned key = kp[mm];
+        double f = pa[(key & 255u) * 5] * pb[(key >> 8) * 4];
+        f = mI < n ? f : 0.0;
+        if (TORQUE) {
+            a0 = __fma_rn(cp[mm], f, a0);
+        } else {
+            a0 = __fma_rn(cp[mm * 3], f, a0);
+            a1 = __fma_rn(cp[mm * 3 + 1], f, a1);
+            a2 = __fma_rn(cp[mm * 3 + 2], f, a2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 2)
 k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac, int cand_arena) {
     extern __shared__ __align__(16) unsigned char k3_raw[];
     K3Smem& S = *reinterpret_cast<K3Smem*>(k3_raw);
-    const int tb = blockIdx.x, p = B.plist ? B.plist[blockIdx.y] : int(blockIdx.y);
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int m = B.m();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rows = NJ * TB * O;
-    unsigned* s_meta = reinterpret_cast<unsigned*>(k3_raw + sizeof(K3Smem));
-    double* s_cand = reinterpret_cast<double*>(k3_raw + sizeof(K3Smem) + r16(unsigned(rows) * 4u));
-    const size_t chunk = size_t(p) * (T / TB) + tb;
-    const size_t t0 = size_t(p) * T + size_t(tb) * TB;  // first (problem, interval) of the chunk
-    double* gp = g ? g + size_t(p) * m : nullptr;
-    double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
+    const unsigned meta_bytes = r16(unsigned(rows) * 4u);
+    unsigned* const s_meta0 = reinterpret_cast<unsigned*>(k3_raw + sizeof(K3Smem));
+    double* const s_cand0 = reinterpret_cast<double*>(k3_raw + sizeof(K3Smem) + 2 * meta_bytes);
+    const int cpp = T / TB;  // chunks per problem
+    const long long nchunks = (long long)B.nprob * cpp;
+    const int c_begin = int(nchunks * blockIdx.x / gridDim.x), c_end = int(nchunks * (blockIdx.x + 1) / gridDim.x);
+    if (c_begin >= c_end) return;
+    const int ntab = TB * (NF + NJ);
+    const float invO = O > 0 ? 1.0f / float(O) : 0.0f;
+    const size_t rec_per_chunk = B.hp_chunk_records();
 
-    if (B.status[p] != 0) {
-        // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe rows:
-        // every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
-        for (int i = tid; i < TB * NF; i += K3_THREADS) {
-            if (gp) gp[size_t(tb) * TB * NF + i] = 1e300;
-            if (jp)
-                for (int v = 0; v < NF; v++) jp[(size_t(tb) * TB * NF + i) * NF + v] = 0.0;
-        }
-        for (int x = tid; x < rows; x += K3_THREADS) {
-            const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
-            const size_t r = size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o;
-            if (gp) gp[r] = 1e300;
-            if (jp)
-                for (int v = 0; v < NF; v++) jp[r * NF + v] = 0.0;
-        }
-        if (tb == 0 && tid < 4 * NF) {
-            const size_t r = size_t(NF) * T + size_t(NJ) * T * O + tid;
-            if (gp) gp[r] = 0.0;
-            if (jp)
-                for (int v = 0; v < NF; v++) jp[r * NF + v] = 0.0;
-        }
-        return;
-    }
-
-    // ---- round 1
-    if (tid == 0) {
-        mbar_init(&S.bar[0], 1);
-        mbar_init(&S.bar[1], 32);
-        mbar_init(&S.bar[2], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        S.task = 0;
-        S.rownext = 0;
-        bool in = true;
-        for (int j = 0; j < NF; j++) {
-            const double k = kin[size_t(p) * NF + j];
-            S.k[j] = k;
-            in = in && (fabs(k) <= K_DOMAIN);
-        }
-        S.in_domain = in ? 1 : 0;
-        int tot = O > 0 ? *B.hp_total_of(p, tb) : 0;
-        const int cap = int(B.hp_chunk_records());
-        S.total = tot < cap ? tot : cap;
-    }
-    __syncthreads();
-    if (tid == 0) {
+    auto problem_of = [&](int c) { return B.plist ? B.plist[c / cpp] : c / cpp; };
+    // round 1 of chunk c into stage s (one thread)
+    auto issue_r1 = [&](int c, int s) {
+        const int p = problem_of(c), tb = c % cpp;
+        const size_t t0 = size_t(p) * T + size_t(tb) * TB;
+        K3Stage& Q = S.st[s];
         const unsigned b_nl = unsigned(TB * NJ) * 4u, b_nu = unsigned(TB * NF) * 4u, b_l = unsigned(TB * NJ) * 24u,
                        b_u = unsigned(TB * NF) * 8u, b_meta = unsigned(rows) * 4u;
-        mbar_arrive_expect_tx(&S.bar[0], b_nl + b_nu + 2 * b_l + 2 * b_u + b_meta);
-        bulk_g2s(S.nl, B.link_n + t0 * NJ, b_nl, &S.bar[0]);
-        bulk_g2s(S.nu, B.u_n + t0 * NF, b_nu, &S.bar[0]);
-        bulk_g2s(S.cen_l, B.link_c + t0 * NJ * 3, b_l, &S.bar[0]);
-        bulk_g2s(S.rad_l, B.link_r + t0 * NJ * 3, b_l, &S.bar[0]);
-        bulk_g2s(S.cen_u, B.u_c + t0 * NF, b_u, &S.bar[0]);
-        bulk_g2s(S.rad_u, B.u_r + t0 * NF, b_u, &S.bar[0]);
-        if (b_meta) bulk_g2s(s_meta, B.hp_meta + chunk * rows, b_meta, &S.bar[0]);
-    }
-    // power-product tables (while round 1 is in flight): entry e of table A / B / C, all eight lane variants
-    if (tid < 96) {
-        const int tab = tid < 64 ? 0 : (tid < 80 ? 1 : 2);
-        const int e = tid < 64 ? tid : (tid < 80 ? tid - 64 : tid - 80);
-        const int j0 = tab == 0 ? 0 : (tab == 1 ? 3 : 5), nv = tab == 0 ? 3 : 2;
-        double f[3] = {1.0, 1.0, 1.0}, d[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            if (q < nv) {
-                const double k = S.k[j0 + q];
-                const int dg = (e >> (2 * q)) & 3;
-                f[q] = dg == 0 ? 1.0 : (dg == 1 ? k : (dg == 2 ? k * k : k * k * k));
-                d[q] = dg == 0 ? 0.0 : (dg == 1 ? 1.0 : (dg == 2 ? 2.0 * k : 3.0 * (k * k)));
-            }
-        }
-        const double plain = f[0] * f[1] * f[2];
-        double* row = S.pw[tid];
-#pragma unroll
-        for (int v = 0; v < 8; v++) row[v] = plain;
-        // lane v = 1 + j owns d/dk_j
-        row[1 + j0] = d[0] * f[1] * f[2];
-        row[2 + j0] = f[0] * d[1] * f[2];
-        if (nv == 3) row[3 + j0] = f[0] * f[1] * d[2];
-    }
-    __syncthreads();
-    mbar_wait(&S.bar[0], 0);
-
-    // ---- round 2: warp 0 places and fetches the tables (task-major: q = task*TB + tt, tasks = 7 joints, then NJ links),
-    // thread 32 fetches the candidate records in use
-    const int ntab = TB * (NF + NJ);
-    if (warp == 0) {
+        mbar_arrive_expect_tx(&S.bar_r1[s], b_nl + b_nu + 2 * b_l + 2 * b_u + b_meta);
+        bulk_g2s(Q.nl, B.link_n + t0 * NJ, b_nl, &S.bar_r1[s]);
+        bulk_g2s(Q.nu, B.u_n + t0 * NF, b_nu, &S.bar_r1[s]);
+        bulk_g2s(Q.cen_l, B.link_c + t0 * NJ * 3, b_l, &S.bar_r1[s]);
+        bulk_g2s(Q.rad_l, B.link_r + t0 * NJ * 3, b_l, &S.bar_r1[s]);
+        bulk_g2s(Q.cen_u, B.u_c + t0 * NF, b_u, &S.bar_r1[s]);
+        bulk_g2s(Q.rad_u, B.u_r + t0 * NF, b_u, &S.bar_r1[s]);
+        if (b_meta)
+            bulk_g2s(reinterpret_cast<unsigned char*>(s_meta0) + size_t(s) * meta_bytes,
+                     B.hp_meta + (size_t(p) * cpp + tb) * rows, b_meta, &S.bar_r1[s]);
+    };
+    // round 2 of chunk c into stage s (warp 0, after round 1 of that stage has landed): the tables, task-major
+    // (q = task*TB + tt, tasks = 7 joints, then NJ links), two per lane; lane 0 adds the candidate records in use
+    auto issue_r2 = [&](int c, int s, int total) {
+        const int p = problem_of(c), tb = c % cpp;
+        const size_t t0 = size_t(p) * T + size_t(tb) * TB;
+        K3Stage& Q = S.st[s];
         unsigned kb[2], cb[2], bytes[2];
-        const uint16_t* ksrc[2];
+        const unsigned short* ksrc[2];
         const double* csrc[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -530,7 +510,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             if (q < ntab) {
                 const int task = q / TB, tt = q % TB;
                 if (task < NF) {
-                    const int n = S.nu[tt * NF + task];
+                    const int n = Q.nu[tt * NF + task];
                     const size_t idx = (t0 + tt) * NF + task;
                     kb[h] = r16(unsigned(n) * 2u);
                     cb[h] = r16(unsigned(n) * 8u);
@@ -538,7 +518,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                     csrc[h] = B.u_g + idx * B.capU;
                 } else {
                     const int l = task - NF;
-                    const int n = S.nl[tt * NJ + l];
+                    const int n = Q.nl[tt * NJ + l];
                     const size_t idx = (t0 + tt) * NJ + l;
                     kb[h] = r16(unsigned(n) * 2u);
                     cb[h] = r16(unsigned(n) * 24u);
@@ -548,228 +528,340 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             }
             bytes[h] = kb[h] + cb[h];
         }
-        // exclusive prefix over the 64 slots
-        unsigned inc0 = bytes[0], inc1 = bytes[1];
+        unsigned inc0 = bytes[0], inc1 = bytes[1];  // exclusive prefix over the 64 slots
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned a0 = __shfl_up_sync(0xffffffffu, inc0, d), a1 = __shfl_up_sync(0xffffffffu, inc1, d);
+            const unsigned x0 = __shfl_up_sync(0xffffffffu, inc0, d), x1 = __shfl_up_sync(0xffffffffu, inc1, d);
             if (lane >= d) {
-                inc0 += a0;
-                inc1 += a1;
+                inc0 += x0;
+                inc1 += x1;
             }
         }
         const unsigned tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-        unsigned off[2] = {inc0 - bytes[0], tot0 + inc1 - bytes[1]};
+        const unsigned off[2] = {inc0 - bytes[0], tot0 + inc1 - bytes[1]};
         unsigned tx = 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int q = lane + 32 * h;
             if (q < ntab) {
                 const bool staged = off[h] + bytes[h] <= unsigned(K3_TABLE_ARENA);
-                S.toff[q] = staged ? int(off[h]) : -1;
+                Q.toff[q] = staged ? int(off[h]) : -1;
                 if (staged) tx += bytes[h];
                 else bytes[h] = 0;
             } else {
                 bytes[h] = 0;
             }
         }
-        mbar_arrive_expect_tx(&S.bar[1], tx);
+        mbar_arrive_expect_tx(&S.bar_tab[s], tx);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             if (bytes[h]) {  // keys first, then the coefficients (both 16-byte aligned)
-                bulk_g2s(S.arena + off[h], ksrc[h], kb[h], &S.bar[1]);
-                bulk_g2s(S.arena + off[h] + kb[h], csrc[h], cb[h], &S.bar[1]);
+                bulk_g2s(Q.arena + off[h], ksrc[h], kb[h], &S.bar_tab[s]);
+                bulk_g2s(Q.arena + off[h] + kb[h], csrc[h], cb[h], &S.bar_tab[s]);
             }
         }
-    } else if (tid == 32) {
-        const int nrec = S.total < cand_arena ? S.total : cand_arena;
-        mbar_arrive_expect_tx(&S.bar[2], unsigned(nrec) * 32u);
-        if (nrec > 0) bulk_g2s(s_cand, B.hp_cand + chunk * B.hp_chunk_records() * 4, unsigned(nrec) * 32u, &S.bar[2]);
-    }
-    __syncthreads();  // S.toff
-    mbar_wait(&S.bar[1], 0);
+        if (lane == 0) {
+            int nrec = total < int(rec_per_chunk) ? total : int(rec_per_chunk);
+            nrec = nrec < cand_arena ? nrec : cand_arena;
+            Q.staged = nrec;
+            mbar_arrive_expect_tx(&S.bar_cand[s], unsigned(nrec) * 32u);
+            if (nrec > 0)
+                bulk_g2s(s_cand0 + size_t(s) * cand_arena * 4, B.hp_cand + (size_t(p) * cpp + tb) * rec_per_chunk * 4,
+                         unsigned(nrec) * 32u, &S.bar_cand[s]);
+        }
+    };
+    auto total_of = [&](int c) { return O > 0 ? *B.hp_total_of(problem_of(c), c % cpp) : 0; };
 
-    // ---- slices
-    {
-        const int grp = lane >> 3, v = lane & 7;
-        const double* pwA = &S.pw[0][v];
-        const double* pwB = &S.pw[64][v];
-        const double* pwC = &S.pw[80][v];
-        const int ntask = (NF + NJ) * (TB / 4);
-        for (;;) {
-            int task = 0;
-            if (lane == 0) task = atomicAdd(&S.task, 1);
-            task = __shfl_sync(0xffffffffu, task, 0);
-            if (task >= ntask) break;
-            const int sub = task % (TB / 4), which = task / (TB / 4);  // longest tables (torques) first
-            const int tt = sub * 4 + grp;
-            const bool torque = which < NF;
-            const int l = which - NF;
-            const int q = which * TB + tt;
-            const int n = torque ? S.nu[tt * NF + which] : S.nl[tt * NJ + l];
-            const int cs = torque ? 1 : 3;
-            const uint16_t* keys;
-            const double* coef;
-            const int to = S.toff[q];
-            if (to >= 0) {
-                keys = reinterpret_cast<const uint16_t*>(S.arena + to);
-                coef = reinterpret_cast<const double*>(S.arena + to + r16(unsigned(n) * 2u));
-            } else if (torque) {
-                const size_t idx = (t0 + tt) * NF + which;
-                keys = B.u_key + idx * B.capU;
-                coef = B.u_g + idx * B.capU;
-            } else {
-                const size_t idx = (t0 + tt) * NJ + l;
-                keys = B.link_key + idx * B.capL;
-                coef = B.link_g + idx * B.capL * 3;
-            }
-            int nmax = n;
-            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
-            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, pbc = 1.0;
-            unsigned last_hi = 0xffffffffu;
-            for (int mI = 0; mI < nmax; mI++) {
-                const bool on = mI < n;
-                const unsigned key = on ? keys[mI] : 0u;
-                const unsigned hi = key >> 6;
-                if (hi != last_hi) {
-                    pbc = pwB[(hi & 15u) * 8] * pwC[(hi >> 4) * 8];
-                    last_hi = hi;
-                }
-                const double f = pwA[(key & 63u) * 8] * pbc;
-                if (on) {
-                    a0 = __fma_rn(coef[mI * cs], f, a0);
-                    if (!torque) {
-                        a1 = __fma_rn(coef[mI * cs + 1], f, a1);
-                        a2 = __fma_rn(coef[mI * cs + 2], f, a2);
-                    }
-                }
-            }
-            if (torque) {
-                const int i = tt * NF + which;
-                if (v == 0) {
-                    const double value = S.cen_u[i] + a0;
-                    const double r = S.rad_u[i];
-                    S.tg[i] = ((value - r) + (value + r)) * 0.5;  // centre of Interval(c - r, c + r) (KPR/NLPclass.cu:306)
-                } else {
-                    S.tj[i * NF + (v - 1)] = a0;
-                }
-            } else {
-                const int i = tt * NJ + l;
-                if (v == 0) {
-                    const double acc[3] = {a0, a1, a2};
-#pragma unroll
-                    for (int e = 0; e < 3; e++) {
-                        const double value = S.cen_l[i * 3 + e] + acc[e];
-                        const double r = S.rad_l[i * 3 + e];
-                        S.lc[tt][l][e] = ((value - r) + (value + r)) * 0.5;  // getCenter(slice()) (KPR/NLPclass.cu:313)
-                    }
-                } else {
-                    S.dlc[tt][l][v - 1][0] = a0;
-                    S.dlc[tt][l][v - 1][1] = a1;
-                    S.dlc[tt][l][v - 1][2] = a2;
-                }
-            }
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&S.bar_r1[s], 1);
+            mbar_init(&S.bar_tab[s], 32);
+            mbar_init(&S.bar_cand[s], 1);
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.task = 0;
+        S.rownext = 0;
+        for (int i = 0; i < 4; i++) S.zero_d[i] = 0.0;
+        for (int i = 0; i < 8; i++) S.zero_k[i] = 0;
     }
     __syncthreads();
+    int next_total = 0;  // (thread 0) candidate records in use of the chunk whose round 2 is issued next
+    if (tid == 0) {
+        issue_r1(c_begin, 0);
+        next_total = total_of(c_begin);
+    }
+    if (warp == 0) {
+        mbar_wait(&S.bar_r1[0], 0);
+        issue_r2(c_begin, 0, __shfl_sync(0xffffffffu, next_total, 0));
+    }
+    int cur_p = -1;
+    const int grp = lane >> 3, v = lane & 7;
+    const double* const pa = &S.pwA[0][v <= 4 ? v : 0];
+    const double* const pb = &S.pwB[0][v >= 5 ? v - 4 : 0];
 
-    // torque rows tb*TB*NF + i, i < TB*NF: contiguous runs of g and of the Jacobian
-    if (gp)
-        for (int i = tid; i < TB * NF; i += K3_THREADS) gp[size_t(tb) * TB * NF + i] = S.tg[i];
-    if (jp)
-        for (int i = tid; i < TB * NF * NF; i += K3_THREADS) jp[size_t(tb) * TB * NF * NF + i] = S.tj[i];
-    if (p == 0 && B.link_sliced)
-        for (int i = tid; i < TB * NJ * 3; i += K3_THREADS)
-            B.link_sliced[(size_t(tb) * TB * NJ) * 3 + i] = S.lc[i / (NJ * 3)][(i / 3) % NJ][i % 3];
+    for (int c = c_begin; c < c_end; c++) {
+        const int it = c - c_begin, s = it & 1;
+        const unsigned ph = unsigned(it >> 1) & 1u;
+        const int p = problem_of(c), tb = c % cpp;
+        K3Stage& Q = S.st[s];
+        const unsigned* s_meta = reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(s_meta0) + size_t(s) * meta_bytes);
+        const double* s_cand = s_cand0 + size_t(s) * cand_arena * 4;
+        const size_t t0 = size_t(p) * T + size_t(tb) * TB;
+        double* gp = g ? g + size_t(p) * m : nullptr;
+        double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
+        const bool failed = B.status[p] != 0;
+        const bool more = c + 1 < c_end;
 
-    // ---- collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
-    mbar_wait(&S.bar[2], 0);  // (also when the rows are skipped: no bulk copy may be in flight when the CTA exits)
-    if (O > 0 && S.in_domain) {
-        const double* gcand = B.hp_cand + chunk * B.hp_chunk_records() * 4;
-        const int staged = S.total < cand_arena ? S.total : cand_arena;
-        double* stage = reinterpret_cast<double*>(S.arena) + warp * (32 * NF);
-        for (;;) {
-            int x0 = 0;
-            if (lane == 0) x0 = atomicAdd(&S.rownext, 1) * 32;
-            x0 = __shfl_sync(0xffffffffu, x0, 0);
-            if (x0 >= rows) break;
-            const int x = x0 + lane;
-            bool active = x < rows;
-            double max_elt = -100000000;
-            double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
-            int l = 0, tt = 0, o = 0;
-            if (active) {
-                o = x % O;
-                const int ltt = x / O;
-                tt = ltt % TB;
-                l = ltt / TB;
-                const unsigned meta = s_meta[x];
-                const int n = int(meta & 255u), off = int(meta >> 8);
-                if (n == HP_OVERFLOW) {
-                    active = false;  // no stored list: k_constraints_slow writes this row
+        if (tid == 0 && more) {
+            issue_r1(c + 1, s ^ 1);
+            next_total = total_of(c + 1);
+        }
+        if (p != cur_p) {  // power-product tables of this problem's k
+            cur_p = p;
+            if (tid < NF) S.k[tid] = kin[size_t(p) * NF + tid];
+            __syncthreads();
+            if (tid == 0) {
+                bool in = true;
+                for (int j = 0; j < NF; j++) in = in && (fabs(S.k[j]) <= K_DOMAIN);
+                S.in_domain = in ? 1 : 0;
+            }
+            {   // table A: entry tid of 256, variables k0..k3;  table B: entry tid of 64 (threads 0..63), k4..k6
+                double f[4], d[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double k = S.k[q];
+                    const int dg = (tid >> (2 * q)) & 3;
+                    f[q] = dg == 0 ? 1.0 : (dg == 1 ? k : (dg == 2 ? k * k : k * k * k));
+                    d[q] = dg == 0 ? 0.0 : (dg == 1 ? 1.0 : (dg == 2 ? 2.0 * k : 3.0 * (k * k)));
+                }
+                const double p01 = f[0] * f[1], p23 = f[2] * f[3];
+                double* row = S.pwA[tid];
+                row[0] = p01 * p23;
+                row[1] = d[0] * f[1] * p23;
+                row[2] = f[0] * d[1] * p23;
+                row[3] = p01 * (d[2] * f[3]);
+                row[4] = p01 * (f[2] * d[3]);
+            }
+            if (tid < 64) {
+                double f[3], d[3];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double k = S.k[4 + q];
+                    const int dg = (tid >> (2 * q)) & 3;
+                    f[q] = dg == 0 ? 1.0 : (dg == 1 ? k : (dg == 2 ? k * k : k * k * k));
+                    d[q] = dg == 0 ? 0.0 : (dg == 1 ? 1.0 : (dg == 2 ? 2.0 * k : 3.0 * (k * k)));
+                }
+                double* row = S.pwB[tid];
+                row[0] = f[0] * f[1] * f[2];
+                row[1] = d[0] * f[1] * f[2];
+                row[2] = f[0] * d[1] * f[2];
+                row[3] = f[0] * f[1] * d[2];
+            }
+            __syncthreads();
+        }
+
+        // ---- slices of chunk c
+        mbar_wait(&S.bar_tab[s], ph);
+        if (!failed) {
+            const int ntask = (NF + NJ) * (TB / 4);
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(&S.task, 1);
+                task = __shfl_sync(0xffffffffu, task, 0);
+                if (task >= ntask) break;
+                const int sub = task % (TB / 4), which = task / (TB / 4);  // longest tables (torques) first
+                const int tt = sub * 4 + grp;
+                const bool torque = which < NF;
+                const int l = which - NF;
+                const int n = torque ? Q.nu[tt * NF + which] : Q.nl[tt * NJ + l];
+                const int to = Q.toff[which * TB + tt];
+                int nmax = n;
+                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
+                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
+                const bool all_staged = __all_sync(0xffffffffu, to >= 0);
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                if (all_staged) {
+                    const unsigned short* kp = n > 0 ? reinterpret_cast<const unsigned short*>(Q.arena + to) : S.zero_k;
+                    const double* cp = n > 0 ? reinterpret_cast<const double*>(Q.arena + to + r16(unsigned(n) * 2u)) : S.zero_d;
+                    if (torque) slice_group<true>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
+                    else slice_group<false>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
+                } else {  // a table that did not fit the arena: same walk over global memory
+                    const size_t idx = torque ? (t0 + tt) * NF + which : (t0 + tt) * NJ + l;
+                    const unsigned short* kp = torque ? B.u_key + idx * B.capU : B.link_key + idx * B.capL;
+                    const double* cp = torque ? B.u_g + idx * B.capU : B.link_g + idx * B.capL * 3;
+                    if (n == 0) {
+                        kp = S.zero_k;
+                        cp = S.zero_d;
+                    }
+                    if (torque) slice_group<true>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
+                    else slice_group<false>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
+                }
+                if (torque) {
+                    const int i = tt * NF + which;
+                    if (v == 0) {
+                        const double value = Q.cen_u[i] + a0;
+                        const double r = Q.rad_u[i];
+                        S.tg[i] = ((value - r) + (value + r)) * 0.5;  // centre of Interval(c - r, c + r) (KPR/NLPclass.cu:306)
+                    } else {
+                        S.tj[i * NF + (v - 1)] = a0;
+                    }
                 } else {
-                    const double c0 = S.lc[tt][l][0], c1 = S.lc[tt][l][1], c2 = S.lc[tt][l][2];
-                    const double2* rec = reinterpret_cast<const double2*>(off + n <= staged ? s_cand + size_t(off) * 4
-                                                                                             : gcand + size_t(off) * 4);
-                    for (int q = 0; q < n; q++) {
-                        const double2 u = rec[2 * q], w = rec[2 * q + 1];
-                        const double val = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
-                        if (val > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
-                            max_elt = val;
-                            A0 = -u.x; A1 = -u.y; A2 = -w.x;
+                    const int i = tt * NJ + l;
+                    if (v == 0) {
+                        const double acc[3] = {a0, a1, a2};
+#pragma unroll
+                        for (int e = 0; e < 3; e++) {
+                            const double value = Q.cen_l[i * 3 + e] + acc[e];
+                            const double r = Q.rad_l[i * 3 + e];
+                            S.lc[tt][l][e] = ((value - r) + (value + r)) * 0.5;  // getCenter(slice()) (KPR/NLPclass.cu:313)
+                        }
+                    } else {
+                        S.dlc[tt][l][v - 1][0] = a0;
+                        S.dlc[tt][l][v - 1][1] = a1;
+                        S.dlc[tt][l][v - 1][2] = a2;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) S.task = 0;
+
+        // ---- warp 0: round 2 of the next chunk (its round 1 was issued at the top of this iteration)
+        if (warp == 0 && more) {
+            mbar_wait(&S.bar_r1[s ^ 1], unsigned((it + 1) >> 1) & 1u);
+            issue_r2(c + 1, s ^ 1, __shfl_sync(0xffffffffu, next_total, 0));
+        }
+
+        mbar_wait(&S.bar_cand[s], ph);  // (always: no bulk copy may be in flight when its stage is reused or the CTA exits)
+        if (failed) {
+            // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe
+            // rows: every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
+            for (int i = tid; i < TB * NF; i += K3_THREADS) {
+                if (gp) gp[size_t(tb) * TB * NF + i] = 1e300;
+                if (jp)
+                    for (int q = 0; q < NF; q++) jp[(size_t(tb) * TB * NF + i) * NF + q] = 0.0;
+            }
+            for (int x = tid; x < rows; x += K3_THREADS) {
+                const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
+                const size_t r = size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o;
+                if (gp) gp[r] = 1e300;
+                if (jp)
+                    for (int q = 0; q < NF; q++) jp[r * NF + q] = 0.0;
+            }
+        } else {
+            // torque rows tb*TB*NF + i, i < TB*NF: contiguous runs of g and of the Jacobian
+            if (gp)
+                for (int i = tid; i < TB * NF; i += K3_THREADS) gp[size_t(tb) * TB * NF + i] = S.tg[i];
+            if (jp)
+                for (int i = tid; i < TB * NF * NF; i += K3_THREADS) jp[size_t(tb) * TB * NF * NF + i] = S.tj[i];
+            if (p == 0 && B.link_sliced)
+                for (int i = tid; i < TB * NJ * 3; i += K3_THREADS)
+                    B.link_sliced[(size_t(tb) * TB * NJ) * 3 + i] = S.lc[i / (NJ * 3)][(i / 3) % NJ][i % 3];
+
+            // ---- collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
+            if (O > 0 && S.in_domain) {
+                const double* gcand = B.hp_cand + (size_t(p) * cpp + tb) * rec_per_chunk * 4;
+                const int staged = Q.staged;
+#if K3_TRANSPOSE
+                double* stage = reinterpret_cast<double*>(Q.arena) + warp * (32 * NF);
+#endif
+                const int row_base = NF * T + tb * TB * O;  // row of (l, tt, o) = row_base + l*T*O + tt*O + o
+                for (;;) {
+                    int x0 = 0;
+                    if (lane == 0) x0 = atomicAdd(&S.rownext, 1) * 32;
+                    x0 = __shfl_sync(0xffffffffu, x0, 0);
+                    if (x0 >= rows) break;
+                    const int x = x0 + lane;
+                    bool active = x < rows;
+                    double max_elt = -100000000;
+                    double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
+                    int row_i = -1;
+                    int tt = 0, l = 0;
+                    if (active) {
+                        const int ltt = __float2int_rz((float(x) + 0.5f) * invO);  // x / O (exact: x < 2^22)
+                        const int o = x - ltt * O;
+                        tt = ltt % TB;
+                        l = ltt / TB;
+                        const unsigned meta = s_meta[x];
+                        const int n = int(meta & 255u), off = int(meta >> 8);
+                        if (n == HP_OVERFLOW) {
+                            active = false;  // no stored list: k_constraints_slow writes this row
+                        } else {
+                            row_i = row_base + (l * T + tt) * O + o;
+                            const double c0 = S.lc[tt][l][0], c1 = S.lc[tt][l][1], c2 = S.lc[tt][l][2];
+                            const double2* rec = reinterpret_cast<const double2*>(off + n <= staged ? s_cand + size_t(off) * 4
+                                                                                                     : gcand + size_t(off) * 4);
+                            for (int q = 0; q < n; q++) {
+                                const double2 u = rec[2 * q], w = rec[2 * q + 1];
+                                const double val = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
+                                if (val > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
+                                    max_elt = val;
+                                    A0 = -u.x; A1 = -u.y; A2 = -w.x;
+                                }
+                            }
                         }
                     }
+                    if (gp && active) gp[row_i] = -max_elt;
+                    if (jp && active) {
+                        const double2* dk = reinterpret_cast<const double2*>(&S.dlc[tt][l][0][0]);
+                        double* out = jp + size_t(row_i) * NF;
+#pragma unroll
+                        for (int q = 0; q < NF; q++) {
+                            const double2 xy = dk[2 * q];
+                            const double z = dk[2 * q + 1].x;
+                            // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A.
+                            // Fused like the reference's own kernel (nvcc contracts max_A_elt.dot(dk))
+#if K3_TRANSPOSE
+                            stage[lane * NF + q] = __fma_rn(A0, xy.x, __fma_rn(A1, xy.y, A2 * z));
+#else
+                            out[q] = __fma_rn(A0, xy.x, __fma_rn(A1, xy.y, A2 * z));  // 56 contiguous bytes per lane
+#endif
+                        }
+                    }
+#if K3_TRANSPOSE
+                    if (jp) {
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < NF; q++) {
+                            const int e = q * 32 + lane;
+                            const int r = e / NF;
+                            const int rr = __shfl_sync(0xffffffffu, row_i, r);
+                            if (rr >= 0) jp[size_t(rr) * NF + (e - r * NF)] = stage[e];
+                        }
+                        __syncwarp();
+                    }
+#endif
                 }
             }
-            const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
-            if (gp && active) gp[row_i] = -max_elt;
-            if (jp) {
-                if (active) {
-#pragma unroll
-                    for (int v = 0; v < NF; v++) {
-                        const double* dk = S.dlc[tt][l][v];
-                        // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
-                        stage[lane * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+        }
+
+        // Bezier joint-limit rows (KPR/Trajectory.cu:256-540), once per problem
+        if (tb == 0 && tid < NF) {
+            const int i = tid;
+            const double D = c_robot.duration;
+            const double q0 = B.q0[size_t(p) * NF + i];
+            const double a = B.qd0[size_t(p) * NF + i] * D;
+            const double b = B.qdd0[size_t(p) * NF + i] * D * D;
+            const double kn = kin[size_t(p) * NF + i];
+            const int off = NF * T + NJ * T * O;
+            for (int vel = 0; vel < 2; vel++) {
+                double mn, mx, dmn, dmx;
+                bez_extrema(vel == 1, q0, a, b, c_robot.k_range[i], D, kn, &mn, &mx, &dmn, &dmx);
+                const int r0 = off + vel * 2 * NF + i;
+                if (gp) {
+                    gp[r0] = failed ? 0.0 : mn;
+                    gp[r0 + NF] = failed ? 0.0 : mx;
+                }
+                if (jp) {
+                    for (int j = 0; j < NF; j++) {
+                        jp[size_t(r0) * NF + j] = (j == i && !failed) ? dmn : 0.0;
+                        jp[size_t(r0 + NF) * NF + j] = (j == i && !failed) ? dmx : 0.0;
                     }
                 }
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < NF; q++) {
-                    const int e = q * 32 + lane;
-                    const int r = e / NF;
-                    const long long rr = __shfl_sync(0xffffffffu, row_i, r);
-                    if (rr >= 0) jp[rr * NF + (e - r * NF)] = stage[e];
-                }
-                __syncwarp();
             }
         }
-    }
-
-    // Bezier joint-limit rows (KPR/Trajectory.cu:256-540), once per problem
-    if (tb == 0 && tid < NF) {
-        const int i = tid;
-        const double D = c_robot.duration;
-        const double q0 = B.q0[size_t(p) * NF + i];
-        const double a = B.qd0[size_t(p) * NF + i] * D;
-        const double b = B.qdd0[size_t(p) * NF + i] * D * D;
-        const double kn = kin[size_t(p) * NF + i];
-        const int off = NF * T + NJ * T * O;
-        for (int vel = 0; vel < 2; vel++) {
-            double mn, mx, dmn, dmx;
-            bez_extrema(vel == 1, q0, a, b, c_robot.k_range[i], D, kn, &mn, &mx, &dmn, &dmx);
-            const int r0 = off + vel * 2 * NF + i;
-            if (gp) {
-                gp[r0] = mn;
-                gp[r0 + NF] = mx;
-            }
-            if (jp) {
-                for (int j = 0; j < NF; j++) {
-                    jp[size_t(r0) * NF + j] = (j == i) ? dmn : 0.0;
-                    jp[size_t(r0 + NF) * NF + j] = (j == i) ? dmx : 0.0;
-                }
-            }
-        }
+        __syncthreads();  // stage s, lc / dlc / tg / tj are free again
+        if (tid == 0) S.rownext = 0;
     }
 }
 
@@ -892,30 +984,40 @@ cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// Shared memory of one k_constraints CTA: the fixed part, the row words and as many candidate records as keep three
-// (else two, else one) CTAs per SM resident while covering the chunk's expected 2.5 records per row.
-constexpr int K3_SMEM_MAX = 200 * 1024;
-inline void k3_smem_plan(const Batch& B, int* smem_bytes, int* cand_arena) {
+// Shared memory of one persistent k_constraints CTA: the fixed part plus, per pipeline stage, the row words and a
+// candidate arena sized for the chunk's expected 2.5 records per row — bounded so that two CTAs stay resident per SM
+// (else one).
+constexpr int K3_SMEM_MAX = 220 * 1024;
+inline void k3_smem_plan(const Batch& B, int* smem_bytes, int* cand_arena, int* ctas_per_sm) {
     const int rows = B.chunk_rows();
-    const int fixed = int(sizeof(K3Smem)) + int((size_t(rows) * 4 + 15) & ~size_t(15));
-    const int want = rows * 5 / 2 + 32;
-    const int budgets[3] = {74 * 1024, 110 * 1024, K3_SMEM_MAX};
-    int rec = 0;
-    for (int b = 0; b < 3; b++) {
-        rec = (budgets[b] - fixed) / 32;
-        if (rec >= want) break;
+    const int fixed = int(sizeof(K3Smem)) + 2 * int((size_t(rows) * 4 + 15) & ~size_t(15));
+    int want = rows * 5 / 2 + 32;
+    if (want > int(B.hp_chunk_records())) want = int(B.hp_chunk_records());
+    const int budgets[2] = {112 * 1024, K3_SMEM_MAX};
+    int rec = 0, b = 0;
+    for (b = 0; b < 2; b++) {
+        rec = (budgets[b] - fixed) / 64;  // two stages of 32-byte records
+        if (rec >= want || b == 1) break;
     }
     if (rec < 0) rec = 0;
-    if (rec > want) rec = want > int(B.hp_chunk_records()) ? int(B.hp_chunk_records()) : want;
+    if (rec > want) rec = want;
     *cand_arena = rec;
-    *smem_bytes = fixed + rec * 32;
+    *smem_bytes = fixed + 2 * rec * 32;
+    *ctas_per_sm = (b == 0) ? 2 : 1;
 }
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
-    int smem = 0, arena = 0;
-    k3_smem_plan(B, &smem, &arena);
-    if (smem > K3_SMEM_MAX) return cudaErrorInvalidValue;  // (armour_ctx_create bounds max_obstacles accordingly)
-    dim3 grid(B.T / TB, B.nprob);
+    int smem = 0, arena = 0, per_sm = 1;
+    k3_smem_plan(B, &smem, &arena, &per_sm);
+    if (smem > K3_SMEM_MAX) return cudaErrorInvalidValue;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long nchunks = (long long)B.nprob * (B.T / TB);
+    const int grid = int(nchunks < (long long)sms * per_sm ? nchunks : (long long)sms * per_sm);
     k_constraints<<<grid, K3_THREADS, smem, st>>>(B, d_k, d_g, d_jac, arena);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || B.O == 0) return e;
