@@ -376,82 +376,107 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 __device__ __forceinline__ unsigned r16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
-// k_constraints: persistent CTAs (two per SM), each walks a contiguous range of chunks = (problem, TB intervals) through a
-// two-stage TMA pipeline, so the DRAM latency of a chunk is paid while the previous chunk computes.
+// k_constraints: persistent CTAs (two per SM); each walks a contiguous range of chunks = (problem, TB intervals) as a
+// software pipeline fed by TMA bulk copies, so that neither the DRAM latency of a chunk nor the uneven length of its
+// pieces leaves warps idle.
 //
-// Everything a chunk needs comes in two rounds of bulk copies into shared memory:
-//   round 1 (fixed sizes): monomial counts, centres and radii of its TB*(NJ+NF) reach-set tables, the (first
-//            record, count) word of its NJ*TB*O collision rows;
-//   round 2 (sizes known from round 1): every table, exactly its n monomials (16-bit keys, coefficients), and the
-//            candidate half-space records in use of the chunk: one contiguous run.
-// Schedule of iteration i (stage s = i & 1):  issue round 1 of chunk i+1  |  wait tables(i), slice  |  warp 0: place and
-// issue round 2 of chunk i+1  |  torque rows, collision rows of chunk i  |  barrier.
-// Slices: eight lanes per table, lane v owns output v (the value, or d/dk_{v-1}); a warp walks the tables of four
-// consecutive intervals of one link / one joint together (similar lengths), branch-free, operands in shared memory.
+// Loads of chunk c (all cp.async.bulk into shared memory, completion on mbarriers, buffers by parity of c):
+//   G1(c)   fixed sizes: monomial counts, centres and radii of its TB*(NJ+NF) reach-set tables;
+//   TAB(c)  every table, exactly its n monomials (16-bit keys, coefficients) — sizes known from G1(c);
+//   ROW(c)  the (first record, count) words of its NJ*TB*O collision rows and the candidate half-space records in use of
+//           the chunk: one contiguous run.
+// Iteration j of a CTA works on TWO chunks at once — the slices of chunk j and the collision rows of chunk j-1 — as one
+// pool of items handed to its warps by ticket: 7 torque + NJ link slice items (a warp slices the tables of four
+// consecutive intervals of one joint / link, eight lanes per table, lane v owns output v = the value or d/dk_{v-1}),
+// NJ*TB*O/32 row tiles (one lane per collision row), the torque rows of chunk j-1, and the placement + issue of TAB(j+1).
+// One __syncthreads per iteration.  G1(j+1) and ROW(j) are issued at the top of iteration j.
 // The power product of a monomial comes from two tables in shared memory, k0..k3 (256 entries) and k4..k6 (64), whose
 // columns hold the plain product and its derivatives: term_v = coeff * A[key & 255][colA(v)] * B[key >> 8][colB(v)].
-// They depend on k only, i.e. on the problem: a CTA rebuilds them when its chunk range crosses into the next problem.
-// (The reference applies the factors one variable after the other, KPR/PZsparse.cu:404-555: same value up to a few ulp.)
-// Rows: one lane per collision row, records read from the staged run (or from global memory for the part of a chunk that
-// does not fit), g and the Jacobian rows leave transposed through shared memory, coalesced.
+// They depend on k only, i.e. on the problem: there is one pair per chunk parity, rebuilt when the chunk range crosses
+// into the next problem.  (The reference applies the factors one variable after the other, KPR/PZsparse.cu:404-555:
+// same value up to a few ulp.)
 #ifndef K3_THREADS_N
-#define K3_THREADS_N 256
-#endif
-#ifndef K3_TRANSPOSE
-#define K3_TRANSPOSE 0   // 1: Jacobian rows leave through a shared-memory transposition (coalesced), 0: 56 B per lane
+#define K3_THREADS_N 384
 #endif
 constexpr int K3_THREADS = K3_THREADS_N;
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int K3_TABLE_ARENA = 14336;  // bytes of staged tables per stage (later the warps' transposition buffers)
-static_assert(!K3_TRANSPOSE || K3_WARPS * 32 * NF * 8 <= K3_TABLE_ARENA, "transposition buffers reuse the table arena");
-constexpr int K3_NTAB = TB * (MAXJ + NF);               // tables of a chunk (upper bound)
+constexpr int K3_TABLE_ARENA = 12288;      // bytes of staged tables per stage
+constexpr int K3_NTAB = TB * (MAXJ + NF);  // tables of a chunk (upper bound)
 static_assert(TB % 4 == 0, "a warp slices four intervals of a link / joint together");
 static_assert(K3_NTAB <= 64, "one warp issues the table copies, two tables per lane");
+static_assert(K3_THREADS >= 256, "the power-product tables are built by 256 threads");
 
-struct K3Stage {
+struct K3Stage {  // slice side of a chunk
     int nl[TB * MAXJ], nu[TB * NF + 4];
     double cen_l[TB * MAXJ * 3], rad_l[TB * MAXJ * 3], cen_u[TB * NF + 4], rad_u[TB * NF + 4];
     int toff[K3_NTAB];  // byte offset of a staged table in the arena, -1: read it from global memory
-    int staged;         // candidate records staged
-    int pad[3];
+    int pad[4];
     __align__(16) unsigned char arena[K3_TABLE_ARENA];
 };
+struct K3Rows {  // row side of a chunk: what its slices leave for the collision rows
+    double lc[TB][MAXJ][4];       // sliced link centres
+    double dlc[TB][MAXJ][NF][4];  // and their d/dk
+    double tg[TB * NF + 4];       // torque rows of g
+    double tj[TB * NF * NF + 4];  // torque rows of the Jacobian
+    int staged, in_domain, pad[2];
+};
 struct K3Smem {  // fixed part of the dynamic shared memory; 2 x row words and 2 x candidate arena follow
-    unsigned long long bar_r1[2], bar_tab[2], bar_cand[2];
-    double pwA[256][5];            // k0..k3: plain product, d/dk0 .. d/dk3
-    double pwB[64][4];             // k4..k6: plain product, d/dk4 .. d/dk6
-    double lc[TB][MAXJ][4];        // sliced link centres
-    double dlc[TB][MAXJ][NF][4];   // and their d/dk
-    double tg[TB * NF + 4];        // torque rows of g
-    double tj[TB * NF * NF + 4];   // torque rows of the Jacobian
+    unsigned long long bar_g1[2], bar_tab[2], bar_row[2];
+    double pwA[256][5];  // k0..k3: plain product, d/dk0 .. d/dk3
+    double pwB[64][4];   // k4..k6: plain product, d/dk4 .. d/dk6
     double k[8];
-    double zero_d[4];              // operands of an empty table
+    double zero_d[4];    // operands of an empty table
     unsigned short zero_k[8];
-    int task, rownext, in_domain, pad;
+    int ticket, pad[3];
     K3Stage st[2];
+    K3Rows rw[2];
 };
 
 // one table sliced by an 8-lane group, operands in shared memory.  n >= 0 own monomials, nmax = longest of the warp's
-// four tables (lanes past their own n re-read their last monomial with a zero factor: no branch, no garbage)
+// four tables (lanes past their own n re-read their last monomial with a zero factor: no branch, no garbage).  Two
+// accumulator sets: consecutive monomials do not wait for each other's multiply-add.
 template <bool TORQUE>
 __device__ __forceinline__ void slice_group(const unsigned short* __restrict__ kp, const double* __restrict__ cp, int n,
                                             int nmax, const double* __restrict__ pa, const double* __restrict__ pb,
                                             double& a0, double& a1, double& a2) {
     const int nlast = n > 0 ? n - 1 : 0;
-#pragma unroll 4
-    for (int mI = 0; mI < nmax; mI++) {
-        const int mm = mI < nlast ? mI : nlast;
-        const unsigned key = kp[mm];
-        double f = pa[(key & 255u) * 5] * pb[(key >> 8) * 4];
-        f = mI < n ? f : 0.0;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    int mI = 0;
+    for (; mI + 1 < nmax; mI += 2) {
+        const int m0 = mI < nlast ? mI : nlast, m1 = mI + 1 < nlast ? mI + 1 : nlast;
+        const unsigned key0 = kp[m0], key1 = kp[m1];
+        double f0 = pa[(key0 & 255u) * 5] * pb[(key0 >> 8) * 4];
+        double f1 = pa[(key1 & 255u) * 5] * pb[(key1 >> 8) * 4];
+        f0 = mI < n ? f0 : 0.0;
+        f1 = mI + 1 < n ? f1 : 0.0;
         if (TORQUE) {
-            a0 = __fma_rn(cp[mm], f, a0);
+            a0 = __fma_rn(cp[m0], f0, a0);
+            b0 = __fma_rn(cp[m1], f1, b0);
         } else {
-            a0 = __fma_rn(cp[mm * 3], f, a0);
-            a1 = __fma_rn(cp[mm * 3 + 1], f, a1);
-            a2 = __fma_rn(cp[mm * 3 + 2], f, a2);
+            a0 = __fma_rn(cp[m0 * 3], f0, a0);
+            a1 = __fma_rn(cp[m0 * 3 + 1], f0, a1);
+            a2 = __fma_rn(cp[m0 * 3 + 2], f0, a2);
+            b0 = __fma_rn(cp[m1 * 3], f1, b0);
+            b1 = __fma_rn(cp[m1 * 3 + 1], f1, b1);
+            b2 = __fma_rn(cp[m1 * 3 + 2], f1, b2);
         }
     }
+    if (mI < nmax) {
+        const int m0 = mI < nlast ? mI : nlast;
+        const unsigned key0 = kp[m0];
+        double f0 = pa[(key0 & 255u) * 5] * pb[(key0 >> 8) * 4];
+        f0 = mI < n ? f0 : 0.0;
+        if (TORQUE) {
+            a0 = __fma_rn(cp[m0], f0, a0);
+        } else {
+            a0 = __fma_rn(cp[m0 * 3], f0, a0);
+            a1 = __fma_rn(cp[m0 * 3 + 1], f0, a1);
+            a2 = __fma_rn(cp[m0 * 3 + 2], f0, a2);
+        }
+    }
+    a0 += b0;
+    a1 += b1;
+    a2 += b2;
 }
 
 __global__ void __launch_bounds__(K3_THREADS, 2)
@@ -463,38 +488,54 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rows = NJ * TB * O;
     const unsigned meta_bytes = r16(unsigned(rows) * 4u);
-    unsigned* const s_meta0 = reinterpret_cast<unsigned*>(k3_raw + sizeof(K3Smem));
+    unsigned char* const s_meta0 = k3_raw + sizeof(K3Smem);
     double* const s_cand0 = reinterpret_cast<double*>(k3_raw + sizeof(K3Smem) + 2 * meta_bytes);
     const int cpp = T / TB;  // chunks per problem
     const long long nchunks = (long long)B.nprob * cpp;
     const int c_begin = int(nchunks * blockIdx.x / gridDim.x), c_end = int(nchunks * (blockIdx.x + 1) / gridDim.x);
-    if (c_begin >= c_end) return;
+    const int nmine = c_end - c_begin;
+    if (nmine <= 0) return;
     const int ntab = TB * (NF + NJ);
     const float invO = O > 0 ? 1.0f / float(O) : 0.0f;
-    const size_t rec_per_chunk = B.hp_chunk_records();
+    const int rec_per_chunk = int(B.hp_chunk_records());
+    const int n_slice_items = (NF + NJ) * (TB / 4), n_row_tiles = (rows + 31) >> 5;
+    const int I_ISSUE = n_slice_items / 2;                  // position of the "place and issue TAB(j+1)" item
+    const int I_TORQUE = n_slice_items + 1 + n_row_tiles;   // torque rows of chunk j-1
+    const int ITEMS = n_slice_items + n_row_tiles + 2;
 
     auto problem_of = [&](int c) { return B.plist ? B.plist[c / cpp] : c / cpp; };
-    // round 1 of chunk c into stage s (one thread)
-    auto issue_r1 = [&](int c, int s) {
+    auto issue_g1 = [&](int c) {  // one thread
+        const int s = (c - c_begin) & 1;
         const int p = problem_of(c), tb = c % cpp;
         const size_t t0 = size_t(p) * T + size_t(tb) * TB;
         K3Stage& Q = S.st[s];
         const unsigned b_nl = unsigned(TB * NJ) * 4u, b_nu = unsigned(TB * NF) * 4u, b_l = unsigned(TB * NJ) * 24u,
-                       b_u = unsigned(TB * NF) * 8u, b_meta = unsigned(rows) * 4u;
-        mbar_arrive_expect_tx(&S.bar_r1[s], b_nl + b_nu + 2 * b_l + 2 * b_u + b_meta);
-        bulk_g2s(Q.nl, B.link_n + t0 * NJ, b_nl, &S.bar_r1[s]);
-        bulk_g2s(Q.nu, B.u_n + t0 * NF, b_nu, &S.bar_r1[s]);
-        bulk_g2s(Q.cen_l, B.link_c + t0 * NJ * 3, b_l, &S.bar_r1[s]);
-        bulk_g2s(Q.rad_l, B.link_r + t0 * NJ * 3, b_l, &S.bar_r1[s]);
-        bulk_g2s(Q.cen_u, B.u_c + t0 * NF, b_u, &S.bar_r1[s]);
-        bulk_g2s(Q.rad_u, B.u_r + t0 * NF, b_u, &S.bar_r1[s]);
-        if (b_meta)
-            bulk_g2s(reinterpret_cast<unsigned char*>(s_meta0) + size_t(s) * meta_bytes,
-                     B.hp_meta + (size_t(p) * cpp + tb) * rows, b_meta, &S.bar_r1[s]);
+                       b_u = unsigned(TB * NF) * 8u;
+        mbar_arrive_expect_tx(&S.bar_g1[s], b_nl + b_nu + 2 * b_l + 2 * b_u);
+        bulk_g2s(Q.nl, B.link_n + t0 * NJ, b_nl, &S.bar_g1[s]);
+        bulk_g2s(Q.nu, B.u_n + t0 * NF, b_nu, &S.bar_g1[s]);
+        bulk_g2s(Q.cen_l, B.link_c + t0 * NJ * 3, b_l, &S.bar_g1[s]);
+        bulk_g2s(Q.rad_l, B.link_r + t0 * NJ * 3, b_l, &S.bar_g1[s]);
+        bulk_g2s(Q.cen_u, B.u_c + t0 * NF, b_u, &S.bar_g1[s]);
+        bulk_g2s(Q.rad_u, B.u_r + t0 * NF, b_u, &S.bar_g1[s]);
     };
-    // round 2 of chunk c into stage s (warp 0, after round 1 of that stage has landed): the tables, task-major
-    // (q = task*TB + tt, tasks = 7 joints, then NJ links), two per lane; lane 0 adds the candidate records in use
-    auto issue_r2 = [&](int c, int s, int total) {
+    auto issue_row = [&](int c, int total) {  // one thread: row words + candidate records in use
+        const int s = (c - c_begin) & 1;
+        const int p = problem_of(c), tb = c % cpp;
+        int nrec = total < rec_per_chunk ? total : rec_per_chunk;
+        nrec = nrec < cand_arena ? nrec : cand_arena;
+        S.rw[s].staged = nrec;
+        const unsigned b_meta = unsigned(rows) * 4u;
+        mbar_arrive_expect_tx(&S.bar_row[s], b_meta + unsigned(nrec) * 32u);
+        if (b_meta) bulk_g2s(s_meta0 + size_t(s) * meta_bytes, B.hp_meta + (size_t(p) * cpp + tb) * rows, b_meta, &S.bar_row[s]);
+        if (nrec > 0)
+            bulk_g2s(s_cand0 + size_t(s) * cand_arena * 4, B.hp_cand + (size_t(p) * cpp + tb) * size_t(rec_per_chunk) * 4,
+                     unsigned(nrec) * 32u, &S.bar_row[s]);
+    };
+    // TAB(c): one warp, after G1(c) has landed.  Tables task-major (q = task*TB + tt, tasks = 7 joints, then NJ links),
+    // two per lane, packed in the arena in that order
+    auto issue_tab = [&](int c) {
+        const int s = (c - c_begin) & 1;
         const int p = problem_of(c), tb = c % cpp;
         const size_t t0 = size_t(p) * T + size_t(tb) * TB;
         K3Stage& Q = S.st[s];
@@ -560,72 +601,55 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                 bulk_g2s(Q.arena + off[h] + kb[h], csrc[h], cb[h], &S.bar_tab[s]);
             }
         }
-        if (lane == 0) {
-            int nrec = total < int(rec_per_chunk) ? total : int(rec_per_chunk);
-            nrec = nrec < cand_arena ? nrec : cand_arena;
-            Q.staged = nrec;
-            mbar_arrive_expect_tx(&S.bar_cand[s], unsigned(nrec) * 32u);
-            if (nrec > 0)
-                bulk_g2s(s_cand0 + size_t(s) * cand_arena * 4, B.hp_cand + (size_t(p) * cpp + tb) * rec_per_chunk * 4,
-                         unsigned(nrec) * 32u, &S.bar_cand[s]);
-        }
     };
     auto total_of = [&](int c) { return O > 0 ? *B.hp_total_of(problem_of(c), c % cpp) : 0; };
 
     if (tid == 0) {
         for (int s = 0; s < 2; s++) {
-            mbar_init(&S.bar_r1[s], 1);
+            mbar_init(&S.bar_g1[s], 1);
             mbar_init(&S.bar_tab[s], 32);
-            mbar_init(&S.bar_cand[s], 1);
+            mbar_init(&S.bar_row[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        S.task = 0;
-        S.rownext = 0;
+        S.ticket = 0;
         for (int i = 0; i < 4; i++) S.zero_d[i] = 0.0;
         for (int i = 0; i < 8; i++) S.zero_k[i] = 0;
     }
     __syncthreads();
-    int next_total = 0;  // (thread 0) candidate records in use of the chunk whose round 2 is issued next
+    int next_total = 0;  // (thread 0) candidate records in use of the chunk whose ROW copy is issued next
     if (tid == 0) {
-        issue_r1(c_begin, 0);
+        issue_g1(c_begin);
         next_total = total_of(c_begin);
     }
     if (warp == 0) {
-        mbar_wait(&S.bar_r1[0], 0);
-        issue_r2(c_begin, 0, __shfl_sync(0xffffffffu, next_total, 0));
+        mbar_wait(&S.bar_g1[0], 0);
+        issue_tab(c_begin);
     }
     int cur_p = -1;
     const int grp = lane >> 3, v = lane & 7;
     const double* const pa = &S.pwA[0][v <= 4 ? v : 0];
     const double* const pb = &S.pwB[0][v >= 5 ? v - 4 : 0];
+    int ticket = -1;  // warp-uniform: the item this warp holds
 
-    for (int c = c_begin; c < c_end; c++) {
-        const int it = c - c_begin, s = it & 1;
-        const unsigned ph = unsigned(it >> 1) & 1u;
-        const int p = problem_of(c), tb = c % cpp;
-        K3Stage& Q = S.st[s];
-        const unsigned* s_meta = reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(s_meta0) + size_t(s) * meta_bytes);
-        const double* s_cand = s_cand0 + size_t(s) * cand_arena * 4;
-        const size_t t0 = size_t(p) * T + size_t(tb) * TB;
-        double* gp = g ? g + size_t(p) * m : nullptr;
-        double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
-        const bool failed = B.status[p] != 0;
-        const bool more = c + 1 < c_end;
-
-        if (tid == 0 && more) {
-            issue_r1(c + 1, s ^ 1);
-            next_total = total_of(c + 1);
+    // iteration j: slices of chunk c_begin + j (j < nmine) and rows of chunk c_begin + j - 1 (j >= 1)
+    for (int j = 0; j <= nmine; j++) {
+        const int c = c_begin + j;
+        const bool has_slices = j < nmine, has_rows = j >= 1;
+        const int s = j & 1;
+        if (tid == 0) {
+            if (j + 1 < nmine) issue_g1(c + 1);
+            if (has_slices) {
+                issue_row(c, next_total);
+                if (j + 1 < nmine) next_total = total_of(c + 1);
+            }
         }
-        if (p != cur_p) {  // power-product tables of this problem's k
+        const int p = has_slices ? problem_of(c) : cur_p;
+        if (has_slices && p != cur_p) {
+            // power-product tables of this problem's k.  The rows of chunk j-1 (previous problem) do not read them.
             cur_p = p;
             if (tid < NF) S.k[tid] = kin[size_t(p) * NF + tid];
             __syncthreads();
-            if (tid == 0) {
-                bool in = true;
-                for (int j = 0; j < NF; j++) in = in && (fabs(S.k[j]) <= K_DOMAIN);
-                S.in_domain = in ? 1 : 0;
-            }
-            {   // table A: entry tid of 256, variables k0..k3;  table B: entry tid of 64 (threads 0..63), k4..k6
+            if (tid < 256) {  // table A: entry tid, variables k0..k3
                 double f[4], d[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -642,7 +666,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                 row[3] = p01 * (d[2] * f[3]);
                 row[4] = p01 * (f[2] * d[3]);
             }
-            if (tid < 64) {
+            if (tid < 64) {  // table B: entry tid, variables k4..k6
                 double f[3], d[3];
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
@@ -657,18 +681,50 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                 row[2] = f[0] * d[1] * f[2];
                 row[3] = f[0] * f[1] * d[2];
             }
+            if (tid == 0) {
+                bool in = true;
+                for (int q = 0; q < NF; q++) in = in && (fabs(S.k[q]) <= K_DOMAIN);
+                S.rw[s].in_domain = in ? 1 : 0;
+            }
             __syncthreads();
+        } else if (has_slices && tid == 0) {
+            S.rw[s].in_domain = S.rw[s ^ 1].in_domain;  // same problem as the previous chunk
         }
 
-        // ---- slices of chunk c
-        mbar_wait(&S.bar_tab[s], ph);
-        if (!failed) {
-            const int ntask = (NF + NJ) * (TB / 4);
-            for (;;) {
-                int task = 0;
-                if (lane == 0) task = atomicAdd(&S.task, 1);
-                task = __shfl_sync(0xffffffffu, task, 0);
-                if (task >= ntask) break;
+        // slice side: chunk c, stage s.  row side: chunk c - 1, stage s ^ 1
+        K3Stage& Q = S.st[s];
+        K3Rows& RS = S.rw[s];
+        const K3Rows& RR = S.rw[s ^ 1];
+        const int tb = c % cpp;
+        const size_t t0 = size_t(p) * T + size_t(tb) * TB;
+        const bool failed = has_slices && B.status[p] != 0;
+        const int pr = has_rows ? problem_of(c - 1) : 0, tbr = (c - 1) % cpp;
+        const bool failed_r = has_rows && B.status[pr] != 0;
+        double* gpr = g ? g + size_t(pr) * m : nullptr;
+        double* jpr = jac ? jac + size_t(pr) * m * NF : nullptr;
+        const unsigned* s_meta = reinterpret_cast<const unsigned*>(s_meta0 + size_t(s ^ 1) * meta_bytes);
+        const double* s_cand = s_cand0 + size_t(s ^ 1) * cand_arena * 4;
+        bool tab_ready = false, row_ready = false;
+
+        for (;;) {
+            if (ticket < 0) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&S.ticket, 1);
+                ticket = __shfl_sync(0xffffffffu, t, 0);
+            }
+            if (ticket >= (j + 1) * ITEMS) break;  // an item of the next iteration: keep it, go to the barrier
+            const int item = ticket - j * ITEMS;
+            ticket = -1;
+
+            if (item < n_slice_items + 1 && item != I_ISSUE) {
+                // ---- slice item: the tables of four consecutive intervals of one joint / link of chunk c
+                if (!has_slices) continue;
+                const int task = item < I_ISSUE ? item : item - 1;
+                if (!tab_ready) {
+                    mbar_wait(&S.bar_tab[s], unsigned(j >> 1) & 1u);
+                    tab_ready = true;
+                }
+                if (failed) continue;
                 const int sub = task % (TB / 4), which = task / (TB / 4);  // longest tables (torques) first
                 const int tt = sub * 4 + grp;
                 const bool torque = which < NF;
@@ -701,9 +757,9 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                     if (v == 0) {
                         const double value = Q.cen_u[i] + a0;
                         const double r = Q.rad_u[i];
-                        S.tg[i] = ((value - r) + (value + r)) * 0.5;  // centre of Interval(c - r, c + r) (KPR/NLPclass.cu:306)
+                        RS.tg[i] = ((value - r) + (value + r)) * 0.5;  // centre of Interval(c - r, c + r) (KPR/NLPclass.cu:306)
                     } else {
-                        S.tj[i * NF + (v - 1)] = a0;
+                        RS.tj[i * NF + (v - 1)] = a0;
                     }
                 } else {
                     const int i = tt * NJ + l;
@@ -713,155 +769,118 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                         for (int e = 0; e < 3; e++) {
                             const double value = Q.cen_l[i * 3 + e] + acc[e];
                             const double r = Q.rad_l[i * 3 + e];
-                            S.lc[tt][l][e] = ((value - r) + (value + r)) * 0.5;  // getCenter(slice()) (KPR/NLPclass.cu:313)
+                            RS.lc[tt][l][e] = ((value - r) + (value + r)) * 0.5;  // getCenter(slice()) (KPR/NLPclass.cu:313)
                         }
                     } else {
-                        S.dlc[tt][l][v - 1][0] = a0;
-                        S.dlc[tt][l][v - 1][1] = a1;
-                        S.dlc[tt][l][v - 1][2] = a2;
+                        RS.dlc[tt][l][v - 1][0] = a0;
+                        RS.dlc[tt][l][v - 1][1] = a1;
+                        RS.dlc[tt][l][v - 1][2] = a2;
                     }
                 }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) S.task = 0;
-
-        // ---- warp 0: round 2 of the next chunk (its round 1 was issued at the top of this iteration)
-        if (warp == 0 && more) {
-            mbar_wait(&S.bar_r1[s ^ 1], unsigned((it + 1) >> 1) & 1u);
-            issue_r2(c + 1, s ^ 1, __shfl_sync(0xffffffffu, next_total, 0));
-        }
-
-        mbar_wait(&S.bar_cand[s], ph);  // (always: no bulk copy may be in flight when its stage is reused or the CTA exits)
-        if (failed) {
-            // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe
-            // rows: every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
-            for (int i = tid; i < TB * NF; i += K3_THREADS) {
-                if (gp) gp[size_t(tb) * TB * NF + i] = 1e300;
-                if (jp)
-                    for (int q = 0; q < NF; q++) jp[(size_t(tb) * TB * NF + i) * NF + q] = 0.0;
-            }
-            for (int x = tid; x < rows; x += K3_THREADS) {
-                const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
-                const size_t r = size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o;
-                if (gp) gp[r] = 1e300;
-                if (jp)
-                    for (int q = 0; q < NF; q++) jp[r * NF + q] = 0.0;
-            }
-        } else {
-            // torque rows tb*TB*NF + i, i < TB*NF: contiguous runs of g and of the Jacobian
-            if (gp)
-                for (int i = tid; i < TB * NF; i += K3_THREADS) gp[size_t(tb) * TB * NF + i] = S.tg[i];
-            if (jp)
-                for (int i = tid; i < TB * NF * NF; i += K3_THREADS) jp[size_t(tb) * TB * NF * NF + i] = S.tj[i];
-            if (p == 0 && B.link_sliced)
-                for (int i = tid; i < TB * NJ * 3; i += K3_THREADS)
-                    B.link_sliced[(size_t(tb) * TB * NJ) * 3 + i] = S.lc[i / (NJ * 3)][(i / 3) % NJ][i % 3];
-
-            // ---- collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
-            if (O > 0 && S.in_domain) {
-                const double* gcand = B.hp_cand + (size_t(p) * cpp + tb) * rec_per_chunk * 4;
-                const int staged = Q.staged;
-#if K3_TRANSPOSE
-                double* stage = reinterpret_cast<double*>(Q.arena) + warp * (32 * NF);
-#endif
-                const int row_base = NF * T + tb * TB * O;  // row of (l, tt, o) = row_base + l*T*O + tt*O + o
-                for (;;) {
-                    int x0 = 0;
-                    if (lane == 0) x0 = atomicAdd(&S.rownext, 1) * 32;
-                    x0 = __shfl_sync(0xffffffffu, x0, 0);
-                    if (x0 >= rows) break;
-                    const int x = x0 + lane;
-                    bool active = x < rows;
-                    double max_elt = -100000000;
-                    double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
-                    int row_i = -1;
-                    int tt = 0, l = 0;
-                    if (active) {
-                        const int ltt = __float2int_rz((float(x) + 0.5f) * invO);  // x / O (exact: x < 2^22)
-                        const int o = x - ltt * O;
-                        tt = ltt % TB;
-                        l = ltt / TB;
-                        const unsigned meta = s_meta[x];
-                        const int n = int(meta & 255u), off = int(meta >> 8);
-                        if (n == HP_OVERFLOW) {
-                            active = false;  // no stored list: k_constraints_slow writes this row
-                        } else {
-                            row_i = row_base + (l * T + tt) * O + o;
-                            const double c0 = S.lc[tt][l][0], c1 = S.lc[tt][l][1], c2 = S.lc[tt][l][2];
-                            const double2* rec = reinterpret_cast<const double2*>(off + n <= staged ? s_cand + size_t(off) * 4
-                                                                                                     : gcand + size_t(off) * 4);
-                            for (int q = 0; q < n; q++) {
-                                const double2 u = rec[2 * q], w = rec[2 * q + 1];
-                                const double val = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
-                                if (val > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
-                                    max_elt = val;
-                                    A0 = -u.x; A1 = -u.y; A2 = -w.x;
-                                }
+            } else if (item == I_ISSUE) {
+                // ---- place and fetch the tables of chunk c + 1 (its G1 was issued at the top of this iteration)
+                if (j + 1 < nmine) {
+                    mbar_wait(&S.bar_g1[s ^ 1], unsigned((j + 1) >> 1) & 1u);
+                    issue_tab(c + 1);
+                }
+            } else if (item == I_TORQUE) {
+                // ---- torque rows of chunk c - 1: contiguous runs of g and of the Jacobian; Bezier rows once per problem
+                if (!has_rows) continue;
+                if (failed_r) {
+                    // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.
+                    // Fail-safe rows: every torque and collision row violated, zero Jacobian.
+                    for (int i = lane; i < TB * NF; i += 32) {
+                        if (gpr) gpr[size_t(tbr) * TB * NF + i] = 1e300;
+                        if (jpr)
+                            for (int q = 0; q < NF; q++) jpr[(size_t(tbr) * TB * NF + i) * NF + q] = 0.0;
+                    }
+                    for (int x = lane; x < rows; x += 32) {
+                        const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
+                        const size_t r = size_t(NF) * T + (size_t(l) * T + tbr * TB + tt) * O + o;
+                        if (gpr) gpr[r] = 1e300;
+                        if (jpr)
+                            for (int q = 0; q < NF; q++) jpr[r * NF + q] = 0.0;
+                    }
+                } else {
+                    if (gpr)
+                        for (int i = lane; i < TB * NF; i += 32) gpr[size_t(tbr) * TB * NF + i] = RR.tg[i];
+                    if (jpr)
+                        for (int i = lane; i < TB * NF * NF; i += 32) jpr[size_t(tbr) * TB * NF * NF + i] = RR.tj[i];
+                    if (pr == 0 && B.link_sliced)
+                        for (int i = lane; i < TB * NJ * 3; i += 32)
+                            B.link_sliced[(size_t(tbr) * TB * NJ) * 3 + i] = RR.lc[i / (NJ * 3)][(i / 3) % NJ][i % 3];
+                }
+                if (tbr == 0 && lane < NF) {  // Bezier joint-limit rows (KPR/Trajectory.cu:256-540)
+                    const int i = lane;
+                    const double D = c_robot.duration;
+                    const double q0 = B.q0[size_t(pr) * NF + i];
+                    const double a = B.qd0[size_t(pr) * NF + i] * D;
+                    const double b = B.qdd0[size_t(pr) * NF + i] * D * D;
+                    const double kn = kin[size_t(pr) * NF + i];
+                    const int off = NF * T + NJ * T * O;
+                    for (int vel = 0; vel < 2; vel++) {
+                        double mn, mx, dmn, dmx;
+                        bez_extrema(vel == 1, q0, a, b, c_robot.k_range[i], D, kn, &mn, &mx, &dmn, &dmx);
+                        const int r0 = off + vel * 2 * NF + i;
+                        if (gpr) {
+                            gpr[r0] = failed_r ? 0.0 : mn;
+                            gpr[r0 + NF] = failed_r ? 0.0 : mx;
+                        }
+                        if (jpr) {
+                            for (int q = 0; q < NF; q++) {
+                                jpr[size_t(r0) * NF + q] = (q == i && !failed_r) ? dmn : 0.0;
+                                jpr[size_t(r0 + NF) * NF + q] = (q == i && !failed_r) ? dmx : 0.0;
                             }
                         }
                     }
-                    if (gp && active) gp[row_i] = -max_elt;
-                    if (jp && active) {
-                        const double2* dk = reinterpret_cast<const double2*>(&S.dlc[tt][l][0][0]);
-                        double* out = jp + size_t(row_i) * NF;
-#pragma unroll
-                        for (int q = 0; q < NF; q++) {
-                            const double2 xy = dk[2 * q];
-                            const double z = dk[2 * q + 1].x;
-                            // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A.
-                            // Fused like the reference's own kernel (nvcc contracts max_A_elt.dot(dk))
-#if K3_TRANSPOSE
-                            stage[lane * NF + q] = __fma_rn(A0, xy.x, __fma_rn(A1, xy.y, A2 * z));
-#else
-                            out[q] = __fma_rn(A0, xy.x, __fma_rn(A1, xy.y, A2 * z));  // 56 contiguous bytes per lane
-#endif
-                        }
-                    }
-#if K3_TRANSPOSE
-                    if (jp) {
-                        __syncwarp();
-#pragma unroll
-                        for (int q = 0; q < NF; q++) {
-                            const int e = q * 32 + lane;
-                            const int r = e / NF;
-                            const int rr = __shfl_sync(0xffffffffu, row_i, r);
-                            if (rr >= 0) jp[size_t(rr) * NF + (e - r * NF)] = stage[e];
-                        }
-                        __syncwarp();
-                    }
-#endif
                 }
-            }
-        }
-
-        // Bezier joint-limit rows (KPR/Trajectory.cu:256-540), once per problem
-        if (tb == 0 && tid < NF) {
-            const int i = tid;
-            const double D = c_robot.duration;
-            const double q0 = B.q0[size_t(p) * NF + i];
-            const double a = B.qd0[size_t(p) * NF + i] * D;
-            const double b = B.qdd0[size_t(p) * NF + i] * D * D;
-            const double kn = kin[size_t(p) * NF + i];
-            const int off = NF * T + NJ * T * O;
-            for (int vel = 0; vel < 2; vel++) {
-                double mn, mx, dmn, dmx;
-                bez_extrema(vel == 1, q0, a, b, c_robot.k_range[i], D, kn, &mn, &mx, &dmn, &dmx);
-                const int r0 = off + vel * 2 * NF + i;
-                if (gp) {
-                    gp[r0] = failed ? 0.0 : mn;
-                    gp[r0 + NF] = failed ? 0.0 : mx;
+            } else {
+                // ---- row tile of chunk c - 1: rows x = (l*TB + tt)*O + o, one lane each
+                if (!has_rows || failed_r || O == 0 || !RR.in_domain) continue;
+                if (!row_ready) {
+                    mbar_wait(&S.bar_row[s ^ 1], unsigned((j - 1) >> 1) & 1u);
+                    row_ready = true;
                 }
-                if (jp) {
-                    for (int j = 0; j < NF; j++) {
-                        jp[size_t(r0) * NF + j] = (j == i && !failed) ? dmn : 0.0;
-                        jp[size_t(r0 + NF) * NF + j] = (j == i && !failed) ? dmx : 0.0;
+                const int x = (item - (n_slice_items + 1)) * 32 + lane;
+                if (x >= rows) continue;
+                const int ltt = __float2int_rz((float(x) + 0.5f) * invO);  // x / O (exact: x < 2^22)
+                const int o = x - ltt * O;
+                const int tt = ltt % TB, l = ltt / TB;
+                const unsigned meta = s_meta[x];
+                const int n = int(meta & 255u), off = int(meta >> 8);
+                if (n == HP_OVERFLOW) continue;  // no stored list: k_constraints_slow writes this row
+                const int row_i = NF * T + (l * T + tbr * TB + tt) * O + o;
+                const double c0 = RR.lc[tt][l][0], c1 = RR.lc[tt][l][1], c2 = RR.lc[tt][l][2];
+                const double2* rec = reinterpret_cast<const double2*>(
+                    off + n <= RR.staged ? s_cand + size_t(off) * 4
+                                         : B.hp_cand + ((size_t(pr) * cpp + tbr) * size_t(rec_per_chunk) + off) * 4);
+                double max_elt = -100000000;
+                double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
+                for (int q = 0; q < n; q++) {
+                    const double2 u = rec[2 * q], w = rec[2 * q + 1];
+                    const double val = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
+                    if (val > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
+                        max_elt = val;
+                        A0 = -u.x; A1 = -u.y; A2 = -w.x;
+                    }
+                }
+                if (gpr) gpr[row_i] = -max_elt;
+                if (jpr) {
+                    const double2* dk = reinterpret_cast<const double2*>(&RR.dlc[tt][l][0][0]);
+                    double* out = jpr + size_t(row_i) * NF;
+#pragma unroll
+                    for (int q = 0; q < NF; q++) {
+                        const double2 xy = dk[2 * q];
+                        const double z = dk[2 * q + 1].x;
+                        // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A.  Fused like
+                        // the reference's own kernel (nvcc contracts max_A_elt.dot(dk)); 56 contiguous bytes per lane
+                        out[q] = __fma_rn(A0, xy.x, __fma_rn(A1, xy.y, A2 * z));
                     }
                 }
             }
         }
-        __syncthreads();  // stage s, lc / dlc / tg / tj are free again
-        if (tid == 0) S.rownext = 0;
+        if (j == nmine && has_rows && !row_ready) mbar_wait(&S.bar_row[s ^ 1], unsigned((j - 1) >> 1) & 1u);  // nothing in flight at exit
+        __syncthreads();
     }
 }
 
@@ -984,7 +1003,7 @@ cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// Shared memory of one persistent k_constraints CTA: the fixed part plus, per pipeline stage, the row words and a
+// Shared memory of one persistent k_constraints CTA: the fixed part plus, per chunk parity, the row words and a
 // candidate arena sized for the chunk's expected 2.5 records per row — bounded so that two CTAs stay resident per SM
 // (else one).
 constexpr int K3_SMEM_MAX = 220 * 1024;
