@@ -178,23 +178,23 @@ int ensure_obstacle_buffers(armour_ctx* ctx, int nprob, int nobs) {
     Batch& B = ctx->B;
     B.O = nobs;
     B.nprob = nprob;
-    const size_t chunks = size_t(nprob) * (B.T / TB);
-    const size_t need_hp = chunks * B.hp_chunk_records() * 4;  // doubles
+    const size_t need_hp = size_t(nprob) * (B.T / TB) * B.hp_chunk();
     if (ctx->hp_capacity < need_hp || ctx->hp_nprob < nprob) {
         // (the candidate lists of the current batch go with the old buffers: whatever was built must be rebuilt)
         if (B.hp_cand) cudaFree(B.hp_cand);
-        if (B.hp_meta) cudaFree(B.hp_meta);
-        if (B.hp_total) cudaFree(B.hp_total);
+        if (B.hp_cnt) cudaFree(B.hp_cnt);
+        if (B.hp_slow) cudaFree(B.hp_slow);
         B.hp_cand = nullptr;
-        B.hp_meta = nullptr;
-        B.hp_total = nullptr;
+        B.hp_cnt = nullptr;
+        B.hp_slow = nullptr;
         ctx->hp_capacity = 0;
         ctx->hp_nprob = 0;
         ctx->built_nprob = 0;
+        const size_t np = std::max(nprob, ctx->hp_nprob);
         CU(dalloc(&B.hp_cand, need_hp));
-        CU(dalloc(&B.hp_meta, chunks * size_t(B.chunk_rows())));
-        CU(dalloc(&B.hp_total, size_t(nprob) * (B.T / TB + 1)));
-        CU(cudaMemsetAsync(B.hp_total, 0, size_t(nprob) * (B.T / TB + 1) * sizeof(int), ctx->stream));
+        CU(dalloc(&B.hp_cnt, need_hp / (HP_CAP * 4)));
+        CU(dalloc(&B.hp_slow, np));
+        CU(cudaMemsetAsync(B.hp_slow, 0, np * sizeof(int), ctx->stream));
         ctx->hp_capacity = need_hp;
         ctx->hp_nprob = nprob;
     }
@@ -385,8 +385,6 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
         if ((e = cudaFuncGetAttributes(&fa, k1lat::k_reachsets)) != cudaSuccess) return bail("load k_reachsets", e);
         if ((e = cudaFuncGetAttributes(&fa, k_hyperplanes)) != cudaSuccess) return bail("load k_hyperplanes", e);
         if ((e = cudaFuncGetAttributes(&fa, k_constraints)) != cudaSuccess) return bail("load k_constraints", e);
-        if ((e = cudaFuncSetAttribute(k_constraints, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_MAX)) != cudaSuccess)
-            return bail("k_constraints shared memory", e);
         if ((e = cudaFuncGetAttributes(&fa, k_constraints_slow)) != cudaSuccess) return bail("load k_constraints_slow", e);
         if ((e = cudaFuncGetAttributes(&fa, k_verdict)) != cudaSuccess) return bail("load k_verdict", e);
     }
@@ -401,7 +399,7 @@ int armour_ctx_destroy(armour_ctx* ctx) {
     Batch& B = ctx->B;
     void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io,
                     ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
-                    B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.link_r, B.hp_cand, B.hp_meta, B.hp_total,
+                    B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.link_r, B.hp_cand, B.hp_cnt, B.hp_slow,
                     B.link_sliced, B.status};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -540,12 +538,8 @@ int armour_batch_get_monomial_counts(armour_ctx* ctx, int nprob, int* link_n, in
 int armour_batch_get_candidate_counts(armour_ctx* ctx, int nprob, unsigned char* out) {
     if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
     const size_t rows = size_t(ctx->B.NJ) * ctx->B.T * ctx->B.O;
-    if (rows) {
-        std::vector<unsigned> meta(nprob * rows);
-        CU(cudaMemcpyAsync(meta.data(), ctx->B.hp_meta, meta.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i < meta.size(); i++) out[i] = (unsigned char)(meta[i] & 255u);
-    }
+    if (rows) CU(cudaMemcpyAsync(out, ctx->B.hp_cnt, nprob * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return ARMOUR_OK;
 }
 

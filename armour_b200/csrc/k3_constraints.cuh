@@ -9,6 +9,9 @@
 //                    checkCollisionKernel (KPR/CollisionChecking.cu:230-299) and the row assembly of
 //                    armtd_NLP::eval_g / eval_jac_g (KPR/NLPclass.cu:272-396): 1 launch instead of
 //                    7 launches + 8-9 blocking PCIe copies per call.
+//   k_constraints_slow — the few collision rows without a stored candidate list, or all of them when k lies outside
+//                    the box the lists were built for: full 72-plane scan from the generators.  Its own launch, so that
+//                    k_constraints carries no stack frame for it.
 //   k_verdict      — feasibility predicate of armtd_NLP::finalize_solution (KPR/NLPclass.cu:449-537).
 //
 // One CTA handles TB = 8 consecutive intervals of one problem, so that each output run per link is
@@ -277,47 +280,37 @@ __global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
         }
     }
     __syncthreads();
-    // step 4: the row's list is packed behind the lists already placed in its chunk (one atomic per row: the order
-    // of the rows inside a chunk is arrival order and differs run to run, the content of every list does not), so
-    // that an evaluation fetches exactly the records in use with one bulk copy.  Survivors keep their scan order.
-    __shared__ int s_off[HP_ROWS];
-    int count = 0, before[2] = {0, 0};
-    if (live && (keep[0] || keep[1] || pi == 0)) {
+    if (live) {  // step 4: survivors to their scan-order positions (counted over the short list)
+        const size_t chunk = size_t(p) * (T / TB) + tb;
+        double* row = B.hp_cand + chunk * B.hp_chunk() + size_t(x) * 4;
+        const size_t cstride = size_t(per_pair) * 4;
         const int nl = s_nlist[lr];
+        if (keep[0] || keep[1] || pi == 0) {
+            int count = 0, before[2] = {0, 0};
 #pragma unroll 1
-        for (int c = 0; c < nl; c++) {
-            const int q = s_list[lr][c];
-            if (s_flag[lr][q]) {
-                count++;
-                before[0] += (q < 2 * pi);
-                before[1] += (q < 2 * pi + 1);
+            for (int c = 0; c < nl; c++) {
+                const int q = s_list[lr][c];
+                if (s_flag[lr][q]) {
+                    count++;
+                    before[0] += (q < 2 * pi);
+                    before[1] += (q < 2 * pi + 1);
+                }
             }
-        }
-    }
-    const size_t chunk = size_t(p) * (T / TB) + tb;
-    if (live && pi == 0) {
-        int off = -1;
-        if (count <= HP_CAP) {
-            off = atomicAdd(B.hp_total_of(p, tb), count);
-            if (size_t(off) + count > B.hp_chunk_records()) off = -1;  // chunk full: the row goes to the slow path
-        }
-        s_off[lr] = off;
-        if (off < 0) atomicAdd(B.hp_slow_of(p), 1);
-        B.hp_meta[chunk * per_pair + x] = off < 0 ? unsigned(HP_OVERFLOW) : ((unsigned(off) << 8) | unsigned(count));
-    }
-    __syncthreads();
-    if (live && s_off[lr] >= 0) {
-        double* row = B.hp_cand + (chunk * B.hp_chunk_records() + size_t(s_off[lr])) * 4;
+            if (count <= HP_CAP) {
 #pragma unroll 1
-        for (int sgn = 0; sgn < 2; sgn++) {
-            if (keep[sgn]) {
-                const double sg = sgn ? -1.0 : 1.0;
-                double* e = row + size_t(before[sgn]) * 4;
-                e[0] = sg * s_A[lr][pi][0];
-                e[1] = sg * s_A[lr][pi][1];
-                e[2] = sg * s_A[lr][pi][2];
-                e[3] = s_b[lr][2 * pi + sgn];
+                for (int sgn = 0; sgn < 2; sgn++) {
+                    if (keep[sgn]) {
+                        const double sg = sgn ? -1.0 : 1.0;
+                        double* e = row + size_t(before[sgn]) * cstride;
+                        e[0] = sg * s_A[lr][pi][0];
+                        e[1] = sg * s_A[lr][pi][1];
+                        e[2] = sg * s_A[lr][pi][2];
+                        e[3] = s_b[lr][2 * pi + sgn];
+                    }
+                }
             }
+            if (pi == 0) B.hp_cnt[chunk * per_pair + x] = (count > HP_CAP) ? (unsigned char)HP_OVERFLOW : (unsigned char)count;
+            if (pi == 0 && count > HP_CAP) atomicAdd(&B.hp_slow[p], 1);  // k_constraints_slow evaluates the row
         }
     }
 }
@@ -352,598 +345,296 @@ __device__ __noinline__ void row_from_generators(const double* __restrict__ ob, 
     *A2o = A2;
 }
 
-// ---- TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier) ---------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// One component of one reach set sliced at k: value and all seven d/dk in a single pass over the
+// monomials.  Per monomial the factors k_j^{d_j} are applied in ascending j exactly like
+// PZsparse::slice (KPR/PZsparse.cu:404-435) and its gradient overloads (:477-555); a factor with
+// d_j = 0 is 1.0 and is skipped (exact).  D[v] carries coef * prod_{j<v} f_j * f'_v * prod_{v<j} f_j.
+__device__ __forceinline__ void slice_component(const uint16_t* __restrict__ keys, const double* __restrict__ coef,
+                                                int n, int kstride, int cstride, const double2 (*kpd)[4], double& value,
+                                                double (&grad)[NF]) {
+    constexpr int CH = K3_CH;  // monomials fetched together: the loads of a chunk are independent and overlap
+    for (int m0 = 0; m0 < n; m0 += CH) {
+        unsigned kk[CH];
+        double cc[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const bool on = m0 + i < n;
+            kk[i] = on ? keys[(m0 + i) * kstride] : 0u;
+            cc[i] = on ? coef[(m0 + i) * cstride] : 0.0;
+        }
+#pragma unroll 1
+        for (int i = 0; i < CH; i++) {
+            if (m0 + i >= n) break;
+            // (dynamic index into kk / cc would spill: rotate instead)
+            const unsigned key = kk[0];
+            double val = cc[0];
+#pragma unroll
+            for (int q = 0; q + 1 < CH; q++) {
+                kk[q] = kk[q + 1];
+                cc[q] = cc[q + 1];
+            }
+            // No branch on the degree: kpd[j][0] = {1, 0}, and x * 1.0 is exact, val * 0.0 adds a zero to the
+            // gradient: the same values as skipping the factor, without seven divergent branches per monomial.
+            double D[NF];
+#pragma unroll
+            for (int j = 0; j < NF; j++) {
+                const double2 fd = kpd[j][(key >> (2 * j)) & 3];
+                D[j] = val * fd.y;
+#pragma unroll
+                for (int v = 0; v < j; v++) D[v] *= fd.x;
+                val *= fd.x;
+            }
+            value += val;
+#pragma unroll
+            for (int v = 0; v < NF; v++) grad[v] += D[v];
+        }
+    }
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ unsigned r16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
-// k_constraints: persistent CTAs (two per SM); each walks a contiguous range of chunks = (problem, TB intervals) as a
-// software pipeline fed by TMA bulk copies, so that neither the DRAM latency of a chunk nor the uneven length of its
-// pieces leaves warps idle.
-//
-// Loads of chunk c (all cp.async.bulk into shared memory, completion on mbarriers, buffers by parity of c):
-//   G1(c)   fixed sizes: monomial counts, centres and radii of its TB*(NJ+NF) reach-set tables;
-//   TAB(c)  every table, exactly its n monomials (16-bit keys, coefficients) — sizes known from G1(c);
-//   ROW(c)  the (first record, count) words of its NJ*TB*O collision rows and the candidate half-space records in use of
-//           the chunk: one contiguous run.
-// Iteration j of a CTA works on TWO chunks at once — the slices of chunk j and the collision rows of chunk j-1 — as one
-// pool of items handed to its warps by ticket: 7 torque + NJ link slice items (a warp slices the tables of four
-// consecutive intervals of one joint / link, eight lanes per table, lane v owns output v = the value or d/dk_{v-1}),
-// NJ*TB*O/32 row tiles (one lane per collision row), the torque rows of chunk j-1, and the placement + issue of TAB(j+1).
-// One __syncthreads per iteration.  G1(j+1) and ROW(j) are issued at the top of iteration j.
-// The power product of a monomial comes from two tables in shared memory, k0..k3 (256 entries) and k4..k6 (64), whose
-// columns hold the plain product and its derivatives: term_v = coeff * A[key & 255][colA(v)] * B[key >> 8][colB(v)].
-// They depend on k only, i.e. on the problem: there is one pair per chunk parity, rebuilt when the chunk range crosses
-// into the next problem.  (The reference applies the factors one variable after the other, KPR/PZsparse.cu:404-555:
-// same value up to a few ulp.)
-#ifndef K3_THREADS_N
-#define K3_THREADS_N 384
-#endif
-constexpr int K3_THREADS = K3_THREADS_N;
+// Warp roles: warps [0, 6) slice the link reach sets (one thread per (interval, link, component)), warps
+// [6, 10) slice the torque reach sets, two lanes per (interval, joint) table (the torque tables are ~3x longer).
+// The link warps meet on named barrier 1 and go straight to the collision rows; the torque warps write their
+// rows, then join through barrier 2 (on which the link warps only arrive), so nobody waits for the slowest
+// slice.  Collision rows are handed out in chunks of 32 from a shared counter.
+constexpr int K3_LINK_THREADS = 192;
+constexpr int K3_TORQUE_LANES = 2;
+constexpr int K3_THREADS = 320;
+constexpr int K3_CNT_SMEM = 2048;  // rows per CTA whose candidate counts are staged in shared memory
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int K3_TABLE_ARENA = 12288;      // bytes of staged tables per stage
-constexpr int K3_NTAB = TB * (MAXJ + NF);  // tables of a chunk (upper bound)
-static_assert(TB % 4 == 0, "a warp slices four intervals of a link / joint together");
-static_assert(K3_NTAB <= 64, "one warp issues the table copies, two tables per lane");
-static_assert(K3_THREADS >= 256, "the power-product tables are built by 256 threads");
+constexpr int K3_TORQUE_T0 = K3_LINK_THREADS;
+static_assert(TB * 3 * MAXJ <= K3_LINK_THREADS && K3_TORQUE_T0 + TB * NF * K3_TORQUE_LANES <= K3_THREADS,
+              "thread map of the slice phase");
 
-struct K3Desc {  // what every thread needs to know about a chunk, computed once by thread 0 one iteration ahead
-    int p, tb, failed, in_domain;
-    long long g_off;  // p * m
-    long long t0;     // p * T + tb * TB
-};
-struct K3Stage {  // slice side of a chunk
-    int nl[TB * MAXJ], nu[TB * NF + 4];
-    double cen_l[TB * MAXJ * 3], rad_l[TB * MAXJ * 3], cen_u[TB * NF + 4], rad_u[TB * NF + 4];
-    int2 tinfo[K3_NTAB];  // per table q = task*TB + tt: {byte offset of its keys in the arena (-1: not staged), n}
-    __align__(16) unsigned char arena[K3_TABLE_ARENA];
-};
-struct K3Rows {  // row side of a chunk: what its slices leave for the collision rows
-    double lc[TB * MAXJ][4];       // sliced link centres, [tt*MAXJ + l]
-    double dlc[TB * MAXJ][NF][4];  // and their d/dk
-    double tg[TB * NF + 4];        // torque rows of g
-    double tj[TB * NF * NF + 4];   // torque rows of the Jacobian
-    int staged, pad[3];
-};
-struct K3Smem {  // fixed part of the dynamic shared memory; row decode table, 2 x row words, 2 x candidate arena follow
-    unsigned long long bar_g1[2], bar_tab[2], bar_row[2];
-    double pwA[256][5];  // k0..k3: plain product, d/dk0 .. d/dk3
-    double pwB[64][4];   // k4..k6: plain product, d/dk4 .. d/dk6
-    double k[8];
-    double zero_d[4];    // operands of an empty table
-    unsigned short zero_k[8];
-    int ticket, pad[3];
-    K3Desc desc[2];
-    K3Stage st[2];
-    K3Rows rw[2];
-};
-
-// one table sliced by an 8-lane group, operands in shared memory.  n >= 0 own monomials, nmax = longest of the warp's
-// four tables (lanes past their own n re-read their last monomial with a zero factor: no branch, no garbage).  Two
-// accumulator sets: consecutive monomials do not wait for each other's multiply-add.
-template <bool TORQUE>
-__device__ __forceinline__ void slice_group(const unsigned short* __restrict__ kp, const double* __restrict__ cp, int n,
-                                            int nmax, const double* __restrict__ pa, const double* __restrict__ pb,
-                                            double& a0, double& a1, double& a2) {
-    const int nlast = n > 0 ? n - 1 : 0;
-    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
-    int mI = 0;
-    for (; mI + 1 < nmax; mI += 2) {
-        const int m0 = mI < nlast ? mI : nlast, m1 = mI + 1 < nlast ? mI + 1 : nlast;
-        const unsigned key0 = kp[m0], key1 = kp[m1];
-        double f0 = pa[(key0 & 255u) * 5] * pb[(key0 >> 8) * 4];
-        double f1 = pa[(key1 & 255u) * 5] * pb[(key1 >> 8) * 4];
-        f0 = mI < n ? f0 : 0.0;
-        f1 = mI + 1 < n ? f1 : 0.0;
-        if (TORQUE) {
-            a0 = __fma_rn(cp[m0], f0, a0);
-            b0 = __fma_rn(cp[m1], f1, b0);
-        } else {
-            a0 = __fma_rn(cp[m0 * 3], f0, a0);
-            a1 = __fma_rn(cp[m0 * 3 + 1], f0, a1);
-            a2 = __fma_rn(cp[m0 * 3 + 2], f0, a2);
-            b0 = __fma_rn(cp[m1 * 3], f1, b0);
-            b1 = __fma_rn(cp[m1 * 3 + 1], f1, b1);
-            b2 = __fma_rn(cp[m1 * 3 + 2], f1, b2);
-        }
-    }
-    if (mI < nmax) {
-        const int m0 = mI < nlast ? mI : nlast;
-        const unsigned key0 = kp[m0];
-        double f0 = pa[(key0 & 255u) * 5] * pb[(key0 >> 8) * 4];
-        f0 = mI < n ? f0 : 0.0;
-        if (TORQUE) {
-            a0 = __fma_rn(cp[m0], f0, a0);
-        } else {
-            a0 = __fma_rn(cp[m0 * 3], f0, a0);
-            a1 = __fma_rn(cp[m0 * 3 + 1], f0, a1);
-            a2 = __fma_rn(cp[m0 * 3 + 2], f0, a2);
-        }
-    }
-    a0 += b0;
-    a1 += b1;
-    a2 += b2;
-}
-
-__global__ void __launch_bounds__(K3_THREADS, 2)
-k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac, int cand_arena) {
-    extern __shared__ __align__(16) unsigned char k3_raw[];
-    K3Smem& S = *reinterpret_cast<K3Smem*>(k3_raw);
+// Register budget (round-1 sweep on B200, 1 024 worlds, ms per launch): 64 registers / 3 CTAs per SM with 8 monomials and
+// 4 candidate records in flight per thread 0.81; the same at 96 registers / 2 CTAs 0.98, at 48 / 4 CTAs 1.68 (spills);
+// 2 monomials + 2 records in flight at 64 / 3 CTAs 0.73, at 48 / 4 CTAs 0.66, at 40 / 5 CTAs 0.81.  The kernel lives
+// on resident warps, not on loads in flight per warp: anything that spills or costs a CTA per SM loses.
+__global__ void __launch_bounds__(K3_THREADS, K3_MINB)
+k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
+    const int tb = blockIdx.x, p = B.plist ? B.plist[blockIdx.y] : int(blockIdx.y);
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int m = B.m();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rows = NJ * TB * O;
-    const unsigned meta_bytes = r16(unsigned(rows) * 4u);
-    // row decode table, chunk-independent: {row of (l, tt, o) relative to the chunk's first collision row, tt*MAXJ + l}
-    int2* const s_rowdec = reinterpret_cast<int2*>(k3_raw + sizeof(K3Smem));
-    unsigned char* const s_meta0 = k3_raw + sizeof(K3Smem) + r16(unsigned(rows) * 8u);
-    double* const s_cand0 = reinterpret_cast<double*>(s_meta0 + 2 * meta_bytes);
-    const int cpp = T / TB;  // chunks per problem
-    const long long nchunks = (long long)B.nprob * cpp;
-    const int c_begin = int(nchunks * blockIdx.x / gridDim.x), c_end = int(nchunks * (blockIdx.x + 1) / gridDim.x);
-    const int nmine = c_end - c_begin;
-    if (nmine <= 0) return;
-    const int ntab = TB * (NF + NJ);
-    const int rec_per_chunk = int(B.hp_chunk_records());
-    // items of an iteration, handed to the warps by ticket, in this order: the row tiles of chunk j-1, then one item
-    // that places and issues TAB(j+1) and writes the torque rows of chunk j-1, then the slice items of chunk j
-    const int n_slice_items = (NF + NJ) * (TB / 4), n_row_tiles = (rows + 31) >> 5;
-#ifndef K3_ORDER
-#define K3_ORDER 0
-#endif
-#if K3_ORDER == 0   // slices of chunk j first (longest items), the issue / torque item in their middle, then the row tiles
-    const int I_ISSUE = n_slice_items / 2;
-#else               // row tiles first
-    const int I_ISSUE = n_row_tiles;
-#endif
-    const int ITEMS = n_row_tiles + 1 + n_slice_items;
+    __shared__ double2 kpd[NF][4];  // {k_j^d, d/dk_j k_j^d} for d = 0..3
+    __shared__ __align__(4) unsigned char s_cnt[K3_CNT_SMEM];  // candidate counts of this CTA's rows
+    __shared__ double s_lc[TB][MAXJ][3];
+    __shared__ double s_dlc[TB][MAXJ][NF][3];
+    __shared__ double s_stage[K3_WARPS][32 * NF];  // per-warp transpose buffer: Jacobian rows leave coalesced
+    __shared__ int s_in_domain;
+    __shared__ int s_next;  // next chunk of 32 collision rows
 
-    // ---- loads.  Thread 0 keeps the (problem ordinal, tb) of the chunk it describes next
-    auto describe = [&](int ord, int tb, int s) {  // thread 0: descriptor of chunk (ord, tb) into desc[s]; returns p
-        const int p = B.plist ? B.plist[ord] : ord;
-        K3Desc& D = S.desc[s];
-        D.p = p;
-        D.tb = tb;
-        D.g_off = (long long)p * m;
-        D.t0 = (long long)p * T + (long long)tb * TB;
-        return p;
-    };
-    auto issue_g1 = [&](int s) {  // thread 0, after describe(.., s)
-        const size_t t0 = size_t(S.desc[s].t0);
-        K3Stage& Q = S.st[s];
-        const unsigned b_nl = unsigned(TB * NJ) * 4u, b_nu = unsigned(TB * NF) * 4u, b_l = unsigned(TB * NJ) * 24u,
-                       b_u = unsigned(TB * NF) * 8u;
-        mbar_arrive_expect_tx(&S.bar_g1[s], b_nl + b_nu + 2 * b_l + 2 * b_u);
-        bulk_g2s(Q.nl, B.link_n + t0 * NJ, b_nl, &S.bar_g1[s]);
-        bulk_g2s(Q.nu, B.u_n + t0 * NF, b_nu, &S.bar_g1[s]);
-        bulk_g2s(Q.cen_l, B.link_c + t0 * NJ * 3, b_l, &S.bar_g1[s]);
-        bulk_g2s(Q.rad_l, B.link_r + t0 * NJ * 3, b_l, &S.bar_g1[s]);
-        bulk_g2s(Q.cen_u, B.u_c + t0 * NF, b_u, &S.bar_g1[s]);
-        bulk_g2s(Q.rad_u, B.u_r + t0 * NF, b_u, &S.bar_g1[s]);
-    };
-    auto issue_row = [&](int s, int total) {  // thread 0: row words + candidate records in use of chunk desc[s]
-        const size_t chunk = size_t(S.desc[s].p) * cpp + S.desc[s].tb;
-        int nrec = total < rec_per_chunk ? total : rec_per_chunk;
-        nrec = nrec < cand_arena ? nrec : cand_arena;
-        S.rw[s].staged = nrec;
-        const unsigned b_meta = unsigned(rows) * 4u;
-        mbar_arrive_expect_tx(&S.bar_row[s], b_meta + unsigned(nrec) * 32u);
-        if (b_meta) bulk_g2s(s_meta0 + size_t(s) * meta_bytes, B.hp_meta + chunk * rows, b_meta, &S.bar_row[s]);
-        if (nrec > 0)
-            bulk_g2s(s_cand0 + size_t(s) * cand_arena * 4, B.hp_cand + chunk * size_t(rec_per_chunk) * 4, unsigned(nrec) * 32u,
-                     &S.bar_row[s]);
-    };
-    // TAB of the chunk described in desc[s]: one warp, after its G1 has landed.  Tables task-major (q = task*TB + tt,
-    // tasks = 7 joints, then NJ links), two per lane, packed in the arena in that order
-    auto issue_tab = [&](int s) {
-        const size_t t0 = size_t(S.desc[s].t0);
-        K3Stage& Q = S.st[s];
-        unsigned kb[2], cb[2], bytes[2];
-        int nn[2];
-        const unsigned short* ksrc[2];
-        const double* csrc[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int q = lane + 32 * h;
-            kb[h] = cb[h] = 0;
-            nn[h] = 0;
-            ksrc[h] = nullptr;
-            csrc[h] = nullptr;
-            if (q < ntab) {
-                const int task = q / TB, tt = q % TB;
-                if (task < NF) {
-                    const int n = Q.nu[tt * NF + task];
-                    const size_t idx = (t0 + tt) * NF + task;
-                    nn[h] = n;
-                    kb[h] = r16(unsigned(n) * 2u);
-                    cb[h] = r16(unsigned(n) * 8u);
-                    ksrc[h] = B.u_key + idx * B.capU;
-                    csrc[h] = B.u_g + idx * B.capU;
-                } else {
-                    const int l = task - NF;
-                    const int n = Q.nl[tt * NJ + l];
-                    const size_t idx = (t0 + tt) * NJ + l;
-                    nn[h] = n;
-                    kb[h] = r16(unsigned(n) * 2u);
-                    cb[h] = r16(unsigned(n) * 24u);
-                    ksrc[h] = B.link_key + idx * B.capL;
-                    csrc[h] = B.link_g + idx * B.capL * 3;
-                }
-            }
-            bytes[h] = kb[h] + cb[h];
+    if (B.status[p] != 0) {
+        // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe rows:
+        // every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
+        double* gp0 = g ? g + size_t(p) * m : nullptr;
+        double* jp0 = jac ? jac + size_t(p) * m * NF : nullptr;
+        for (int i = tid; i < TB * NF; i += K3_THREADS) {
+            if (gp0) gp0[size_t(tb) * TB * NF + i] = 1e300;
+            if (jp0)
+                for (int v = 0; v < NF; v++) jp0[(size_t(tb) * TB * NF + i) * NF + v] = 0.0;
         }
-        unsigned inc0 = bytes[0], inc1 = bytes[1];  // exclusive prefix over the 64 slots
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned x0 = __shfl_up_sync(0xffffffffu, inc0, d), x1 = __shfl_up_sync(0xffffffffu, inc1, d);
-            if (lane >= d) {
-                inc0 += x0;
-                inc1 += x1;
-            }
+        for (int x = tid; x < NJ * TB * O; x += K3_THREADS) {
+            const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
+            const size_t r = size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o;
+            if (gp0) gp0[r] = 1e300;
+            if (jp0)
+                for (int v = 0; v < NF; v++) jp0[r * NF + v] = 0.0;
         }
-        const unsigned tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-        const unsigned off[2] = {inc0 - bytes[0], tot0 + inc1 - bytes[1]};
-        unsigned tx = 0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int q = lane + 32 * h;
-            if (q < ntab) {
-                const bool staged = off[h] + bytes[h] <= unsigned(K3_TABLE_ARENA);
-                Q.tinfo[q] = make_int2(staged ? int(off[h]) : -1, nn[h]);
-                if (staged) tx += bytes[h];
-                else bytes[h] = 0;
-            } else {
-                bytes[h] = 0;
-            }
+        if (tb == 0 && tid < 4 * NF) {
+            const size_t r = size_t(NF) * T + size_t(NJ) * T * O + tid;
+            if (gp0) gp0[r] = 0.0;
+            if (jp0)
+                for (int v = 0; v < NF; v++) jp0[r * NF + v] = 0.0;
         }
-        mbar_arrive_expect_tx(&S.bar_tab[s], tx);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            if (bytes[h]) {  // keys first, then the coefficients (both 16-byte aligned)
-                bulk_g2s(Q.arena + off[h], ksrc[h], kb[h], &S.bar_tab[s]);
-                bulk_g2s(Q.arena + off[h] + kb[h], csrc[h], cb[h], &S.bar_tab[s]);
-            }
-        }
-    };
-    auto total_of = [&](int p, int tb) { return O > 0 ? *B.hp_total_of(p, tb) : 0; };
-
-    int d_ord = c_begin / cpp, d_tb = c_begin % cpp;  // (thread 0) chunk to describe next
-    // (thread 0) loads in flight for the NEXT chunk: its build status and its candidate records in use.  They are issued at
-    // the top of an iteration and consumed at its end, so thread 0 never waits for them
-    int r_status = 0, r_total = 0, tot_cur = 0;
-    if (tid == 0) {
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&S.bar_g1[s], 1);
-            mbar_init(&S.bar_tab[s], 32);
-            mbar_init(&S.bar_row[s], 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        S.ticket = 0;
-        for (int i = 0; i < 4; i++) S.zero_d[i] = 0.0;
-        for (int i = 0; i < 8; i++) S.zero_k[i] = 0;
-        const int p0 = describe(d_ord, d_tb, 0);
-        S.desc[0].failed = B.status[p0] != 0;
-        tot_cur = total_of(p0, d_tb);
-        if (++d_tb == cpp) {
-            d_tb = 0;
-            d_ord++;
-        }
+        return;
     }
-    for (int x = tid; x < rows; x += K3_THREADS) {
-        const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
-        s_rowdec[x] = make_int2((l * T + tt) * O + o, tt * MAXJ + l);
+    if (tid == 32) {
+        bool in = true;
+        for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
+        s_in_domain = in ? 1 : 0;
+        s_next = 0;
     }
+    if (tid < NF) {
+        const double k = kin[size_t(p) * NF + tid];
+        kpd[tid][0] = make_double2(1.0, 0.0);
+        kpd[tid][1] = make_double2(k, 1.0);
+        kpd[tid][2] = make_double2(k * k, 2.0 * k);
+        kpd[tid][3] = make_double2(k * k * k, 3.0 * (k * k));
+    }
+    const int per_pair = NJ * TB * O;
+    const size_t chunk = size_t(p) * (T / TB) + tb;
+    const bool cnt_in_smem = per_pair <= K3_CNT_SMEM;
     __syncthreads();
-    if (tid == 0) issue_g1(0);
-    if (warp == 0) {
-        mbar_wait(&S.bar_g1[0], 0);
-        issue_tab(0);
+
+    double* gp = g ? g + size_t(p) * m : nullptr;
+    double* jp = jac ? jac + size_t(p) * m * NF : nullptr;
+
+    // ---- phase 1: slices
+    if (tid < K3_LINK_THREADS) {
+        // candidate counts of the CTA's rows: fetched now, parked in shared memory after the slice (the loads are in
+        // flight meanwhile), visible to everybody through barriers 1 and 2.  per_pair is a multiple of 8: whole words
+        constexpr int CW = (K3_CNT_SMEM / 4 + K3_LINK_THREADS - 1) / K3_LINK_THREADS;
+        unsigned cw[CW];
+        if (cnt_in_smem) {
+            const unsigned* src = reinterpret_cast<const unsigned*>(B.hp_cnt + chunk * per_pair);
+#pragma unroll
+            for (int q = 0; q < CW; q++) cw[q] = (tid + q * K3_LINK_THREADS < per_pair / 4) ? __ldg(src + tid + q * K3_LINK_THREADS) : 0u;
+        }
+        if (tid < TB * NJ * 3) {
+            const int e = tid % 3;
+            const int l = (tid / 3) % NJ;
+            const int tt = tid / (3 * NJ);
+            const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+            double value = B.link_c[idx * 3 + e];
+            double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
+            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 1, 3, kpd, value, grad);
+            // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
+            const double r = B.link_r[idx * 3 + e];
+            const double c = ((value - r) + (value + r)) * 0.5;
+            s_lc[tt][l][e] = c;
+            if (p == 0) B.link_sliced[((size_t(tb) * TB + tt) * NJ + l) * 3 + e] = c;  // armtd_NLP::link_sliced_center
+#pragma unroll
+            for (int v = 0; v < NF; v++) s_dlc[tt][l][v][e] = grad[v];
+        }
+        if (cnt_in_smem) {
+#pragma unroll
+            for (int q = 0; q < CW; q++)
+                if (tid + q * K3_LINK_THREADS < per_pair / 4) reinterpret_cast<unsigned*>(s_cnt)[tid + q * K3_LINK_THREADS] = cw[q];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(K3_LINK_THREADS) : "memory");    // link slices complete
+        asm volatile("bar.arrive 2, %0;" ::"n"(K3_THREADS) : "memory");       // tell the torque warps, do not wait
+    } else {
+        const int tq = tid - K3_TORQUE_T0;
+        const int i = tq / K3_TORQUE_LANES, part = tq % K3_TORQUE_LANES;  // table tt*NF + j, lane of the table
+        double value = 0.0;
+        double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
+        const bool on = i < TB * NF;
+        const size_t idx = (size_t(p) * T + tb * TB) * NF + (on ? i : 0);
+        if (on) {
+            // lane `part` takes the monomials part, part + 2, ...; the two partial sums are added below
+            // (the oracle adds the monomials one after the other: a difference of a few ulp)
+            const int n = B.u_n[idx];
+            const int mine = (n - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
+            slice_component(B.u_key + idx * B.capU + part, B.u_g + idx * B.capU + part, mine > 0 ? mine : 0,
+                            K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
+        }
+        value += __shfl_xor_sync(0xffffffffu, value, 1);
+#pragma unroll
+        for (int v = 0; v < NF; v++) grad[v] += __shfl_xor_sync(0xffffffffu, grad[v], 1);
+        double* st = &s_stage[K3_TORQUE_T0 / 32][0];  // the stages of the four torque warps are contiguous
+        if (on && part == 0) {
+            value = B.u_c[idx] + value;
+            const double r = B.u_r[idx];
+            if (gp) gp[tb * TB * NF + i] = ((value - r) + (value + r)) * 0.5;
+#pragma unroll
+            for (int v = 0; v < NF; v++) st[i * NF + v] = grad[v];
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(K3_THREADS - K3_LINK_THREADS) : "memory");
+        if (jp) {  // rows tb*TB*NF + i, i < 56: 392 contiguous doubles
+            double* dst = jp + size_t(tb) * TB * NF * NF;
+            for (int q = tq; q < TB * NF * NF; q += K3_THREADS - K3_TORQUE_T0) dst[q] = st[q];
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(K3_THREADS - K3_LINK_THREADS) : "memory");  // stage free again
+        asm volatile("bar.sync 2, %0;" ::"n"(K3_THREADS) : "memory");                      // link slices are complete
     }
-    int cur_p = -1;
-    const int grp = lane >> 3, v = lane & 7;
-    const double* const pa = &S.pwA[0][v <= 4 ? v : 0];
-    const double* const pb = &S.pwB[0][v >= 5 ? v - 4 : 0];
-    int ticket = -1;  // warp-uniform: the item this warp holds
-    K3Desc DR = {0, 0, 0, 0, 0, 0};  // descriptor of the chunk on the row side (chunk j-1)
-    bool in_dom = true, in_dom_r = true;  // |k| inside the box the candidate lists were built for (slice / row side)
 
-    // iteration j: slices of chunk c_begin + j (j < nmine) and rows of chunk c_begin + j - 1 (j >= 1)
-    for (int j = 0; j <= nmine; j++) {
-        const bool has_slices = j < nmine, has_rows = j >= 1;
-        const int s = j & 1;
-        if (tid == 0) {
-            if (has_slices) issue_row(s, tot_cur);
-            if (j + 1 < nmine) {
-                const int pn = describe(d_ord, d_tb, s ^ 1);
-                issue_g1(s ^ 1);
-                r_status = B.status[pn];
-                r_total = total_of(pn, d_tb);
-                if (++d_tb == cpp) {
-                    d_tb = 0;
-                    d_ord++;
-                }
-            }
-        }
-        // desc[s] was written by thread 0 one iteration ago; the row side (chunk j-1) works from the register copy DR taken
-        // then, because thread 0 is rewriting desc[s ^ 1] for chunk j+1 right now
-        const K3Desc DS = S.desc[s];
-        if (has_slices && DS.p != cur_p) {
-            // power-product tables of this problem's k.  The rows of chunk j-1 (previous problem) do not read them.
-            cur_p = DS.p;
-            if (tid < NF) S.k[tid] = kin[size_t(DS.p) * NF + tid];
-            __syncthreads();
-            if (tid < 256) {  // table A: entry tid, variables k0..k3
-                double f[4], d[4];
+    // ---- phase 2: collision rows.  x = (l*TB + tt)*O + o; 32 consecutive rows per warp pass
+    const double* cand = B.hp_cand + chunk * B.hp_chunk();
+    const unsigned char* cnt = B.hp_cnt + chunk * per_pair;
+    const size_t cstride2 = size_t(per_pair) * 2;  // candidate stride in double2 units
+    const bool in_domain = s_in_domain != 0;
+    double* stage = &s_stage[warp][0];
+    for (;;) {
+        int x0 = 0;
+        if (lane == 0) x0 = atomicAdd(&s_next, 1) * 32;
+        x0 = __shfl_sync(0xffffffffu, x0, 0);
+        if (x0 >= per_pair) break;
+        const int x = x0 + lane;
+        bool active = x < per_pair;
+        double max_elt = -100000000;
+        double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
+        int l = 0, tt = 0, o = 0;
+        if (active) {
+            o = x % O;
+            const int ltt = x / O;
+            tt = ltt % TB;
+            l = ltt / TB;
+            const double c0 = s_lc[tt][l][0], c1 = s_lc[tt][l][1], c2 = s_lc[tt][l][2];
+            const int n = cnt_in_smem ? s_cnt[x] : cnt[x];
+            if (n != HP_OVERFLOW && in_domain) {
+                const double2* row = reinterpret_cast<const double2*>(cand) + size_t(x) * 2;
+                // K3_CQ candidate records in flight per thread (the scan itself stays in order)
+                for (int q0 = 0; q0 < n; q0 += K3_CQ) {
+                    double2 u[K3_CQ], w[K3_CQ];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const double k = S.k[q];
-                    const int dg = (tid >> (2 * q)) & 3;
-                    f[q] = dg == 0 ? 1.0 : (dg == 1 ? k : (dg == 2 ? k * k : k * k * k));
-                    d[q] = dg == 0 ? 0.0 : (dg == 1 ? 1.0 : (dg == 2 ? 2.0 * k : 3.0 * (k * k)));
-                }
-                const double p01 = f[0] * f[1], p23 = f[2] * f[3];
-                double* row = S.pwA[tid];
-                row[0] = p01 * p23;
-                row[1] = d[0] * f[1] * p23;
-                row[2] = f[0] * d[1] * p23;
-                row[3] = p01 * (d[2] * f[3]);
-                row[4] = p01 * (f[2] * d[3]);
-            }
-            if (tid < 64) {  // table B: entry tid, variables k4..k6
-                double f[3], d[3];
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    const double k = S.k[4 + q];
-                    const int dg = (tid >> (2 * q)) & 3;
-                    f[q] = dg == 0 ? 1.0 : (dg == 1 ? k : (dg == 2 ? k * k : k * k * k));
-                    d[q] = dg == 0 ? 0.0 : (dg == 1 ? 1.0 : (dg == 2 ? 2.0 * k : 3.0 * (k * k)));
-                }
-                double* row = S.pwB[tid];
-                row[0] = f[0] * f[1] * f[2];
-                row[1] = d[0] * f[1] * f[2];
-                row[2] = f[0] * d[1] * f[2];
-                row[3] = f[0] * f[1] * d[2];
-            }
-            __syncthreads();
-            bool in = true;
-#pragma unroll
-            for (int q = 0; q < NF; q++) in = in && (fabs(S.k[q]) <= K_DOMAIN);
-            in_dom = in;
-        }
-
-        // slice side: chunk j, stage s.  row side: chunk j - 1, stage s ^ 1
-        K3Stage& Q = S.st[s];
-        K3Rows& RS = S.rw[s];
-        const K3Rows& RR = S.rw[s ^ 1];
-        bool tab_ready = false, row_ready = false;
-
-        for (;;) {
-            if (ticket < 0) {
-                int t = 0;
-                if (lane == 0) t = atomicAdd(&S.ticket, 1);
-                ticket = __shfl_sync(0xffffffffu, t, 0);
-            }
-            if (ticket >= (j + 1) * ITEMS) break;  // an item of the next iteration: keep it, go to the barrier
-            const int item = ticket - j * ITEMS;
-            ticket = -1;
-#if K3_ORDER == 0
-            const bool is_slice = item != I_ISSUE && item <= n_slice_items;
-            const int task = item < I_ISSUE ? item : item - 1;
-            const int tile = item - (n_slice_items + 1);
-#else
-            const bool is_slice = item > I_ISSUE;
-            const int task = item - (I_ISSUE + 1);
-            const int tile = item;
-#endif
-            if (is_slice) {
-                // ---- slice item: the tables of four consecutive intervals of one joint / link of chunk j
-                if (!has_slices) continue;
-                if (!tab_ready) {
-                    mbar_wait(&S.bar_tab[s], unsigned(j >> 1) & 1u);
-                    tab_ready = true;
-                }
-                if (DS.failed) continue;
-                const int sub = task % (TB / 4), which = task / (TB / 4);  // longest tables (torques) first
-                const int tt = sub * 4 + grp;
-                const bool torque = which < NF;
-                const int l = which - NF;
-                const int2 ti = Q.tinfo[which * TB + tt];
-                const int n = ti.y, to = ti.x;
-                int nmax = n;
-                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
-                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
-                const bool all_staged = __all_sync(0xffffffffu, to >= 0);
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-                if (all_staged) {
-                    const unsigned short* kp = n > 0 ? reinterpret_cast<const unsigned short*>(Q.arena + to) : S.zero_k;
-                    const double* cp = n > 0 ? reinterpret_cast<const double*>(Q.arena + to + r16(unsigned(n) * 2u)) : S.zero_d;
-                    if (torque) slice_group<true>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
-                    else slice_group<false>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
-                } else {  // a table that did not fit the arena: same walk over global memory
-                    const size_t idx = torque ? (size_t(DS.t0) + tt) * NF + which : (size_t(DS.t0) + tt) * NJ + l;
-                    const unsigned short* kp = torque ? B.u_key + idx * B.capU : B.link_key + idx * B.capL;
-                    const double* cp = torque ? B.u_g + idx * B.capU : B.link_g + idx * B.capL * 3;
-                    if (n == 0) {
-                        kp = S.zero_k;
-                        cp = S.zero_d;
-                    }
-                    if (torque) slice_group<true>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
-                    else slice_group<false>(kp, cp, n, nmax, pa, pb, a0, a1, a2);
-                }
-                if (torque) {
-                    const int i = tt * NF + which;
-                    if (v == 0) {
-                        const double value = Q.cen_u[i] + a0;
-                        const double r = Q.rad_u[i];
-                        RS.tg[i] = ((value - r) + (value + r)) * 0.5;  // centre of Interval(c - r, c + r) (KPR/NLPclass.cu:306)
-                    } else {
-                        RS.tj[i * NF + (v - 1)] = a0;
-                    }
-                } else {
-                    const int i = tt * NJ + l;
-                    if (v == 0) {
-                        const double acc[3] = {a0, a1, a2};
-#pragma unroll
-                        for (int e = 0; e < 3; e++) {
-                            const double value = Q.cen_l[i * 3 + e] + acc[e];
-                            const double r = Q.rad_l[i * 3 + e];
-                            RS.lc[tt * MAXJ + l][e] = ((value - r) + (value + r)) * 0.5;  // getCenter(slice()) (KPR/NLPclass.cu:313)
+                    for (int i = 0; i < K3_CQ; i++) {
+                        if (q0 + i < n) {
+                            u[i] = __ldg(row + (q0 + i) * cstride2);
+                            w[i] = __ldg(row + (q0 + i) * cstride2 + 1);
                         }
-                    } else {
-                        double* d3 = RS.dlc[tt * MAXJ + l][v - 1];
-                        d3[0] = a0;
-                        d3[1] = a1;
-                        d3[2] = a2;
                     }
-                }
-            } else if (item == I_ISSUE) {
-                // ---- place and fetch the tables of chunk j + 1 (its G1 was issued at the top of this iteration) ...
-                if (j + 1 < nmine) {
-                    mbar_wait(&S.bar_g1[s ^ 1], unsigned((j + 1) >> 1) & 1u);
-                    issue_tab(s ^ 1);
-                }
-                // ---- ... and the torque rows of chunk j - 1: contiguous runs of g and of the Jacobian; Bezier rows once per problem
-                if (!has_rows) continue;
-                double* gpr = g ? g + DR.g_off : nullptr;
-                double* jpr = jac ? jac + DR.g_off * NF : nullptr;
-                const int tbr = DR.tb;
-                if (DR.failed) {
-                    // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.
-                    // Fail-safe rows: every torque and collision row violated, zero Jacobian.
-                    for (int i = lane; i < TB * NF; i += 32) {
-                        if (gpr) gpr[size_t(tbr) * TB * NF + i] = 1e300;
-                        if (jpr)
-                            for (int q = 0; q < NF; q++) jpr[(size_t(tbr) * TB * NF + i) * NF + q] = 0.0;
-                    }
-                    for (int x = lane; x < rows; x += 32) {
-                        const size_t r = size_t(NF) * T + size_t(tbr) * TB * O + s_rowdec[x].x;
-                        if (gpr) gpr[r] = 1e300;
-                        if (jpr)
-                            for (int q = 0; q < NF; q++) jpr[r * NF + q] = 0.0;
-                    }
-                } else {
-                    if (gpr)
-                        for (int i = lane; i < TB * NF; i += 32) gpr[size_t(tbr) * TB * NF + i] = RR.tg[i];
-                    if (jpr)
-                        for (int i = lane; i < TB * NF * NF; i += 32) jpr[size_t(tbr) * TB * NF * NF + i] = RR.tj[i];
-                    if (DR.p == 0 && B.link_sliced)
-                        for (int i = lane; i < TB * NJ * 3; i += 32)
-                            B.link_sliced[(size_t(tbr) * TB * NJ) * 3 + i] = RR.lc[(i / (NJ * 3)) * MAXJ + (i / 3) % NJ][i % 3];
-                }
-                if (tbr == 0 && lane < NF) {  // Bezier joint-limit rows (KPR/Trajectory.cu:256-540)
-                    const int i = lane;
-                    const double D = c_robot.duration;
-                    const double q0 = B.q0[size_t(DR.p) * NF + i];
-                    const double a = B.qd0[size_t(DR.p) * NF + i] * D;
-                    const double b = B.qdd0[size_t(DR.p) * NF + i] * D * D;
-                    const double kn = kin[size_t(DR.p) * NF + i];
-                    const int off = NF * T + NJ * T * O;
-                    for (int vel = 0; vel < 2; vel++) {
-                        double mn, mx, dmn, dmx;
-                        bez_extrema(vel == 1, q0, a, b, c_robot.k_range[i], D, kn, &mn, &mx, &dmn, &dmx);
-                        const int r0 = off + vel * 2 * NF + i;
-                        if (gpr) {
-                            gpr[r0] = DR.failed ? 0.0 : mn;
-                            gpr[r0 + NF] = DR.failed ? 0.0 : mx;
-                        }
-                        if (jpr) {
-                            for (int q = 0; q < NF; q++) {
-                                jpr[size_t(r0) * NF + q] = (q == i && !DR.failed) ? dmn : 0.0;
-                                jpr[size_t(r0 + NF) * NF + q] = (q == i && !DR.failed) ? dmx : 0.0;
+#pragma unroll
+                    for (int i = 0; i < K3_CQ; i++) {
+                        if (q0 + i < n) {
+                            const double v = (u[i].x * c0 + u[i].y * c1 + w[i].x * c2) - w[i].y;
+                            if (v > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
+                                max_elt = v;
+                                A0 = -u[i].x; A1 = -u[i].y; A2 = -w[i].x;
                             }
                         }
                     }
                 }
             } else {
-                // ---- row tile of chunk j - 1: rows x = (l*TB + tt)*O + o, one lane each
-                if (!has_rows || DR.failed || O == 0 || !in_dom_r) continue;
-                if (!row_ready) {
-                    mbar_wait(&S.bar_row[s ^ 1], unsigned((j - 1) >> 1) & 1u);
-                    row_ready = true;
-                }
-                const int x = tile * 32 + lane;
-                if (x >= rows) continue;
-                const unsigned meta = reinterpret_cast<const unsigned*>(s_meta0 + size_t(s ^ 1) * meta_bytes)[x];
-                const int n = int(meta & 255u), off = int(meta >> 8);
-                if (n == HP_OVERFLOW) continue;  // no stored list: k_constraints_slow writes this row
-                const int2 dec = s_rowdec[x];
-                const double* lc = RR.lc[dec.y];
-                const double c0 = lc[0], c1 = lc[1], c2 = lc[2];
-                const bool in_smem = off + n <= RR.staged;
-                const double2* rec_s = reinterpret_cast<const double2*>(s_cand0 + size_t(s ^ 1) * cand_arena * 4 + size_t(off) * 4);
-                const double2* rec_g = reinterpret_cast<const double2*>(
-                    B.hp_cand + ((size_t(DR.p) * cpp + DR.tb) * size_t(rec_per_chunk) + off) * 4);
-                double max_elt = -100000000;
-                int best = -1;
-                if (in_smem) {
-                    for (int q = 0; q < n; q++) {
-                        const double2 u = rec_s[2 * q], w = rec_s[2 * q + 1];
-                        const double val = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
-                        if (val > max_elt) {  // strict '>' in scan order: KPR/CollisionChecking.cu:264-276
-                            max_elt = val;
-                            best = q;
-                        }
-                    }
-                } else {  // the part of a chunk's records that did not fit the arena
-                    for (int q = 0; q < n; q++) {
-                        const double2 u = __ldg(rec_g + 2 * q), w = __ldg(rec_g + 2 * q + 1);
-                        const double val = (u.x * c0 + u.y * c1 + w.x * c2) - w.y;
-                        if (val > max_elt) {
-                            max_elt = val;
-                            best = q;
-                        }
-                    }
-                }
-                const size_t row_i = size_t(NF) * T + size_t(DR.tb) * TB * O + dec.x;
-                if (g) g[DR.g_off + row_i] = -max_elt;
-                if (jac) {
-                    double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
-                    if (best >= 0) {
-                        const double2 u = in_smem ? rec_s[2 * best] : __ldg(rec_g + 2 * best);
-                        A0 = -u.x;
-                        A1 = -u.y;
-                        A2 = -(in_smem ? rec_s[2 * best + 1].x : __ldg(rec_g + 2 * best + 1).x);
-                    }
-                    const double2* dk = reinterpret_cast<const double2*>(&RR.dlc[dec.y][0][0]);
-                    double* out = jac + (DR.g_off + row_i) * NF;
+                active = false;  // no stored list, or k outside the box the lists were built for: k_constraints_slow
+            }
+        }
+        const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
+        if (gp && active) gp[row_i] = -max_elt;
+        if (jp) {
+            if (active) {
 #pragma unroll
-                    for (int q = 0; q < NF; q++) {
-                        const double2 xy = dk[2 * q];
-                        const double z = dk[2 * q + 1].x;
-                        // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A.  Fused like
-                        // the reference's own kernel (nvcc contracts max_A_elt.dot(dk)); 56 contiguous bytes per lane
-                        out[q] = __fma_rn(A0, xy.x, __fma_rn(A1, xy.y, A2 * z));
-                    }
+                for (int v = 0; v < NF; v++) {
+                    const double* dk = s_dlc[tt][l][v];
+                    // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
+                    stage[lane * NF + v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < NF; q++) {
+                const int e = q * 32 + lane;
+                const int r = e / NF;
+                const long long rr = __shfl_sync(0xffffffffu, row_i, r);
+                if (rr >= 0) jp[rr * NF + (e - r * NF)] = stage[e];
+            }
+            __syncwarp();
+        }
+    }
+
+    // Bezier joint-limit rows (KPR/Trajectory.cu:256-540), once per problem
+    if (tb == 0 && tid < NF) {
+        const int i = tid;
+        const double D = c_robot.duration;
+        const double q0 = B.q0[size_t(p) * NF + i];
+        const double a = B.qd0[size_t(p) * NF + i] * D;
+        const double b = B.qdd0[size_t(p) * NF + i] * D * D;
+        const double kn = kin[size_t(p) * NF + i];
+        const int off = NF * T + NJ * T * O;
+        for (int vel = 0; vel < 2; vel++) {
+            double mn, mx, dmn, dmx;
+            bez_extrema(vel == 1, q0, a, b, c_robot.k_range[i], D, kn, &mn, &mx, &dmn, &dmx);
+            const int r0 = off + vel * 2 * NF + i;
+            if (gp) {
+                gp[r0] = mn;
+                gp[r0 + NF] = mx;
+            }
+            if (jp) {
+                for (int j = 0; j < NF; j++) {
+                    jp[size_t(r0) * NF + j] = (j == i) ? dmn : 0.0;
+                    jp[size_t(r0 + NF) * NF + j] = (j == i) ? dmx : 0.0;
                 }
             }
         }
-        if (j == nmine && has_rows && !row_ready) mbar_wait(&S.bar_row[s ^ 1], unsigned((j - 1) >> 1) & 1u);  // nothing in flight at exit
-        DR = DS;
-        in_dom_r = in_dom;
-        if (tid == 0 && j + 1 < nmine) {  // the loads issued at the top have landed long ago
-            S.desc[s ^ 1].failed = r_status != 0;
-            tot_cur = r_total;
-        }
-        __syncthreads();
     }
 }
 
@@ -954,13 +645,29 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 // the generators (KPR/CollisionChecking.cu:169-299).
 __global__ void __launch_bounds__(128)
 k_constraints_slow(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
-    const int p = B.plist ? B.plist[blockIdx.x] : int(blockIdx.x);
     const int NJ = B.NJ, O = B.O, T = B.T;
-    if (O == 0 || B.status[p] != 0) return;
+    __shared__ int s_list[128], s_n;
     __shared__ double2 kpd[NF][4];  // {k_j^d, d/dk_j k_j^d} for d = 0..3
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    {   // one thread per problem: does it have anything for this kernel?  (usually none does: 128 problems per CTA)
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < B.nprob && O > 0) {
+            const int p = B.plist ? B.plist[i] : i;
+            if (B.status[p] == 0) {
+                bool in = true;
+                for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
+                if (!in || B.hp_slow[p] != 0) s_list[atomicAdd(&s_n, 1)] = p;
+            }
+        }
+    }
+    __syncthreads();
+    const int nlist = s_n;
+    for (int li = 0; li < nlist; li++) {
+    const int p = s_list[li];
     bool in = true;
     for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
-    if (in && *B.hp_slow_of(p) == 0) return;
+    __syncthreads();
     if (threadIdx.x < NF) {
         const double k = kin[size_t(p) * NF + threadIdx.x];
         kpd[threadIdx.x][0] = make_double2(1.0, 0.0);
@@ -976,7 +683,7 @@ k_constraints_slow(Batch B, const double* __restrict__ kin, double* __restrict__
     for (int r = threadIdx.x; r < per_chunk * (T / TB); r += blockDim.x) {
         const int tb = r / per_chunk, x = r - tb * per_chunk;
         const size_t chunk = size_t(p) * (T / TB) + tb;
-        if (in && (B.hp_meta[chunk * per_chunk + x] & 255u) != HP_OVERFLOW) continue;
+        if (in && B.hp_cnt[chunk * per_chunk + x] != HP_OVERFLOW) continue;
         const int o = x % O, ltt = x / O, tt = ltt % TB, l = ltt / TB;
         const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
         double c[3], dk[NF][3];
@@ -1011,6 +718,7 @@ k_constraints_slow(Batch B, const double* __restrict__ kin, double* __restrict__
         if (gp) gp[row] = -r_max;
         if (jp)
             for (int v = 0; v < NF; v++) jp[row * NF + v] = A0 * dk[v][0] + A1 * dk[v][1] + A2 * dk[v][2];
+    }
     }
 }
 
@@ -1058,52 +766,20 @@ k_verdict(Batch B, const double* __restrict__ g, int* __restrict__ feasible, int
 // host launchers (called from capi.cu)
 cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
     if (B.O == 0 || B.nprob == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(B.hp_total, 0, size_t(B.nprob) * (B.T / TB + 1) * sizeof(int), st);
+    cudaError_t e = cudaMemsetAsync(B.hp_slow, 0, size_t(B.nprob) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     const int rows = B.NJ * B.T * B.O;
     dim3 grid((rows + HP_ROWS - 1) / HP_ROWS, B.nprob);
     k_hyperplanes<<<grid, HP_THREADS, 0, st>>>(B);
     return cudaGetLastError();
 }
-
-// Shared memory of one persistent k_constraints CTA: the fixed part plus, per chunk parity, the row words and a
-// candidate arena sized for the chunk's expected 2.5 records per row — bounded so that two CTAs stay resident per SM
-// (else one).
-constexpr int K3_SMEM_MAX = 220 * 1024;
-inline void k3_smem_plan(const Batch& B, int* smem_bytes, int* cand_arena, int* ctas_per_sm) {
-    const int rows = B.chunk_rows();
-    const int fixed = int(sizeof(K3Smem)) + int((size_t(rows) * 8 + 15) & ~size_t(15)) + 2 * int((size_t(rows) * 4 + 15) & ~size_t(15));
-    int want = rows * 5 / 2 + 32;
-    if (want > int(B.hp_chunk_records())) want = int(B.hp_chunk_records());
-    const int budgets[2] = {112 * 1024, K3_SMEM_MAX};
-    int rec = 0, b = 0;
-    for (b = 0; b < 2; b++) {
-        rec = (budgets[b] - fixed) / 64;  // two stages of 32-byte records
-        if (rec >= want || b == 1) break;
-    }
-    if (rec < 0) rec = 0;
-    if (rec > want) rec = want;
-    *cand_arena = rec;
-    *smem_bytes = fixed + 2 * rec * 32;
-    *ctas_per_sm = (b == 0) ? 2 : 1;
-}
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
-    int smem = 0, arena = 0, per_sm = 1;
-    k3_smem_plan(B, &smem, &arena, &per_sm);
-    if (smem > K3_SMEM_MAX) return cudaErrorInvalidValue;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    const long long nchunks = (long long)B.nprob * (B.T / TB);
-    const int grid = int(nchunks < (long long)sms * per_sm ? nchunks : (long long)sms * per_sm);
-    k_constraints<<<grid, K3_THREADS, smem, st>>>(B, d_k, d_g, d_jac, arena);
+    dim3 grid(B.T / TB, B.nprob);
+    k_constraints<<<grid, K3_THREADS, 0, st>>>(B, d_k, d_g, d_jac);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || B.O == 0) return e;
-    k_constraints_slow<<<B.nprob, 128, 0, st>>>(B, d_k, d_g, d_jac);
+    k_constraints_slow<<<(B.nprob + 127) / 128, 128, 0, st>>>(B, d_k, d_g, d_jac);
     return cudaGetLastError();
 }
 cudaError_t launch_verdict(const Batch& B, const double* d_g, int* d_feasible, int* d_first, cudaStream_t st) {

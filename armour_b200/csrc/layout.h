@@ -11,11 +11,10 @@
 namespace armour {
 
 #ifndef ARMOUR_TB
-#define ARMOUR_TB 4
+#define ARMOUR_TB 8
 #endif
 constexpr int TB = ARMOUR_TB;      // time intervals per CTA ("chunk") in the constraint kernels
 constexpr int HP_CAP = 32;         // most candidate half-spaces stored for one (link, interval, obstacle) row
-constexpr int HP_RESERVE = 12;     // candidate records reserved per row, on average over the rows of a chunk
 constexpr int HP_OVERFLOW = 255;   // row count marker: no stored list, evaluate the row from the generators
 constexpr double K_DOMAIN = 1.0 + 1e-6;        // the candidate lists are exact for |k_j| <= K_DOMAIN
 constexpr double HP_RHO_SCALE = 1.0 + 3e-5;    // >= K_DOMAIN^21 (largest total degree of a link monomial)
@@ -45,15 +44,12 @@ struct Batch {
     double* torque_radius;    // [p][j*T + t]
     double* link_gens;        // [p][t][NJ][18]     column-major 3x6
     double* link_r;           // [p][t][NJ][3]      diag of the radius block of link_gens (all an evaluation needs)
-    // collision half-space candidates, packed per chunk c = p*(T/TB) + t/TB (rows x = (l*TB + t%TB)*O + o):
-    //   hp_cand [c][hp_chunk_records()][4]  records (s*Cx, s*Cy, s*Cz, b) of 32 B; the list of a row is contiguous and
-    //                                       in the reference's scan order; rows are placed in arrival order
-    //   hp_meta [c][rows]                   (first record << 8) | count, count = HP_OVERFLOW: no list
-    //   hp_total[p][T/TB + 1]               [tb]: records in use in chunk (p, tb) (what an evaluation streams: one bulk
-    //                                       copy); [T/TB]: rows of the problem without a list (k_constraints_slow)
+    // collision half-space candidates: records [p][t/TB][candidate][l][t%TB][o][4] = (s*Cx, s*Cy, s*Cz, b): candidate-
+    // major inside a chunk, so that the q-th records of 32 consecutive rows are one contiguous KB; the number of candidates
+    // per row [p][t/TB][l][t%TB][o] (HP_OVERFLOW: no list); and per problem the number of rows without a list
     double* hp_cand;
-    unsigned* hp_meta;
-    int* hp_total;
+    unsigned char* hp_cnt;
+    int* hp_slow;
     // outputs of the last evaluation
     double* link_sliced;      // [t][NJ][3] of problem 0 (armtd_NLP::link_sliced_center)
     int* status;              // [p] 0, or the capacity failure of the build: evaluations then return fail-safe rows
@@ -61,10 +57,7 @@ struct Batch {
     // CTA row y works on problem plist[y]; nullptr = identity
     const int* plist;
 
-    __host__ __device__ int chunk_rows() const { return NJ * TB * O; }
-    __host__ __device__ int* hp_total_of(int p, int tb) const { return hp_total + size_t(p) * (T / TB + 1) + tb; }
-    __host__ __device__ int* hp_slow_of(int p) const { return hp_total + size_t(p) * (T / TB + 1) + T / TB; }
-    __host__ __device__ size_t hp_chunk_records() const { return size_t(HP_RESERVE) * NJ * TB * O; }
+    __host__ __device__ size_t hp_chunk() const { return size_t(HP_CAP) * 4 * NJ * TB * O; }
     __host__ __device__ int m() const { return NF * T + NJ * T * O + 4 * NF; }
 };
 
