@@ -55,6 +55,17 @@ K1_DI Itv iv_fmod(const Itv& x, const Itv& y) {
     const double n = floor(__ddiv_rd(x.lo, yb));
     return iv_sub(x, iv_muld(n, y));
 }
+// cos(x) rounded outward.  The device cos() is accurate to 2 ulp, not correctly rounded (the reference evaluates glibc's
+// cos, < 1 ulp, under Boost's rounded_transc_std): three ulp outward make the bound both sound and a superset of the
+// reference's; what it adds to a remainder radius is ~1e-18.
+K1_DI double cos_dn(double x) {
+    const double c = cos(x);
+    return fmax(-1.0, __dsub_rd(c, __dadd_ru(__dmul_ru(fabs(c), 7e-16), 1e-300)));
+}
+K1_DI double cos_up(double x) {
+    const double c = cos(x);
+    return fmin(1.0, __dadd_ru(c, __dadd_ru(__dmul_ru(fabs(c), 7e-16), 1e-300)));
+}
 K1_DI Itv iv_cos(Itv x) {
     const Itv pi2 = iv(PI_LO * 2, PI_HI * 2);
     const Itv pi = iv(PI_LO, PI_HI);
@@ -70,9 +81,9 @@ K1_DI Itv iv_cos(Itv x) {
         const double l = tmp.lo, u = tmp.hi;
         Itv r;
         if (u <= PI_LO)
-            r = iv(cos(u), cos(l));
+            r = iv(cos_dn(u), cos_up(l));
         else if (u <= pi2.lo)
-            r = iv(-1.0, cos(fmin(__dsub_rd(pi2.lo, u), l)));
+            r = iv(-1.0, cos_up(fmin(__dsub_rd(pi2.lo, u), l)));
         else
             r = iv(-1.0, 1.0);
         return negate ? iv_neg(r) : r;

@@ -32,14 +32,17 @@ def test_config3_gripper_40_obstacles_uncertain_payload(built):
     _check(eng, ref, [np.zeros(7), K_TEST])
 
 
-@pytest.mark.parametrize("thr", [5e-4, 2e-4, 5e-5])
+@pytest.mark.parametrize("thr", [5e-4, 2e-4, 5e-5, 5e-6])
 def test_config4_100_obstacles_lower_threshold(built, thr):
+    """BASELINE config 4: 100 obstacles, SIMPLIFY_THRESHOLD down to 5e-6, where intermediates reach 4 403
+    monomials and a cross product 113 121 terms on this problem (oracle statistics) — beyond the 16-bit term lists,
+    so the accumulator-table path of the cross product is exercised too."""
     from armour_b200 import ReachSetEngine, worlds
     from oracle.pyoracle import OracleProblem
     q0, qd0, qdd0, _, obs = worlds.random_problems(1, 100, seed=4)
     ref = OracleProblem(simplify_threshold=thr, max_obstacles=100).build(q0[0], qd0[0], qdd0[0], obs[0])
     eng = ReachSetEngine(max_problems=1, max_obstacles=100, simplify_threshold=thr, cap_link=128, cap_torque=256,
-                         cap_work=4096)
+                         cap_work=8192 if thr < 5e-5 else 4096)
     eng.build(q0[0], qd0[0], qdd0[0], obs[0])
     assert eng.m == 7 * 128 + 7 * 128 * 100 + 28
     _check(eng, ref, [K_TEST, -K_TEST])

@@ -146,3 +146,29 @@ def test_candidate_lists_are_exact_over_the_whole_box(built):
             g, jac = eng.eval(k)
             assert np.max(np.abs(g[0] - ref.eval_g(k))) <= TOL
             assert np.max(np.abs(jac[0] - ref.eval_jac_g(k))) <= TOL
+
+
+ALL_WORLDS = sorted(glob.glob(os.path.join(WORLDS, "scene_*.csv")))
+
+
+@pytest.mark.parametrize("path", ALL_WORLDS, ids=[os.path.basename(p)[:-4] for p in ALL_WORLDS])
+def test_every_saved_world_on_the_k_schedule(built, path):
+    """every saved world copied into the repository (the 13 ten-obstacle worlds plus two others, 6
+    to 11 obstacles) x the k schedule (k = 0, the PZ_tests point, Halton points, a corner): the WHOLE product path
+    (K1 build + K3a + K3) against the oracle — g, Jacobian, bounds containment, verdict with its first violated row."""
+    from armour_b200 import ReachSetEngine, worlds
+    from oracle.pyoracle import OracleProblem
+    q0, qd0, qdd0, q_des, obs = worlds.config1_problem(path)
+    ref = OracleProblem().build(q0, qd0, qdd0, obs)
+    eng = ReachSetEngine(max_problems=1, max_obstacles=obs.shape[0])
+    eng.build(q0, qd0, qdd0, obs)
+    assert eng.m == ref.m
+    ks = np.vstack([np.zeros(7), K_TEST, worlds.halton_k(3, skip=5), [1, -1, 1, 1, -1, 1, -1]])
+    for k in ks:
+        g, jac = eng.eval(k)
+        g_ref, j_ref = ref.eval_g(k), ref.eval_jac_g(k)
+        assert np.max(np.abs(g[0] - g_ref)) <= 1e-9 and np.max(np.abs(jac[0] - j_ref)) <= 1e-9
+        assert eng.finalize_solution(g[0]) == ref.verdict(g_ref)
+    tr, tr_ref = eng.torque_radius()[0], ref.torque_radius()
+    assert np.all(tr >= tr_ref) and np.max((tr - tr_ref) / tr_ref) <= 1e-10
+    eng.close()

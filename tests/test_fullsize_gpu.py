@@ -103,3 +103,26 @@ def test_problems_do_not_see_each_other(batch):
         one.import_reachsets(0, 1, tables, q0[p], qd0[p], qdd0[p], obs[p])
         g1, j1 = one.eval(k[p])
         assert np.array_equal(g1[0], g[p]) and np.array_equal(j1[0], jac[p])
+
+
+def test_sampled_worlds_of_the_bench_batch_match_the_oracle(batch):
+    """Eight worlds of THE batch bench.py times (seed 20261017), spread over it, against the CPU oracle: g, Jacobian and
+    verdict of the batched build + batched evaluation at two k per world."""
+    from armour_b200 import worlds
+    from oracle.pyoracle import OracleProblem
+    eng, (q0, qd0, qdd0, q_des, obs) = batch
+    ks = worlds.halton_k(2 * N, skip=7).reshape(2, N, 7)
+    ks[0] *= 0.0
+    sample = [0, 1, 127, 300, 511, 640, 900, 1023]
+    for it in range(2):
+        g, jac = eng.eval(ks[it])
+        for p in sample:
+            ref = OracleProblem().build(q0[p], qd0[p], qdd0[p], obs[p])
+            g_ref, j_ref = ref.eval_g(ks[it, p]), ref.eval_jac_g(ks[it, p])
+            assert np.max(np.abs(g[p] - g_ref)) <= 1e-9, (it, p)
+            assert np.max(np.abs(jac[p] - j_ref)) <= 1e-9, (it, p)
+            # the verdict of problem p alone (armour_verdict works on problem 0 of a context: use the bounds)
+            gl, gu = ref.bounds()
+            ok_ref, first_ref = ref.verdict(g_ref)
+            ok_gpu, first_gpu = ref.verdict(g[p])
+            assert (ok_ref, first_ref) == (ok_gpu, first_gpu)
