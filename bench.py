@@ -13,8 +13,17 @@ BASELINE.json targets (< 1 ms for one Kinova planning iteration's build + eval).
             kernel, g and dense Jacobian -> pinned host), copies inside the timed region
   roofline: k_constraints, the only kernel of the timed region; algorithmic bytes per launch = B_eval of
             SURVEY.md 8d from the stored monomial counts of THIS batch
-  cpu_baseline / --impl reference: the CPU oracle (oracle/, a C++ restatement of the reference: the reference
-            itself needs Eigen/Boost/Ipopt and cannot be compiled here) on the box's host cores.
+  cpu_baseline / --impl reference: the REFERENCE ITSELF when oracle/_ref/libarmour_ref_cuda.so travelled to the box
+            (the reference's own PZsparse / Trajectory / Dynamics / CollisionChecking / NLPclass sources compiled by
+            nvcc with its flags against stand-in Eigen / Boost / Ipopt headers: OpenMP host slices on all cores + its
+            7 collision-kernel launches and blocking copies per call, exactly what armtd_NLP::eval_g / eval_jac_g do;
+            kind "reference"), else the CPU oracle (C++ restatement, kind "port").  One world at a time, like the
+            reference; a bounded sample of worlds of the same generator.
+  Extra objects of the line (the driver reads them, the headline stays M2): "m1" (builds), "config1_host_abi" (one
+  planning iteration through host pointers, eval_g and eval_jac_g called separately like Ipopt does), "solver_e2e"
+  (armour_batch_solve, host in/out, beside the CPU planner), "config3" / "config4" (BASELINE configs 3 and 4),
+  "sweep" (BASELINE config 5: 65,536-world sweep split over the ranks, strong scaling, per-world verdicts gathered
+  over NCCL).
 
 Multi-GPU: problems are independent -> every rank owns its own 1,024 worlds, no collective on the data
 path ("weak" scaling); NCCL only reduces the timing (max over ranks) and gathers the verdict counts.
@@ -55,7 +64,25 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-m1", action="store_true")
+    ap.add_argument("--sweep-worlds", type=int, default=65536, help="BASELINE config 5: total worlds of the sweep (0: skip)")
+    ap.add_argument("--sweep-seconds", type=float, default=45.0, help="wall-clock box of the sweep per rank")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 1 / 3 / 4 objects")
     return ap.parse_args()
+
+
+_WORLDS = None
+
+
+def load_worlds():
+    """armour_b200/worlds.py (pure numpy input generators) loaded by path: importing the armour_b200 PACKAGE would map
+    libarmour_b200.so, which the reference arm must never do."""
+    global _WORLDS
+    if _WORLDS is None:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("armour_worlds", os.path.join(ROOT, "armour_b200", "worlds.py"))
+        _WORLDS = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_WORLDS)
+    return _WORLDS
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -145,7 +172,7 @@ def oracle_run(nthreads, nobs, iters, steps, warmup, seed, seconds=None):
     problem.  With `seconds` set, runs steps until the budget is spent (at least one)."""
     from concurrent.futures import ThreadPoolExecutor
 
-    from armour_b200 import worlds  # input generator only (pure numpy); no device work
+    worlds = load_worlds()
     from oracle.pyoracle import OracleProblem, lib
     lib()
     q0, qd0, qdd0, _, obs = worlds.random_problems(nthreads, nobs, seed=seed)
@@ -180,56 +207,294 @@ def oracle_run(nthreads, nobs, iters, steps, warmup, seed, seconds=None):
     return build_s, times
 
 
-def reference_build_timing(nobs, seed):
-    """Reach-set build of ONE world by the REFERENCE's own sources (oracle/_ref: KPR PZsparse / Trajectory / Dynamics
-    compiled against stand-in Eigen / Boost headers, OpenMP over the 128 intervals like the reference).  None if the
-    library did not travel to this box."""
+def reference_available():
+    """The reference's own planner path (oracle/_ref/libarmour_ref_cuda.so) needs the prebuilt library and a GPU."""
     try:
-        from oracle import pyref
-        if not os.path.exists(pyref.LIB_PATH):
-            return None
-        from armour_b200 import worlds
-        q0, qd0, qdd0, _, _ = worlds.random_problems(2, max(nobs, 1), seed=seed)
-        cores = os.cpu_count() or 1
-        best = None
-        for p in range(2):
-            t0 = time.perf_counter()
-            pyref.ReferenceProblem(q0[p], qd0[p], qdd0[p], nthreads=cores)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        return {"build_s_per_world": best, "threads": cores, "worlds_per_s": 1.0 / best,
-                "kind": "reference sources (KPR/PZsparse.cu, Trajectory.cu, Dynamics.cu) + stand-in Eigen/Boost headers, "
-                        "OpenMP over intervals; sections II.A-II.C of main() without the CUDA hyper-plane stage"}
-    except Exception as exc:  # the baseline must never take the bench down
-        return {"error": repr(exc)}
+        from oracle import pyrefcuda
+        return pyrefcuda.available()
+    except Exception:
+        return False
+
+
+def reference_run(nworlds, nobs, iters, steps, warmup, seed, seconds=None):
+    """The REFERENCE ITSELF: `nworlds` worlds, one after the other like kinova_planner_realtime (one process, one world):
+    build (OpenMP over the 128 intervals on all cores, then its hyper-plane kernels), then per step `iters` x (eval_g,
+    eval_jac_g) per world through armtd_NLP.  Returns (build seconds per world, per-step seconds)."""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # before libgomp of the reference library starts (it is loaded lazily)
+    worlds = load_worlds()
+    from oracle import pyrefcuda
+    q0, qd0, qdd0, q_des, obs = worlds.random_problems(nworlds, nobs, seed=seed)
+    ks = worlds.halton_k(iters * max(1, nworlds)).reshape(iters, -1, NF)
+    probs, build_s = [], []
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    for i in range(nworlds):
+        t0 = time.perf_counter()
+        probs.append(pyrefcuda.ReferencePlanner(q0[i], qd0[i], qdd0[i], q_des[i], obs[i], nthreads=cores))
+        build_s.append(time.perf_counter() - t0)
+    os.close(devnull)
+    times, n = [], 0
+    tstart = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        for i in range(nworlds):
+            for it in range(iters):
+                probs[i].eval_g(ks[it, i])
+                probs[i].eval_jac_g(ks[it, i])
+        dt = time.perf_counter() - t0
+        n += 1
+        if n > warmup:
+            times.append(dt)
+        if seconds is None:
+            if len(times) >= steps:
+                break
+        elif len(times) >= 1 and time.perf_counter() - tstart > seconds:
+            break
+    return build_s, times
+
+
+def cpu_leg(nobs, iters, steps, warmup, seconds=None):
+    """The CPU side of the comparison on this box: the reference itself when it travelled, else the port.  Returns the
+    cpu_baseline object (value in M2 units/s) and, for the line, ms per step."""
+    cores = os.cpu_count() or 1
+    if reference_available():
+        nworlds = 4
+        build_s, times = reference_run(nworlds, nobs, iters, steps, warmup, 20261017, seconds)
+        value = nworlds * iters * len(times) / sum(times)
+        obj = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": f"{nworlds} worlds of the same generator (seed 20261017), one after the other like the reference "
+                         f"planner, x {iters} k-iterates x {len(times)} steps ({sum(times):.1f} s); the reference's own "
+                         f"sources (KPR PZsparse / Trajectory / Dynamics / CollisionChecking / NLPclass .cu, nvcc -O2 "
+                         f"-Xcompiler -fopenmp) against stand-in Eigen / Boost.Interval / Ipopt headers: OpenMP slices on "
+                         f"{cores} threads + its own collision kernels on the GPU",
+               "build_s_per_world": float(np.median(build_s)), "builds_per_s": 1.0 / float(np.median(build_s)),
+               "sample_worlds": nworlds}
+    else:
+        build_s, times = oracle_run(cores, nobs, iters, steps, warmup, seed=20261017, seconds=seconds)
+        value = cores * iters * len(times) / sum(times)
+        obj = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} worlds of the same generator (seed 20261017), one per host thread, x {iters} "
+                         f"k-iterates x {len(times)} steps ({sum(times):.1f} s); oracle = C++ restatement of the reference "
+                         f"(oracle/_ref/libarmour_ref_cuda.so absent or no GPU)",
+               "build_s_per_world_1thread": build_s, "builds_per_s_all_cores": cores / build_s, "sample_worlds": cores}
+    return obj, 1e3 * sum(times) / len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    build_s, times = oracle_run(cores, args.nobs, args.iters, args.steps, args.warmup, seed=20261017)
-    total = sum(times)
-    units = cores * args.iters * len(times)
-    value = units / total
-    sample = (f"{cores} worlds (one per host thread, config-2 generator seed 20261017) x {args.iters} k-iterates per "
-              f"step; oracle = C++ restatement of the reference (g++ -O2, no Eigen/Boost/Ipopt in the image)")
+    obj, ms_per_step = cpu_leg(args.nobs, args.iters, args.steps, args.warmup)
+    value = obj["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Kinova Gen3 batched random worlds x {args.nobs} obstacles, one eval_g + eval_jac_g "
-                               f"per world per k-iterate, {args.iters} k-iterates per step (CPU sample: {cores} worlds)",
-                   "time_intervals": T, "obstacles": args.nobs, "k_iterates_per_step": args.iters},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                               f"per world per k-iterate, {args.iters} k-iterates per step",
+                   "time_intervals": T, "obstacles": args.nobs, "k_iterates_per_step": args.iters,
+                   "cpu_sample_worlds": obj["sample_worlds"],
+                   "note": "per-world throughput of the same generator; the GPU arm runs 1,024 worlds per GPU, the CPU arm "
+                           "a bounded sample of them (the reference handles one world per process)"},
+        "cpu_baseline": obj,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "m1": {"build_s_per_world_1thread": build_s, "builds_per_s_all_cores": cores / build_s,
-               "reference_build": reference_build_timing(args.nobs, 20261017)},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def config1_host_abi(device):
+    """BASELINE config 1 through the reference-facing calls: armour_reachsets_build + 20 x (armour_eval_g,
+    armour_eval_jac_g) with HOST pointers on saved world 016_006, wall clock (Python ctypes call overhead included,
+    ~10 us per call).  Beside it the same problem on the CPU: the reference itself when it travelled (OpenMP over the
+    intervals on all cores, its own threading: KPR/armour_main.cu:99,117, KPR/NLPclass.cu:304,376), and the port."""
+    from armour_b200 import ReachSetEngine
+    worlds = load_worlds()
+    q0, qd0, qdd0, q_des, obs = worlds.config1_problem(os.path.join(ROOT, "tests", "golden", "worlds", "scene_016_006.csv"))
+    ks = np.vstack([np.zeros(NF), worlds.halton_k(19)])
+    eng = ReachSetEngine(max_problems=1, max_obstacles=obs.shape[0], device=device)
+    rc = eng.lib.armour_ctx_reserve(eng._h, 1, obs.shape[0])
+    assert rc == 0
+    build, pair, total = [], [], []
+    for rep in range(15):
+        t0 = time.perf_counter()
+        eng.build(q0, qd0, qdd0, obs)
+        t1 = time.perf_counter()
+        for k in ks:
+            eng.eval_g(k)
+            eng.eval_jac_g(k)
+        t2 = time.perf_counter()
+        if rep >= 3:
+            build.append(1e3 * (t1 - t0))
+            pair.append(1e3 * (t2 - t1) / len(ks))
+            total.append(1e3 * (t1 - t0) + 1e3 * (t2 - t1) / len(ks))
+    eng.close()
+    out = {"world": "scene_016_006.csv", "obstacles": int(obs.shape[0]), "iterates": len(ks),
+           "build_ms": float(np.median(build)), "eval_g_plus_eval_jac_g_ms": float(np.median(pair)),
+           "one_iteration_ms": float(np.median(total)), "target_ms": 1.0,
+           "replan_ms_build_plus_20_iterates": float(np.median(build) + len(ks) * np.median(pair)),
+           "timing": "wall clock around the host-pointer C-ABI calls (H2D of inputs / k, kernels, D2H of g / dense J, "
+                     "synchronisation inside each call)"}
+    cores = os.cpu_count() or 1
+    from oracle.pyoracle import OracleProblem
+    orc, ob, op = OracleProblem(), [], []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        orc.build(q0, qd0, qdd0, obs, nthreads=cores)
+        t1 = time.perf_counter()
+        for k in ks[:5]:
+            orc.eval_g(k)
+            orc.eval_jac_g(k)
+        ob.append(1e3 * (t1 - t0))
+        op.append(1e3 * (time.perf_counter() - t1) / 5)
+    out["cpu_port"] = {"build_ms": float(min(ob)), "eval_g_plus_eval_jac_g_ms": float(min(op)), "threads": cores,
+                       "one_iteration_ms": float(min(ob) + min(op))}
+    if reference_available():
+        from oracle import pyrefcuda
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        rb, rp = [], []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            ref = pyrefcuda.ReferencePlanner(q0, qd0, qdd0, q_des, obs, nthreads=cores)
+            t1 = time.perf_counter()
+            for k in ks[:5]:
+                ref.eval_g(k)
+                ref.eval_jac_g(k)
+            rb.append(1e3 * (t1 - t0))
+            rp.append(1e3 * (time.perf_counter() - t1) / 5)
+            del ref
+        out["cpu_reference"] = {"build_ms": float(min(rb)), "eval_g_plus_eval_jac_g_ms": float(min(rp)), "threads": cores,
+                                "one_iteration_ms": float(min(rb) + min(rp)),
+                                "note": "build includes the Obstacles constructor's cudaMalloc calls, as one process per "
+                                        "replan does in the reference"}
+        out["speedup_vs_reference_one_iteration"] = out["cpu_reference"]["one_iteration_ms"] / out["one_iteration_ms"]
+    return out
+
+
+def config_m1(device, stream, dev, nworlds, nobs, seed, label, **engine_kw):
+    """M1 (build + one eval_g + eval_jac_g) of a small batch of another BASELINE configuration on the device, and the
+    share of the evaluation spent on the torque rows (the same launch with the obstacles taken away)."""
+    import torch
+
+    from armour_b200 import ReachSetEngine
+    worlds = load_worlds()
+    q0, qd0, qdd0, _, obs = worlds.random_problems(nworlds, nobs, seed=seed)
+    eng = ReachSetEngine(max_problems=nworlds, max_obstacles=nobs, device=device, **engine_kw)
+    eng.set_stream(stream.cuda_stream)
+    t = [torch.tensor(x, dtype=torch.float64, device=dev) for x in (q0, qd0, qdd0, obs)]
+    m = eng.lib.armour_num_constraints(eng._h, nobs)
+    d_k = torch.tensor(worlds.halton_k(nworlds), dtype=torch.float64, device=dev)
+    d_g = torch.empty((nworlds, m), dtype=torch.float64, device=dev)
+    d_j = torch.empty((nworlds, m, NF), dtype=torch.float64, device=dev)
+    tb, te = [], []
+    for rep in range(3):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        eng.build_device(nworlds, nobs, *(x.data_ptr() for x in t))
+        e1.record(stream)
+        eng.eval_device(nworlds, d_k.data_ptr(), d_g.data_ptr(), d_j.data_ptr())
+        e2.record(stream)
+        torch.cuda.synchronize()
+        tb.append(e0.elapsed_time(e1))
+        te.append(e1.elapsed_time(e2))
+    failures = int((eng.build_status() != 0).sum())
+    ln, un = eng.monomial_counts()
+    # torque-row share: the same reach sets evaluated without obstacles (torque + Bezier rows only)
+    eng.build_device(nworlds, 0, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), 0)
+    m0 = eng.lib.armour_num_constraints(eng._h, 0)
+    tt = []
+    for rep in range(3):
+        e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        e1.record(stream)
+        eng.eval_device(nworlds, d_k.data_ptr(), d_g.data_ptr(), d_j.data_ptr())
+        e2.record(stream)
+        torch.cuda.synchronize()
+        tt.append(e1.elapsed_time(e2))
+    eng.close()
+    b, e, t0 = min(tb), min(te), min(tt)
+    return {"label": label, "worlds": nworlds, "obstacles": nobs, "constraints_per_world": int(m),
+            "capacity_failures": failures, "build_ms_per_world": b / nworlds, "eval_ms_per_batch": e,
+            "m1_problems_per_s": nworlds / ((b + e) * 1e-3), "m2_evals_per_s": nworlds / (e * 1e-3),
+            "torque_rows_share_of_eval": t0 / e, "torque_only_eval_ms": t0, "rows_without_obstacles": int(m0),
+            "link_monomials_max": int(ln.max()), "torque_monomials_max": int(un.max())}
+
+
+def run_sweep(args, eng, stream, dev, rank, world, dist):
+    """BASELINE config 5: `--sweep-worlds` random worlds (config-2 generator), split over the ranks with
+    sharding.shard_bounds (STRONG scaling: the total is fixed), each rank walking its shard in batches through the
+    bench's context: build (M1) + 4 eval_g + eval_jac_g pairs per world (M2) + device verdict of the last iterate.
+    Device-timed (CUDA events, max over ranks); the next batch's inputs are generated on the host while the GPU works.
+    Per-world verdicts come back in global world order through sharding.gather_results (NCCL all-gather)."""
+    import zlib
+
+    import torch
+
+    from armour_b200 import sharding
+    worlds = load_worlds()
+    nobs, iters, total = args.nobs, 4, args.sweep_worlds
+    batch = min(args.nprob, 2048)
+    lo, hi = sharding.shard_bounds(total, world, rank)
+    m = eng.lib.armour_num_constraints(eng._h, nobs)
+    d_g = torch.empty((batch, m), dtype=torch.float64, device=dev)
+    d_j = torch.empty((batch, m, NF), dtype=torch.float64, device=dev)
+    ks = torch.tensor(worlds.halton_k(iters * batch).reshape(iters, batch, NF), dtype=torch.float64, device=dev)
+    verdict = torch.full((hi - lo,), -2, dtype=torch.int32, device=dev)  # -2: not run (time box), else feasible 0 / 1
+    first = torch.full((hi - lo,), -2, dtype=torch.int32, device=dev)
+    d_ok = torch.empty(batch, dtype=torch.int32, device=dev)
+    d_first = torch.empty(batch, dtype=torch.int32, device=dev)
+    t_build = t_eval = 0.0
+    done = failed = 0
+    wall0 = time.perf_counter()
+
+    def gen(b0):
+        n = min(batch, hi - b0)
+        q0, qd0, qdd0, _, obs = worlds.random_problems(n, nobs, seed=1000003 + b0)
+        return n, [torch.tensor(x, dtype=torch.float64).pin_memory() for x in (q0, qd0, qdd0, obs)]
+
+    nxt = gen(lo) if hi > lo else None
+    b0 = lo
+    while nxt is not None:
+        n, host = nxt
+        t = [x.to(dev, non_blocking=True) for x in host]
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        eng.build_device(n, nobs, *(x.data_ptr() for x in t))
+        e1.record(stream)
+        for it in range(iters):
+            eng.eval_device(n, ks[it].data_ptr(), d_g.data_ptr(), d_j.data_ptr())
+        eng.verdict_device(n, d_g.data_ptr(), d_ok.data_ptr(), d_first.data_ptr())
+        e2.record(stream)
+        verdict[b0 - lo:b0 - lo + n].copy_(d_ok[:n], non_blocking=True)
+        first[b0 - lo:b0 - lo + n].copy_(d_first[:n], non_blocking=True)
+        b0 += n
+        # host work for the next batch overlaps the device work of this one
+        nxt = gen(b0) if (b0 < hi and time.perf_counter() - wall0 < args.sweep_seconds) else None
+        torch.cuda.synchronize()
+        t_build += e0.elapsed_time(e1)
+        t_eval += e1.elapsed_time(e2)
+        failed += int((eng.build_status()[:n] != 0).sum())
+        done += n
+    wall = time.perf_counter() - wall0
+    tb, te = sharding.reduce_max(t_build, dev), sharding.reduce_max(t_eval, dev)
+    counts = torch.tensor([done, failed], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(counts)
+    res = sharding.gather_results({"feasible": verdict, "first_violation": first}, total)
+    if rank != 0:
+        return None
+    v = res["feasible"].cpu().numpy()
+    f = res["first_violation"].cpu().numpy()
+    n_done = int(counts[0].item())
+    return {"config": "BASELINE config 5: replanning sweep, strong scaling", "worlds": total, "worlds_done": n_done,
+            "complete": n_done == total, "n_gpus": world, "batch_per_context": batch, "obstacles": nobs,
+            "k_iterates_per_world": iters, "build_s": tb * 1e-3, "eval_s": te * 1e-3, "wall_s_rank0": wall,
+            "m1_problems_per_s": n_done / ((tb + te / iters) * 1e-3), "m2_evals_per_s": n_done * iters / (te * 1e-3),
+            "feasible_last_iterate": int((v == 1).sum()), "capacity_failures": int(counts[1].item()),
+            "verdicts_gathered": int((v >= 0).sum()), "verdict_crc32": int(zlib.crc32(v.tobytes()) ^ zlib.crc32(f.tobytes())),
+            "gather": "sharding.gather_results: all_gather of the per-world (feasible, first violated row) over NCCL",
+            "timing": "CUDA events on the launching stream per batch, summed per rank, max over ranks"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -309,10 +574,13 @@ def run_b200(args):
         barrier()
         t1 = time.time()
         ms = e0.elapsed_time(e1)
-        if dist is not None:
+        timed.per_rank = [ms]
+        if dist is not None:  # max over ranks is the time of the job; the per-rank list tells variance from contention
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            timed.per_rank = [float(x.item()) for x in parts]
+            ms = max(timed.per_rank)
         return ms, t0, t1
 
     clocks = ClockSampler(local).start()
@@ -320,6 +588,7 @@ def run_b200(args):
     la = eng.kernel_launches
     ms_dev, c0, c1 = timed(step_device, args.steps, args.warmup)
     launches_timed = timed.launches
+    per_rank_dev = list(timed.per_rank)
     clock_windows = [(c0, c1)]
     value = world * nprob * iters * args.steps / (ms_dev * 1e-3)
 
@@ -346,7 +615,8 @@ def run_b200(args):
     roofline = {"kernel": "k_constraints", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kernel_ms,
-                "bytes_per_unit": alg_bytes / nprob}
+                "launch_ms_per_rank": [x / n_launch for x in per_rank_dev], "bytes_per_unit": alg_bytes / nprob,
+                "note": "launch = k_constraints + k_constraints_slow (the latter returns at once here: ~1 % of the time)"}
     prof = os.path.join(ROOT, "profiles", "k_constraints_traffic.json")
     if os.path.exists(prof):  # dram bytes per launch from the committed ncu --set full capture of this command
         with open(prof) as f:
@@ -371,7 +641,9 @@ def run_b200(args):
         clock_windows.append((h0, h1))
         e2e = {"value": world * nprob * iters * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": iters * nprob * NF * 8, "d2h_bytes_per_step": iters * nprob * m * (1 + NF) * 8,
-               "ms_per_step": ms_e2e / args.steps}
+               "ms_per_step": ms_e2e / args.steps, "ms_per_step_per_rank": [x / args.steps for x in timed.per_rank],
+               "note": "dense m x 7 Jacobian of every world crosses PCIe every iterate (the reference's TNLP contract): "
+                       "PCIe-bound; see solver_e2e for the path that keeps g and J on the device"}
         # the host path must deliver what the device path computed
         eng.eval_device(nprob, d_k[iters - 1].data_ptr(), d_g.data_ptr(), d_j.data_ptr())
         torch.cuda.synchronize()
@@ -427,34 +699,90 @@ def run_b200(args):
         # ~83-89 MFLOP per problem at the default threshold)
         m1["fp64_peak_tflops_measured"] = fp64
 
-    # ---- batched device solver: whole NLP loops on the device, only k_opt and verdicts come back --------
-    solver = None
-    if not args.no_m1 and rank == 0:
+    # ---- BASELINE config 1 where the reference measures it: ONE planning problem through HOST pointers, eval_g and
+    # eval_jac_g called separately like Ipopt does (KPR/NLPclass.cu:272-396), wall clock around the C-ABI calls
+    config1 = None
+    if rank == 0 and not args.no_configs:
+        try:
+            config1 = config1_host_abi(local)
+        except Exception as exc:
+            config1 = {"error": repr(exc)}
+
+    # ---- batched planning end to end: q_des in (host), k_opt / verdict out (host); g and J never leave the device
+    solver_e2e = None
+    if rank == 0 and not args.no_m1:
         try:
             eng.solve(q_des)  # warm-up: workspace allocation
-            t0s = time.perf_counter()
-            ksol, oksol, _, itsol = eng.solve(q_des)
-            dts = time.perf_counter() - t0s
-            solver = {"metric": "plans/s (armour_batch_solve: trust-region SQP per world on the device, host in/out)",
-                      "value": nprob / dts, "seconds": dts, "feasible": int(oksol.sum()),
-                      "iterations_mean": float(itsol.mean()), "iterations_max": int(itsol.max()),
-                      "constraint_evals_per_s": float((2 * itsol + 2).sum() / dts)}
+            reps = []
+            for _ in range(3):
+                t0s = time.perf_counter()
+                ksol, oksol, firstsol, itsol = eng.solve(q_des)
+                reps.append(time.perf_counter() - t0s)
+            dts = float(np.median(reps))
+            solver_e2e = {"metric": "plans/s (armour_batch_solve: whole NLP loop per world on the device; host q_des in, "
+                                    "k_opt + verdict + iterations out)", "value": nprob / dts, "unit": "plans/s",
+                          "seconds": dts, "worlds": nprob, "feasible": int(oksol.sum()),
+                          "iterations_mean": float(itsol.mean()), "iterations_max": int(itsol.max()),
+                          "h2d_bytes": nprob * NF * 8, "d2h_bytes": nprob * (NF * 8 + 12),
+                          "constraint_evals_per_s": float((2 * itsol + 2).sum() / dts)}
+            if world == 1 and not args.no_cpu_baseline:
+                # CPU arm: the same solver algorithm (armour_b200/host/local_solver.cpp) over the CPU oracle, one world per
+                # host thread, on the first worlds of the same batch; no wall-clock limit on either side
+                from concurrent.futures import ThreadPoolExecutor
+
+                from oracle.pyoracle import OracleProblem
+                cores = os.cpu_count() or 1
+                nw = min(2 * cores, nprob)
+                probs = [OracleProblem(max_obstacles=max(40, nobs)) for _ in range(nw)]
+                pool = ThreadPoolExecutor(cores)
+                list(pool.map(lambda i: probs[i].build(q0[i], qd0[i], qdd0[i], obs[i], nthreads=1), range(nw)))
+                t0c = time.perf_counter()
+                res = list(pool.map(lambda i: probs[i].solve(q_des[i]), range(nw)))
+                dtc = time.perf_counter() - t0c
+                pool.shutdown()
+                agree = sum(int(res[i][1] == bool(oksol[i])) for i in range(nw))
+                solver_e2e["cpu"] = {"value": nw / dtc, "unit": "plans/s", "cores": cores, "worlds": nw, "seconds": dtc,
+                                     "kind": "host local solver over the CPU oracle (reach sets already built)",
+                                     "verdicts_agreeing_with_device": agree,
+                                     "max_abs_k_opt_diff": float(max(np.max(np.abs(res[i][0] - ksol[i])) for i in range(nw)))}
+                solver_e2e["ratio_vs_cpu"] = solver_e2e["value"] / solver_e2e["cpu"]["value"]
         except Exception as exc:  # an extra, never allowed to take the bench line down
-            solver = {"error": repr(exc)}
+            solver_e2e = {"error": repr(exc)}
+
+    # ---- BASELINE configs 3 and 4 (rank 0; small batches, M1 = build + one evaluation, torque-row share of the eval)
+    config3 = config4 = None
+    if rank == 0 and not args.no_configs:
+        try:
+            config3 = config_m1(local, stream, dev, nworlds=128, nobs=40, seed=3, robot_model=1, mass_uncertainty=0.10,
+                                inertia_uncertainty=0.10, cap_link=64, cap_torque=128,
+                                label="config 3: gripper link (8 links), 40 obstacles, 10 % mass / inertia uncertainty")
+            config4 = [config_m1(local, stream, dev, nworlds=16, nobs=100, seed=4, simplify_threshold=thr, cap_link=128,
+                                 cap_torque=256, cap_work=cw, label=f"config 4: 100 obstacles, SIMPLIFY_THRESHOLD {thr:g}")
+                       for thr, cw in ((5e-5, 4096), (5e-6, 16384))]
+        except Exception as exc:
+            config3 = config3 or {"error": repr(exc)}
+            config4 = config4 or {"error": repr(exc)}
+
+    # ---- BASELINE config 5: the 65,536-world sweep, split over the ranks (strong scaling), per-world verdicts gathered
+    sweep = None
+    if args.sweep_worlds > 0:
+        try:
+            sweep = run_sweep(args, eng, stream, dev, rank, world, dist)
+        except Exception as exc:
+            sweep = {"error": repr(exc)}
 
     clocks.stop()
     clk = clocks.summary(clock_windows)
 
-    # ---- CPU baseline: the oracle on the host cores, bounded sample --------------------------------------
+    # ---- CPU baseline on this box's host cores, bounded sample: the reference itself when it travelled, else the port
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        build_s, times = oracle_run(cores, nobs, iters, 1, 0, seed=20261017, seconds=args.cpu_seconds)
-        cpu = {"value": cores * iters * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} worlds of the same generator (one per host thread) x {iters} k-iterates x "
-                         f"{len(times)} repetitions ({sum(times):.1f} s); oracle = C++ restatement of the reference",
-               "build_s_per_world_1thread": build_s, "builds_per_s_all_cores": cores / build_s,
-               "reference_build": reference_build_timing(nobs, 20261017)}
+        cpu, _ = cpu_leg(nobs, iters, 1, 0, seconds=args.cpu_seconds)
+        if cpu["kind"] == "reference":  # the port beside it, for the record (one world per host thread)
+            pb, pt = oracle_run(cores, nobs, iters, 1, 0, seed=20261017, seconds=min(6.0, args.cpu_seconds))
+            cpu["port"] = {"value": cores * iters * len(pt) / sum(pt), "unit": UNIT, "cores": cores,
+                           "build_s_per_world_1thread": pb, "builds_per_s_all_cores": cores / pb}
         if m1 is not None:
             # FP64 roofline of the build kernel: flops counted by the oracle on one problem of this batch
             from oracle.pyoracle import OracleProblem
@@ -476,8 +804,10 @@ def run_b200(args):
                                    f"eval_jac_g per world per k-iterate, {iters} k-iterates per step",
                        "time_intervals": T, "obstacles": nobs, "constraints_per_world": m,
                        "k_iterates_per_step": iters, "worlds_per_gpu": nprob, "parallelism": f"worlds sharded x{world}",
+                       "cpu_sample_worlds": (cpu or {}).get("sample_worlds"),
                        "l2": "outputs (g + dense Jacobian) and reach-set tables per launch exceed the 126 MB L2"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "m1": m1, "solver": solver,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "m1": m1, "config1_host_abi": config1,
+            "solver_e2e": solver_e2e, "config3": config3, "config4": config4, "sweep": sweep,
             "gpu_launches": int(launches_timed), "clocks": clk,
             "feasible_worlds_last_iterate": feasible_total, "build_launches": int(la - launches0),
         }

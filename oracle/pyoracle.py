@@ -50,6 +50,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p, dp]
         L.orc_get_hyperplanes.argtypes = [C.c_void_p, dp, dp, dp]
         L.orc_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        L.orc_solve.argtypes = [C.c_void_p, dp, C.c_int, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int)]
         ip = C.POINTER(C.c_int)
         up = C.POINTER(C.c_ulonglong)
         L.orc_export_reachsets.argtypes = [C.c_void_p, C.c_int, ip, dp, up, dp, C.c_int, ip, dp, up, dp, dp]
@@ -128,6 +130,15 @@ class OracleProblem:
         out = np.empty(NF)
         lib().orc_cost_grad(self._h, _dp(q_des), _dp(k), _dp(out))
         return out
+
+    def solve(self, q_des, max_iter=0, max_wall_time=0.0):
+        """Plan on the CPU: the product's host-side local solver (stand-in for Ipopt) driving this oracle through the
+        TNLP callbacks (oracle/cpu_planner.cpp).  Returns (k_opt, feasible, first violated row, iterations)."""
+        q_des = _f64(q_des)
+        k = np.empty(NF)
+        ok, first, it = C.c_int(0), C.c_int(-1), C.c_int(0)
+        lib().orc_solve(self._h, _dp(q_des), max_iter, max_wall_time, _dp(k), C.byref(ok), C.byref(first), C.byref(it))
+        return k, bool(ok.value), first.value, it.value
 
     def torque_radius(self):
         out = np.empty((NF, self.T))

@@ -35,3 +35,21 @@ def test_short_device_window_falls_back_to_all_timed_regions_and_keeps_reasons()
 def test_no_samples_is_reported_as_such():
     out = _bench().ClockSampler(0).summary([(0.0, 1.0)])
     assert out["samples"] == 0 and out["sm_mhz"] is None
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """bench.py --impl reference must time the CPU side only: it may load oracle/ libraries, never libarmour_b200.so
+    (round-1 verdict: the arm imported the armour_b200 package for its input generators and mapped the product)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, argparse; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0','--iters','1'];"
+        "import bench; bench.main();"
+        "maps=open('/proc/self/maps').read();"
+        "assert 'armour_b200' not in sys.modules, 'package imported';"
+        "assert 'libarmour_b200' not in maps, 'product library mapped';"
+        "assert 'liboracle' in maps or 'libarmour_ref' in maps; print('CLEAN')")
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "CLEAN" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

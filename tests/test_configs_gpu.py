@@ -41,9 +41,21 @@ def test_config4_100_obstacles_lower_threshold(built, thr):
     from oracle.pyoracle import OracleProblem
     q0, qd0, qdd0, _, obs = worlds.random_problems(1, 100, seed=4)
     ref = OracleProblem(simplify_threshold=thr, max_obstacles=100).build(q0[0], qd0[0], qdd0[0], obs[0])
-    eng = ReachSetEngine(max_problems=1, max_obstacles=100, simplify_threshold=thr, cap_link=128, cap_torque=256,
-                         cap_work=8192 if thr < 5e-5 else 4096)
-    eng.build(q0[0], qd0[0], qdd0[0], obs[0])
+    from armour_b200 import ArmourError
+    eng = None
+    for cap_work in ((16384, 32768) if thr < 5e-5 else (4096,)):
+        # at 5e-6 the F / N blocks kept for the backward pass hold ~4 000 monomials each: the work capacity that fits them
+        # is found here, and a capacity that does not must fail loudly (ARMOUR_ERR_CAPACITY), never truncate
+        eng = ReachSetEngine(max_problems=1, max_obstacles=100, simplify_threshold=thr, cap_link=128, cap_torque=256,
+                             cap_work=cap_work)
+        try:
+            eng.build(q0[0], qd0[0], qdd0[0], obs[0])
+            break
+        except ArmourError as exc:
+            assert exc.code == -4
+            eng.close()
+            eng = None
+    assert eng is not None, "no tested work capacity fits threshold %g" % thr
     assert eng.m == 7 * 128 + 7 * 128 * 100 + 28
     _check(eng, ref, [K_TEST, -K_TEST])
 
