@@ -94,6 +94,7 @@ struct armour_ctx {
     int built_nprob = 0;     // problems with valid reach sets
     size_t hp_capacity = 0;  // doubles allocated for B.hp_cand
     int hp_nprob = 0;        // problems the candidate buffers were sized for
+    int* d_unit_flag = nullptr;  // [max_problems * T] completion stamps of the reach-set units (latency path)
     size_t obs_capacity = 0;
     double* d_in = nullptr;  // [3][max_problems][NF] q0, qd0, qdd0
     double* d_obs = nullptr;
@@ -204,17 +205,18 @@ int ensure_obstacle_buffers(armour_ctx* ctx, int nprob, int nobs) {
 
 // Pick the kernel configuration by batch size: up to two waves of the latency configuration's CTAs are
 // faster there; beyond that the lock-step throughput configuration wins.
-int launch_build(armour_ctx* ctx, int* nl) {
-    const long long nunits = (long long)ctx->B.nprob * ctx->B.T;
+int launch_build(armour_ctx* ctx, const Batch& B, int* nl, bool* latency) {
+    const long long nunits = (long long)B.nprob * B.T;
     const bool thr = ctx->cfg.max_problems > 1 && nunits > 2LL * ctx->k1_lat.grid;
+    *latency = !thr;
     if (thr) {
         if (!ctx->k1_thr_ready) {
             CU(k1thr::k1_scratch_create(&ctx->k1_thr, ctx->cfg, ctx->rc, ctx->stream));
             ctx->k1_thr_ready = true;
         }
-        CU(k1thr::launch_reachsets(ctx->B, ctx->k1_thr, ctx->stream, nl));
+        CU(k1thr::launch_reachsets(B, ctx->k1_thr, ctx->stream, nl));
     } else {
-        CU(k1lat::launch_reachsets(ctx->B, ctx->k1_lat, ctx->stream, nl));
+        CU(k1lat::launch_reachsets(B, ctx->k1_lat, ctx->stream, nl, ctx->d_unit_flag));
     }
     return ARMOUR_OK;
 }
@@ -363,6 +365,7 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     ALLOC(B.link_r, P * T * NJ * 3);
     ALLOC(B.link_sliced, P * T * NJ * 3);
     ALLOC(B.status, P);
+    ALLOC(ctx->d_unit_flag, P * T);
     ALLOC(ctx->d_k, P * NF);
     ALLOC(ctx->d_verdict, 2 * P);
 #undef ALLOC
@@ -370,6 +373,7 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
     B.qd0 = ctx->d_in + P * NF;
     B.qdd0 = ctx->d_in + 2 * P * NF;
     if ((e = cudaMemsetAsync(B.status, 0, P * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = cudaMemsetAsync(ctx->d_unit_flag, 0, P * T * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
     // no table may ever be read with an uninitialised count (a failed build leaves its tables untouched)
     if ((e = cudaMemsetAsync(B.link_n, 0, P * T * NJ * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
     if ((e = cudaMemsetAsync(B.u_n, 0, P * T * NF * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
@@ -397,7 +401,7 @@ int armour_ctx_destroy(armour_ctx* ctx) {
     if (!ctx) return ARMOUR_OK;
     cudaSetDevice(ctx->cfg.device);
     Batch& B = ctx->B;
-    void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io,
+    void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io, ctx->d_unit_flag,
                     ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
                     B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.link_r, B.hp_cand, B.hp_cnt, B.hp_slow,
                     B.link_sliced, B.status};
@@ -456,18 +460,30 @@ int armour_batch_reachsets_build_device(armour_ctx* ctx, int nprob, const double
     rc = ensure_obstacle_buffers(ctx, nprob, nobs);
     if (rc) return rc;
     const size_t P = size_t(ctx->cfg.max_problems);
-    const size_t nb = size_t(nprob) * NF * sizeof(double);
-    CU(cudaMemcpyAsync(ctx->d_in, d_q0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_in + P * NF, d_qd0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_in + 2 * P * NF, d_qdd0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (nobs > 0)
-        CU(cudaMemcpyAsync(ctx->d_obs, d_obstacles, size_t(nprob) * nobs * 12 * sizeof(double),
-                           cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->B.epoch++;
     int nl = 0;
-    { int rc2 = launch_build(ctx, &nl); if (rc2) return rc2; }
+    bool latency = false;
+    if (nobs > 0) {
+        // the kernels read the caller's buffers; k_hyperplanes copies them into the context's own (for the evaluations that
+        // follow) — no copies in front of the build.  In the latency configuration k_hyperplanes is a programmatic dependent
+        // of k_reachsets and starts on the intervals that are complete.
+        Batch Bb = ctx->B;
+        Bb.q0 = d_q0;
+        Bb.qd0 = d_qd0;
+        Bb.qdd0 = d_qdd0;
+        Bb.obstacles = d_obstacles;
+        { int rc2 = launch_build(ctx, Bb, &nl, &latency); if (rc2) return rc2; }
+        HpStage stage{ctx->d_in, ctx->d_in + P * NF, ctx->d_in + 2 * P * NF, ctx->d_obs};
+        CU(launch_hyperplanes(Bb, ctx->stream, latency ? ctx->d_unit_flag : nullptr, stage));
+        nl++;
+    } else {
+        const size_t nb = size_t(nprob) * NF * sizeof(double);
+        CU(cudaMemcpyAsync(ctx->d_in, d_q0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_in + P * NF, d_qd0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_in + 2 * P * NF, d_qdd0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        { int rc2 = launch_build(ctx, ctx->B, &nl, &latency); if (rc2) return rc2; }
+    }
     ctx->launches += nl;
-    CU(launch_hyperplanes(ctx->B, ctx->stream));
-    ctx->launches += (nobs > 0);
     ctx->built_nprob = nprob;
     ctx->h_torque_valid = false;
     ctx->h_q0.clear();
@@ -491,10 +507,12 @@ int armour_batch_reachsets_build(armour_ctx* ctx, int nprob, const double* q0, c
     if (nobs > 0)
         CU(cudaMemcpyAsync(ctx->d_obs, obstacles, size_t(nprob) * nobs * 12 * sizeof(double), cudaMemcpyHostToDevice,
                            ctx->stream));
+    ctx->B.epoch++;
     int nl = 0;
-    { int rc2 = launch_build(ctx, &nl); if (rc2) return rc2; }
+    bool latency = false;
+    { int rc2 = launch_build(ctx, ctx->B, &nl, &latency); if (rc2) return rc2; }
     ctx->launches += nl;
-    CU(launch_hyperplanes(ctx->B, ctx->stream));
+    CU(launch_hyperplanes(ctx->B, ctx->stream, (latency && nobs > 0) ? ctx->d_unit_flag : nullptr));
     ctx->launches += (nobs > 0);
     ctx->built_nprob = nprob;
     ctx->h_torque_valid = false;
@@ -506,10 +524,10 @@ int armour_batch_reachsets_build(armour_ctx* ctx, int nprob, const double* q0, c
     CU(cudaMemcpyAsync(st.data(), ctx->B.status, nprob * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int p = 0; p < nprob; p++)
-        if (st[p] != 0)
+        if ((st[p] >> 3) == ctx->B.epoch && (st[p] & 7) != 0)
             return fail(ctx, ARMOUR_ERR_CAPACITY,
                         "reach-set build overflowed a monomial table (problem " + std::to_string(p) + ", code " +
-                            std::to_string(st[p]) + ")");
+                            std::to_string(st[p] & 7) + ")");
     return ARMOUR_OK;
 }
 
@@ -522,6 +540,8 @@ int armour_batch_get_build_status(armour_ctx* ctx, int nprob, int* out) {
     if (!ctx || !out || nprob < 1 || nprob > ctx->built_nprob) return ARMOUR_ERR_ARG;
     CU(cudaMemcpyAsync(out, ctx->B.status, nprob * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < nprob; p++)  // device words are stamped with the build ordinal: report this build's code only
+        out[p] = ((out[p] >> 3) == ctx->B.epoch && (out[p] & 7) != 0) ? ARMOUR_ERR_CAPACITY : ARMOUR_OK;
     return ARMOUR_OK;
 }
 
@@ -976,6 +996,7 @@ int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const ar
         rc = ensure_obstacle_buffers(ctx, nprob_total, nobs);
         if (rc) return rc;
     }
+    if (prob == 0) ctx->B.epoch++;  // imported tables: no build failure can be pending
     const Batch& B = ctx->B;
     const size_t T = B.T, NJ = B.NJ, P = size_t(ctx->cfg.max_problems);
     std::vector<uint16_t> lk(T * NJ * B.capL, 0), uk(T * NF * B.capU, 0);
@@ -1018,6 +1039,7 @@ int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const ar
 #undef H2D
     CU(cudaStreamSynchronize(st));  // the staging vectors die at return
     if (prob == nprob_total - 1) {
+        if (nobs > 0) CU(cudaMemsetAsync(ctx->B.hp_slow, 0, size_t(nprob_total) * sizeof(int), ctx->stream));
         CU(launch_hyperplanes(ctx->B, ctx->stream));
         ctx->launches += (nobs > 0);
         ctx->built_nprob = nprob_total;

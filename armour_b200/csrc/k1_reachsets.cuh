@@ -31,7 +31,10 @@ constexpr double RADIUS_SLACK = 1.0 + 0x1p-40;  // outward slack on exported rad
 
 struct K1Params {
     Batch B;
-    int* work;          // global unit counter (reset before every launch)
+    int* work;          // [2]: global unit counter and count of finished CTAs; the last CTA to finish resets both, so
+                        // a launch needs no memset in front of it
+    int* unit_flag;     // optional [p*T + t]: set to B.epoch when the unit is complete (release); lets the half-space
+                        // kernel, launched as a programmatic dependent, start on finished intervals.  nullptr: unused
     double* gscr;       // [grid][gscr_words]: per CTA [arena spill space | F / N blocks of one unit]
     int gscr_words;
     int fn_words;       // words of the F / N part (the last fn_words of a CTA's scratch)
@@ -1040,6 +1043,11 @@ K1_DI int run_task(const Batch& B, int p, int t, int kind, int i) {
 constexpr int K1_FIXED_BYTES = K1S_BYTES + JRS_WORDS * 8;  // per group: control block + joint reachable set region
 
 __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params P) {
+#ifndef ARMOUR_EMU
+    // a kernel launched behind this one with programmatic stream serialisation (k_hyperplanes in the latency path) may
+    // start as soon as every CTA of this grid is resident; it synchronises on P.unit_flag, not on this grid's end
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 #if K1_MG
     if (threadIdx.x == 0) {
         K1X& X0 = k1x();
@@ -1181,7 +1189,7 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
         const int failed = S.fail;
         if (failed) {
             if (!extra && (!MG || k1_group() == 0)) nfail++;
-            if (tid == 0) atomicMax(&P.B.status[p], failed);
+            if (tid == 0) atomicMax(&P.B.status[p], P.B.epoch * 8 + failed);  // (epochs grow: no reset between builds)
             // a failed operation may leave a table half-built: restore the all-zero invariant
             for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
             for (int i = tid; i < P.gtab_bytes / 8; i += NT) reinterpret_cast<u64*>(S.tab_g)[i] = 0;
@@ -1189,10 +1197,26 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
         }
         k1_sync();
         if (MG) __syncthreads();  // the unit is complete in every group before the mailbox is reused
+#ifndef ARMOUR_EMU
+        if (MG ? threadIdx.x == 0 : (tid == 0 && !extra)) {
+            if (t == 0 && P.B.hp_slow) P.B.hp_slow[p] = 0;  // rows without a candidate list are counted by k_hyperplanes
+            if (P.unit_flag) {
+                __threadfence();
+                atomicExch(&P.unit_flag[size_t(p) * P.B.T + t], P.B.epoch);
+            }
+        }
+#endif
 #if defined(K1_PROFILE) && K1_MG
         if (threadIdx.x == 0) g_k1prof[(size_t(t) * 256 + 255) * 4] = clock64() - _u0;
 #endif
     }
+#ifndef ARMOUR_EMU
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(P.work + 1, 1) == int(gridDim.x) - 1) {  // every other CTA is past its last fetch
+        P.work[0] = 0;
+        P.work[1] = 0;
+    }
+#endif
     if (tid == 0 && P.stats) {
         atomicMax(&P.stats[0], top_max - JRS_WORDS);
         atomicAdd(&P.stats[1], S.n_tab_global);
@@ -1253,7 +1277,8 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     s->fn_words = 2 * MAXJ * (9 + capw * 2);
     s->gscr_words = s->fn_words + 24 * capw;
     s->gtab_bytes = 16 * capw * 8 * 7;  // a cross product table for up to ~10 * capw candidate keys
-    if ((e = cudaMalloc(&s->work, sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&s->work, 2 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s->work, 0, 2 * sizeof(int), st)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->stats, 4 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->gscr, size_t(s->grid) * GROUPS * s->gscr_words * 8)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->gtab, size_t(s->grid) * GROUPS * s->gtab_bytes)) != cudaSuccess) return e;
@@ -1266,15 +1291,15 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     return cudaFuncSetAttribute(k_reachsets, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->smem_bytes));
 }
 
-inline cudaError_t launch_reachsets(const Batch& B, K1Scratch& s, cudaStream_t st, int* nlaunch) {
+inline cudaError_t launch_reachsets(const Batch& B, K1Scratch& s, cudaStream_t st, int* nlaunch, int* unit_flag = nullptr) {
     *nlaunch = 0;
     if (B.nprob == 0) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(s.work, 0, sizeof(int), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(B.status, 0, size_t(B.nprob) * sizeof(int), st)) != cudaSuccess) return e;
+    // nothing in front of the kernel: the unit counter is reset by the previous launch's last CTA, the build status and the
+    // unit flags carry the build epoch
     K1Params P;
     P.B = B;
     P.work = s.work;
+    P.unit_flag = unit_flag;
     P.gscr = s.gscr;
     P.gscr_words = s.gscr_words;
     P.fn_words = s.fn_words;

@@ -108,8 +108,52 @@ __device__ __forceinline__ void load_row_generators(const double* __restrict__ o
 constexpr int HP_ROWS = 8;
 constexpr int HP_STAGE = 24;  // link monomials staged in shared memory per row (longer tables are read from global)
 constexpr int HP_THREADS = HP_ROWS * NCOMB;  // 288
-__global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B) {
+// Two optional extras of the latency path (one planning problem, device pointers):
+//   * unit_flag: the kernel was launched as a programmatic dependent of k_reachsets and may start before that grid has
+//     finished; a CTA then waits until the intervals of ITS rows are flagged complete (acquire) — the half-space stage of
+//     the early intervals runs under the tail of the reach-set kernel;
+//   * stage: B.q0 / qd0 / qdd0 / obstacles point at the CALLER's buffers during the build; the first CTA of each problem
+//     copies them into the context's own buffers (for the evaluations that follow), which saves four copies in front of
+//     the build.
+struct HpStage {
+    double* q0;
+    double* qd0;
+    double* qdd0;
+    double* obstacles;
+};
+__global__ void __launch_bounds__(HP_THREADS) k_hyperplanes(Batch B, const int* __restrict__ unit_flag, HpStage stage) {
     const int p = blockIdx.y;
+    if (stage.q0 && blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < NF; i += HP_THREADS) {
+            stage.q0[size_t(p) * NF + i] = B.q0[size_t(p) * NF + i];
+            stage.qd0[size_t(p) * NF + i] = B.qd0[size_t(p) * NF + i];
+            stage.qdd0[size_t(p) * NF + i] = B.qdd0[size_t(p) * NF + i];
+        }
+        for (int i = threadIdx.x; i < B.O * 12; i += HP_THREADS)
+            stage.obstacles[size_t(p) * B.O * 12 + i] = B.obstacles[size_t(p) * B.O * 12 + i];
+    }
+    if (unit_flag) {
+        if (threadIdx.x == 0) {
+            const int per = B.NJ * TB * B.O, total = per * (B.T / TB);
+            int r0 = blockIdx.x * HP_ROWS, r1 = r0 + HP_ROWS - 1;
+            if (r1 >= total) r1 = total - 1;
+            // rows are chunk-major, x = (l*TB + tt)*O + o inside a chunk
+            int t_seen = -1;
+            for (int r = r0; r <= r1; r++) {
+                const int t = (r / per) * TB + ((r % per) / B.O) % TB;
+                if (t == t_seen) continue;
+                t_seen = t;
+                const int* f = unit_flag + size_t(p) * B.T + t;
+                int v;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    if (v == B.epoch) break;
+                    __nanosleep(200);
+                }
+            }
+        }
+        __syncthreads();
+    }
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int per_pair = NJ * TB * O;          // rows of one (problem, TB intervals) chunk
     const int rows_total = per_pair * (T / TB);
@@ -423,7 +467,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     __shared__ int s_in_domain;
     __shared__ int s_next;  // next chunk of 32 collision rows
 
-    if (B.status[p] != 0) {
+    if (B.failed(p) != 0) {
         // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe rows:
         // every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
         double* gp0 = g ? g + size_t(p) * m : nullptr;
@@ -654,7 +698,7 @@ k_constraints_slow(Batch B, const double* __restrict__ kin, double* __restrict__
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i < B.nprob && O > 0) {
             const int p = B.plist ? B.plist[i] : i;
-            if (B.status[p] == 0) {
+            if (B.failed(p) == 0) {
                 bool in = true;
                 for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
                 if (!in || B.hp_slow[p] != 0) s_list[atomicAdd(&s_n, 1)] = p;
@@ -764,13 +808,25 @@ k_verdict(Batch B, const double* __restrict__ g, int* __restrict__ feasible, int
 
 // ---------------------------------------------------------------------------------------------------
 // host launchers (called from capi.cu)
-cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st) {
+cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st, const int* unit_flag = nullptr, HpStage stage = HpStage{nullptr, nullptr, nullptr, nullptr}) {
     if (B.O == 0 || B.nprob == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(B.hp_slow, 0, size_t(B.nprob) * sizeof(int), st);
-    if (e != cudaSuccess) return e;
+    // (B.hp_slow was zeroed by k_reachsets, or by the caller when the tables were imported)
     const int rows = B.NJ * B.T * B.O;
     dim3 grid((rows + HP_ROWS - 1) / HP_ROWS, B.nprob);
-    k_hyperplanes<<<grid, HP_THREADS, 0, st>>>(B);
+    if (unit_flag) {  // programmatic dependent of the reach-set kernel launched just before on this stream
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(HP_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_hyperplanes, B, unit_flag, stage);
+    }
+    k_hyperplanes<<<grid, HP_THREADS, 0, st>>>(B, unit_flag, stage);
     return cudaGetLastError();
 }
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {

@@ -26,6 +26,7 @@ struct Batch {
     int O;         // obstacles per problem (same for the whole batch)
     int capL;      // stored k-only monomials per link reach set
     int capU;      // stored k-only monomials per torque reach set
+    int epoch;     // ordinal of the build that filled the tables (> 0); status[] and the unit flags are stamped with it
     // inputs
     const double* q0;         // [p][NF]
     const double* qd0;        // [p][NF]
@@ -52,13 +53,16 @@ struct Batch {
     int* hp_slow;
     // outputs of the last evaluation
     double* link_sliced;      // [t][NJ][3] of problem 0 (armtd_NLP::link_sliced_center)
-    int* status;              // [p] 0, or the capacity failure of the build: evaluations then return fail-safe rows
+    int* status;              // [p] epoch * 8 + failure code of a build that overflowed a table (see failed()): evaluations
+                              // of such a problem return fail-safe rows
     // optional indirection for launches over a subset of the problems (the batched solver's still-running list):
     // CTA row y works on problem plist[y]; nullptr = identity
     const int* plist;
 
     __host__ __device__ size_t hp_chunk() const { return size_t(HP_CAP) * 4 * NJ * TB * O; }
     __host__ __device__ int m() const { return NF * T + NJ * T * O + 4 * NF; }
+    // failure code of problem p in the CURRENT build (0: none); stamps of older builds do not count
+    __device__ int failed(int p) const { return (status[p] >> 3) == epoch ? (status[p] & 7) : 0; }
 };
 
 }  // namespace armour

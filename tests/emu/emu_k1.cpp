@@ -25,6 +25,8 @@ extern "C" int emu_k1_build(int model_id, int T, double thr, const double* k_ran
     Batch B;
     std::memset(&B, 0, sizeof(B));
     B.nprob = 1;
+    B.epoch = 0;
+    B.hp_slow = nullptr;
     B.T = T;
     B.NJ = rc.num_joints;
     B.O = 0;
