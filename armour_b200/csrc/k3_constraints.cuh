@@ -467,6 +467,9 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     __shared__ int s_in_domain;
     __shared__ int s_next;  // next chunk of 32 collision rows
 
+    // k_constraints_slow is launched behind this kernel as a programmatic dependent: it shares no data with it (it writes
+    // only the rows this kernel leaves out), so the two may run side by side
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (B.failed(p) != 0) {
         // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe rows:
         // every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
@@ -835,8 +838,17 @@ cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, d
     k_constraints<<<grid, K3_THREADS, 0, st>>>(B, d_k, d_g, d_jac);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || B.O == 0) return e;
-    k_constraints_slow<<<(B.nprob + 127) / 128, 128, 0, st>>>(B, d_k, d_g, d_jac);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((B.nprob + 127) / 128);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_constraints_slow, B, d_k, d_g, d_jac);
 }
 cudaError_t launch_verdict(const Batch& B, const double* d_g, int* d_feasible, int* d_first, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;

@@ -75,3 +75,48 @@ def test_batched_solve_is_consistent_with_the_oracle(built):
         # (the batch was built by the lock-step kernel, the single problem by the latency kernel: radii agree to
         # 1e-13 relative, not bitwise, and so do the bounds the solver sees)
         assert np.max(np.abs(k1[0] - k[p])) <= 1e-8 and ok1[0] == ok[p]
+
+
+def test_device_solver_against_an_independent_optimiser(built):
+    """Optimality, checked by a solver that shares nothing with the product: scipy's SLSQP on the ORACLE's f, g and
+    Jacobian (exact derivatives, bounds -1 <= k <= 1).  On the saved worlds: wherever SLSQP ends at a point the oracle's
+    verdict calls feasible, the device plan must be feasible too and must not cost more (1e-6); the device never
+    reports a plan the oracle's verdict rejects."""
+    import glob
+
+    from scipy.optimize import minimize
+
+    from armour_b200 import ReachSetEngine, worlds
+    from oracle.pyoracle import OracleProblem
+    paths = sorted(glob.glob(os.path.join(WORLDS, "scene_*.csv")))[:8]
+    both = 0
+    for path in paths:
+        q0, qd0, qdd0, q_des, obs = worlds.config1_problem(path)
+        orc = OracleProblem().build(q0, qd0, qdd0, obs)
+        gl, gu = orc.bounds()
+        fin = gl > -1e18
+
+        def cons(x):
+            g = orc.eval_g(x)
+            return np.concatenate([g[fin] - gl[fin], gu - g])
+
+        def cjac(x):
+            J = orc.eval_jac_g(x)
+            return np.vstack([J[fin], -J])
+
+        r = minimize(lambda x: orc.cost(q_des, x), np.zeros(7), jac=lambda x: orc.cost_grad(q_des, x),
+                     bounds=[(-1, 1)] * 7, constraints=[{"type": "ineq", "fun": cons, "jac": cjac}], method="SLSQP",
+                     options={"maxiter": 200, "ftol": 1e-12})
+        ok_ref, _ = orc.verdict(orc.eval_g(r.x))
+        eng = ReachSetEngine(max_problems=1, max_obstacles=obs.shape[0])
+        eng.build(q0, qd0, qdd0, obs)
+        k, ok, first, iters = eng.solve(q_des)
+        eng.close()
+        if ok[0]:
+            good, row = orc.verdict(orc.eval_g(k[0]))
+            assert good, f"{os.path.basename(path)}: the oracle rejects the device plan at row {row}"
+        if ok_ref:
+            assert ok[0], f"{os.path.basename(path)}: SLSQP found a feasible plan, the device solver did not"
+            assert orc.cost(q_des, k[0]) <= r.fun + 1e-6, (os.path.basename(path), orc.cost(q_des, k[0]), r.fun)
+            both += 1
+    assert both >= 4, "expected most saved worlds to be feasible for both solvers"
