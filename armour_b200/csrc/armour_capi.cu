@@ -750,7 +750,8 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     CU(cudaMemsetAsync(S.xt, 0, size_t(nprob) * NF * sizeof(double), st));
     CU(launch_constraints(B, S.x, ctx->d_g, nullptr, st));
     k_solver_start<<<nprob, SOLVER_THREADS, 0, st>>>(B, S, ctx->d_g);
-    ctx->launches += 2;
+    CU(cudaGetLastError());
+    ctx->launches += 2 + (B.O > 0);
     Batch Ba = B;      // launches over the problems still running (all of them at first)
     int nactive = nprob;
     for (int it = 0; it < opt.max_iter && nactive > 0; it++) {
@@ -759,7 +760,8 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
         k_solver_step<<<nactive, SOLVER_THREADS, SOLVER_ROWCAP * sizeof(double), st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
         CU(launch_constraints(Ba, S.xt, d_gt, nullptr, st));
         k_solver_accept<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
-        ctx->launches += 4;
+        CU(cudaGetLastError());  // (covers k_solver_step too: launch errors are sticky until read)
+        ctx->launches += 4 + 2 * (B.O > 0);
         if ((it & 3) == 3 && it + 1 < opt.max_iter) {  // every fourth iteration: who is still running?
             CU(cudaMemsetAsync(d_running, 0, sizeof(int), st));
             k_solver_compact<<<(nprob + 255) / 256, 256, 0, st>>>(S, nprob, d_running, d_list);
