@@ -82,6 +82,11 @@ SIGNATURES = {
     "armour_batch_get_monomial_counts": (C.c_int, [C.c_void_p, C.c_int, ip, ip]),
     "armour_batch_get_candidate_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "armour_chunk_intervals": (C.c_int, []),
+    "armour_jacobian_nnz": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "armour_jacobian_structure": (C.c_int, [C.c_void_p, C.c_int, ip, ip]),
+    "armour_eval_jac_g_structured": (C.c_int, [C.c_void_p, dp, dp]),
+    "armour_batch_eval_structured": (C.c_int, [C.c_void_p, C.c_int, dp, dp, dp]),
+    "armour_batch_eval_structured_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "armour_measure_fp64_peak": (C.c_int, [C.c_void_p, dp]),
     "armour_solver_options_default": (None, [C.c_void_p]),
     "armour_batch_solve_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

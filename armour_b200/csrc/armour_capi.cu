@@ -102,6 +102,8 @@ struct armour_ctx {
     double* d_g = nullptr;
     double* d_jac = nullptr;
     size_t g_capacity = 0, jac_capacity = 0;
+    double* d_jnz = nullptr;  // packed non-zeros of the Jacobian (structured evaluation)
+    size_t jnz_capacity = 0;
     int* d_verdict = nullptr;  // [2][max_problems]
     // batched device solver (allocated on first use)
     double* d_solver = nullptr;   // state arrays + second g buffer + linearised rows
@@ -401,7 +403,7 @@ int armour_ctx_destroy(armour_ctx* ctx) {
     if (!ctx) return ARMOUR_OK;
     cudaSetDevice(ctx->cfg.device);
     Batch& B = ctx->B;
-    void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io, ctx->d_unit_flag,
+    void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io, ctx->d_unit_flag, ctx->d_jnz,
                     ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
                     B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.link_r, B.hp_cand, B.hp_cnt, B.hp_slow,
                     B.link_sliced, B.status};
@@ -645,6 +647,77 @@ int armour_batch_eval(armour_ctx* ctx, int nprob, const double* k, double* g, do
         CU(cudaMemcpyAsync(values, ctx->d_jac, nprob * m * NF * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return ARMOUR_OK;
+}
+
+// ---- structured Jacobian (offered beside the dense one; the reference declares its Jacobian dense) ------------------
+long long armour_jacobian_nnz(const armour_ctx* ctx, int nobs) {
+    if (!ctx || nobs < 0) return ARMOUR_ERR_ARG;
+    return jac_nnz(ctx->B.T, ctx->B.NJ, nobs);
+}
+
+int armour_jacobian_structure(const armour_ctx* ctx, int nobs, int* iRow, int* jCol) {
+    if (!ctx || nobs < 0 || !iRow || !jCol) return ARMOUR_ERR_ARG;
+    const int T = ctx->B.T, NJ = ctx->B.NJ;
+    size_t n = 0;
+    for (int r = 0; r < NF * T; r++)
+        for (int c = 0; c < NF; c++, n++) {
+            iRow[n] = r;
+            jCol[n] = c;
+        }
+    for (int l = 0; l < NJ; l++)
+        for (int r = 0; r < T * nobs; r++)
+            for (int c = 0; c < jac_link_width(l); c++, n++) {
+                iRow[n] = NF * T + l * T * nobs + r;
+                jCol[n] = c;
+            }
+    for (int r = 0; r < 4 * NF; r++, n++) {
+        iRow[n] = NF * T + NJ * T * nobs + r;
+        jCol[n] = r % NF;
+    }
+    return ARMOUR_OK;
+}
+
+int armour_batch_eval_structured_device(armour_ctx* ctx, int nprob, const double* d_k, double* d_g, double* d_values_nnz) {
+    if (!ctx || !d_k || !d_values_nnz) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "evaluate before build");
+    CU(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_eval_buffers(ctx, nprob, false, true);
+    if (rc) return rc;
+    rc = armour_batch_eval_device(ctx, nprob, d_k, d_g, ctx->d_jac);
+    if (rc) return rc;
+    Batch B = ctx->B;
+    B.nprob = nprob;
+    CU(launch_pack_jacobian(B, ctx->d_jac, d_values_nnz, ctx->stream));
+    ctx->launches += 1;
+    return ARMOUR_OK;
+}
+
+int armour_batch_eval_structured(armour_ctx* ctx, int nprob, const double* k, double* g, double* values_nnz) {
+    if (!ctx || !k || !values_nnz) return ARMOUR_ERR_ARG;
+    if (nprob < 1 || nprob > ctx->built_nprob) return fail(ctx, ARMOUR_ERR_STATE, "evaluate before build");
+    CU(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_eval_buffers(ctx, nprob, g != nullptr, true);
+    if (rc) return rc;
+    const size_t m = size_t(ctx->B.m());
+    const size_t nnz = size_t(jac_nnz(ctx->B.T, ctx->B.NJ, ctx->B.O));
+    if (ctx->jnz_capacity < nprob * nnz) {
+        if (ctx->d_jnz) cudaFree(ctx->d_jnz);
+        ctx->d_jnz = nullptr;
+        ctx->jnz_capacity = 0;
+        CU(dalloc(&ctx->d_jnz, nprob * nnz));
+        ctx->jnz_capacity = nprob * nnz;
+    }
+    CU(cudaMemcpyAsync(ctx->d_k, k, size_t(nprob) * NF * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = armour_batch_eval_structured_device(ctx, nprob, ctx->d_k, g ? ctx->d_g : nullptr, ctx->d_jnz);
+    if (rc) return rc;
+    if (g) CU(cudaMemcpyAsync(g, ctx->d_g, nprob * m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(values_nnz, ctx->d_jnz, nprob * nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+
+int armour_eval_jac_g_structured(armour_ctx* ctx, const double* k, double* values_nnz) {
+    return armour_batch_eval_structured(ctx, 1, k, nullptr, values_nnz);
 }
 
 int armour_eval_g(armour_ctx* ctx, const double* k, double* g) { return armour_batch_eval(ctx, 1, k, g, nullptr); }

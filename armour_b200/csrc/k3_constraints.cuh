@@ -770,6 +770,57 @@ k_constraints_slow(Batch B, const double* __restrict__ kin, double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Structured Jacobian.  The reference declares the Jacobian dense (KPR/NLPclass.cu:348-357), but its pattern is fixed by the
+// kinematics: a collision row of link l depends on k_0..k_l only (the link's reach set has no monomial in a later joint's
+// parameter: those entries are exact zeros), a Bezier row on its own joint only; torque rows are full.  jac_row_width() is
+// that pattern; k_pack_jacobian gathers the non-zeros of the dense rows (row-major, columns ascending) so that a caller
+// which gives Ipopt the sparse structure moves 39 % fewer Jacobian bytes over PCIe (10 obstacles: 42 140 of 69 188 values).
+__host__ __device__ inline int jac_link_width(int l) { return l + 1 < NF ? l + 1 : NF; }
+__host__ __device__ inline long long jac_nnz(int T, int NJ, int O) {
+    long long w = 0;
+    for (int l = 0; l < NJ; l++) w += jac_link_width(l);
+    return (long long)NF * NF * T + (long long)T * O * w + 4 * NF;
+}
+__global__ void __launch_bounds__(256)
+k_pack_jacobian(Batch B, const double* __restrict__ jac, double* __restrict__ out, long long nnz) {
+    const int p = blockIdx.y;
+    const int T = B.T, NJ = B.NJ, O = B.O;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nnz) return;
+    const double* jp = jac + size_t(p) * B.m() * NF;
+    long long row, col;
+    const long long n_t = (long long)NF * NF * T;
+    if (idx < n_t) {
+        row = idx / NF;
+        col = idx % NF;
+    } else {
+        long long r = idx - n_t;
+        int l = 0;
+        for (; l < NJ; l++) {
+            const long long blk = (long long)T * O * jac_link_width(l);
+            if (r < blk) break;
+            r -= blk;
+        }
+        if (l < NJ) {
+            const int w = jac_link_width(l);
+            row = (long long)NF * T + (long long)l * T * O + r / w;
+            col = r % w;
+        } else {  // Bezier rows: min / max position, min / max velocity of joint i -> column i
+            row = (long long)NF * T + (long long)NJ * T * O + r;
+            col = r % NF;
+        }
+    }
+    out[size_t(p) * nnz + idx] = jp[row * NF + col];
+}
+cudaError_t launch_pack_jacobian(const Batch& B, const double* d_jac, double* d_out, cudaStream_t st) {
+    if (B.nprob == 0) return cudaSuccess;
+    const long long nnz = jac_nnz(B.T, B.NJ, B.O);
+    dim3 grid((unsigned)((nnz + 255) / 256), B.nprob);
+    k_pack_jacobian<<<grid, 256, 0, st>>>(B, d_jac, d_out, nnz);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // verdict: first violated row in the reference's check order (= ascending row index), one CTA per problem
 __global__ void __launch_bounds__(256)
 k_verdict(Batch B, const double* __restrict__ g, int* __restrict__ feasible, int* __restrict__ first) {

@@ -195,6 +195,30 @@ class ReachSetEngine:
         self._check(self.lib.armour_batch_eval(self._h, n, _dp(k), _dp(g) if g is not None else None,
                                                _dp(jac) if jac is not None else None))
 
+    # -- structured Jacobian (offered beside the dense one) --------------------------------------------
+    @property
+    def jacobian_nnz(self):
+        return int(self.lib.armour_jacobian_nnz(self._h, self.nobs))
+
+    def jacobian_structure(self):
+        """(iRow, jCol) of the non-zeros, C-style indices, in the order eval_structured returns the values."""
+        n = self.jacobian_nnz
+        ir, jc = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(self.lib.armour_jacobian_structure(self._h, self.nobs, ir.ctypes.data_as(_lib.ip), jc.ctypes.data_as(_lib.ip)))
+        return ir, jc
+
+    def eval_structured(self, k, want_g=True):
+        """eval_g + the non-zeros of the Jacobian per problem with host buffers: (g [n, m] or None, values [n, nnz])."""
+        k = _f64(k).reshape(-1, NF)
+        n = k.shape[0]
+        g = np.empty((n, self.m)) if want_g else None
+        vals = np.empty((n, self.jacobian_nnz))
+        self._check(self.lib.armour_batch_eval_structured(self._h, n, _dp(k), _dp(g) if want_g else None, _dp(vals)))
+        return g, vals
+
+    def eval_structured_into(self, k, g, vals):
+        self._check(self.lib.armour_batch_eval_structured(self._h, k.shape[0], _dp(k), _dp(g) if g is not None else None, _dp(vals)))
+
     def eval_device(self, nprob, d_k, d_g, d_jac):
         """Asynchronous evaluation on device pointers (ints; 0/None to skip an output)."""
         self._check(self.lib.armour_batch_eval_device(self._h, nprob, d_k, d_g or None, d_jac or None))

@@ -172,3 +172,32 @@ def test_every_saved_world_on_the_k_schedule(built, path):
     tr, tr_ref = eng.torque_radius()[0], ref.torque_radius()
     assert np.all(tr >= tr_ref) and np.max((tr - tr_ref) / tr_ref) <= 1e-10
     eng.close()
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_structured_jacobian_is_the_dense_one_without_its_exact_zeros(built, model):
+    """armour_jacobian_structure / armour_batch_eval_structured: the non-zeros returned are the dense entries at (iRow, jCol),
+    and every dense entry outside the structure is an exact zero (a collision row of link l depends on k_0..k_l only)."""
+    from armour_b200 import ReachSetEngine, worlds
+    n, nobs = 3, 6
+    q0, qd0, qdd0, _, obs = worlds.random_problems(n, nobs, seed=61)
+    eng = ReachSetEngine(max_problems=n, max_obstacles=nobs, robot_model=model, cap_link=64, cap_torque=128)
+    eng.build(q0, qd0, qdd0, obs)
+    ks = worlds.halton_k(n, skip=9)
+    g, J = eng.eval(ks)
+    g2, vals = eng.eval_structured(ks)
+    ir, jc = eng.jacobian_structure()
+    NJ = eng.NJ
+    assert eng.jacobian_nnz == 49 * 128 + 128 * nobs * sum(min(l + 1, 7) for l in range(NJ)) + 28 == ir.size
+    assert np.array_equal(g, g2)
+    mask = np.zeros((eng.m, 7), bool)
+    mask[ir, jc] = True
+    assert mask.sum() == ir.size, "duplicate entries in the structure"
+    for p in range(n):
+        assert np.array_equal(vals[p], J[p][ir, jc])
+        assert np.all(J[p][~mask] == 0.0)
+    # single-problem entry point
+    single = np.empty(eng.jacobian_nnz)
+    eng._check(eng.lib.armour_eval_jac_g_structured(eng._h, ks[0].ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)),
+                                                    single.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))))
+    assert np.array_equal(single, vals[0])
