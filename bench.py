@@ -541,6 +541,7 @@ def run_b200(args):
     launches0 = eng.kernel_launches
     eng.build_device(nprob, nobs, tq0.data_ptr(), tqd0.data_ptr(), tqdd0.data_ptr(), tobs.data_ptr())
     torch.cuda.synchronize()
+    build_launches = eng.kernel_launches - launches0
     status = eng.build_status()
     if status.any():
         raise SystemExit(f"reach-set build overflowed a monomial table for {int((status != 0).sum())} problems")
@@ -583,11 +584,32 @@ def run_b200(args):
             ms = max(timed.per_rank)
         return ms, t0, t1
 
+    # One step = 16 k-iterates x (k_constraints + k_constraints_slow), captured ONCE in a CUDA graph and replayed: the
+    # device-timed region then does not depend on how fast each rank's host thread can enqueue 32 launches per step
+    # (with 8 ranks + NCCL threads + clock samplers sharing the host, slow enqueueing showed up as 10-30 % slower ranks).
+    step_timed, launches_per_step, graph_used = step_device, None, False
+    try:
+        step_device()  # warm: modules loaded, nothing allocated inside the capture
+        torch.cuda.synchronize()
+        l0 = eng.kernel_launches
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            step_device()
+        launches_per_step = eng.kernel_launches - l0
+        torch.cuda.set_stream(stream)
+        graph.replay()
+        torch.cuda.synchronize()
+        step_timed, graph_used = graph.replay, True
+    except Exception as exc:  # capture not possible on this stack: plain launches
+        sys.stderr.write(f"bench.py: CUDA graph capture of the step failed ({exc!r}); timing plain launches\n")
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(stream)
+
     clocks = ClockSampler(local).start()
     time.sleep(0.3)
     la = eng.kernel_launches
-    ms_dev, c0, c1 = timed(step_device, args.steps, args.warmup)
-    launches_timed = timed.launches
+    ms_dev, c0, c1 = timed(step_timed, args.steps, args.warmup)
+    launches_timed = timed.launches if not graph_used else launches_per_step * args.steps
     per_rank_dev = list(timed.per_rank)
     clock_windows = [(c0, c1)]
     value = world * nprob * iters * args.steps / (ms_dev * 1e-3)
@@ -836,11 +858,12 @@ def run_b200(args):
                        "time_intervals": T, "obstacles": nobs, "constraints_per_world": m,
                        "k_iterates_per_step": iters, "worlds_per_gpu": nprob, "parallelism": f"worlds sharded x{world}",
                        "cpu_sample_worlds": (cpu or {}).get("sample_worlds"),
-                       "l2": "outputs (g + dense Jacobian) and reach-set tables per launch exceed the 126 MB L2"},
+                       "l2": "outputs (g + dense Jacobian) and reach-set tables per launch exceed the 126 MB L2",
+                       "step_submission": "CUDA graph replay (one graph = one step)" if graph_used else "plain launches"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "m1": m1, "config1_host_abi": config1,
             "solver_e2e": solver_e2e, "config3": config3, "config4": config4, "sweep": sweep,
             "gpu_launches": int(launches_timed), "clocks": clk,
-            "feasible_worlds_last_iterate": feasible_total, "build_launches": int(la - launches0),
+            "feasible_worlds_last_iterate": feasible_total, "build_launches": int(build_launches),
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
