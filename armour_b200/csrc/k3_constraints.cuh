@@ -467,9 +467,6 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     __shared__ int s_in_domain;
     __shared__ int s_next;  // next chunk of 32 collision rows
 
-    // k_constraints_slow is launched behind this kernel as a programmatic dependent: it shares no data with it (it writes
-    // only the rows this kernel leaves out), so the two may run side by side
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (B.failed(p) != 0) {
         // the build of this problem overflowed a table (ARMOUR_ERR_CAPACITY): its reach sets are not valid.  Fail-safe rows:
         // every torque and collision row violated, zero Jacobian -> no caller can take the problem for feasible.
@@ -690,15 +687,20 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 // for.  One CTA per problem, which returns at once in the usual case (no such row); otherwise one thread per row slices
 // the link reach set in the reference's factor order (KPR/PZsparse.cu:404-555) and scans all 72 half-spaces computed from
 // the generators (KPR/CollisionChecking.cu:169-299).
+constexpr int K3S_PROBLEMS = 16;  // problems per CTA of k_constraints_slow
 __global__ void __launch_bounds__(128)
 k_constraints_slow(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
+    // k_constraints is launched right behind this kernel as a programmatic dependent and runs BESIDE it: the two share no
+    // data (this kernel writes only the rows that one leaves out), so whatever this kernel has to do — usually nothing, a few
+    // dozen rows for some batches — is hidden under the 0.6 ms of the main kernel instead of being added to it
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int NJ = B.NJ, O = B.O, T = B.T;
-    __shared__ int s_list[128], s_n;
+    __shared__ int s_list[K3S_PROBLEMS], s_n;
     __shared__ double2 kpd[NF][4];  // {k_j^d, d/dk_j k_j^d} for d = 0..3
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    {   // one thread per problem: does it have anything for this kernel?  (usually none does: 128 problems per CTA)
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x < K3S_PROBLEMS) {  // one thread per problem: does it have anything for this kernel?  (usually not)
+        const int i = blockIdx.x * K3S_PROBLEMS + threadIdx.x;
         if (i < B.nprob && O > 0) {
             const int p = B.plist ? B.plist[i] : i;
             if (B.failed(p) == 0) {
@@ -886,12 +888,18 @@ cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st, const int* unit_
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
     dim3 grid(B.T / TB, B.nprob);
-    k_constraints<<<grid, K3_THREADS, 0, st>>>(B, d_k, d_g, d_jac);
+    if (B.O == 0) {
+        k_constraints<<<grid, K3_THREADS, 0, st>>>(B, d_k, d_g, d_jac);
+        return cudaGetLastError();
+    }
+    // slow path first (a normal launch: it waits for whatever precedes it on the stream), the main kernel behind it as a
+    // programmatic dependent: it starts as soon as the slow kernel's few CTAs are resident and runs beside them
+    k_constraints_slow<<<(B.nprob + K3S_PROBLEMS - 1) / K3S_PROBLEMS, 128, 0, st>>>(B, d_k, d_g, d_jac);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || B.O == 0) return e;
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((B.nprob + 127) / 128);
-    cfg.blockDim = dim3(128);
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(K3_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -899,7 +907,7 @@ cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, d
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_constraints_slow, B, d_k, d_g, d_jac);
+    return cudaLaunchKernelEx(&cfg, k_constraints, B, d_k, d_g, d_jac);
 }
 cudaError_t launch_verdict(const Batch& B, const double* d_g, int* d_feasible, int* d_first, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
