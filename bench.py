@@ -207,6 +207,16 @@ def oracle_run(nthreads, nobs, iters, steps, warmup, seed, seconds=None):
     return build_s, times
 
 
+def workload_config(nprob, nobs, iters, world):
+    """The `config` object of the line: identical in both arms (the reference arm times a bounded SAMPLE of this workload,
+    described in its cpu_baseline.sample)."""
+    return {"workload": f"Kinova Gen3 batched {nprob} random worlds x {nobs} obstacles per GPU, one eval_g + eval_jac_g per "
+                        f"world per k-iterate, {iters} k-iterates per step",
+            "time_intervals": T, "obstacles": nobs, "constraints_per_world": NF * T + 7 * T * nobs + 4 * NF,
+            "k_iterates_per_step": iters, "worlds_per_gpu": nprob, "parallelism": f"worlds sharded x{world}",
+            "l2": "outputs (g + dense Jacobian) and reach-set tables per launch exceed the 126 MB L2"}
+
+
 def reference_available():
     """The reference's own planner path (oracle/_ref/libarmour_ref_cuda.so) needs the prebuilt library and a GPU."""
     try:
@@ -290,12 +300,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Kinova Gen3 batched random worlds x {args.nobs} obstacles, one eval_g + eval_jac_g "
-                               f"per world per k-iterate, {args.iters} k-iterates per step",
-                   "time_intervals": T, "obstacles": args.nobs, "k_iterates_per_step": args.iters,
-                   "cpu_sample_worlds": obj["sample_worlds"],
-                   "note": "per-world throughput of the same generator; the GPU arm runs 1,024 worlds per GPU, the CPU arm "
-                           "a bounded sample of them (the reference handles one world per process)"},
+        "config": workload_config(args.nprob, args.nobs, args.iters, args.gpus),
+        "sample_note": "per-world throughput of the same generator; the GPU arm runs 1,024 worlds per GPU, the CPU arm a "
+                       "bounded sample of them, one world at a time like the reference planner (cpu_baseline.sample)",
         "cpu_baseline": obj,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -862,13 +869,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Kinova Gen3 batched {nprob} random worlds x {nobs} obstacles per GPU, one eval_g + "
-                                   f"eval_jac_g per world per k-iterate, {iters} k-iterates per step",
-                       "time_intervals": T, "obstacles": nobs, "constraints_per_world": m,
-                       "k_iterates_per_step": iters, "worlds_per_gpu": nprob, "parallelism": f"worlds sharded x{world}",
-                       "cpu_sample_worlds": (cpu or {}).get("sample_worlds"),
-                       "l2": "outputs (g + dense Jacobian) and reach-set tables per launch exceed the 126 MB L2",
-                       "step_submission": "CUDA graph replay (one graph = one step)" if graph_used else "plain launches"},
+            "config": workload_config(nprob, nobs, iters, world),
+            "step_submission": "CUDA graph replay (one graph = one step)" if graph_used else "plain launches",
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "m1": m1, "config1_host_abi": config1,
             "solver_e2e": solver_e2e, "config3": config3, "config4": config4, "sweep": sweep,
             "gpu_launches": int(launches_timed), "clocks": clk,
