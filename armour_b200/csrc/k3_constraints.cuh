@@ -440,6 +440,21 @@ __device__ __forceinline__ void slice_component(const uint16_t* __restrict__ key
 // The link warps meet on named barrier 1 and go straight to the collision rows; the torque warps write their
 // rows, then join through barrier 2 (on which the link warps only arrive), so nobody waits for the slowest
 // slice.  Collision rows are handed out in chunks of 32 from a shared counter.
+#ifndef K3_STAGE_TABLES
+#define K3_STAGE_TABLES 0  // 1: the tables of the chunk are fetched with cp.async into fixed shared-memory slots, then walked
+                           // there.  Measured (r2s): 635 us against 560 without — the barrier in front of the walk costs
+                           // more than the serial walk from global memory, whose latency the other 39 warps hide
+#endif
+#ifndef K3_DIRECT_J
+#define K3_DIRECT_J 1      // 1: a lane stores the 7 Jacobian entries of its row itself (56 contiguous bytes); 0: transposition
+#endif
+constexpr int K3_LSLOT = 12;   // monomials of a link table staged in shared memory (longer tables: the rest from global memory)
+constexpr int K3_USLOT = 32;   // same for a torque table
+constexpr int K3_LTAB_BYTES = 32 + K3_LSLOT * 24;  // keys (24 B used), then coefficients [m][3]
+constexpr int K3_UTAB_BYTES = K3_USLOT * 2 + K3_USLOT * 8;
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 constexpr int K3_LINK_THREADS = 192;
 constexpr int K3_TORQUE_LANES = 2;
 constexpr int K3_THREADS = 320;
@@ -463,7 +478,11 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     __shared__ __align__(4) unsigned char s_cnt[K3_CNT_SMEM];  // candidate counts of this CTA's rows
     __shared__ double s_lc[TB][MAXJ][3];
     __shared__ double s_dlc[TB][MAXJ][NF][3];
+#if !K3_DIRECT_J
     __shared__ double s_stage[K3_WARPS][32 * NF];  // per-warp transpose buffer: Jacobian rows leave coalesced
+#endif
+    __shared__ double s_tj[TB * NF * NF];          // torque rows of the Jacobian: leave as one contiguous run
+    extern __shared__ __align__(16) unsigned char k3_tab[];  // staged tables: TB*NJ link slots, then TB*NF torque slots
     __shared__ int s_in_domain;
     __shared__ int s_next;  // next chunk of 32 collision rows
 
@@ -524,14 +543,42 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 #pragma unroll
             for (int q = 0; q < CW; q++) cw[q] = (tid + q * K3_LINK_THREADS < per_pair / 4) ? __ldg(src + tid + q * K3_LINK_THREADS) : 0u;
         }
-        if (tid < TB * NJ * 3) {
-            const int e = tid % 3;
-            const int l = (tid / 3) % NJ;
-            const int tt = tid / (3 * NJ);
-            const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+        const bool slicer = tid < TB * NJ * 3;
+        const int e = tid % 3;
+        const int l = (tid / 3) % NJ;
+        const int tt = slicer ? tid / (3 * NJ) : 0;
+        const size_t idx = (size_t(p) * T + tb * TB + tt) * NJ + l;
+        const int n = slicer ? B.link_n[idx] : 0;
+#if K3_STAGE_TABLES
+        // the three component threads of a table fetch its first K3_LSLOT monomials in 16-byte pieces (cp.async), all link
+        // warps meet (at a point where every warp is convergent: bar.sync is the aligned form), then each thread walks its
+        // table in shared memory: two DRAM round trips instead of one per pair of monomials
+        unsigned char* slot = k3_tab + (tt * NJ + l) * K3_LTAB_BYTES;
+        const int ns = n < K3_LSLOT ? n : K3_LSLOT;
+        if (slicer) {
+            const char* ksrc = reinterpret_cast<const char*>(B.link_key + idx * B.capL);
+            const char* csrc = reinterpret_cast<const char*>(B.link_g + idx * B.capL * 3);
+            const int kc = (ns * 2 + 15) >> 4, cc = (ns * 24 + 15) >> 4;
+            if (e == 0)
+                for (int c = 0; c < kc; c++) cp_async16(slot + 16 * c, ksrc + 16 * c);
+            for (int c = e; c < cc; c += 3) cp_async16(slot + 32 + 16 * c, csrc + 16 * c);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.sync 4, %0;" ::"n"(K3_LINK_THREADS) : "memory");
+#endif
+        if (slicer) {
             double value = B.link_c[idx * 3 + e];
             double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
-            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, B.link_n[idx], 1, 3, kpd, value, grad);
+#if K3_STAGE_TABLES
+            slice_component(reinterpret_cast<const uint16_t*>(slot), reinterpret_cast<const double*>(slot + 32) + e, ns, 1, 3, kpd,
+                            value, grad);
+            if (n > ns)
+                slice_component(B.link_key + idx * B.capL + ns, B.link_g + (idx * B.capL + ns) * 3 + e, n - ns, 1, 3, kpd, value, grad);
+#else
+            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, n, 1, 3, kpd, value, grad);
+#endif
             // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
             const double r = B.link_r[idx * 3 + e];
             const double c = ((value - r) + (value + r)) * 0.5;
@@ -558,14 +605,43 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             // lane `part` takes the monomials part, part + 2, ...; the two partial sums are added below
             // (the oracle adds the monomials one after the other: a difference of a few ulp)
             const int n = B.u_n[idx];
+#if K3_STAGE_TABLES
+            unsigned char* slot = k3_tab + TB * NJ * K3_LTAB_BYTES + i * K3_UTAB_BYTES;
+            const int ns = n < K3_USLOT ? n : K3_USLOT;
+            {
+                const char* ksrc = reinterpret_cast<const char*>(B.u_key + idx * B.capU);
+                const char* csrc = reinterpret_cast<const char*>(B.u_g + idx * B.capU);
+                const int kc = (ns * 2 + 15) >> 4, cc = (ns * 8 + 15) >> 4;
+                for (int c = part; c < kc; c += K3_TORQUE_LANES) cp_async16(slot + 16 * c, ksrc + 16 * c);
+                for (int c = part; c < cc; c += K3_TORQUE_LANES) cp_async16(slot + K3_USLOT * 2 + 16 * c, csrc + 16 * c);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.sync 5, %0;" ::"n"(K3_THREADS - K3_LINK_THREADS) : "memory");
+        if (on) {
+            const int n = B.u_n[idx];
+            unsigned char* slot = k3_tab + TB * NJ * K3_LTAB_BYTES + i * K3_UTAB_BYTES;
+            const int ns = n < K3_USLOT ? n : K3_USLOT;
+            const int mine_s = (ns - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
+            slice_component(reinterpret_cast<const uint16_t*>(slot) + part, reinterpret_cast<const double*>(slot + K3_USLOT * 2) + part,
+                            mine_s > 0 ? mine_s : 0, K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
+            if (n > ns) {  // K3_USLOT is even: lane `part` continues at monomial K3_USLOT + part
+                const int rest = (n - ns - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
+                slice_component(B.u_key + idx * B.capU + ns + part, B.u_g + idx * B.capU + ns + part, rest > 0 ? rest : 0,
+                                K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
+            }
+#else
             const int mine = (n - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
             slice_component(B.u_key + idx * B.capU + part, B.u_g + idx * B.capU + part, mine > 0 ? mine : 0,
                             K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
+#endif
         }
         value += __shfl_xor_sync(0xffffffffu, value, 1);
 #pragma unroll
         for (int v = 0; v < NF; v++) grad[v] += __shfl_xor_sync(0xffffffffu, grad[v], 1);
-        double* st = &s_stage[K3_TORQUE_T0 / 32][0];  // the stages of the four torque warps are contiguous
+        double* st = s_tj;
         if (on && part == 0) {
             value = B.u_c[idx] + value;
             const double r = B.u_r[idx];
@@ -587,7 +663,10 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     const unsigned char* cnt = B.hp_cnt + chunk * per_pair;
     const size_t cstride2 = size_t(per_pair) * 2;  // candidate stride in double2 units
     const bool in_domain = s_in_domain != 0;
+    const float inv_O = O > 0 ? 1.0f / float(O) : 0.0f;
+#if !K3_DIRECT_J
     double* stage = &s_stage[warp][0];
+#endif
     for (;;) {
         int x0 = 0;
         if (lane == 0) x0 = atomicAdd(&s_next, 1) * 32;
@@ -599,8 +678,8 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
         double A0 = 0, A1 = 0, A2 = 0;  // minus the winning signed normal
         int l = 0, tt = 0, o = 0;
         if (active) {
-            o = x % O;
-            const int ltt = x / O;
+            const int ltt = __float2int_rz((float(x) + 0.5f) * inv_O);  // x / O, exact for x < 2^22
+            o = x - ltt * O;
             tt = ltt % TB;
             l = ltt / TB;
             const double c0 = s_lc[tt][l][0], c1 = s_lc[tt][l][1], c2 = s_lc[tt][l][2];
@@ -634,6 +713,17 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
         }
         const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
         if (gp && active) gp[row_i] = -max_elt;
+#if K3_DIRECT_J
+        if (jp && active) {
+            double* out = jp + row_i * NF;
+#pragma unroll
+            for (int v = 0; v < NF; v++) {
+                const double* dk = s_dlc[tt][l][v];
+                // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
+                out[v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+            }
+        }
+#else
         if (jp) {
             if (active) {
 #pragma unroll
@@ -653,6 +743,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             }
             __syncwarp();
         }
+#endif
     }
 
     // Bezier joint-limit rows (KPR/Trajectory.cu:256-540), once per problem
@@ -888,8 +979,9 @@ cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st, const int* unit_
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
     dim3 grid(B.T / TB, B.nprob);
+    const size_t dyn = K3_STAGE_TABLES ? size_t(TB) * (B.NJ * K3_LTAB_BYTES + NF * K3_UTAB_BYTES) : 0;
     if (B.O == 0) {
-        k_constraints<<<grid, K3_THREADS, 0, st>>>(B, d_k, d_g, d_jac);
+        k_constraints<<<grid, K3_THREADS, dyn, st>>>(B, d_k, d_g, d_jac);
         return cudaGetLastError();
     }
     // slow path first (a normal launch: it waits for whatever precedes it on the stream), the main kernel behind it as a
@@ -900,7 +992,7 @@ cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, d
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(K3_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = dyn;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
