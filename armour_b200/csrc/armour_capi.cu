@@ -392,7 +392,7 @@ int armour_ctx_create(const armour_config* cfg, armour_ctx** out) {
         if ((e = cudaFuncGetAttributes(&fa, k_hyperplanes)) != cudaSuccess) return bail("load k_hyperplanes", e);
         if ((e = cudaFuncGetAttributes(&fa, k_constraints)) != cudaSuccess) return bail("load k_constraints", e);
         if ((e = cudaFuncSetAttribute(k_constraints, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      TB * (MAXJ * K3_LTAB_BYTES + NF * K3_UTAB_BYTES))) != cudaSuccess)
+                                      TB * (MAXJ * K3_LTAB_BYTES + NF * K3_UTAB_BYTES) + K3_CAND_ARENA)) != cudaSuccess)
             return bail("k_constraints shared memory", e);
         if ((e = cudaFuncGetAttributes(&fa, k_constraints_slow)) != cudaSuccess) return bail("load k_constraints_slow", e);
         if ((e = cudaFuncGetAttributes(&fa, k_verdict)) != cudaSuccess) return bail("load k_verdict", e);

@@ -440,6 +440,34 @@ __device__ __forceinline__ void slice_component(const uint16_t* __restrict__ key
 // The link warps meet on named barrier 1 and go straight to the collision rows; the torque warps write their
 // rows, then join through barrier 2 (on which the link warps only arrive), so nobody waits for the slowest
 // slice.  Collision rows are handed out in chunks of 32 from a shared counter.
+// ---- TMA bulk copy (cp.async.bulk global -> shared, completion on an mbarrier) --------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+#ifndef K3_STAGE_CAND
+#define K3_STAGE_CAND 0    // (measured r2t: 577 us against 565 without) 1: the first two candidate records of every row of the chunk (one contiguous run per level) are
+                           // fetched by ONE thread with TMA bulk copies at the start of the CTA and wait in shared memory when
+                           // the scan gets there: the scan's DRAM round trip (the largest stall of the kernel) is gone
+#endif
+constexpr int K3_CAND_ARENA = 36864;  // bytes of staged records: two levels x 576 rows x 32 B
 #ifndef K3_STAGE_TABLES
 #define K3_STAGE_TABLES 0  // 1: the tables of the chunk are fetched with cp.async into fixed shared-memory slots, then walked
                            // there.  Measured (r2s): 635 us against 560 without — the barrier in front of the walk costs
@@ -455,6 +483,71 @@ constexpr int K3_UTAB_BYTES = K3_USLOT * 2 + K3_USLOT * 8;
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+#ifndef K3_POWER_TABLES
+#define K3_POWER_TABLES 1  // 1: slices against two power-product tables built per CTA (2 products + 8 fused multiply-adds + 5
+                           // look-ups per monomial); 0: factor by factor like the reference (35 + 7 look-ups)
+#endif
+// Power-product tables of one k (built per CTA, one entry per thread, before the slices).  A k-only monomial key holds seven
+// 2-bit degrees: the key is split into its low 6 bits (k_0..k_2, 64 entries {M, dM/dk_0..2}) and its high 8 bits
+// (k_3..k_6, 256 entries {M, dM/dk_3..6}).  A factor of degree 0 is the exact 1.0 and its derivative the exact 0.0, as in
+// PZsparse::slice (KPR/PZsparse.cu:404-555); the association differs from the reference's coef * f_0 * f_1 * ... by a few ulp
+// of each term (bar: 1e-9).
+constexpr int PT_LO = 64, PT_LO_STRIDE = 4;    // doubles per entry: 32 B, two 16-byte loads
+constexpr int PT_HI = 256, PT_HI_STRIDE = 6;   // 5 used + 1 pad: 48 B, three 16-byte loads
+__device__ __forceinline__ void power_and_slope(double k, int d, double& f, double& fp) {
+    f = d == 0 ? 1.0 : d == 1 ? k : d == 2 ? k * k : k * k * k;
+    fp = d == 0 ? 0.0 : d == 1 ? 1.0 : d == 2 ? 2.0 * k : 3.0 * (k * k);
+}
+// entry `e` of the table over the NV variables v0 .. v0+NV-1: out[0] = prod f_v, out[1+i] = f'_{v0+i} prod_{u != i} f_u
+template <int NV>
+__device__ __forceinline__ void power_table_entry(const double* __restrict__ k, int v0, int e, double* out) {
+    double f[NV], fp[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) power_and_slope(k[v0 + i], (e >> (2 * i)) & 3, f[i], fp[i]);
+    double M = f[0];
+#pragma unroll
+    for (int i = 1; i < NV; i++) M *= f[i];
+    out[0] = M;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double G = fp[i];
+#pragma unroll
+        for (int u = 0; u < NV; u++)
+            if (u != i) G *= f[u];
+        out[1 + i] = G;
+    }
+}
+__device__ __forceinline__ void slice_component_pt(const uint16_t* __restrict__ keys, const double* __restrict__ coef, int n,
+                                                   int kstride, int cstride, const double* __restrict__ pt_lo,
+                                                   const double* __restrict__ pt_hi, double& value, double (&grad)[NF]) {
+    constexpr int CH = K3_CH;
+    for (int m0 = 0; m0 < n; m0 += CH) {
+        unsigned kk[CH];
+        double cc[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const bool on = m0 + i < n;
+            kk[i] = on ? keys[(m0 + i) * kstride] : 0u;
+            cc[i] = on ? coef[(m0 + i) * cstride] : 0.0;
+        }
+        // a monomial past the end has coefficient 0 and key 0: it adds exact zeros, so the chunk needs no tail test
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const double2* L = reinterpret_cast<const double2*>(pt_lo + (kk[i] & (PT_LO - 1)) * PT_LO_STRIDE);
+            const double2* H = reinterpret_cast<const double2*>(pt_hi + ((kk[i] >> 6) & (PT_HI - 1)) * PT_HI_STRIDE);
+            const double2 l0 = L[0], l1 = L[1], h0 = H[0], h1 = H[1], h2 = H[2];
+            const double cl = cc[i] * l0.x, ch = cc[i] * h0.x;
+            value = fma(cl, h0.x, value);
+            grad[0] = fma(ch, l0.y, grad[0]);
+            grad[1] = fma(ch, l1.x, grad[1]);
+            grad[2] = fma(ch, l1.y, grad[2]);
+            grad[3] = fma(cl, h0.y, grad[3]);
+            grad[4] = fma(cl, h1.x, grad[4]);
+            grad[5] = fma(cl, h1.y, grad[5]);
+            grad[6] = fma(cl, h2.x, grad[6]);
+        }
+    }
+}
 constexpr int K3_LINK_THREADS = 192;
 constexpr int K3_TORQUE_LANES = 2;
 constexpr int K3_THREADS = 320;
@@ -468,13 +561,25 @@ static_assert(TB * 3 * MAXJ <= K3_LINK_THREADS && K3_TORQUE_T0 + TB * NF * K3_TO
 // 4 candidate records in flight per thread 0.81; the same at 96 registers / 2 CTAs 0.98, at 48 / 4 CTAs 1.68 (spills);
 // 2 monomials + 2 records in flight at 64 / 3 CTAs 0.73, at 48 / 4 CTAs 0.66, at 40 / 5 CTAs 0.81.  The kernel lives
 // on resident warps, not on loads in flight per warp: anything that spills or costs a CTA per SM loses.
+#if K3_POWER_TABLES
+#define K3_SLICE slice_component_pt
+#define K3_SLICE_TABLES pt_lo, pt_hi
+#else
+#define K3_SLICE slice_component
+#define K3_SLICE_TABLES kpd
+#endif
 __global__ void __launch_bounds__(K3_THREADS, K3_MINB)
 k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, double* __restrict__ jac) {
     const int tb = blockIdx.x, p = B.plist ? B.plist[blockIdx.y] : int(blockIdx.y);
     const int NJ = B.NJ, O = B.O, T = B.T;
     const int m = B.m();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if K3_POWER_TABLES
+    __shared__ __align__(16) double pt_lo[PT_LO * PT_LO_STRIDE];  // power products of k_0..k_2 and their slopes
+    __shared__ __align__(16) double pt_hi[PT_HI * PT_HI_STRIDE];  // the same for k_3..k_6
+#else
     __shared__ double2 kpd[NF][4];  // {k_j^d, d/dk_j k_j^d} for d = 0..3
+#endif
     __shared__ __align__(4) unsigned char s_cnt[K3_CNT_SMEM];  // candidate counts of this CTA's rows
     __shared__ double s_lc[TB][MAXJ][3];
     __shared__ double s_dlc[TB][MAXJ][NF][3];
@@ -482,7 +587,8 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     __shared__ double s_stage[K3_WARPS][32 * NF];  // per-warp transpose buffer: Jacobian rows leave coalesced
 #endif
     __shared__ double s_tj[TB * NF * NF];          // torque rows of the Jacobian: leave as one contiguous run
-    extern __shared__ __align__(16) unsigned char k3_tab[];  // staged tables: TB*NJ link slots, then TB*NF torque slots
+    extern __shared__ __align__(16) unsigned char k3_tab[];  // staged tables (K3_STAGE_TABLES), then staged candidate records
+    __shared__ unsigned long long s_bar;                     // completion of the candidate copy
     __shared__ int s_in_domain;
     __shared__ int s_next;  // next chunk of 32 collision rows
 
@@ -511,12 +617,37 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
         }
         return;
     }
+#if K3_STAGE_CAND
+    // rows [0, rows_staged) of candidate levels 0 and 1: [level][row][4] in shared memory
+    const int rows_all = NJ * TB * O;
+    const int rows_staged = rows_all < K3_CAND_ARENA / 64 ? rows_all : K3_CAND_ARENA / 64;
+    double* const s_rec = reinterpret_cast<double*>(k3_tab + (K3_STAGE_TABLES ? TB * (NJ * K3_LTAB_BYTES + NF * K3_UTAB_BYTES) : 0));
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const double* src = B.hp_cand + (size_t(p) * (T / TB) + tb) * B.hp_chunk();
+        const unsigned bytes = unsigned(rows_staged) * 32u;
+        mbar_arrive_expect_tx(&s_bar, rows_staged > 0 ? 2 * bytes : 0);
+        if (rows_staged > 0) {
+            bulk_g2s(s_rec, src, bytes, &s_bar);
+            bulk_g2s(s_rec + size_t(rows_staged) * 4, src + size_t(rows_all) * 4, bytes, &s_bar);
+        }
+    }
+#endif
     if (tid == 32) {
         bool in = true;
         for (int j = 0; j < NF; j++) in = in && (fabs(kin[size_t(p) * NF + j]) <= K_DOMAIN);
         s_in_domain = in ? 1 : 0;
         s_next = 0;
     }
+#if K3_POWER_TABLES
+    if (tid < PT_HI) {  // one table entry per thread (320 entries, 320 threads)
+        power_table_entry<4>(kin + size_t(p) * NF, 3, tid, pt_hi + tid * PT_HI_STRIDE);
+        pt_hi[tid * PT_HI_STRIDE + 5] = 0.0;
+    } else {
+        power_table_entry<3>(kin + size_t(p) * NF, 0, tid - PT_HI, pt_lo + (tid - PT_HI) * PT_LO_STRIDE);
+    }
+#else
     if (tid < NF) {
         const double k = kin[size_t(p) * NF + tid];
         kpd[tid][0] = make_double2(1.0, 0.0);
@@ -524,6 +655,7 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
         kpd[tid][2] = make_double2(k * k, 2.0 * k);
         kpd[tid][3] = make_double2(k * k * k, 3.0 * (k * k));
     }
+#endif
     const int per_pair = NJ * TB * O;
     const size_t chunk = size_t(p) * (T / TB) + tb;
     const bool cnt_in_smem = per_pair <= K3_CNT_SMEM;
@@ -572,12 +704,12 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             double value = B.link_c[idx * 3 + e];
             double grad[NF] = {0, 0, 0, 0, 0, 0, 0};
 #if K3_STAGE_TABLES
-            slice_component(reinterpret_cast<const uint16_t*>(slot), reinterpret_cast<const double*>(slot + 32) + e, ns, 1, 3, kpd,
+            K3_SLICE(reinterpret_cast<const uint16_t*>(slot), reinterpret_cast<const double*>(slot + 32) + e, ns, 1, 3, K3_SLICE_TABLES,
                             value, grad);
             if (n > ns)
-                slice_component(B.link_key + idx * B.capL + ns, B.link_g + (idx * B.capL + ns) * 3 + e, n - ns, 1, 3, kpd, value, grad);
+                K3_SLICE(B.link_key + idx * B.capL + ns, B.link_g + (idx * B.capL + ns) * 3 + e, n - ns, 1, 3, K3_SLICE_TABLES, value, grad);
 #else
-            slice_component(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, n, 1, 3, kpd, value, grad);
+            K3_SLICE(B.link_key + idx * B.capL, B.link_g + idx * B.capL * 3 + e, n, 1, 3, K3_SLICE_TABLES, value, grad);
 #endif
             // centre of Interval(c - r, c + r), as getCenter(slice()) does (KPR/NLPclass.cu:313)
             const double r = B.link_r[idx * 3 + e];
@@ -625,17 +757,17 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             unsigned char* slot = k3_tab + TB * NJ * K3_LTAB_BYTES + i * K3_UTAB_BYTES;
             const int ns = n < K3_USLOT ? n : K3_USLOT;
             const int mine_s = (ns - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
-            slice_component(reinterpret_cast<const uint16_t*>(slot) + part, reinterpret_cast<const double*>(slot + K3_USLOT * 2) + part,
-                            mine_s > 0 ? mine_s : 0, K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
+            K3_SLICE(reinterpret_cast<const uint16_t*>(slot) + part, reinterpret_cast<const double*>(slot + K3_USLOT * 2) + part,
+                            mine_s > 0 ? mine_s : 0, K3_TORQUE_LANES, K3_TORQUE_LANES, K3_SLICE_TABLES, value, grad);
             if (n > ns) {  // K3_USLOT is even: lane `part` continues at monomial K3_USLOT + part
                 const int rest = (n - ns - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
-                slice_component(B.u_key + idx * B.capU + ns + part, B.u_g + idx * B.capU + ns + part, rest > 0 ? rest : 0,
-                                K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
+                K3_SLICE(B.u_key + idx * B.capU + ns + part, B.u_g + idx * B.capU + ns + part, rest > 0 ? rest : 0,
+                                K3_TORQUE_LANES, K3_TORQUE_LANES, K3_SLICE_TABLES, value, grad);
             }
 #else
             const int mine = (n - part + K3_TORQUE_LANES - 1) / K3_TORQUE_LANES;
-            slice_component(B.u_key + idx * B.capU + part, B.u_g + idx * B.capU + part, mine > 0 ? mine : 0,
-                            K3_TORQUE_LANES, K3_TORQUE_LANES, kpd, value, grad);
+            K3_SLICE(B.u_key + idx * B.capU + part, B.u_g + idx * B.capU + part, mine > 0 ? mine : 0,
+                            K3_TORQUE_LANES, K3_TORQUE_LANES, K3_SLICE_TABLES, value, grad);
 #endif
         }
         value += __shfl_xor_sync(0xffffffffu, value, 1);
@@ -667,6 +799,9 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 #if !K3_DIRECT_J
     double* stage = &s_stage[warp][0];
 #endif
+#if K3_STAGE_CAND
+    mbar_wait(&s_bar, 0);  // issued before the slices: complete long ago (and nothing may be in flight when the CTA exits)
+#endif
     for (;;) {
         int x0 = 0;
         if (lane == 0) x0 = atomicAdd(&s_next, 1) * 32;
@@ -689,6 +824,18 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                 // K3_CQ candidate records in flight per thread (the scan itself stays in order)
                 for (int q0 = 0; q0 < n; q0 += K3_CQ) {
                     double2 u[K3_CQ], w[K3_CQ];
+#if K3_STAGE_CAND
+                    static_assert(K3_CQ == 2, "the staged levels are the first pass of the scan");
+                    if (q0 == 0 && x < rows_staged) {
+                        const double2* sr = reinterpret_cast<const double2*>(s_rec) + size_t(x) * 2;
+                        u[0] = sr[0];
+                        w[0] = sr[1];
+                        if (n > 1) {
+                            u[1] = sr[size_t(rows_staged) * 2];
+                            w[1] = sr[size_t(rows_staged) * 2 + 1];
+                        }
+                    } else
+#endif
 #pragma unroll
                     for (int i = 0; i < K3_CQ; i++) {
                         if (q0 + i < n) {
@@ -773,6 +920,8 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
     }
 }
 
+#undef K3_SLICE
+#undef K3_SLICE_TABLES
 // k_constraints_slow: the collision rows k_constraints leaves out — rows without a stored candidate list (more than HP_CAP
 // survivors, or no room left in the chunk) and every row of a problem whose k lies outside the box the lists were built
 // for.  One CTA per problem, which returns at once in the usual case (no such row); otherwise one thread per row slices
@@ -979,7 +1128,9 @@ cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st, const int* unit_
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
     dim3 grid(B.T / TB, B.nprob);
-    const size_t dyn = K3_STAGE_TABLES ? size_t(TB) * (B.NJ * K3_LTAB_BYTES + NF * K3_UTAB_BYTES) : 0;
+    const int rows_all = B.NJ * TB * B.O;
+    const size_t dyn = (K3_STAGE_TABLES ? size_t(TB) * (B.NJ * K3_LTAB_BYTES + NF * K3_UTAB_BYTES) : 0) +
+                       (K3_STAGE_CAND ? size_t(rows_all < K3_CAND_ARENA / 64 ? rows_all : K3_CAND_ARENA / 64) * 64 : 0);
     if (B.O == 0) {
         k_constraints<<<grid, K3_THREADS, dyn, st>>>(B, d_k, d_g, d_jac);
         return cudaGetLastError();
