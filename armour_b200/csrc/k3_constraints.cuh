@@ -483,6 +483,9 @@ constexpr int K3_UTAB_BYTES = K3_USLOT * 2 + K3_USLOT * 8;
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+#ifndef K3_LD256
+#define K3_LD256 1
+#endif
 #ifndef K3_POWER_TABLES
 #define K3_POWER_TABLES 1  // 1: slices against two power-product tables built per CTA (2 products + 8 fused multiply-adds + 5
                            // look-ups per monomial); 0: factor by factor like the reference (35 + 7 look-ups)
@@ -632,6 +635,17 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             bulk_g2s(s_rec, src, bytes, &s_bar);
             bulk_g2s(s_rec + size_t(rows_staged) * 4, src + size_t(rows_all) * 4, bytes, &s_bar);
         }
+    }
+#endif
+#ifndef K3_PREFETCH_L2
+#define K3_PREFETCH_L2 0   // measured r2v: 553 us with, 551 without
+#endif
+#if K3_PREFETCH_L2
+    {   // the first two candidate records of every row of the chunk are two contiguous runs: ask L2 for them now, the scan
+        // reads them after the slices (no registers, no shared memory, no wait)
+        const char* c0p = reinterpret_cast<const char*>(B.hp_cand + (size_t(p) * (T / TB) + tb) * B.hp_chunk());
+        const int lines = (NJ * TB * O * 32 * 2 + 127) / 128;
+        for (int i = tid; i < lines; i += K3_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(c0p + size_t(i) * 128));
     }
 #endif
     if (tid == 32) {
@@ -839,8 +853,15 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 #pragma unroll
                     for (int i = 0; i < K3_CQ; i++) {
                         if (q0 + i < n) {
+#if K3_LD256
+                            // one 32-byte record = one 256-bit load (sm_100: ld.global.v4.f64)
+                            asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                                         : "=d"(u[i].x), "=d"(u[i].y), "=d"(w[i].x), "=d"(w[i].y)
+                                         : "l"(row + (q0 + i) * cstride2));
+#else
                             u[i] = __ldg(row + (q0 + i) * cstride2);
                             w[i] = __ldg(row + (q0 + i) * cstride2 + 1);
+#endif
                         }
                     }
 #pragma unroll
@@ -863,11 +884,25 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
 #if K3_DIRECT_J
         if (jp && active) {
             double* out = jp + row_i * NF;
+            double jv[NF];
 #pragma unroll
             for (int v = 0; v < NF; v++) {
                 const double* dk = s_dlc[tt][l][v];
                 // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
-                out[v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+                jv[v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
+            }
+            // 56 contiguous bytes per row, 16-byte aligned for even rows (the Jacobian of a problem starts 16-byte aligned and
+            // m is even): three 16-byte stores and one 8-byte store instead of seven 8-byte stores
+            if ((row_i & 1) == 0) {
+                *reinterpret_cast<double2*>(out) = make_double2(jv[0], jv[1]);
+                *reinterpret_cast<double2*>(out + 2) = make_double2(jv[2], jv[3]);
+                *reinterpret_cast<double2*>(out + 4) = make_double2(jv[4], jv[5]);
+                out[6] = jv[6];
+            } else {
+                out[0] = jv[0];
+                *reinterpret_cast<double2*>(out + 1) = make_double2(jv[1], jv[2]);
+                *reinterpret_cast<double2*>(out + 3) = make_double2(jv[3], jv[4]);
+                *reinterpret_cast<double2*>(out + 5) = make_double2(jv[5], jv[6]);
             }
         }
 #else
