@@ -552,8 +552,11 @@ __device__ __forceinline__ void slice_component_pt(const uint16_t* __restrict__ 
     }
 }
 constexpr int K3_LINK_THREADS = 192;
-constexpr int K3_TORQUE_LANES = 2;
-constexpr int K3_THREADS = 320;
+#ifndef K3_TORQUE_LANES_N
+#define K3_TORQUE_LANES_N 2
+#endif
+constexpr int K3_TORQUE_LANES = K3_TORQUE_LANES_N;  // lanes per torque table in the slice phase (a power of two)
+constexpr int K3_THREADS = K3_LINK_THREADS + ((TB * NF * K3_TORQUE_LANES + 31) / 32) * 32;
 constexpr int K3_CNT_SMEM = 2048;  // rows per CTA whose candidate counts are staged in shared memory
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_TORQUE_T0 = K3_LINK_THREADS;
@@ -655,11 +658,13 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
         s_next = 0;
     }
 #if K3_POWER_TABLES
-    if (tid < PT_HI) {  // one table entry per thread (320 entries, 320 threads)
-        power_table_entry<4>(kin + size_t(p) * NF, 3, tid, pt_hi + tid * PT_HI_STRIDE);
-        pt_hi[tid * PT_HI_STRIDE + 5] = 0.0;
-    } else {
-        power_table_entry<3>(kin + size_t(p) * NF, 0, tid - PT_HI, pt_lo + (tid - PT_HI) * PT_LO_STRIDE);
+    for (int q = tid; q < PT_HI + PT_LO; q += K3_THREADS) {  // one table entry per thread (320 entries)
+        if (q < PT_HI) {
+            power_table_entry<4>(kin + size_t(p) * NF, 3, q, pt_hi + q * PT_HI_STRIDE);
+            pt_hi[q * PT_HI_STRIDE + 5] = 0.0;
+        } else {
+            power_table_entry<3>(kin + size_t(p) * NF, 0, q - PT_HI, pt_lo + (q - PT_HI) * PT_LO_STRIDE);
+        }
     }
 #else
     if (tid < NF) {
@@ -784,9 +789,12 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                             K3_TORQUE_LANES, K3_TORQUE_LANES, K3_SLICE_TABLES, value, grad);
 #endif
         }
-        value += __shfl_xor_sync(0xffffffffu, value, 1);
 #pragma unroll
-        for (int v = 0; v < NF; v++) grad[v] += __shfl_xor_sync(0xffffffffu, grad[v], 1);
+        for (int d = 1; d < K3_TORQUE_LANES; d <<= 1) {
+            value += __shfl_xor_sync(0xffffffffu, value, d);
+#pragma unroll
+            for (int v = 0; v < NF; v++) grad[v] += __shfl_xor_sync(0xffffffffu, grad[v], d);
+        }
         double* st = s_tj;
         if (on && part == 0) {
             value = B.u_c[idx] + value;
