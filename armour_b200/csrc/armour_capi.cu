@@ -529,10 +529,21 @@ int armour_batch_reachsets_build(armour_ctx* ctx, int nprob, const double* q0, c
     CU(cudaMemcpyAsync(st.data(), ctx->B.status, nprob * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int p = 0; p < nprob; p++)
-        if ((st[p] >> 3) == ctx->B.epoch && (st[p] & 7) != 0)
+        if ((st[p] >> 3) == ctx->B.epoch && (st[p] & 7) != 0) {
+            // which check failed first, and where (diagnostics of the build kernel: stats[4..6])
+            int site[3] = {0, 0, 0};
+            const int* dstats = latency ? ctx->k1_lat.stats : ctx->k1_thr.stats;
+            std::string where;
+            if (dstats && cudaMemcpy(site, dstats + 4, sizeof(site), cudaMemcpyDeviceToHost) == cudaSuccess && site[2] == ctx->B.epoch) {
+                const int line = site[0] >> 3;
+                where = "; first failing check: code " + std::to_string(site[0] & 7) + " at " +
+                        (line >= 10000 ? "k1_reachsets.cuh:" + std::to_string(line - 10000) : "k1_pz.cuh:" + std::to_string(line)) +
+                        ", problem " + std::to_string(site[1] / ctx->B.T) + " interval " + std::to_string(site[1] % ctx->B.T);
+            }
             return fail(ctx, ARMOUR_ERR_CAPACITY,
                         "reach-set build overflowed a monomial table (problem " + std::to_string(p) + ", code " +
-                            std::to_string(st[p] & 7) + ")");
+                            std::to_string(st[p] & 7) + ")" + where);
+        }
     return ARMOUR_OK;
 }
 

@@ -120,6 +120,7 @@ struct K1S {
     int GW, FW;
     int tab_s_bytes, tab_g_bytes;
     int fail;        // first failure code of the current unit (0 = none)
+    int fail_line;   // source line of the check that set it (k1_pz.cuh; 10000 + line for k1_reachsets.cuh)
     int n_tab_global;  // statistics
     int unit;
     int cnt[NW];     // survivor counts per warp
@@ -193,10 +194,15 @@ K1_DI K1S& k1s() { return *reinterpret_cast<K1S*>(smem_base()); }
 K1_DI double* arena0() { return reinterpret_cast<double*>(smem_base() + K1S_BYTES); }
 K1_DI char* tab_s0() { return reinterpret_cast<char*>(arena0() + k1s().AW); }
 
-K1_DI void set_fail(int code) {
+K1_DI void set_fail_at(int code, int line) {
     K1S& S = k1s();
-    if (!S.fail) S.fail = code;  // every thread writes the same value
+    if (!S.fail) {  // every thread of a site writes the same values
+        S.fail = code;
+        S.fail_line = line;
+    }
 }
+// the source line of the capacity check that failed first is kept for the error message (armour_last_error)
+#define set_fail(code) set_fail_at(code, __LINE__)
 
 // The arena is one virtual offset space over two segments: [0, AW) in shared memory (the fixed JRS region
 // first), then the CTA's global scratch: [AW, AW + GW) is spill space for the few long intervals whose live
@@ -572,16 +578,17 @@ struct Dense {
 };
 K1_DI bool dense_select(int M, int sz, Dense& d) {
     K1S& S = k1s();
-    if (M > 32 * MASK_WORDS) {
-        set_fail(FAIL_TABLE);
-        return false;
-    }
-    const int bytes = M * 8 * (1 + sz);
+    // More candidates than the survivor masks of the control block hold (32 * MASK_WORDS; thresholds far below the default
+    // get there): the mask then lives behind the scratch itself, in the global pool, whose all-zero invariant gives the
+    // "all zero on entry" the mask needs; dense_emit clears it again.  d.flip = 2 marks that case.
+    const bool big = M > 32 * MASK_WORDS;
+    const size_t data_bytes = size_t(M) * 8 * (1 + sz);
+    const size_t bytes = data_bytes + (big ? size_t((M + 63) >> 6) * 8 : 0);
     char* base;
     d.global = false;
-    if (bytes <= S.tab_s_bytes) {
+    if (!big && bytes <= size_t(S.tab_s_bytes)) {
         base = tab_s0();
-    } else if (bytes <= S.tab_g_bytes) {
+    } else if (bytes <= size_t(S.tab_g_bytes)) {
         base = S.tab_g;
         d.global = true;
         if (k1_tid() == 0) S.n_tab_global++;
@@ -594,8 +601,8 @@ K1_DI bool dense_select(int M, int sz, Dense& d) {
     }
     d.keys = reinterpret_cast<u64*>(base);
     d.coef = reinterpret_cast<double*>(base + size_t(M) * 8);
-    const int f = S.flip;
-    d.mask = S.mask[f];
+    const int f = big ? 2 : S.flip;
+    d.mask = big ? reinterpret_cast<unsigned*>(base + data_bytes) : S.mask[f];
     d.flip = f;
     d.M = M;
     return true;
@@ -642,12 +649,13 @@ K1_DI void rad_collect(double* rad_total) {
 // allocate the output block at `top` and copy them in merged (= key) order.  The caller writes the
 // centre / radii and ends with __syncthreads().  Kept out of line and with run-time loops: one copy of this
 // code per element size serves every merge operation (code size is what bounds this kernel).
-template <int SZ>
+template <int SZ, bool BIG>
 K1_OP PZ8 dense_emit_impl(int top, u64* keys, int M, int flip, int global) {
     K1S& S = k1s();
     const int tid = k1_tid(), lane = tid & 31, warp = tid >> 5;
-    const unsigned* mask = S.mask[flip];
     double* coef = reinterpret_cast<double*>(keys + M);
+    unsigned* big_mask = reinterpret_cast<unsigned*>(coef + size_t(M) * SZ);  // (BIG: see dense_select)
+    const unsigned* mask = BIG ? big_mask : S.mask[flip];
     const int nwords = (M + 31) >> 5;
     const int rounds = (nwords + 31) >> 5;
     int total = 0;
@@ -659,8 +667,10 @@ K1_OP PZ8 dense_emit_impl(int top, u64* keys, int M, int flip, int global) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     // prepare the mask buffer of the next merge operation; its last readers finished before the barrier above
-    for (int i = tid; i < MASK_WORDS; i += NT) S.mask[flip ^ 1][i] = 0u;
-    if (tid == 0) S.flip = flip ^ 1;
+    if (!BIG) {
+        for (int i = tid; i < MASK_WORDS; i += NT) S.mask[flip ^ 1][i] = 0u;
+        if (tid == 0) S.flip = flip ^ 1;
+    }
     bool ok;
     const PZ8 h8 = pz_alloc<SZ>(top, total, &ok);
     const PZH h = view<SZ>(h8);
@@ -700,11 +710,16 @@ K1_OP PZ8 dense_emit_impl(int top, u64* keys, int M, int flip, int global) {
             }
         }
     }
+    if (BIG) {  // the mask behind the scratch goes back all-zero too (every warp is done reading it)
+        k1_sync();
+        for (int i = tid; i < nwords; i += NT) big_mask[i] = 0u;
+    }
     return h8;
 }
 template <int SZ>
 K1_DI PZ8 dense_emit(int top, const Dense& d, bool* ok_out) {
-    const PZ8 h8 = dense_emit_impl<SZ>(top, d.keys, d.M, d.flip, d.global ? 1 : 0);
+    const PZ8 h8 = d.flip == 2 ? dense_emit_impl<SZ, true>(top, d.keys, d.M, d.flip, 1)
+                               : dense_emit_impl<SZ, false>(top, d.keys, d.M, d.flip, d.global ? 1 : 0);
     *ok_out = !k1s().fail;
     return h8;
 }
@@ -725,12 +740,37 @@ K1_DI void sort_block(PZ8 h8, bool ok) {
     const int tid = k1_tid();
     const PZH h = view<SZ>(h8);
     const int n = ok ? h.n : 0;
-    if (n > R * NT) {
-        set_fail(FAIL_TABLE);
-        return;
-    }
     u64* keys = pz_keys(h);
     double* cf = pz_coef(h);
+    if (n > R * NT) {
+        // more survivors than the register path holds (thresholds far below the default): rank every monomial, scatter into
+        // the global table pool, copy back, hand the pool back all-zero
+        K1S& S = k1s();
+        if (size_t(n) * 8 * (1 + SZ) > size_t(S.tab_g_bytes)) {
+            set_fail(FAIL_TABLE);
+            return;
+        }
+        u64* sk = reinterpret_cast<u64*>(S.tab_g);
+        double* sv = reinterpret_cast<double*>(S.tab_g + size_t(n) * 8);
+        for (int i = tid; i < n; i += NT) {
+            const u64 ki = keys[i];
+            int c = 0;
+            for (int q = 0; q < n; q++) c += (keys[q] < ki);
+            sk[c] = ki;
+            for (int e = 0; e < SZ; e++) sv[size_t(c) * SZ + e] = cf[size_t(i) * SZ + e];
+        }
+        k1_sync();
+        for (int i = tid; i < n; i += NT) {
+            keys[i] = sk[i];
+            sk[i] = 0;
+            for (int e = 0; e < SZ; e++) {
+                cf[size_t(i) * SZ + e] = sv[size_t(i) * SZ + e];
+                sv[size_t(i) * SZ + e] = 0.0;
+            }
+        }
+        k1_sync();
+        return;
+    }
     u64 k[R];
     double v[R][SZ];
     int rank[R];

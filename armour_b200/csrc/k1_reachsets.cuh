@@ -17,6 +17,8 @@
 #include "bezier.cuh"
 #include "device_constants.cuh"
 #include "k1_pz.cuh"
+#undef set_fail
+#define set_fail(code) set_fail_at(code, 10000 + __LINE__)
 #include "k1_interval.cuh"
 #include "layout.h"
 
@@ -1189,7 +1191,13 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
         const int failed = S.fail;
         if (failed) {
             if (!extra && (!MG || k1_group() == 0)) nfail++;
-            if (tid == 0) atomicMax(&P.B.status[p], P.B.epoch * 8 + failed);  // (epochs grow: no reset between builds)
+            if (tid == 0) {
+                atomicMax(&P.B.status[p], P.B.epoch * 8 + failed);  // (epochs grow: no reset between builds)
+                if (P.stats && atomicMax(&P.stats[6], P.B.epoch) < P.B.epoch) {  // first failing unit of this build
+                    P.stats[4] = S.fail_line * 8 + failed;
+                    P.stats[5] = p * P.B.T + t;
+                }
+            }
             // a failed operation may leave a table half-built: restore the all-zero invariant
             for (int i = tid; i < P.tab_s_bytes / 8; i += NT) s_tab[i] = 0;
             for (int i = tid; i < P.gtab_bytes / 8; i += NT) reinterpret_cast<u64*>(S.tab_g)[i] = 0;
@@ -1279,7 +1287,8 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     s->gtab_bytes = 16 * capw * 8 * 7;  // a cross product table for up to ~10 * capw candidate keys
     if ((e = cudaMalloc(&s->work, 2 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s->work, 0, 2 * sizeof(int), st)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&s->stats, 4 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&s->stats, 8 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s->stats, 0, 8 * sizeof(int), st)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->gscr, size_t(s->grid) * GROUPS * s->gscr_words * 8)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&s->gtab, size_t(s->grid) * GROUPS * s->gtab_bytes)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s->gtab, 0, size_t(s->grid) * GROUPS * s->gtab_bytes, st)) != cudaSuccess) return e;

@@ -3,6 +3,7 @@
 // Built by tests/test_k1_emu.py with g++ -O1 -ffp-contract=off; never part of the product.
 #include "cuda_emu.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -53,9 +54,10 @@ extern "C" int emu_k1_build(int model_id, int T, double thr, const double* k_ran
     k1::K1Params P;
     P.B = B;
     P.work = &work;
-    const int gscr_words = 2 * MAXJ * (9 + 4096 * 4);
+    const int emu_capw = std::getenv("EMU_CAPW") ? std::atoi(std::getenv("EMU_CAPW")) : 4096;  // developer knob
+    const int gscr_words = 2 * MAXJ * (9 + emu_capw * 4);
     std::vector<double> gscr(gscr_words);
-    const int gtab_bytes = 1 << 22;
+    const int gtab_bytes = std::getenv("EMU_GTAB") ? std::atoi(std::getenv("EMU_GTAB")) : (1 << 22);
     std::vector<char> gtab(gtab_bytes, 0);
     P.gscr = gscr.data();
     P.gscr_words = gscr_words;

@@ -48,7 +48,7 @@ def run_units(lib, q0, qd0, qdd0, ts, model_id=0, thr=5e-4, capL=64, capU=128, a
                gl=np.zeros((T * NJ, capL, 3)), nu=np.zeros(T * NF, np.int32), cu=np.zeros(T * NF), ru=np.zeros(T * NF),
                hu=np.zeros((T * NF, capU), np.uint16), gu=np.zeros((T * NF, capU)), torque_radius=np.zeros((NF, T)),
                link_gens=np.zeros((T, NJ, 18)))
-    stats = np.zeros(4, np.int32)
+    stats = np.zeros(8, np.int32)
     dp, ip, sp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_ushort)
     d = lambda a: a.ctypes.data_as(dp)
     rc = lib.emu_k1_build(model_id, T, thr, d(kr), mass_unc, inertia_unc, d(q0), d(qd0), d(qdd0),
