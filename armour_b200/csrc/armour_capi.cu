@@ -825,13 +825,6 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     S.qp_sweeps = opt.qp_sweeps;
     S.qp_update_budget = opt.qp_update_budget;
     cudaStream_t st = ctx->stream;
-    static int attr_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (attr_dev != dev) {
-        CU(cudaFuncSetAttribute(k_solver_step, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SOLVER_ROWCAP * sizeof(double))));
-        attr_dev = dev;
-    }
     // x = 0 (armtd_NLP::get_starting_point), g(0)
     CU(cudaMemsetAsync(S.x, 0, size_t(nprob) * NF * sizeof(double), st));
     CU(cudaMemsetAsync(S.xt, 0, size_t(nprob) * NF * sizeof(double), st));
@@ -844,7 +837,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     for (int it = 0; it < opt.max_iter && nactive > 0; it++) {
         Ba.nprob = nactive;
         CU(launch_constraints(Ba, S.x, ctx->d_g, ctx->d_jac, st));
-        k_solver_step<<<nactive, SOLVER_THREADS, SOLVER_ROWCAP * sizeof(double), st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
+        k_solver_step<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
         CU(launch_constraints(Ba, S.xt, d_gt, nullptr, st));
         k_solver_accept<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
         CU(cudaGetLastError());  // (covers k_solver_step too: launch errors are sticky until read)
@@ -862,7 +855,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     CU(launch_constraints(B, d_k_opt, ctx->d_g, nullptr, st));
     CU(launch_verdict(B, ctx->d_g, d_feasible, d_first, st));
     if (d_iters) CU(cudaMemcpyAsync(d_iters, S.iters, size_t(nprob) * sizeof(int), cudaMemcpyDeviceToDevice, st));
-    if (std::getenv("ARMOUR_SOLVER_DEBUG")) {  // developer aid: row / sweep / update counts of the last step per problem
+    if (std::getenv("ARMOUR_SOLVER_DEBUG")) {  // developer aid: row / active-set iteration / drop counts of the last step per problem
         std::vector<int> dbg(size_t(nprob) * 3);
         CU(cudaMemcpyAsync(dbg.data(), S.dbg, dbg.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -875,7 +868,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
             rmax = std::max(rmax, dbg[p * 3]);
             mvmax = std::max(mvmax, dbg[p * 3 + 2]);
         }
-        std::printf("solver debug: last step per problem: rows mean %.0f max %d, sweeps mean %.1f, row updates mean %.0f max %d\n",
+        std::printf("solver debug: last step per problem: rows mean %.0f max %d, active-set iterations mean %.1f, dropped rows mean %.1f max %d\n",
                     double(r) / nprob, rmax, double(sw) / nprob, double(mv) / nprob, mvmax);
     }
     ctx->launches += 3;

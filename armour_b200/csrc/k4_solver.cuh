@@ -9,12 +9,14 @@
 // statement for statement, so that both give the same iterates: the planner's cost is an exactly spherical
 // quadratic in k (KPR/NLPclass.cu:207-268), each iteration solves
 //     min 1/2 h |d|^2 + grad_f . d   s.t.  g_l <= g + J d <= g_u,  -1 <= x + d <= 1,  |d|_inf <= Delta
-// by Hildreth's dual coordinate ascent over the rows that can become active inside the trust region (Gauss-Seidel
-// in row order: one thread), then accepts / rejects on (violation, cost).  Per iteration: k_constraints (g, J at x),
+// exactly, by the dual active-set method of host/active_set_qp.h over the rows that can become active inside the trust
+// region (the CTA searches the most violated row, one thread does the 7 x 7 algebra of taking it in), then accepts /
+// rejects on (violation, cost).  Per iteration: k_constraints (g, J at x),
 // k_solver_step, k_constraints (g at the trial point), k_solver_accept.
 #pragma once
 #include <cuda_runtime.h>
 
+#include "../host/active_set_qp.h"
 #include "bezier.cuh"
 #include "device_constants.cuh"
 #include "layout.h"
@@ -23,7 +25,7 @@ namespace armour {
 
 constexpr int SOLVER_THREADS = 256;
 constexpr int SOLVER_ROWCAP = 2048;   // linearised rows kept per problem; more -> status ROW_OVERFLOW
-constexpr int SOLVER_ROWW = 18;       // doubles per row: a[7], b, |a|^2 / h, a[7] / h, sqrt(|a|^2 / h * h), h / |a|^2
+constexpr int SOLVER_ROWW = 9;        // doubles per row: a[7], b, 1 / |a|
 enum { SOLVER_RUNNING = 0, SOLVER_SUCCESS = 1, SOLVER_MAXITER = 2, SOLVER_TINY_STEP = 3, SOLVER_INFEASIBLE = 4,
        SOLVER_ROW_OVERFLOW = 5 };
 
@@ -39,7 +41,7 @@ struct SolverState {   // structure of arrays, [nprob] or [nprob][NF]
     int* status;       // SOLVER_*
     int* iters;
     int* evals;
-    int* dbg;          // [nprob][3]: rows, sweeps, row updates of the last step (diagnostics)
+    int* dbg;          // [nprob][3]: rows, active-set iterations, dropped rows of the last step (diagnostics)
     double* rows;      // [nprob][SOLVER_ROWCAP][SOLVER_ROWW]
     const double* q_des;  // [nprob][NF]
     double tol, torque_tol, collision_tol;
@@ -195,10 +197,9 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
             double gl, gu, tol;
             solver_row_bounds(B, p, i, S.torque_tol, S.collision_tol, &gl, &gu, &tol);
             tol *= 0.5;  // aim inside the acceptance band
-            double a[NF], aa = 0, l1 = 0;
+            double a[NF], l1 = 0;
             for (int j = 0; j < NF; j++) {
                 a[j] = J[size_t(i) * NF + j];
-                aa += a[j] * a[j];
                 l1 += fabs(a[j]);
             }
             const double bu = gu + tol - g[i];
@@ -210,19 +211,13 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                     double* r = rows + size_t(at + n) * SOLVER_ROWW;
                     for (int j = 0; j < NF; j++) r[j] = 1.0 * a[j];
                     r[7] = bu;
-                    r[8] = aa / h;
-                    for (int j = 0; j < NF; j++) r[9 + j] = r[j] / h;
-                    r[16] = sqrt(r[8] * h);
-                    r[17] = r[8] > 0 ? 1.0 / r[8] : 0.0;
+                    r[8] = asqp::row_scale(r, NF);
                 }
                 if (pl && at + n + (pu ? 1 : 0) < SOLVER_ROWCAP) {
                     double* r = rows + size_t(at + n + (pu ? 1 : 0)) * SOLVER_ROWW;
                     for (int j = 0; j < NF; j++) r[j] = -1.0 * a[j];
                     r[7] = bl;
-                    r[8] = aa / h;
-                    for (int j = 0; j < NF; j++) r[9 + j] = r[j] / h;
-                    r[16] = sqrt(r[8] * h);
-                    r[17] = r[8] > 0 ? 1.0 / r[8] : 0.0;
+                    r[8] = asqp::row_scale(r, NF);
                 }
             }
             n += (pu ? 1 : 0) + (pl ? 1 : 0);
@@ -255,10 +250,7 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                     for (int q = 0; q < NF; q++) r[q] = 0.0;
                     r[j] = sgn == 0 ? 1.0 : -1.0;
                     r[7] = b;
-                    r[8] = 1.0 / h;
-                    for (int q = 0; q < NF; q++) r[9 + q] = r[q] / h;
-                    r[16] = sqrt(r[8] * h);
-                    r[17] = r[8] > 0 ? 1.0 / r[8] : 0.0;
+                    r[8] = asqp::row_scale(r, NF);
                     nrows++;
                 }
             }
@@ -267,67 +259,71 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
     }
     __syncthreads();
     const int nrows = s_nrows;
-    if (nrows < 0 || tid >= 32) return;
-    // Hildreth's method on the dual (lambda >= 0), d(lambda) = -(c + sum lambda_i a_i) / h: Gauss-Seidel over the rows in
-    // order.  A row whose multiplier stays put (lambda = 0 and satisfied: almost all of them) leaves d unchanged, so
-    // one warp tests 32 consecutive rows against the current d at once, applies the update of the FIRST row that moves,
-    // re-tests the rows behind it, and so on: the arithmetic and its order are those of the sequential loop of the host
-    // solver, the cost is ~rows/32 + (rows that move) steps per sweep.  The multipliers live in dynamic shared memory.
-    extern __shared__ double s_lam[];
-    const int lane = tid;
-    for (int i = lane; i < nrows; i += 32) s_lam[i] = 0.0;
-    __syncwarp();
-    double d[NF];
-    for (int j = 0; j < NF; j++) d[j] = -s_gf[j] / h;
-    int n_sweeps = 0, n_moves = 0;
-    for (int s = 0; s < S.qp_sweeps; s++) {
-        double moved = 0.0;
-        n_sweeps++;
-        for (int base = 0; base < nrows; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < nrows;
-            double a[NF], ah[NF], b = 0, raa = 0, sq = 0, inv = 0, lam = 0;
-            for (int j = 0; j < NF; j++) a[j] = ah[j] = 0;
-            if (valid) {
-                const double* r = rows + size_t(i) * SOLVER_ROWW;
-                for (int j = 0; j < NF; j++) a[j] = r[j];
-                b = r[7];
-                raa = r[8];
-                for (int j = 0; j < NF; j++) ah[j] = r[9 + j];
-                sq = r[16];
-                inv = r[17];
-                lam = s_lam[i];
-            }
-            int from = 0;  // lanes below `from` are done for this sweep
-            for (;;) {
-                double nl = 0, dl = 0;
-                bool moves = false;
-                if (valid && lane >= from && raa > 0) {
-                    double viol = -b;
-                    for (int j = 0; j < NF; j++) viol += a[j] * d[j];
-                    nl = lam + viol * inv;  // exact coordinate maximisation
-                    if (nl < 0) nl = 0;
-                    dl = nl - lam;
-                    moves = dl != 0.0;
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, moves);
-                if (mask == 0) break;
-                const int first = __ffs(mask) - 1;
-                const double bdl = __shfl_sync(0xffffffffu, dl, first);
-                const double bsq = __shfl_sync(0xffffffffu, sq, first);
-                for (int j = 0; j < NF; j++) d[j] -= bdl * __shfl_sync(0xffffffffu, ah[j], first);
-                if (lane == first) {
-                    lam = nl;
-                    s_lam[i] = nl;
-                }
-                moved = fmax(moved, fabs(bdl) * bsq);
-                from = first + 1;
-                n_moves++;
+    if (nrows < 0) return;
+    // exact QP (host/active_set_qp.h; same statements as solve_qp() of the host solver): every round the CTA finds the
+    // most violated row at the current d (scaled by 1 / |a|; ties: lowest index — what the host's ascending scan with a
+    // strict comparison picks), thread 0 takes it into the active set
+    __shared__ asqp::State<NF> s_qp;
+    __shared__ double s_bv[SOLVER_THREADS / 32];
+    __shared__ int s_bi[SOLVER_THREADS / 32], s_stop;
+    if (tid == 0) {
+        asqp::init(s_qp, NF, h, s_gf);
+        s_stop = 0;
+    }
+    __syncthreads();
+    int qp_it = 0;
+    for (; qp_it < S.qp_sweeps; qp_it++) {
+        double d[NF];
+        for (int j = 0; j < NF; j++) d[j] = s_qp.d[j];
+        double bv = asqp::VIOLATION_TOL;
+        int bi = -1;
+        for (int i = tid; i < nrows; i += SOLVER_THREADS) {
+            const double* r = rows + size_t(i) * SOLVER_ROWW;
+            const double v = asqp::row_violation(r, r[7], r[8], d, NF);
+            if (v > bv && !asqp::is_excluded(s_qp, i)) {
+                bv = v;
+                bi = i;
             }
         }
-        if (moved < 1e-12) break;
-        if (S.qp_update_budget > 0 && n_moves >= S.qp_update_budget) break;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if ((tid & 31) == 0) {
+            s_bv[tid >> 5] = bv;
+            s_bi[tid >> 5] = bi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < SOLVER_THREADS / 32; w++) {
+                const double ov = s_bv[w];
+                const int oi = s_bi[w];
+                if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+            if (bi < 0) {
+                s_stop = 1;
+            } else {
+                const double* r = rows + size_t(bi) * SOLVER_ROWW;
+                double a[NF];
+                for (int j = 0; j < NF; j++) a[j] = r[j];
+                if (asqp::add_row(s_qp, bi, a, r[7]) == 2) s_stop = 2;
+            }
+        }
+        __syncthreads();
+        if (s_stop) break;
     }
+    if (tid != 0) return;
+    const int lane = 0;
+    double d[NF];
+    for (int j = 0; j < NF; j++) d[j] = s_qp.d[j];
+    const int n_sweeps = qp_it, n_moves = s_qp.drops;
     if (lane == 0) {
         S.dbg[p * 3 + 0] = nrows;
         S.dbg[p * 3 + 1] = n_sweeps;

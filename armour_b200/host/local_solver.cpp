@@ -1,5 +1,7 @@
 #include "local_solver.h"
 
+#include "active_set_qp.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -9,41 +11,35 @@ using namespace Ipopt;
 
 namespace {
 
+constexpr int NMAX = 16;  // most optimisation variables (the planner has 7)
+
 struct Lin {  // one linearised inequality  a . d <= b
-    double a[16];
+    double a[NMAX];
     double b;
-    double aa;      // |a|^2 / h
-    double ah[16];  // a / h: the primal step of a unit multiplier change (computed once per row, not per update)
-    double sq;      // sqrt(aa * h) = |a|: scale of the progress measure
-    double inv;     // 1 / aa: the coordinate step is viol * inv (one division per row instead of one per visit)
+    double scale;  // 1 / |a|
 };
 
-// min 1/2 h |d|^2 + c . d  s.t.  a_i . d <= b_i : Hildreth's method on the dual (lambda >= 0).
-// d(lambda) = -(c + sum lambda_i a_i) / h.  Returns the primal step.
-void hildreth(int n, double h, const double* c, std::vector<Lin>& rows, double* d, int sweeps, int update_budget) {
-    std::vector<double> lam(rows.size(), 0.0);
-    for (int j = 0; j < n; j++) d[j] = -c[j] / h;
-    long long updates = 0;
-    for (int s = 0; s < sweeps; s++) {
-        double moved = 0.0;
+// min 1/2 h |d|^2 + c . d  s.t.  a_i . d <= b_i, exactly (active_set_qp.h).  Returns the primal step; iters / drops
+// for the statistics.
+void solve_qp(int n, double h, const double* c, const std::vector<Lin>& rows, double* d, int max_outer, int* iters) {
+    asqp::State<NMAX> S;
+    asqp::init(S, n, h, c);
+    int it = 0;
+    for (; it < max_outer; it++) {
+        double best = asqp::VIOLATION_TOL;
+        int p = -1;
         for (size_t i = 0; i < rows.size(); i++) {
-            const Lin& r = rows[i];
-            if (r.aa <= 0) continue;
-            double viol = -r.b;
-            for (int j = 0; j < n; j++) viol += r.a[j] * d[j];
-            double nl = lam[i] + viol * r.inv;  // exact coordinate maximisation
-            if (nl < 0) nl = 0;
-            const double dl = nl - lam[i];
-            if (dl != 0.0) {
-                for (int j = 0; j < n; j++) d[j] -= dl * r.ah[j];
-                lam[i] = nl;
-                moved = std::max(moved, std::fabs(dl) * r.sq);
-                updates++;
+            const double v = asqp::row_violation(rows[i].a, rows[i].b, rows[i].scale, S.d, n);
+            if (v > best && !asqp::is_excluded(S, int(i))) {
+                best = v;
+                p = int(i);
             }
         }
-        if (moved < 1e-12) break;
-        if (update_budget > 0 && updates >= update_budget) break;  // diverging multipliers: an infeasible QP
+        if (p < 0) break;
+        if (asqp::add_row(S, p, rows[p].a, rows[p].b) == 2) break;
     }
+    for (int j = 0; j < n; j++) d[j] = S.d[j];
+    if (iters) *iters = it;
 }
 
 }  // namespace
@@ -116,18 +112,14 @@ SolverReturn local_solve(TNLP& nlp, const LocalSolverOptions& opt, LocalSolverSt
         std::vector<Lin> rows;
         auto push = [&](const Number* a, double sign, double b) {
             Lin r;
-            double aa = 0, l1 = 0;
+            double l1 = 0;
             for (Index j = 0; j < n; j++) {
                 r.a[j] = sign * a[j];
-                aa += r.a[j] * r.a[j];
                 l1 += std::fabs(r.a[j]);
             }
             if (b > l1 * delta) return;  // cannot become active within |d|_inf <= delta
             r.b = b;
-            r.aa = aa / h;
-            for (Index j = 0; j < n; j++) r.ah[j] = r.a[j] / h;
-            r.sq = std::sqrt(r.aa * h);
-            r.inv = r.aa > 0 ? 1.0 / r.aa : 0.0;
+            r.scale = asqp::row_scale(r.a, n);
             rows.push_back(r);
         };
         for (Index i = 0; i < m; i++) {
@@ -144,7 +136,9 @@ SolverReturn local_solve(TNLP& nlp, const LocalSolverOptions& opt, LocalSolverSt
             push(e.data(), -1.0, std::min(delta, x[j] - xl[j]));
         }
         std::vector<double> d(n);
-        hildreth(n, h, gf.data(), rows, d.data(), opt.qp_sweeps, opt.qp_update_budget);
+        int qp_it = 0;
+        solve_qp(n, h, gf.data(), rows, d.data(), opt.qp_sweeps, &qp_it);
+        st.qp_iterations += qp_it;
         double dn = 0;
         for (Index j = 0; j < n; j++) {
             d[j] = std::max(-delta, std::min(delta, d[j]));

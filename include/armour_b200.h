@@ -158,9 +158,9 @@ typedef struct armour_solver_options {
     double tol;            /* 1e-4 = IPOPT_OPTIMIZATION_TOLERANCE (KPR/Parameters.h:51): step-size stopping test */
     double torque_tol;     /* 1e-2 N m, the verdict's tolerances (KPR/Parameters.h:40-43) */
     double collision_tol;  /* 1e-4 m */
-    int qp_sweeps;         /* 200: cap on the Hildreth sweeps of one QP (most QPs run into it; cost scales with it) */
-    int qp_update_budget;  /* 16384: no further sweep once this many multiplier updates were made in a QP (0 = no limit);
-                              only near-infeasible QPs, whose multipliers diverge, get there */
+    int qp_sweeps;         /* 200: cap on the active-set iterations of one QP (a guard: the QP of a step is solved exactly
+                              by a dual active-set method, which is finite; typical QPs take 2-15 iterations) */
+    int qp_update_budget;  /* ignored since round 2 (was the update budget of the Hildreth iteration); kept for the layout */
 } armour_solver_options;
 void armour_solver_options_default(armour_solver_options* opt);
 int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des, const armour_solver_options* opt,
