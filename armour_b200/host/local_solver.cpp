@@ -44,6 +44,19 @@ void solve_qp(int n, double h, const double* c, const std::vector<Lin>& rows, do
 
 }  // namespace
 
+int local_qp(int n, double h, const double* c, int nrows, const double* A, const double* b, double* d, int max_outer) {
+    if (n < 1 || n > NMAX || !(h > 0)) return -1;
+    std::vector<Lin> rows(nrows);
+    for (int i = 0; i < nrows; i++) {
+        for (int j = 0; j < n; j++) rows[i].a[j] = A[size_t(i) * n + j];
+        rows[i].b = b[i];
+        rows[i].scale = asqp::row_scale(rows[i].a, n);
+    }
+    int it = 0;
+    solve_qp(n, h, c, rows, d, max_outer, &it);
+    return it;
+}
+
 SolverReturn local_solve(TNLP& nlp, const LocalSolverOptions& opt, LocalSolverStats* stats) {
     const auto t0 = std::chrono::steady_clock::now();
     auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };

@@ -26,3 +26,7 @@ struct LocalSolverStats {
 };
 
 Ipopt::SolverReturn local_solve(Ipopt::TNLP& nlp, const LocalSolverOptions& opt, LocalSolverStats* stats);
+
+// The QP of one step on its own (tests): min 1/2 h |d|^2 + c . d  s.t.  A d <= b  with A row-major [nrows][n], n <= 16.
+// Returns the number of active-set iterations, -1 for bad arguments.
+int local_qp(int n, double h, const double* c, int nrows, const double* A, const double* b, double* d, int max_outer);

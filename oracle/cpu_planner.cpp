@@ -86,3 +86,8 @@ extern "C" int orc_solve(void* h, const double* q_des, int max_iter, double max_
     if (iterations) *iterations = st.iterations;
     return 0;
 }
+
+// the QP sub-solver of the host solver on its own, for tests/test_active_set_qp.py
+extern "C" int orc_qp(int n, double h, const double* c, int nrows, const double* A, const double* b, double* d) {
+    return local_qp(n, h, c, nrows, A, b, d, 200);
+}
