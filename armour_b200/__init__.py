@@ -10,7 +10,8 @@ from ._lib import ArmourError, NF
 _lib.load()  # no CPU fallback: a missing extension is an ImportError here
 
 from .planner import ReachSetEngine  # noqa: E402
+from .controller import RobustController  # noqa: E402
 from . import worlds  # noqa: E402
 from . import sharding  # noqa: E402
 
-__all__ = ["ReachSetEngine", "ArmourError", "NF", "worlds", "sharding"]
+__all__ = ["ReachSetEngine", "RobustController", "ArmourError", "NF", "worlds", "sharding"]

@@ -97,6 +97,31 @@ SIGNATURES = {
                                           C.c_int]),
 }
 
+
+class ControllerGains(C.Structure):
+    """armour_controller_gains (include/armour_b200.h)."""
+    _fields_ = [("Kr", dp), ("alpha", C.c_double), ("V_max", C.c_double), ("r_norm_threshold", C.c_double),
+                ("apply_friction", C.c_int)]
+
+
+_gp = C.POINTER(ControllerGains)
+SIGNATURES.update({
+    "armour_controller_create": (C.c_int, [C.c_char_p, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
+    "armour_controller_create_error": (C.c_char_p, []),
+    "armour_controller_destroy": (None, [C.c_void_p]),
+    "armour_controller_num_joints": (C.c_int, [C.c_void_p]),
+    "armour_controller_last_error": (C.c_char_p, [C.c_void_p]),
+    "armour_controller_kernel_launches": (C.c_longlong, [C.c_void_p]),
+    "armour_controller_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "armour_controller_synchronize": (C.c_int, [C.c_void_p]),
+    "armour_controller_get_interval_model": (C.c_int, [C.c_void_p, dp]),
+    "armour_controller_rnea": (C.c_int, [C.c_void_p, C.c_int, dp, dp, dp, dp, C.c_int, C.c_int, dp, dp, dp]),
+    "armour_controller_rnea_device": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int] + [C.c_void_p] * 3),
+    "armour_controller_update": (C.c_int, [C.c_void_p, C.c_int, _gp, dp, dp, dp, dp, dp, dp, dp, dp, ip]),
+    "armour_controller_update_device": (C.c_int, [C.c_void_p, C.c_int, _gp] + [C.c_void_p] * 10),
+})
+
+
 class SolverOptions(C.Structure):
     """armour_solver_options (include/armour_b200.h)."""
     _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("torque_tol", C.c_double), ("collision_tol", C.c_double),

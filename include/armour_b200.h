@@ -211,6 +211,57 @@ int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const ar
                             const double q0[ARMOUR_NF], const double qd0[ARMOUR_NF], const double qdd0[ARMOUR_NF],
                             const double* obstacles, int nobs);
 
+/* ---- robust controller: interval Newton-Euler pass and robust input, batched over states -------------
+ *
+ * Replaces, for a batch of n sampled states, what the reference's MEX entry computes for ONE state per call:
+ *   [u, tau, v] = kinova_controller(Kr, alpha, V_max, r_norm_threshold, q, qd, q_des, qd_des, qdd_des [, eps])
+ * (MEX/kinova_controller.cpp:19-99): Robot(RobotFilePath, eps) -> armour_controller_create, RobustController::update
+ * (MEX/robust_controller.cpp:67-181, ARMOUR method) -> armour_controller_update, and the two passes under it, passRNEA /
+ * passRNEA_Int (MEX/rnea.cpp:6-94 / 96-187) -> armour_controller_rnea.  All state arrays are [n][numJoints] row-major.
+ * Interval end points are outward rounded at every operation exactly as Boost.Interval does in the reference.
+ * The host-pointer calls compute sin / cos of the joint angles with the host's libm like the reference and are bit-exact
+ * against it for the interval outputs; the *_device calls take device pointers and, when d_sincos is NULL, use the device's
+ * sincos (end points within a few ulp).  d_sincos: [n][numJoints][2] = sin(-q), cos(-q).
+ * A controller object is thread-compatible, not thread-safe; it owns one stream (armour_controller_set_stream adopts the
+ * caller's).  There is no CPU fallback. */
+typedef struct armour_controller armour_controller;
+typedef struct armour_controller_gains {
+    const double* Kr;          /* [numJoints] diagonal of Kr (kinova_controller.cpp:36-40) */
+    double alpha;              /* ARMOUR robust input: lambda = max(0, -alpha (V_max - sup V) / |r| + |bound|) */
+    double V_max;
+    double r_norm_threshold;   /* v = 0 below this |r| */
+    int apply_friction;        /* RobustController::applyFriction; the MEX entry sets 0 */
+} armour_controller_gains;
+/* model_file: the reference's robot text format (MEX/kinova_without_gripper.txt); model_uncertainty: eps of the interval
+ * model (0.03 in the MEX entry).  On failure *out is untouched and armour_controller_create_error() tells why. */
+int armour_controller_create(const char* model_file, double model_uncertainty, int device, armour_controller** out);
+const char* armour_controller_create_error(void);
+void armour_controller_destroy(armour_controller* ctl);
+int armour_controller_num_joints(const armour_controller* ctl);
+const char* armour_controller_last_error(const armour_controller* ctl);
+long long armour_controller_kernel_launches(const armour_controller* ctl);
+int armour_controller_set_stream(armour_controller* ctl, void* cuda_stream);
+int armour_controller_synchronize(armour_controller* ctl);
+/* The interval model after the conversion of IntModel::IntModel (MEX/robot_models.cpp:175-237), per joint
+ * S.w[3] S.v[3] XTree.R[9] XTree.p[3] m I_bar[9] m_c_hat[9], each as (lower, upper): out[numJoints * 74]. */
+int armour_controller_get_interval_model(const armour_controller* ctl, double* out);
+/* passRNEA (tau, may be NULL) and / or passRNEA_Int (tau_lo, tau_hi, may both be NULL) of n states. */
+int armour_controller_rnea(armour_controller* ctl, int n, const double* q, const double* qd, const double* qda,
+                           const double* qdd, int apply_friction, int apply_gravity, double* tau, double* tau_lo,
+                           double* tau_hi);
+int armour_controller_rnea_device(armour_controller* ctl, int n, const double* d_q, const double* d_qd,
+                                  const double* d_qda, const double* d_qdd, const double* d_sincos, int apply_friction,
+                                  int apply_gravity, double* d_tau, double* d_tau_lo, double* d_tau_hi);
+/* RobustController::update for n states: u = u_nominal - v; u_nominal, v, status may be NULL.  status[i] = 1 where the
+ * nominal torque is outside the interval torque (the reference throws there), else 0. */
+int armour_controller_update(armour_controller* ctl, int n, const armour_controller_gains* gains, const double* q,
+                             const double* qd, const double* q_des, const double* qd_des, const double* qdd_des, double* u,
+                             double* u_nominal, double* v, int* status);
+int armour_controller_update_device(armour_controller* ctl, int n, const armour_controller_gains* gains, const double* d_q,
+                                    const double* d_qd, const double* d_q_des, const double* d_qd_des,
+                                    const double* d_qdd_des, const double* d_sincos, double* d_u, double* d_u_nominal,
+                                    double* d_v, int* d_status);
+
 #ifdef __cplusplus
 }
 #endif

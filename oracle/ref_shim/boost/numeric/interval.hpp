@@ -3,7 +3,8 @@
 // Stand-in for Boost.Interval (the reference pins Boost 1.71 only in prose; Boost is NOT in /root/reference
 // nor in this image) restricted to what the reference planner uses (KPR/Headers.h:26-36):
 //     boost::numeric::interval<double, policies<save_state<rounded_transc_std<double>>, checking_base<double>>>
-// with + - * (interval/interval and double/interval), unary -, +=, cos, sin, pow(I, int), sqrt, lower(), upper().
+// with + - * (interval/interval and double/interval), unary -, +=, cos, sin, pow(I, int), sqrt, lower(), upper(); the
+// robust-controller sources (MEX/*.cpp, same interval type: MEX/headers.hpp:19-28) add -=, *=, /, assign().
 // It restates the library's published algorithms (boost/numeric/interval/{arith,arith2,transc,utility}.hpp):
 // outward rounding for every arithmetic operation, cos by reduction modulo the interval 2*pi and monotone
 // pieces, sin(x) = cos(x - pi/2), pow by repeated squaring with directed rounding.
@@ -84,6 +85,13 @@ public:
     const T& upper() const { return hi_; }
     interval& operator+=(const interval& o) { return *this = *this + o; }
     interval& operator+=(const T& o) { return *this = *this + o; }
+    interval& operator-=(const interval& o) { return *this = *this - o; }
+    interval& operator*=(const interval& o) { return *this = *this * o; }
+    interval& operator/=(const interval& o) { return *this = *this / o; }
+    void assign(const T& l, const T& u) {  // interval.hpp: assign(); checking_base: l <= u is the caller's duty
+        lo_ = l;
+        hi_ = u;
+    }
 };
 
 namespace ish = interval_lib::shim;
@@ -132,6 +140,22 @@ IV operator*(const T& x, const I& y) {
     return I(ish::mul_down(x, y.lower()), ish::mul_up(x, y.upper()));
 }
 IV operator*(const I& x, const T& y) { return y * x; }
+// arith.hpp operator/(interval, interval) for a divisor that does not contain zero (the only case the reference's
+// sources can reach: Vector::normalize() of a twist axis); a divisor containing zero gives the whole line
+IV operator/(const I& x, const I& y) {
+    const T xl = x.lower(), xu = x.upper(), yl = y.lower(), yu = y.upper();
+    if (!(yl > 0) && !(yu < 0)) return I(-HUGE_VAL, HUGE_VAL);
+    if (xu < 0) {
+        if (yu < 0) return I(ish::div_down(xu, yl), ish::div_up(xl, yu));
+        return I(ish::div_down(xl, yl), ish::div_up(xu, yu));
+    }
+    if (xl < 0) {
+        if (yu < 0) return I(ish::div_down(xu, yu), ish::div_up(xl, yu));
+        return I(ish::div_down(xl, yl), ish::div_up(xu, yl));
+    }
+    if (yu < 0) return I(ish::div_down(xu, yu), ish::div_up(xl, yl));
+    return I(ish::div_down(xl, yu), ish::div_up(xu, yl));
+}
 
 // utility.hpp / arith2.hpp
 IV fmod(const I& x, const I& y) {
