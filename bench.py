@@ -23,7 +23,8 @@ BASELINE.json targets (< 1 ms for one Kinova planning iteration's build + eval).
   planning iteration through host pointers, eval_g and eval_jac_g called separately like Ipopt does), "solver_e2e"
   (armour_batch_solve, host in/out, beside the CPU planner), "config3" / "config4" (BASELINE configs 3 and 4),
   "sweep" (BASELINE config 5: 65,536-world sweep split over the ranks, strong scaling, per-world verdicts gathered
-  over NCCL).
+  over NCCL), "controller" (the robust controller's interval Newton-Euler pass and robust input over 2^20
+  sampled states, beside the reference's own MEX sources on one host thread).
 
 Multi-GPU: problems are independent -> every rank owns its own 1,024 worlds, no collective on the data
 path ("weak" scaling); NCCL only reduces the timing (max over ranks) and gathers the verdict counts.
@@ -437,6 +438,76 @@ def config_m1(device, stream, dev, nworlds, nobs, seed, label, **engine_kw):
             "link_monomials_max": int(ln.max()), "torque_monomials_max": int(un.max())}
 
 
+def controller_leg(device, stream, dev, cpu, n=1 << 20):
+    """SURVEY 8f-4: RobustController::update (MEX/robust_controller.cpp:67-181) for n sampled states in one launch:
+    device-resident states/s (CUDA events), the same through the host-pointer ABI call, and the reference's own sources
+    (oracle/_ref/libarmour_ref_controller.so; the oracle's restatement if that library is absent) on one host thread."""
+    import torch
+
+    from armour_b200 import RobustController
+    model = os.path.join(ROOT, "tests", "golden", "robot_models", "kinova_without_gripper.txt")
+    ctl = RobustController(model, 0.03, device)
+    ctl.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(20261018)
+    q = rng.uniform(-np.pi, np.pi, (n, 7))
+    qd = rng.uniform(-1.5, 1.5, (n, 7))
+    q_des, qd_des, qdd_des = q + rng.uniform(-0.05, 0.05, (n, 7)), qd + rng.uniform(-0.1, 0.1, (n, 7)), rng.uniform(-2, 2, (n, 7))
+    Kr, gains = np.full(7, 10.0), (1.0, 1e-2, 1e-10)
+    host = (q, qd, q_des, qd_des, qdd_des)
+    t = [torch.tensor(a, dtype=torch.float64, device=dev) for a in host]
+    u = torch.empty((n, 7), dtype=torch.float64, device=dev)
+    lo, hi = torch.empty_like(u), torch.empty_like(u)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        ms = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1))
+        return float(np.median(ms))
+
+    ms_upd = timed(lambda: ctl.update_device(n, Kr, *gains, *(x.data_ptr() for x in t), d_u=u.data_ptr(), d_status=st.data_ptr()))
+    ms_int = timed(lambda: ctl.rnea_device(n, *(x.data_ptr() for x in t[:4]), d_tau_lo=lo.data_ptr(), d_tau_hi=hi.data_ptr()))
+    out = {"metric": "controller updates/s (RobustController::update, ARMOUR method: nominal + interval Newton-Euler pass, "
+                     "interval M(q) r, robust input) over sampled states, device-resident", "states": n,
+           "value": n / (ms_upd * 1e-3), "unit": "states/s", "ms_per_launch": ms_upd,
+           "interval_pass_only": {"value": n / (ms_int * 1e-3), "unit": "states/s", "ms_per_launch": ms_int},
+           "status_nonzero": int(st.sum().item()), "kernel_launches": ctl.kernel_launches,
+           "timing": "CUDA events on the launching stream, median of 5 launches after 3 warm-up launches; inputs of "
+                     f"{5 * n * 56 / 1e6:.0f} MB, larger than L2 together with the outputs"}
+    m = 1 << 16
+    sub = [a[:m] for a in host]
+    ctl.update(Kr, *gains, *sub)
+    t0 = time.perf_counter()
+    ctl.update(Kr, *gains, *sub)
+    dt = time.perf_counter() - t0
+    out["e2e"] = {"value": m / dt, "unit": "states/s", "states": m, "h2d_bytes": int(7 * m * 56), "d2h_bytes": int(3 * m * 56 + 4 * m),
+                  "note": "armour_controller_update with host pointers: sin / cos on the host like the reference, copies, "
+                          "launch, copies back, synchronised"}
+    if cpu:
+        from oracle import pycontroller
+        kind = "reference" if pycontroller.reference_available() else "port"
+        ref = (pycontroller.ReferenceController if kind == "reference" else pycontroller.OracleController)()
+        k = 1500
+        t0 = time.perf_counter()
+        for i in range(k):
+            ref.update(Kr, *gains, *(a[i] for a in host))
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": k / dtc, "unit": "states/s", "cores": 1, "kind": kind,
+                               "sample": f"{k} states, one update() per state like the MEX entry (MEX/kinova_controller.cpp), "
+                                         "one host thread"}
+        out["ratio_vs_cpu_one_thread"] = out["value"] / out["cpu_baseline"]["value"]
+    ctl.close()
+    return out
+
+
 def run_sweep(args, eng, stream, dev, rank, world, dist):
     """BASELINE config 5: `--sweep-worlds` random worlds (config-2 generator), split over the ranks with
     sharding.shard_bounds (STRONG scaling: the total is fixed), each rank walking its shard in batches through the
@@ -832,6 +903,14 @@ def run_b200(args):
             config3 = config3 or {"error": repr(exc)}
             config4 = config4 or {"error": repr(exc)}
 
+    # ---- robust controller (interval Newton-Euler pass + robust input) over sampled states, rank 0
+    controller = None
+    if rank == 0 and not args.no_configs:
+        try:
+            controller = controller_leg(local, stream, dev, cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as exc:
+            controller = {"error": repr(exc)}
+
     # ---- BASELINE config 5: the 65,536-world sweep, split over the ranks (strong scaling), per-world verdicts gathered
     sweep = None
     if args.sweep_worlds > 0:
@@ -873,7 +952,7 @@ def run_b200(args):
             "step_submission": "CUDA graph replay (one graph = one step)" if graph_used else "plain launches",
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "m1": m1, "config1_host_abi": config1,
             "solver_e2e": solver_e2e, "config3": config3, "config4": config4, "sweep": sweep,
-            "gpu_launches": int(launches_timed), "clocks": clk,
+            "controller": controller, "gpu_launches": int(launches_timed), "clocks": clk,
             "feasible_worlds_last_iterate": feasible_total, "build_launches": int(build_launches),
         }
         print(json.dumps(line), flush=True)
