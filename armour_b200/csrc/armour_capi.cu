@@ -837,7 +837,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     for (int it = 0; it < opt.max_iter && nactive > 0; it++) {
         Ba.nprob = nactive;
         CU(launch_constraints(Ba, S.x, ctx->d_g, ctx->d_jac, st));
-        k_solver_step<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
+        k_solver_step<<<nactive, SOLVER_THREADS, solver_step_smem(B.m()), st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
         CU(launch_constraints(Ba, S.xt, d_gt, nullptr, st));
         k_solver_accept<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
         CU(cudaGetLastError());  // (covers k_solver_step too: launch errors are sticky until read)

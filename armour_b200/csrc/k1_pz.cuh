@@ -178,7 +178,9 @@ K1_DI void k1_sync() {
 }
 // barrier over the whole CTA: keeps the groups in step between operations
 K1_DI void k1_sync_cta() {
+#ifndef K1_NO_LOCKSTEP
     if (GROUPS > 1 && !MG) __syncthreads();
+#endif
 }
 K1_DI K1X& k1x() { return *reinterpret_cast<K1X*>(smem_cta()); }
 #else

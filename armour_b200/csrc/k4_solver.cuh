@@ -23,7 +23,14 @@
 
 namespace armour {
 
-constexpr int SOLVER_THREADS = 256;
+#ifndef ARMOUR_SOLVER_THREADS
+#define ARMOUR_SOLVER_THREADS 256
+#endif
+constexpr int SOLVER_THREADS = ARMOUR_SOLVER_THREADS;
+constexpr int SOLVER_WARPS = SOLVER_THREADS / 32;
+// steps of 32 rows per warp so that SOLVER_WARPS segments cover m rows; dynamic shared memory of k_solver_step
+__host__ __device__ inline int solver_steps(int m) { return ((m + SOLVER_WARPS - 1) / SOLVER_WARPS + 31) / 32; }
+__host__ __device__ inline size_t solver_step_smem(int m) { return size_t(SOLVER_WARPS) * solver_steps(m) * 2 * sizeof(unsigned); }
 constexpr int SOLVER_ROWCAP = 2048;   // linearised rows kept per problem; more -> status ROW_OVERFLOW
 constexpr int SOLVER_ROWW = 9;        // doubles per row: a[7], b, 1 / |a|
 enum { SOLVER_RUNNING = 0, SOLVER_SUCCESS = 1, SOLVER_MAXITER = 2, SOLVER_TINY_STEP = 3, SOLVER_INFEASIBLE = 4,
@@ -42,7 +49,7 @@ struct SolverState {   // structure of arrays, [nprob] or [nprob][NF]
     int* iters;
     int* evals;
     int* dbg;          // [nprob][3]: rows, active-set iterations, dropped rows of the last step (diagnostics)
-    double* rows;      // [nprob][SOLVER_ROWCAP][SOLVER_ROWW]
+    double* rows;      // [nprob][SOLVER_ROWW][SOLVER_ROWCAP]: component-major, the scan of a QP round reads it lane-contiguously
     const double* q_des;  // [nprob][NF]
     double tol, torque_tol, collision_tol;
     int max_iter;
@@ -148,11 +155,30 @@ __global__ void __launch_bounds__(SOLVER_THREADS) k_solver_start(Batch B, Solver
     }
 }
 
+// row `at` of the component-major row buffer of one problem
+__device__ __forceinline__ void solver_store_row(double* rows, int at, const double* a, double sign, double b) {
+    double r[NF];
+    for (int j = 0; j < NF; j++) {
+        r[j] = sign * a[j];
+        rows[size_t(j) * SOLVER_ROWCAP + at] = r[j];
+    }
+    rows[size_t(7) * SOLVER_ROWCAP + at] = b;
+    rows[size_t(8) * SOLVER_ROWCAP + at] = asqp::row_scale(r, NF);
+}
+__device__ __forceinline__ void solver_load_row(const double* rows, int i, double* a, double* b, double* scale) {
+    for (int j = 0; j < NF; j++) a[j] = rows[size_t(j) * SOLVER_ROWCAP + i];
+    *b = rows[size_t(7) * SOLVER_ROWCAP + i];
+    *scale = rows[size_t(8) * SOLVER_ROWCAP + i];
+}
+
 // one SQP step from (g, J) at x: writes the trial point xt, or ends the problem (step below tolerance)
 __global__ void __launch_bounds__(SOLVER_THREADS)
 k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const double* __restrict__ jac_all, int it) {
     const int p = B.plist ? B.plist[blockIdx.x] : int(blockIdx.x), tid = threadIdx.x;
     if (S.status[p] != SOLVER_RUNNING) return;  // uniform per CTA
+#ifdef SOLVER_PROFILE
+    const long long pc0 = clock64();
+#endif
     const int m = B.m();
     const double* g = g_all + size_t(p) * m;
     const double* J = jac_all + size_t(p) * m * NF;
@@ -183,55 +209,73 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
     }
     __syncthreads();
     const double h = s_h, delta = s_delta;
-    // rows that can be reached inside the trust region, linearised, in row order (upper side, then lower side)
-    const int per = (m + SOLVER_THREADS - 1) / SOLVER_THREADS;
-    const int i0 = tid * per, i1 = (i0 + per) < m ? (i0 + per) : m;
+    // rows that can be reached inside the trust region, linearised, in row order (upper side, then lower side).
+    // Warp w owns the contiguous segment [w * seg, (w + 1) * seg) of the m rows, its lanes take consecutive rows (coalesced
+    // reads of g and J, four steps of 32 rows in flight).  Pass 0 only decides: the ballots of "upper side kept" / "lower
+    // side kept" go to shared memory; the warp totals give every warp its base; pass 1 revisits the steps that keep
+    // anything (a few per cent of them) and writes the rows at base + (kept entries before it), which is row order.
+    extern __shared__ unsigned s_keep[];  // [SOLVER_WARPS][steps][2]
+    const int warp = tid >> 5, lane = tid & 31;
+    const int steps = solver_steps(m), seg = steps * 32;
+    const int w0 = warp * seg;
+    unsigned* keep = s_keep + size_t(warp) * steps * 2;
     double* rows = S.rows + size_t(p) * SOLVER_ROWCAP * SOLVER_ROWW;
-    for (int pass = 0; pass < 2; pass++) {
-        int n = 0;
-        int at = 0;
-        if (pass == 1) {
-            for (int q = 0; q < tid; q++) at += s_cnt[q];  // (256 short sums; the scan is not what costs here)
+    int wcount = 0;
+    for (int st0 = 0; st0 < steps; st0 += 4) {
+        bool pu[4], pl[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = w0 + (st0 + q) * 32 + lane;
+            pu[q] = pl[q] = false;
+            if (st0 + q < steps && i < m) {
+                double gl, gu, tol;
+                solver_row_bounds(B, p, i, S.torque_tol, S.collision_tol, &gl, &gu, &tol);
+                tol *= 0.5;  // aim inside the acceptance band
+                double l1 = 0;
+                for (int j = 0; j < NF; j++) l1 += fabs(J[size_t(i) * NF + j]);
+                const double gi = g[i];
+                const double bu = gu + tol - gi;
+                const double bl = gi - (gl - tol);
+                pu[q] = !(bu > l1 * delta);
+                pl[q] = gl > -1e18 && !(bl > l1 * delta);
+            }
         }
-        for (int i = i0; i < i1; i++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned mu = __ballot_sync(0xffffffffu, pu[q]), ml = __ballot_sync(0xffffffffu, pl[q]);
+            if (st0 + q < steps && lane == 0) {
+                keep[(st0 + q) * 2] = mu;
+                keep[(st0 + q) * 2 + 1] = ml;
+            }
+            wcount += __popc(mu) + __popc(ml);
+        }
+    }
+    s_cnt[tid] = wcount;  // (the same number in every lane of a warp)
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; w++) base += s_cnt[w * 32];
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < SOLVER_WARPS; w++) tot += s_cnt[w * 32];
+        s_total = tot;
+    }
+    for (int st = 0; st < steps; st++) {
+        const unsigned mu = keep[st * 2], ml = keep[st * 2 + 1];
+        if ((mu | ml) == 0) continue;
+        const unsigned below = (1u << lane) - 1u;
+        const int at = base + __popc(mu & below) + __popc(ml & below);
+        const bool ku = (mu >> lane) & 1u, kl = (ml >> lane) & 1u;
+        if (ku || kl) {
+            const int i = w0 + st * 32 + lane;
             double gl, gu, tol;
             solver_row_bounds(B, p, i, S.torque_tol, S.collision_tol, &gl, &gu, &tol);
-            tol *= 0.5;  // aim inside the acceptance band
-            double a[NF], l1 = 0;
-            for (int j = 0; j < NF; j++) {
-                a[j] = J[size_t(i) * NF + j];
-                l1 += fabs(a[j]);
-            }
-            const double bu = gu + tol - g[i];
-            const double bl = g[i] - (gl - tol);
-            const bool pu = !(bu > l1 * delta);
-            const bool pl = gl > -1e18 && !(bl > l1 * delta);
-            if (pass == 1) {
-                if (pu && at + n < SOLVER_ROWCAP) {
-                    double* r = rows + size_t(at + n) * SOLVER_ROWW;
-                    for (int j = 0; j < NF; j++) r[j] = 1.0 * a[j];
-                    r[7] = bu;
-                    r[8] = asqp::row_scale(r, NF);
-                }
-                if (pl && at + n + (pu ? 1 : 0) < SOLVER_ROWCAP) {
-                    double* r = rows + size_t(at + n + (pu ? 1 : 0)) * SOLVER_ROWW;
-                    for (int j = 0; j < NF; j++) r[j] = -1.0 * a[j];
-                    r[7] = bl;
-                    r[8] = asqp::row_scale(r, NF);
-                }
-            }
-            n += (pu ? 1 : 0) + (pl ? 1 : 0);
+            tol *= 0.5;
+            double a[NF];
+            for (int j = 0; j < NF; j++) a[j] = J[size_t(i) * NF + j];
+            if (ku && at < SOLVER_ROWCAP) solver_store_row(rows, at, a, 1.0, gu + tol - g[i]);
+            if (kl && at + (ku ? 1 : 0) < SOLVER_ROWCAP) solver_store_row(rows, at + (ku ? 1 : 0), a, -1.0, g[i] - (gl - tol));
         }
-        if (pass == 0) {
-            s_cnt[tid] = n;
-            __syncthreads();
-            if (tid == 0) {
-                int tot = 0;
-                for (int q = 0; q < SOLVER_THREADS; q++) tot += s_cnt[q];
-                s_total = tot;
-            }
-            __syncthreads();
-        }
+        base += __popc(mu) + __popc(ml);
     }
     __syncthreads();
     __shared__ int s_nrows;
@@ -246,11 +290,10 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
                 for (int sgn = 0; sgn < 2; sgn++) {
                     const double b = sgn == 0 ? fmin(delta, 1.0 - s_x[j]) : fmin(delta, s_x[j] - (-1.0));
                     if (b > 1.0 * delta) continue;  // push(): l1 = 1, the row is kept unless b > delta
-                    double* r = rows + size_t(nrows) * SOLVER_ROWW;
-                    for (int q = 0; q < NF; q++) r[q] = 0.0;
-                    r[j] = sgn == 0 ? 1.0 : -1.0;
-                    r[7] = b;
-                    r[8] = asqp::row_scale(r, NF);
+                    double e[NF];
+                    for (int q = 0; q < NF; q++) e[q] = 0.0;
+                    e[j] = 1.0;
+                    solver_store_row(rows, nrows, e, sgn == 0 ? 1.0 : -1.0, b);
                     nrows++;
                 }
             }
@@ -260,6 +303,9 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
     __syncthreads();
     const int nrows = s_nrows;
     if (nrows < 0) return;
+#ifdef SOLVER_PROFILE
+    const long long pc1 = clock64();
+#endif
     // exact QP (host/active_set_qp.h; same statements as solve_qp() of the host solver): every round the CTA finds the
     // most violated row at the current d (scaled by 1 / |a|; ties: lowest index — what the host's ascending scan with a
     // strict comparison picks), thread 0 takes it into the active set
@@ -278,8 +324,9 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
         double bv = asqp::VIOLATION_TOL;
         int bi = -1;
         for (int i = tid; i < nrows; i += SOLVER_THREADS) {
-            const double* r = rows + size_t(i) * SOLVER_ROWW;
-            const double v = asqp::row_violation(r, r[7], r[8], d, NF);
+            double a[NF], b, sc;
+            solver_load_row(rows, i, a, &b, &sc);
+            const double v = asqp::row_violation(a, b, sc, d, NF);
             if (v > bv && !asqp::is_excluded(s_qp, i)) {
                 bv = v;
                 bi = i;
@@ -310,24 +357,26 @@ k_solver_step(Batch B, SolverState S, const double* __restrict__ g_all, const do
             if (bi < 0) {
                 s_stop = 1;
             } else {
-                const double* r = rows + size_t(bi) * SOLVER_ROWW;
-                double a[NF];
-                for (int j = 0; j < NF; j++) a[j] = r[j];
-                if (asqp::add_row(s_qp, bi, a, r[7]) == 2) s_stop = 2;
+                double a[NF], b, sc;
+                solver_load_row(rows, bi, a, &b, &sc);
+                if (asqp::add_row(s_qp, bi, a, b) == 2) s_stop = 2;
             }
         }
         __syncthreads();
         if (s_stop) break;
     }
     if (tid != 0) return;
-    const int lane = 0;
     double d[NF];
     for (int j = 0; j < NF; j++) d[j] = s_qp.d[j];
     const int n_sweeps = qp_it, n_moves = s_qp.drops;
-    if (lane == 0) {
+    {
         S.dbg[p * 3 + 0] = nrows;
         S.dbg[p * 3 + 1] = n_sweeps;
         S.dbg[p * 3 + 2] = n_moves;
+#ifdef SOLVER_PROFILE
+        S.dbg[p * 3 + 0] = int((pc1 - pc0) >> 4);        // row building, cycles / 16
+        S.dbg[p * 3 + 2] = int((clock64() - pc1) >> 4);  // QP, cycles / 16
+#endif
         double dn = 0;
         for (int j = 0; j < NF; j++) {
             d[j] = fmax(-delta, fmin(delta, d[j]));

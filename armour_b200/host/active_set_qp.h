@@ -33,11 +33,14 @@ constexpr int MAX_OUTER = 200;            // rows taken in per QP (a guard; the 
 template <int NMAX>
 struct State {
     int n, nact, nskip, drops;
+    int nq;                    // leading active rows whose columns of Q and R are valid
     double h;
     double d[NMAX];            // primal iterate: the minimiser over the active rows
     double u[NMAX];            // multipliers of the active rows (>= 0)
     int idx[NMAX];             // their row indices
     double A[NMAX][NMAX];      // their normals
+    double Q[NMAX][NMAX];      // orthonormal basis of the normals (modified Gram-Schmidt, N = Q R), kept between rows:
+    double R[NMAX][NMAX];      // a new row appends one column, a dropped row invalidates the columns from its position on
     int skip[MAX_SKIP];
 };
 
@@ -61,6 +64,7 @@ ASQP_HD void init(State<NMAX>& S, int n, double h, const double* c) {
     S.nact = 0;
     S.nskip = 0;
     S.drops = 0;
+    S.nq = 0;
     S.h = h;
     for (int j = 0; j < n; j++) S.d[j] = -c[j] / h;
 }
@@ -85,36 +89,37 @@ ASQP_HD int add_row(State<NMAX>& S, int p, const double* a, double b) {
     for (int j = 0; j < n; j++) ap2 += a[j] * a[j];
     for (int guard = 0; guard < 2 * NMAX + 2; guard++) {
         const int na = S.nact;
-        // orthonormal basis of the active normals by modified Gram-Schmidt, N = Q R
-        double Q[NMAX][NMAX], R[NMAX][NMAX], y[NMAX], r[NMAX], w[NMAX];
-        for (int k = 0; k < na; k++) {
-            for (int j = 0; j < n; j++) Q[k][j] = S.A[k][j];
+        // orthonormal basis of the active normals by modified Gram-Schmidt, N = Q R: the columns that are not valid yet
+        double y[NMAX], r[NMAX], w[NMAX];
+        for (int k = S.nq; k < na; k++) {
+            for (int j = 0; j < n; j++) S.Q[k][j] = S.A[k][j];
             for (int i = 0; i < k; i++) {
                 double dot = 0;
-                for (int j = 0; j < n; j++) dot += Q[i][j] * Q[k][j];
-                R[i][k] = dot;
-                for (int j = 0; j < n; j++) Q[k][j] -= dot * Q[i][j];
+                for (int j = 0; j < n; j++) dot += S.Q[i][j] * S.Q[k][j];
+                S.R[i][k] = dot;
+                for (int j = 0; j < n; j++) S.Q[k][j] -= dot * S.Q[i][j];
             }
             double nn = 0;
-            for (int j = 0; j < n; j++) nn += Q[k][j] * Q[k][j];
+            for (int j = 0; j < n; j++) nn += S.Q[k][j] * S.Q[k][j];
             const double nr = std::sqrt(nn);
-            R[k][k] = nr;
+            S.R[k][k] = nr;
             const double inv = nr > 0 ? 1.0 / nr : 0.0;
-            for (int j = 0; j < n; j++) Q[k][j] *= inv;
+            for (int j = 0; j < n; j++) S.Q[k][j] *= inv;
         }
+        S.nq = na;
         // w = part of a outside the active span (the primal step direction, times h), y = Q^T a
         for (int j = 0; j < n; j++) w[j] = a[j];
         for (int k = 0; k < na; k++) {
             double dot = 0;
-            for (int j = 0; j < n; j++) dot += Q[k][j] * w[j];
+            for (int j = 0; j < n; j++) dot += S.Q[k][j] * w[j];
             y[k] = dot;
-            for (int j = 0; j < n; j++) w[j] -= dot * Q[k][j];
+            for (int j = 0; j < n; j++) w[j] -= dot * S.Q[k][j];
         }
         // r = R^-1 y: how the active multipliers give way per unit of the new one
         for (int k = na - 1; k >= 0; k--) {
             double s = y[k];
-            for (int i = k + 1; i < na; i++) s -= R[k][i] * r[i];
-            r[k] = R[k][k] > 0 ? s / R[k][k] : 0.0;
+            for (int i = k + 1; i < na; i++) s -= S.R[k][i] * r[i];
+            r[k] = S.R[k][k] > 0 ? s / S.R[k][k] : 0.0;
         }
         double zz = 0;
         for (int j = 0; j < n; j++) zz += w[j] * w[j];
@@ -158,6 +163,15 @@ ASQP_HD int add_row(State<NMAX>& S, int p, const double* a, double b) {
             S.u[na] = up;
             S.idx[na] = p;
             S.nact = na + 1;
+            // the new column of Q R is what was just computed: w is a orthogonalised against the columns before it
+            {
+                for (int i = 0; i < na; i++) S.R[i][na] = y[i];
+                const double nr = std::sqrt(zz);
+                S.R[na][na] = nr;
+                const double inv = nr > 0 ? 1.0 / nr : 0.0;
+                for (int j = 0; j < n; j++) S.Q[na][j] = w[j] * inv;
+                S.nq = na + 1;
+            }
             return 0;
         }
         // partial step: multiplier jdrop reaches zero first; drop that row and try again
@@ -176,6 +190,7 @@ ASQP_HD int add_row(State<NMAX>& S, int p, const double* a, double b) {
             S.idx[k] = S.idx[k + 1];
         }
         S.nact = na - 1;
+        if (S.nq > jdrop) S.nq = jdrop;  // the columns from the dropped position on are recomputed at the next pass
         S.drops++;
     }
     if (S.nskip >= MAX_SKIP) return 2;
