@@ -825,6 +825,10 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     S.qp_sweeps = opt.qp_sweeps;
     S.qp_update_budget = opt.qp_update_budget;
     cudaStream_t st = ctx->stream;
+    const size_t step_smem = solver_step_smem(B.m());  // ballot masks of the row gathering: 64 B per 256 rows
+    if (step_smem > 200 * 1024) return fail(ctx, ARMOUR_ERR_ARG, "too many constraint rows for the batched solver");
+    if (step_smem > 40 * 1024)  // beyond the default limit (a few hundred obstacles): opt in, per device (cheap, idempotent)
+        CU(cudaFuncSetAttribute(k_solver_step, cudaFuncAttributeMaxDynamicSharedMemorySize, int(step_smem)));
     // x = 0 (armtd_NLP::get_starting_point), g(0)
     CU(cudaMemsetAsync(S.x, 0, size_t(nprob) * NF * sizeof(double), st));
     CU(cudaMemsetAsync(S.xt, 0, size_t(nprob) * NF * sizeof(double), st));
@@ -837,7 +841,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     for (int it = 0; it < opt.max_iter && nactive > 0; it++) {
         Ba.nprob = nactive;
         CU(launch_constraints(Ba, S.x, ctx->d_g, ctx->d_jac, st));
-        k_solver_step<<<nactive, SOLVER_THREADS, solver_step_smem(B.m()), st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
+        k_solver_step<<<nactive, SOLVER_THREADS, step_smem, st>>>(Ba, S, ctx->d_g, ctx->d_jac, it);
         CU(launch_constraints(Ba, S.xt, d_gt, nullptr, st));
         k_solver_accept<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
         CU(cudaGetLastError());  // (covers k_solver_step too: launch errors are sticky until read)
