@@ -11,7 +11,9 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/armour_b200.h"
@@ -302,14 +304,31 @@ int ensure_buf(armour_controller* ctl, size_t doubles) {
     ctl->buf_doubles = doubles;
     return ARMOUR_OK;
 }
-// sin(-q), cos(-q) with the host's libm, as the reference computes them (spatial_interval.cpp:150-151 with theta = -q)
+// sin(-q), cos(-q) with the host's libm, as the reference computes them (spatial_interval.cpp:150-151 with theta = -q);
+// large batches are split over the host's threads (each value depends on its own angle only)
 void host_trig(const double* q, size_t count, std::vector<double>& out) {
     out.resize(count * 2);
-    for (size_t i = 0; i < count; i++) {
-        const double theta = -q[i];
-        out[2 * i] = std::sin(theta);
-        out[2 * i + 1] = std::cos(theta);
+    double* o = out.data();
+    auto run = [q, o](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; i++) {
+            const double theta = -q[i];
+            o[2 * i] = std::sin(theta);
+            o[2 * i + 1] = std::cos(theta);
+        }
+    };
+    const size_t min_chunk = 1 << 14;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 16) nt = 16;
+    if (nt < 2 || count < 2 * min_chunk) {
+        run(0, count);
+        return;
     }
+    if (count / min_chunk < nt) nt = unsigned(count / min_chunk);
+    std::vector<std::thread> pool;
+    const size_t per = (count + nt - 1) / nt;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(run, std::min(count, t * per), std::min(count, (t + 1) * per));
+    run(0, std::min(count, per));
+    for (auto& th : pool) th.join();
 }
 int grid(int n) { return (n + CTL_THREADS - 1) / CTL_THREADS; }
 

@@ -483,6 +483,19 @@ constexpr int K3_UTAB_BYTES = K3_USLOT * 2 + K3_USLOT * 8;
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+#ifndef K3_STREAM_STORES
+#define K3_STREAM_STORES 0  // 1: Jacobian rows with st.global.cs (evict-first)
+#endif
+#if K3_STREAM_STORES
+#define K3_ST2(p, a, b) __stcs(reinterpret_cast<double2*>(p), make_double2(a, b))
+#define K3_ST1(p, a) __stcs(p, a)
+#else
+#define K3_ST2(p, a, b) (*reinterpret_cast<double2*>(p) = make_double2(a, b))
+#define K3_ST1(p, a) (*(p) = (a))
+#endif
+#ifndef K3_LD_NOALLOC
+#define K3_LD_NOALLOC 0     // 1: candidate records with ld.global.nc.L1::no_allocate
+#endif
 #ifndef K3_LD256
 #define K3_LD256 1
 #endif
@@ -863,7 +876,11 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
                         if (q0 + i < n) {
 #if K3_LD256
                             // one 32-byte record = one 256-bit load (sm_100: ld.global.v4.f64)
+#if K3_LD_NOALLOC
+                            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+#else
                             asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+#endif
                                          : "=d"(u[i].x), "=d"(u[i].y), "=d"(w[i].x), "=d"(w[i].y)
                                          : "l"(row + (q0 + i) * cstride2));
 #else
@@ -902,15 +919,15 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
             // 56 contiguous bytes per row, 16-byte aligned for even rows (the Jacobian of a problem starts 16-byte aligned and
             // m is even): three 16-byte stores and one 8-byte store instead of seven 8-byte stores
             if ((row_i & 1) == 0) {
-                *reinterpret_cast<double2*>(out) = make_double2(jv[0], jv[1]);
-                *reinterpret_cast<double2*>(out + 2) = make_double2(jv[2], jv[3]);
-                *reinterpret_cast<double2*>(out + 4) = make_double2(jv[4], jv[5]);
-                out[6] = jv[6];
+                K3_ST2(out, jv[0], jv[1]);
+                K3_ST2(out + 2, jv[2], jv[3]);
+                K3_ST2(out + 4, jv[4], jv[5]);
+                K3_ST1(out + 6, jv[6]);
             } else {
-                out[0] = jv[0];
-                *reinterpret_cast<double2*>(out + 1) = make_double2(jv[1], jv[2]);
-                *reinterpret_cast<double2*>(out + 3) = make_double2(jv[3], jv[4]);
-                *reinterpret_cast<double2*>(out + 5) = make_double2(jv[5], jv[6]);
+                K3_ST1(out, jv[0]);
+                K3_ST2(out + 1, jv[1], jv[2]);
+                K3_ST2(out + 3, jv[3], jv[4]);
+                K3_ST2(out + 5, jv[5], jv[6]);
             }
         }
 #else
