@@ -121,6 +121,18 @@ SIGNATURES.update({
     "armour_controller_update_device": (C.c_int, [C.c_void_p, C.c_int, _gp] + [C.c_void_p] * 10),
 })
 
+SIGNATURES.update({
+    "armour_armtd_ctx_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "armour_armtd_build": (C.c_int, [C.c_void_p, dp, dp, dp, dp, dp, C.c_int]),
+    "armour_armtd_num_constraints": (C.c_int, [C.c_void_p]),
+    "armour_armtd_eval": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "armour_armtd_get_bounds": (C.c_int, [C.c_void_p, dp, dp]),
+    "armour_armtd_verdict": (C.c_int, [C.c_void_p, dp, ip, ip]),
+    "armour_armtd_cost": (C.c_int, [C.c_void_p, dp, dp, dp, dp]),
+    "armour_armtd_get_link_sliced_center": (C.c_int, [C.c_void_p, dp]),
+    "armour_armtd_get_link_independent_generators": (C.c_int, [C.c_void_p, dp]),
+})
+
 
 class SolverOptions(C.Structure):
     """armour_solver_options (include/armour_b200.h)."""

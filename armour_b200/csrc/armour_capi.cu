@@ -81,6 +81,7 @@ __device__ int g_k1spill[8];  // arena blocks in global memory, all arena blocks
 #undef K1_GROUPS
 #include "k3_constraints.cuh"
 #include "k4_solver.cuh"
+#include "armtd.cuh"
 #include "layout.h"
 
 using namespace armour;
@@ -118,6 +119,13 @@ struct armour_ctx {
     std::vector<double> h_torque_radius;  // host mirror of problem 0..built_nprob-1 (lazy)
     bool h_torque_valid = false;
     std::vector<double> h_q0, h_qd0, h_qdd0;
+    // ARMTD comparison planner (armour_armtd_*): imported joint reachable set, KPA-layout outputs, trajectory parameters
+    bool armtd = false;
+    double* d_jrs = nullptr;   // [ARMTD_T_PADDED][NF][6]
+    double* d_ga = nullptr;    // [m_armtd]
+    double* d_ja = nullptr;    // [m_armtd][NF]
+    size_t ga_capacity = 0, ja_capacity = 0;
+    ArmtdParams armtd_par;
 };
 
 namespace {
@@ -406,7 +414,7 @@ int armour_ctx_destroy(armour_ctx* ctx) {
     if (!ctx) return ARMOUR_OK;
     cudaSetDevice(ctx->cfg.device);
     Batch& B = ctx->B;
-    void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io, ctx->d_unit_flag, ctx->d_jnz,
+    void* ptrs[] = {ctx->d_solver, ctx->d_solver_i, ctx->d_solver_io, ctx->d_unit_flag, ctx->d_jnz, ctx->d_jrs, ctx->d_ga, ctx->d_ja,
                     ctx->d_in, ctx->d_obs, ctx->d_k, ctx->d_g, ctx->d_jac, ctx->d_verdict, B.link_n, B.link_c,
                     B.link_key, B.link_g, B.u_n, B.u_c, B.u_r, B.u_key, B.u_g, B.torque_radius, B.link_gens, B.link_r, B.hp_cand, B.hp_cnt, B.hp_slow,
                     B.link_sliced, B.status};
@@ -1136,6 +1144,196 @@ int armour_import_reachsets(armour_ctx* ctx, int prob, int nprob_total, const ar
         ctx->h_qd0.assign(qd0, qd0 + NF);
         ctx->h_qdd0.assign(qdd0, qdd0 + NF);
     }
+    return ARMOUR_OK;
+}
+
+
+// ---- ARMTD comparison planner (csrc/armtd.cuh) ---------------------------------------------------------------
+int armour_armtd_ctx_create(const armour_config* cfg_in, armour_ctx** out) {
+    if (!out) return ARMOUR_ERR_ARG;
+    armour_config cfg;
+    if (cfg_in) {
+        cfg = *cfg_in;
+    } else {
+        int rc = armour_config_default(&cfg);
+        if (rc) return rc;
+    }
+    cfg.num_time_steps = ARMTD_T_PADDED;  // 100 intervals of KPA + 4 padding intervals (chunks of 8)
+    cfg.max_problems = 1;
+    cfg.robot_model = 0;  // KPA/Parameters.h:6: KinovaWithoutGripperInfo.h
+    armour_ctx* ctx = nullptr;
+    int rc = armour_ctx_create(&cfg, &ctx);
+    if (rc) return rc;
+    cudaError_t e = dalloc(&ctx->d_jrs, size_t(ARMTD_T_PADDED) * NF * 6);
+    if (e != cudaSuccess) {
+        armour_ctx_destroy(ctx);
+        return ARMOUR_ERR_NOMEM;
+    }
+    ctx->armtd = true;
+    ctx->B.jrs_ext = ctx->d_jrs;
+    *out = ctx;
+    return ARMOUR_OK;
+}
+
+int armour_armtd_num_constraints(const armour_ctx* ctx) {
+    if (!ctx || !ctx->armtd) return ARMOUR_ERR_ARG;
+    return ctx->B.NJ * ARMTD_T * ctx->B.O + 4 * NF;
+}
+
+int armour_armtd_build(armour_ctx* ctx, const double* q0, const double* qd0, const double* jrs, const double* k_range,
+                       const double* obstacles, int nobs) {
+    if (!ctx || !q0 || !qd0 || !jrs || !k_range) return ARMOUR_ERR_ARG;
+    if (!ctx->armtd) return fail(ctx, ARMOUR_ERR_STATE, "not an ARMTD context (armour_armtd_ctx_create)");
+    // ConstantAccelerationCurve::makePolyZono, KPA/Trajectory.cu:29-62: the cos / sin models of joint i over interval t
+    std::vector<double> ext(size_t(ARMTD_T_PADDED) * NF * 6);
+    auto at = [&](int a, int i, int t) { return jrs[(size_t(a) * NF + i) * ARMTD_T + t]; };
+    for (int t = 0; t < ARMTD_T_PADDED; t++) {
+        const int ts = t < ARMTD_T ? t : ARMTD_T - 1;  // padding intervals repeat the last one
+        for (int i = 0; i < NF; i++) {
+            const double cos_q0 = std::cos(q0[i]), sin_q0 = std::sin(q0[i]);
+            double* o = &ext[(size_t(t) * NF + i) * 6];
+            o[0] = cos_q0 * at(0, i, ts) - sin_q0 * at(3, i, ts);
+            o[1] = cos_q0 * at(1, i, ts) - sin_q0 * at(4, i, ts);
+            double e = std::fabs(cos_q0) * at(2, i, ts) + std::fabs(sin_q0) * at(5, i, ts);
+            e *= 4.0;
+            o[2] = e;
+            o[3] = cos_q0 * at(3, i, ts) + sin_q0 * at(0, i, ts);
+            o[4] = cos_q0 * at(4, i, ts) + sin_q0 * at(1, i, ts);
+            e = std::fabs(cos_q0) * at(5, i, ts) + std::fabs(sin_q0) * at(2, i, ts);
+            e *= 4.0;
+            o[5] = e;
+        }
+    }
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->d_jrs, ext.data(), ext.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // ext dies at return
+    for (int i = 0; i < NF; i++) {
+        ctx->armtd_par.q0[i] = q0[i];
+        ctx->armtd_par.qd0[i] = qd0[i];
+        ctx->armtd_par.k_range[i] = k_range[i];
+    }
+    const double zero[NF] = {0, 0, 0, 0, 0, 0, 0};
+    return armour_batch_reachsets_build(ctx, 1, q0, qd0, zero, obstacles, nobs);
+}
+
+int armour_armtd_eval(armour_ctx* ctx, const double* k, double* g, double* values) {
+    if (!ctx || !k || (!g && !values)) return ARMOUR_ERR_ARG;
+    if (!ctx->armtd || ctx->built_nprob < 1) return fail(ctx, ARMOUR_ERR_STATE, "evaluate before armour_armtd_build");
+    CU(cudaSetDevice(ctx->cfg.device));
+    { int rc_c = ensure_constants(ctx); if (rc_c) return rc_c; }
+    int rc = ensure_eval_buffers(ctx, 1, true, values != nullptr);
+    if (rc) return rc;
+    const size_t ma = size_t(armour_armtd_num_constraints(ctx));
+    if (ctx->ga_capacity < ma) {
+        if (ctx->d_ga) cudaFree(ctx->d_ga);
+        ctx->d_ga = nullptr;
+        ctx->ga_capacity = 0;
+        CU(dalloc(&ctx->d_ga, ma));
+        ctx->ga_capacity = ma;
+    }
+    if (values && ctx->ja_capacity < ma * NF) {
+        if (ctx->d_ja) cudaFree(ctx->d_ja);
+        ctx->d_ja = nullptr;
+        ctx->ja_capacity = 0;
+        CU(dalloc(&ctx->d_ja, ma * NF));
+        ctx->ja_capacity = ma * NF;
+    }
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->d_k, k, NF * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = armour_batch_eval_device(ctx, 1, ctx->d_k, ctx->d_g, values ? ctx->d_jac : nullptr);
+    if (rc) return rc;
+    const int rows = ctx->B.NJ * ARMTD_T * ctx->B.O;
+    const int blocks = rows > 0 ? (rows + 255) / 256 : 1;
+    k_armtd_assemble<<<blocks, 256, 0, st>>>(ctx->armtd_par, ctx->B.NJ, ctx->B.O, ctx->d_k, ctx->d_g, values ? ctx->d_jac : nullptr,
+                                             ctx->d_ga, values ? ctx->d_ja : nullptr);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    if (g) CU(cudaMemcpyAsync(g, ctx->d_ga, ma * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (values) CU(cudaMemcpyAsync(values, ctx->d_ja, ma * NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ARMOUR_OK;
+}
+
+int armour_armtd_get_bounds(armour_ctx* ctx, double* g_l, double* g_u) {  // KPA/NLPclass.cu:75-142
+    if (!ctx || !g_l || !g_u || !ctx->armtd || ctx->built_nprob < 1) return ARMOUR_ERR_ARG;
+    const RobotConstants& R = ctx->rc;
+    int off = ctx->B.NJ * ARMTD_T * ctx->B.O;
+    for (int i = 0; i < off; i++) {
+        g_l[i] = -1e19;
+        g_u[i] = 0;
+    }
+    for (int rep = 0; rep < 2; rep++, off += NF)
+        for (int i = 0; i < NF; i++) {
+            g_l[off + i] = R.state_limits_lb[i] + R.qe;
+            g_u[off + i] = R.state_limits_ub[i] - R.qe;
+        }
+    for (int rep = 0; rep < 2; rep++, off += NF)
+        for (int i = 0; i < NF; i++) {
+            g_l[off + i] = -R.speed_limits[i] + R.qde;
+            g_u[off + i] = R.speed_limits[i] - R.qde;
+        }
+    return ARMOUR_OK;
+}
+
+int armour_armtd_verdict(armour_ctx* ctx, const double* g, int* feasible, int* first_violation) {  // KPA/NLPclass.cu:366-455
+    if (!ctx || !g || !feasible || !ctx->armtd || ctx->built_nprob < 1) return ARMOUR_ERR_ARG;
+    const RobotConstants& R = ctx->rc;
+    const int O = ctx->B.O;
+    auto done = [&](int ok, int row) {
+        *feasible = ok;
+        if (first_violation) *first_violation = row;
+        return ARMOUR_OK;
+    };
+    // the reference's loop runs over NUM_FACTORS - 1 links (KPA/NLPclass.cu:400): the rows of the last link are not checked
+    for (int i = 0; i < NF - 1; i++)
+        for (int j = 0; j < ARMTD_T; j++)
+            for (int h = 0; h < O; h++)
+                if (g[(i * ARMTD_T + j) * O + h] > R.collision_violation_threshold) return done(0, (i * ARMTD_T + j) * O + h);
+    int off = ctx->B.NJ * ARMTD_T * O;
+    for (int rep = 0; rep < 2; rep++, off += NF)
+        for (int i = off; i < off + NF; i++)
+            if (g[i] < R.state_limits_lb[i - off] + R.qe || g[i] > R.state_limits_ub[i - off] - R.qe) return done(0, i);
+    for (int rep = 0; rep < 2; rep++, off += NF)
+        for (int i = off; i < off + NF; i++)
+            if (g[i] < -R.speed_limits[i - off] + R.qde || g[i] > R.speed_limits[i - off] - R.qde) return done(0, i);
+    return done(1, -1);
+}
+
+int armour_armtd_cost(armour_ctx* ctx, const double* q_des, const double* k, double* obj, double* grad) {  // KPA/NLPclass.cu:178-243
+    if (!ctx || !q_des || !k || !ctx->armtd || ctx->built_nprob < 1) return ARMOUR_ERR_ARG;
+    const ArmtdParams& A = ctx->armtd_par;
+    auto wrap = [](double a) {
+        while (a < -M_PI) a += 2 * M_PI;
+        while (a > M_PI) a -= 2 * M_PI;
+        return a;
+    };
+    double qp[NF];
+    for (int i = 0; i < NF; i++) qp[i] = A.q0[i] + A.qd0[i] * 0.5 + A.k_range[i] * k[i] * 0.125;
+    if (obj) {
+        const double v = pw2(wrap(q_des[0] - qp[0])) + pw2(wrap(q_des[2] - qp[2])) + pw2(wrap(q_des[4] - qp[4])) +
+                         pw2(wrap(q_des[6] - qp[6])) + pw2(q_des[1] - qp[1]) + pw2(q_des[3] - qp[3]) + pw2(q_des[5] - qp[5]);
+        *obj = v * ctx->rc.cost_scale;
+    }
+    if (grad)
+        for (int i = 0; i < NF; i++) {
+            const double dk = A.k_range[i] * 0.125;
+            grad[i] = (i % 2 == 0) ? (2 * wrap(qp[i] - q_des[i]) * dk) : (2 * (qp[i] - q_des[i]) * dk);
+            grad[i] *= ctx->rc.cost_scale;
+        }
+    return ARMOUR_OK;
+}
+
+// armour_joint_position_center.out / armour_joint_position_radius.out of KPA/armtd_main.cu:232-256: [100][NJ][3] and [100][NJ][18]
+int armour_armtd_get_link_sliced_center(armour_ctx* ctx, double* out) {
+    if (!ctx || !out || !ctx->armtd || ctx->built_nprob < 1) return ARMOUR_ERR_ARG;
+    CU(cudaMemcpyAsync(out, ctx->B.link_sliced, size_t(ARMTD_T) * ctx->B.NJ * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ARMOUR_OK;
+}
+int armour_armtd_get_link_independent_generators(armour_ctx* ctx, double* out) {
+    if (!ctx || !out || !ctx->armtd || ctx->built_nprob < 1) return ARMOUR_ERR_ARG;
+    CU(cudaMemcpyAsync(out, ctx->B.link_gens, size_t(ARMTD_T) * ctx->B.NJ * 18 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return ARMOUR_OK;
 }
 

@@ -115,7 +115,7 @@ K1_DI void write_scalar_pz(double* p, int* n_out, double thr, double center, dou
 // Joint reachable set of joint i over interval t (KPR/Trajectory.cu:15-61 for the extrema of the
 // k-independent parts, :63-254 for the interval itself).  Executed by one thread per joint.
 K1_OP void jrs_joint(int i, int t, int T, double q0, double qd0, double qdd0, double thr, double* rot_blk, int* rot_n,
-                     double* qd_blk, int* qd_n, double* qda_blk, int* qda_n, double* qdda_blk, int* qdda_n) {
+                     double* qd_blk, int* qd_n, double* qda_blk, int* qda_n, double* qdda_blk, int* qdda_n, const double* ext) {
     const RobotConstants& rc = c_robot;
     const double D = rc.duration;
     const double a = qd0 * D, b = qdd0 * D * D;
@@ -146,27 +146,41 @@ K1_OP void jrs_joint(int i, int t, int T, double q0, double qd0, double qdd0, do
         ev[2][1] = bez_qdd_indep(a, b, es[2][1], D);
     }
 
-    // Part 1: position -> cos / sin Taylor models (:75-134)
-    double kd_lb = pw3(s_lb) * (6 * pw2(s_lb) - 15 * s_lb + 10);
-    double kd_ub = pw3(s_ub) * (6 * pw2(s_ub) - 15 * s_ub + 10);
-    double kd_center = (kd_ub + kd_lb) * 0.5;
-    double kd_radius = (kd_ub - kd_lb) * 0.5 * kr;
-    double ki_radius, q_c;
-    indep_range(bez_q_indep(q0, a, b, s_lb), bez_q_indep(q0, a, b, s_ub), s_lb, s_ub, es[0][0], ev[0][0], es[0][1],
-                ev[0][1], &ki_radius, &q_c);
-    const Itv qr = iv(-kd_radius - ki_radius - rc.qe, kd_radius + ki_radius + rc.qe);
-    const Itv kint = iv(-kr, kr);
-    const double sq_c = sin(q_c), cq_c = cos(q_c);
-    const Itv arg = iv_add(iv_addd(q_c, iv_muld(kd_center, kint)), qr);
-    const Itv e2 = iv_pow2(iv_add(qr, iv_muld(kd_center, kint)));
-    Itv cos_r = iv_sub(iv_muld(sq_c, iv_neg(qr)), iv_mul(iv_muld(0.5, iv_cos(arg)), e2));
-    double cos_c = cq_c + iv_mid(cos_r);
-    cos_r = iv_subd(cos_r, iv_mid(cos_r));
-    const double cos_k = -kd_center * kr * sq_c, cos_e = iv_rad(cos_r);
-    Itv sin_r = iv_sub(iv_muld(cq_c, qr), iv_mul(iv_muld(0.5, iv_sin(arg)), e2));
-    double sin_c = sq_c + iv_mid(sin_r);
-    sin_r = iv_subd(sin_r, iv_mid(sin_r));
-    const double sin_k = kd_center * kr * cq_c, sin_e = iv_rad(sin_r);
+    // Part 1: position -> cos / sin Taylor models (:75-134) — or, for the ARMTD comparison planner, the six numbers the caller
+    // derived from its offline joint reachable set (KPA/Trajectory.cu:34-62): same form  c + k-coefficient * k_i + e * cosqe_i
+    double cos_c, cos_k, cos_e, sin_c, sin_k, sin_e;
+    double kd_lb, kd_ub, kd_center, kd_radius, ki_radius;
+    if (ext) {
+        cos_c = ext[0];
+        cos_k = ext[1];
+        cos_e = ext[2];
+        sin_c = ext[3];
+        sin_k = ext[4];
+        sin_e = ext[5];
+    } else {
+        kd_lb = pw3(s_lb) * (6 * pw2(s_lb) - 15 * s_lb + 10);
+        kd_ub = pw3(s_ub) * (6 * pw2(s_ub) - 15 * s_ub + 10);
+        kd_center = (kd_ub + kd_lb) * 0.5;
+        kd_radius = (kd_ub - kd_lb) * 0.5 * kr;
+        double q_c;
+        indep_range(bez_q_indep(q0, a, b, s_lb), bez_q_indep(q0, a, b, s_ub), s_lb, s_ub, es[0][0], ev[0][0], es[0][1],
+                    ev[0][1], &ki_radius, &q_c);
+        const Itv qr = iv(-kd_radius - ki_radius - rc.qe, kd_radius + ki_radius + rc.qe);
+        const Itv kint = iv(-kr, kr);
+        const double sq_c = sin(q_c), cq_c = cos(q_c);
+        const Itv arg = iv_add(iv_addd(q_c, iv_muld(kd_center, kint)), qr);
+        const Itv e2 = iv_pow2(iv_add(qr, iv_muld(kd_center, kint)));
+        Itv cos_r = iv_sub(iv_muld(sq_c, iv_neg(qr)), iv_mul(iv_muld(0.5, iv_cos(arg)), e2));
+        cos_c = cq_c + iv_mid(cos_r);
+        cos_r = iv_subd(cos_r, iv_mid(cos_r));
+        cos_k = -kd_center * kr * sq_c;
+        cos_e = iv_rad(cos_r);
+        Itv sin_r = iv_sub(iv_muld(cq_c, qr), iv_mul(iv_muld(0.5, iv_sin(arg)), e2));
+        sin_c = sq_c + iv_mid(sin_r);
+        sin_r = iv_subd(sin_r, iv_mid(sin_r));
+        sin_k = kd_center * kr * cq_c;
+        sin_e = iv_rad(sin_r);
+    }
 
     // 3x3 rotation about z from the cos / sin models (KPR/PZsparse.cu:179-250), simplified, then
     // R = Rrpy * Rz (KPR/Trajectory.cu:136-144): a product with a constant left operand.
@@ -234,6 +248,12 @@ K1_OP void jrs_joint(int i, int t, int T, double q0, double qd0, double qdd0, do
         *rot_n = no;
     }
 
+    if (ext) {  // forward kinematics only: the velocity / acceleration sets stay empty (zero scalars)
+        write_scalar_pz(qd_blk, qd_n, thr, 0.0, 0.0, key_k(i), 0.0, key_qde(i));
+        write_scalar_pz(qda_blk, qda_n, thr, 0.0, 0.0, key_k(i), 0.0, key_qdae(i));
+        write_scalar_pz(qdda_blk, qdda_n, thr, 0.0, 0.0, key_k(i), 0.0, key_qddae(i));
+        return;
+    }
     // Part 2: velocity (:151-192)
     kd_lb = (30 * pw2(s_lb) * pw2(s_lb - 1)) / D;
     kd_ub = (30 * pw2(s_ub) * pw2(s_ub - 1)) / D;
@@ -398,7 +418,7 @@ K1_DI void build_jrs(const Batch& B, int p, int t) {
         jrs_joint(i, t, T, B.q0[size_t(p) * NF + i], B.qd0[size_t(p) * NF + i], B.qdd0[size_t(p) * NF + i], thr,
                   rot_mem + i * ROT_WORDS, &S.jrs_n[i], scl_mem + (0 * NF + i) * SCL_WORDS, &S.jrs_n[16 + i],
                   scl_mem + (1 * NF + i) * SCL_WORDS, &S.jrs_n[24 + i], scl_mem + (2 * NF + i) * SCL_WORDS,
-                  &S.jrs_n[32 + i]);
+                  &S.jrs_n[32 + i], B.jrs_ext ? B.jrs_ext + ((size_t(p) * T + t) * NF + i) * 6 : nullptr);
     } else if (tid >= 32 && tid < 32 + (NJ + 1 - NF)) {  // fixed joints and the identity after the last one
         const int i = NF + (tid - 32);
         double* blk = rot_mem + i * ROT_WORDS;

@@ -32,6 +32,9 @@ struct Batch {
     const double* qd0;        // [p][NF]
     const double* qdd0;       // [p][NF]
     const double* obstacles;  // [p][O][12]
+    // ARMTD comparison planner only (nullptr otherwise): cos / sin models of the joint reachable set handed in instead of
+    // derived from the Bezier trajectory, [p][t][NF][6] = cos centre, k-coefficient, error coefficient, then the same for sin
+    const double* jrs_ext;
     // reach sets written by the build kernel (or armour_import_reachsets)
     int* link_n;              // [p][t][NJ]
     double* link_c;           // [p][t][NJ][3]

@@ -115,3 +115,57 @@ def halton_k(n, dim=NF, skip=1):
                 x //= b
             out[i, j] = 2 * r - 1
     return out
+
+
+# ---- inputs of the ARMTD comparison planner ------------------------------------------------------------------
+ARMTD_T = 100  # KPA/Parameters.h:17
+
+
+def armtd_k_range(qd0):
+    """k_range of the constant-acceleration parameterisation, as ARMTD's offline tables define it: max(pi/24, |qd0| / 3)"""
+    return np.maximum(np.pi / 24, np.abs(np.asarray(qd0, dtype=np.float64)) / 3)
+
+
+def armtd_offline_jrs(qd0, k_range, T=ARMTD_T):
+    """Synthetic stand-in for the reference's offline joint-reachable-set tables (generated with MATLAB / CORA by
+    KPA/offline_jrs/create_orig_offline_jrs.m and sliced by load_offline_jrs.m: not in the reference tree).  For joint i and
+    interval j it returns zonotope enclosures  cos(q_des - q0) in c + g*k +- r  (same for sin), k in [-1, 1], of the trajectory
+    q_des(t) - q0 = qd0 t + k_a t^2 / 2 (t <= 0.5), braking to a stop at t = 1 afterwards, k_a = k_range * k: centre and slope from
+    the interval's mid-time, r from the largest residual over a sample grid times 1.1.  Returns [6, 7, T] in the input file's
+    order c_cos, g_cos, r_cos, c_sin, g_sin, r_sin (KPA/armtd_main.cu:70-88)."""
+    qd0 = np.asarray(qd0, dtype=np.float64)
+    k_range = np.asarray(k_range, dtype=np.float64)
+    out = np.zeros((6, NF, T))
+    ts = np.linspace(0.0, 1.0, 9)
+    ks = np.linspace(-1.0, 1.0, 33)
+
+    def coeffs(t):  # q_des - q0 = A(t) + B(t) * k_a
+        if t <= 0.5:
+            return qd0 * t, np.full(NF, 0.5 * t * t)
+        tau = t - 0.5  # peak state, then constant deceleration -qd_peak / 0.5
+        return qd0 * 0.5 + qd0 * tau - qd0 * tau * tau, 0.125 + 0.5 * tau - 0.5 * tau * tau
+
+    for j in range(T):
+        t0, t1 = j / T, (j + 1) / T
+        A, B = coeffs(0.5 * (t0 + t1))
+        c_cos, c_sin = np.cos(A), np.sin(A)
+        g_cos, g_sin = -np.sin(A) * B * k_range, np.cos(A) * B * k_range
+        r_cos, r_sin = np.zeros(NF), np.zeros(NF)
+        for s in ts:
+            At, Bt = coeffs(t0 + s * (t1 - t0))
+            for k in ks:
+                d = At + Bt * k_range * k
+                r_cos = np.maximum(r_cos, np.abs(np.cos(d) - (c_cos + g_cos * k)))
+                r_sin = np.maximum(r_sin, np.abs(np.sin(d) - (c_sin + g_sin * k)))
+        out[:, :, j] = np.stack([c_cos, g_cos, 1.1 * r_cos + 1e-6, c_sin, g_sin, 1.1 * r_sin + 1e-6])
+    return out
+
+
+def armtd_problem(path, seed=0):
+    """A planning problem of the comparison planner from a saved world: start from the CSV, a random initial velocity,
+    straight-line waypoint, the synthetic offline JRS.  Returns q0, qd0, q_des, jrs[6, 7, T], k_range, obstacles."""
+    q0, _, _, q_des, obs = config1_problem(path)
+    rng = np.random.default_rng(seed)
+    qd0 = np.round(rng.uniform(-0.4, 0.4, NF), 10)
+    k_range = armtd_k_range(qd0)
+    return q0, qd0, q_des, armtd_offline_jrs(qd0, k_range), k_range, obs

@@ -262,6 +262,30 @@ int armour_controller_update_device(armour_controller* ctl, int n, const armour_
                                     const double* d_qdd_des, const double* d_sincos, double* d_u, double* d_u_nominal,
                                     double* d_v, int* d_status);
 
+/* ---- ARMTD comparison planner ---------------------------------------------------------------------------
+ *
+ * The reference's second planner (kinova_planner_realtime_armtd_comparison/, "KPA": armtd_main.cu, Trajectory.cu, NLPclass.cu):
+ * constant-acceleration trajectories whose cos / sin joint reachable sets come from an OFFLINE table the caller slices and hands
+ * in (the six arrays of KPA's input file, armtd_main.cu:70-88), forward kinematics only, 100 time steps, no torque rows.  It runs
+ * on the kernels of the main path: the build is k_reachsets with the joint reachable set imported + k_hyperplanes, an evaluation
+ * is k_constraints + a kernel that lays the rows out as KPA's armtd_NLP does.  One problem per context, host pointers.
+ *   rows of g: collision (l * 100 + t) * nobs + o  (l < num_joints, t < 100), then 7 minimum joint positions, 7 maximum joint
+ *   positions, 7 minimum joint velocities, 7 maximum joint velocities (KPA/NLPclass.cu:43-44, 248-283);
+ *   values: dense m x 7 row-major like the main planner's; the joint-limit rows are diagonal and, as in the reference, hold the
+ *   derivative with respect to k_range * k (KPA/Trajectory.cu:262-384 writes no k_range factor).
+ * armour_armtd_ctx_create: cfg may be NULL (defaults); num_time_steps, max_problems and robot_model are set by the call.
+ * jrs: [6][7][100] = c_cos, g_cos, r_cos, c_sin, g_sin, r_sin, each joint-major over the 100 intervals. */
+int armour_armtd_ctx_create(const armour_config* cfg, armour_ctx** out);
+int armour_armtd_build(armour_ctx* ctx, const double q0[ARMOUR_NF], const double qd0[ARMOUR_NF], const double* jrs,
+                       const double k_range[ARMOUR_NF], const double* obstacles, int nobs);   /* armtd_main.cu:107-160 */
+int armour_armtd_num_constraints(const armour_ctx* ctx);                                      /* NLPclass.cu:43-44 */
+int armour_armtd_eval(armour_ctx* ctx, const double k[ARMOUR_NF], double* g, double* values); /* eval_g / eval_jac_g; either NULL */
+int armour_armtd_get_bounds(armour_ctx* ctx, double* g_l, double* g_u);                       /* NLPclass.cu:75-142 */
+int armour_armtd_verdict(armour_ctx* ctx, const double* g, int* feasible, int* first_violation);  /* :366-455 */
+int armour_armtd_cost(armour_ctx* ctx, const double q_des[ARMOUR_NF], const double k[ARMOUR_NF], double* obj, double* grad);
+int armour_armtd_get_link_sliced_center(armour_ctx* ctx, double* out);           /* [100][num_joints][3] of the last evaluation */
+int armour_armtd_get_link_independent_generators(armour_ctx* ctx, double* out);  /* [100][num_joints][18], column-major 3x6 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,22 @@ struct Problem {
     double cost(const double* q_des, const double* k) const;    // NLPclass.cu:207-236
     void cost_grad(const double* q_des, const double* k, double* grad) const;  // :241-268
 
+    // ---- ARMTD comparison planner (kinova_planner_realtime_armtd_comparison, "KPA"; oracle/armtd.cpp): constant-acceleration
+    // trajectory with an offline joint reachable set, forward kinematics only, no torque rows
+    double a_q0[NF] = {0}, a_qd0[NF] = {0}, a_k_range[NF] = {0};
+    // jrs: [6][NF][T] = c_cos, g_cos, r_cos, c_sin, g_sin, r_sin (the input file's arrays, KPA/armtd_main.cu:70-88)
+    void build_armtd(const double* q0, const double* qd0, const double* jrs, const double* k_range, const double* obstacles,
+                     int nobs, int nthreads);                                                  // armtd_main.cu:107-160
+    int armtd_num_constraints() const { return NJ * T * O + NF * 4; }                         // KPA/NLPclass.cu:43-44
+    void armtd_eval_g(const double* k, double* g);                                             // :248-283
+    void armtd_eval_jac_g(const double* k, double* values);                                    // :288-336
+    void armtd_bounds(double* g_l, double* g_u) const;                                         // :75-142
+    int armtd_verdict(const double* g, int* first_violation) const;                            // :366-455
+    double armtd_cost(const double* q_des, const double* k) const;                             // :178-212
+    void armtd_cost_grad(const double* q_des, const double* k, double* grad) const;            // :217-243
+    // ConstantAccelerationCurve::returnJointStateExtremum[Gradient] (KPA/Trajectory.cu:88-384): ext[4*NF], grad[4*NF] (diagonal)
+    void armtd_state_extremum(const double* k, double* ext, double* grad_diag) const;
+
 private:
     void init_hyperplanes();
     void link_constraints(bool with_grad, double* link_c, double* grad_link_c);

@@ -197,3 +197,67 @@ class OracleProblem:
         lib().orc_get_link_gens(self._h, _dp(raw))
         r["link_gens"] = raw
         return r
+
+
+class OracleArmtd(OracleProblem):
+    """The ARMTD comparison planner (KPA) evaluated by the CPU oracle (oracle/armtd.cpp): constant-acceleration trajectory,
+    offline joint reachable set handed in, forward kinematics only, 100 time steps."""
+
+    def __init__(self, simplify_threshold=5e-4, max_obstacles=40, num_time_steps=100):
+        super().__init__(0, num_time_steps, simplify_threshold, None, max_obstacles)
+        L = lib()
+        L.orc_armtd_build.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 5 + [C.c_int, C.c_int]
+        L.orc_armtd_num_constraints.argtypes = [C.c_void_p]
+        dp = C.POINTER(C.c_double)
+        L.orc_armtd_eval_g.argtypes = [C.c_void_p, dp, dp]
+        L.orc_armtd_eval_jac_g.argtypes = [C.c_void_p, dp, dp]
+        L.orc_armtd_bounds.argtypes = [C.c_void_p, dp, dp]
+        L.orc_armtd_verdict.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int)]
+        L.orc_armtd_cost.restype = C.c_double
+        L.orc_armtd_cost.argtypes = [C.c_void_p, dp, dp, dp]
+
+    def build(self, q0, qd0, jrs, k_range, obstacles, nthreads=0):
+        q0, qd0, jrs, k_range = _f64(q0), _f64(qd0), _f64(jrs), _f64(k_range)
+        obs = _f64(obstacles).reshape(-1, 12)
+        self.nobs = obs.shape[0]
+        self.T = lib().orc_num_time_steps(self._h)
+        assert jrs.shape == (6, NF, self.T)
+        if lib().orc_armtd_build(self._h, _dp(q0), _dp(qd0), _dp(jrs), _dp(k_range), _dp(obs), self.nobs, nthreads) != 0:
+            raise RuntimeError("oracle build failed (too many obstacles?)")
+        self.NJ = lib().orc_num_joints(self._h)
+        self.m = lib().orc_armtd_num_constraints(self._h)
+        return self
+
+    def eval_g(self, k):
+        k, g = _f64(k), np.empty(self.m)
+        lib().orc_armtd_eval_g(self._h, _dp(k), _dp(g))
+        return g
+
+    def eval_jac_g(self, k):
+        k, v = _f64(k), np.empty((self.m, NF))
+        lib().orc_armtd_eval_jac_g(self._h, _dp(k), _dp(v))
+        return v
+
+    def bounds(self):
+        gl, gu = np.empty(self.m), np.empty(self.m)
+        lib().orc_armtd_bounds(self._h, _dp(gl), _dp(gu))
+        return gl, gu
+
+    def verdict(self, g):
+        g = _f64(g)
+        first = C.c_int(-1)
+        ok = lib().orc_armtd_verdict(self._h, _dp(g), C.byref(first))
+        return bool(ok), first.value
+
+    def cost(self, q_des, k):
+        q_des, k = _f64(q_des), _f64(k)
+        return lib().orc_armtd_cost(self._h, _dp(q_des), _dp(k), None)
+
+    def cost_grad(self, q_des, k):
+        q_des, k, grad = _f64(q_des), _f64(k), np.empty(NF)
+        lib().orc_armtd_cost(self._h, _dp(q_des), _dp(k), _dp(grad))
+        return grad
+
+    def link_tables(self, cap_link=64):
+        r = self.export_reachsets(cap_link, 8)
+        return r["nl"], r["cl"], r["hl"], r["gl"]
