@@ -24,7 +24,8 @@ BASELINE.json targets (< 1 ms for one Kinova planning iteration's build + eval).
   (armour_batch_solve, host in/out, beside the CPU planner), "config3" / "config4" (BASELINE configs 3 and 4),
   "sweep" (BASELINE config 5: 65,536-world sweep split over the ranks, strong scaling, per-world verdicts gathered
   over NCCL), "controller" (the robust controller's interval Newton-Euler pass and robust input over 2^20
-  sampled states, beside the reference's own MEX sources on one host thread).
+  sampled states, beside the reference's own MEX sources on one host thread), "armtd" (the ARMTD comparison
+  planner on one saved world, beside the reference's own KPA sources).
 
 Multi-GPU: problems are independent -> every rank owns its own 1,024 worlds, no collective on the data
 path ("weak" scaling); NCCL only reduces the timing (max over ranks) and gathers the verdict counts.
@@ -436,6 +437,46 @@ def config_m1(device, stream, dev, nworlds, nobs, seed, label, **engine_kw):
             "m1_problems_per_s": nworlds / ((b + e) * 1e-3), "m2_evals_per_s": nworlds / (e * 1e-3),
             "torque_rows_share_of_eval": t0 / e, "torque_only_eval_ms": t0, "rows_without_obstacles": int(m0),
             "link_monomials_max": int(ln.max()), "torque_monomials_max": int(un.max())}
+
+
+def armtd_leg(device, cpu):
+    """the ARMTD comparison planner (KPA) on one saved world through the host-pointer ABI: build (imported joint
+    reachable set -> link reach sets -> half-space candidates) and one eval_g + eval_jac_g pair, wall clock; the reference's own
+    KPA sources (oracle/_ref/libarmour_ref_armtd.so, its CUDA collision kernels included) or the oracle beside it."""
+    from armour_b200 import ArmtdPlanner
+    worlds = load_worlds()
+    q0, qd0, q_des, jrs, k_range, obs = worlds.armtd_problem(os.path.join(ROOT, "tests", "golden", "worlds", "scene_016_006.csv"), 1)
+    k = np.array([0.5, 0.6, 0.7, 0.0, -0.5, -0.6, -0.7])
+    p = ArmtdPlanner(device=device)
+    p.build(q0, qd0, jrs, k_range, obs)
+    p.eval(k)
+
+    def best(fn, reps=7):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * min(ts)
+
+    out = {"world": "scene_016_006.csv", "obstacles": int(obs.shape[0]), "constraints": int(p.m),
+           "build_ms": best(lambda: p.build(q0, qd0, jrs, k_range, obs)), "eval_g_plus_eval_jac_g_ms": best(lambda: p.eval(k)),
+           "timing": "wall clock around the host-pointer C-ABI calls (copies and synchronisation inside)"}
+    out["one_iteration_ms"] = out["build_ms"] + out["eval_g_plus_eval_jac_g_ms"]
+    if cpu:
+        from oracle import pyrefarmtd
+        if pyrefarmtd.available():
+            mk, kind = (lambda: pyrefarmtd.ReferenceArmtd(q0, qd0, q_des, jrs, k_range, obs)), "reference"
+        else:
+            from oracle.pyoracle import OracleArmtd
+            mk, kind = (lambda: OracleArmtd().build(q0, qd0, jrs, k_range, obs)), "port"
+        ref = mk()
+        out["cpu_baseline"] = {"kind": kind, "cores": os.cpu_count() or 1, "build_ms": best(mk, 3),
+                               "eval_g_plus_eval_jac_g_ms": best(lambda: (ref.eval_g(k), ref.eval_jac_g(k)), 5)}
+        out["cpu_baseline"]["one_iteration_ms"] = out["cpu_baseline"]["build_ms"] + out["cpu_baseline"]["eval_g_plus_eval_jac_g_ms"]
+        out["speedup_one_iteration"] = out["cpu_baseline"]["one_iteration_ms"] / out["one_iteration_ms"]
+    p.close()
+    return out
 
 
 def controller_leg(device, stream, dev, cpu, n=1 << 20):
@@ -911,6 +952,14 @@ def run_b200(args):
         except Exception as exc:
             controller = {"error": repr(exc)}
 
+    # ---- ARMTD comparison planner, one problem through the host-pointer ABI, rank 0
+    armtd = None
+    if rank == 0 and not args.no_configs:
+        try:
+            armtd = armtd_leg(local, cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as exc:
+            armtd = {"error": repr(exc)}
+
     # ---- BASELINE config 5: the 65,536-world sweep, split over the ranks (strong scaling), per-world verdicts gathered
     sweep = None
     if args.sweep_worlds > 0:
@@ -952,7 +1001,7 @@ def run_b200(args):
             "step_submission": "CUDA graph replay (one graph = one step)" if graph_used else "plain launches",
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "m1": m1, "config1_host_abi": config1,
             "solver_e2e": solver_e2e, "config3": config3, "config4": config4, "sweep": sweep,
-            "controller": controller, "gpu_launches": int(launches_timed), "clocks": clk,
+            "controller": controller, "armtd": armtd, "gpu_launches": int(launches_timed), "clocks": clk,
             "feasible_worlds_last_iterate": feasible_total, "build_launches": int(build_launches),
         }
         print(json.dumps(line), flush=True)
