@@ -783,6 +783,17 @@ K1_DI int mg_task_list(unsigned short* tasks, int NJ) {
     return n;
 }
 
+// forward kinematics only (ARMTD comparison planner: no Newton-Euler pass, KPA/Dynamics.cu): the chain FKC(0..NJ-1) with the
+// link volume FKL(i) offered right behind FKC(i); every task depends on tasks before it in the list only
+K1_DI int mg_task_list_fk(unsigned short* tasks, int NJ) {
+    int n = 0;
+    for (int i = 0; i < NJ; i++) {
+        tasks[n++] = (unsigned short)((TK_FKC << 8) | i);
+        tasks[n++] = (unsigned short)((TK_FKL << 8) | i);
+    }
+    return n;
+}
+
 #if K1_MG
 // ---- MG mode: one unit built by all groups of the CTA ------------------------------------------------
 // The unit is a list of tasks; operands and results travel through the CTA's mailbox (global memory, written
@@ -1077,7 +1088,7 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
         X0.seq = 0;
         X0.mbox = P.mbox + size_t(blockIdx.x) * MB_SLOTS * P.mbox_words;
         X0.mbox_words = P.mbox_words;
-        X0.ntasks = mg_task_list(X0.tasks, P.B.NJ);
+        X0.ntasks = P.B.jrs_ext ? mg_task_list_fk(X0.tasks, P.B.NJ) : mg_task_list(X0.tasks, P.B.NJ);
     }
     for (int i = threadIdx.x; i < MB_SLOTS; i += NT * GROUPS) k1x().ev[i] = 0;
 #else
