@@ -169,3 +169,19 @@ def armtd_problem(path, seed=0):
     qd0 = np.round(rng.uniform(-0.4, 0.4, NF), 10)
     k_range = armtd_k_range(qd0)
     return q0, qd0, q_des, armtd_offline_jrs(qd0, k_range), k_range, obs
+
+
+def write_armtd_in(path, q0, qd0, q_des, jrs, k_range, obstacles):
+    """buffer/armtd.in as KPA/armtd_main.cu:54-103 parses it: q0, qd0, q_des, then per joint the six offline-JRS arrays
+    (100 values each) followed by its k_range, the obstacle count and 12 numbers per obstacle."""
+    obstacles = np.asarray(obstacles, dtype=np.float64).reshape(-1, 12)
+    with open(path, "w") as f:
+        for v in (q0, qd0, q_des):
+            f.write(" ".join(repr(float(x)) for x in v) + "\n")
+        for i in range(NF):
+            for a in range(6):
+                f.write(" ".join(repr(float(x)) for x in jrs[a, i]) + "\n")
+            f.write(repr(float(k_range[i])) + "\n")
+        f.write(f"{obstacles.shape[0]}\n")
+        for o in obstacles:
+            f.write(" ".join(repr(float(x)) for x in o) + "\n")

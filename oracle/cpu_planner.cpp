@@ -18,10 +18,13 @@ struct OracleNLP : public TNLP {
     double solution[orc::NF];
     bool feasible = false;
     int first_violation = -1;
-    OracleNLP(orc::Problem* p, const double* qd) : P(p), q_des(qd) { std::memset(solution, 0, sizeof(solution)); }
+    bool armtd = false;  // the ARMTD comparison planner's NLP (KPA/NLPclass.cu) instead of the main planner's
+    OracleNLP(orc::Problem* p, const double* qd, bool armtd_ = false) : P(p), q_des(qd), armtd(armtd_) {
+        std::memset(solution, 0, sizeof(solution));
+    }
     bool get_nlp_info(Index& n, Index& m, Index& nnz_jac_g, Index& nnz_h_lag, IndexStyleEnum& st) override {
         n = orc::NF;
-        m = P->num_constraints();
+        m = armtd ? P->armtd_num_constraints() : P->num_constraints();
         nnz_jac_g = m * n;
         nnz_h_lag = 0;
         st = C_STYLE;
@@ -32,7 +35,7 @@ struct OracleNLP : public TNLP {
             x_l[i] = -1.0;
             x_u[i] = 1.0;
         }
-        P->bounds(g_l, g_u);
+        if (armtd) P->armtd_bounds(g_l, g_u); else P->bounds(g_l, g_u);
         return true;
     }
     bool get_starting_point(Index n, bool, Number* x, bool, Number*, Number*, Index, bool, Number*) override {
@@ -40,15 +43,15 @@ struct OracleNLP : public TNLP {
         return true;
     }
     bool eval_f(Index, const Number* x, bool, Number& obj) override {
-        obj = P->cost(q_des, x);
+        obj = armtd ? P->armtd_cost(q_des, x) : P->cost(q_des, x);
         return true;
     }
     bool eval_grad_f(Index, const Number* x, bool, Number* grad) override {
-        P->cost_grad(q_des, x, grad);
+        if (armtd) P->armtd_cost_grad(q_des, x, grad); else P->cost_grad(q_des, x, grad);
         return true;
     }
     bool eval_g(Index, const Number* x, bool, Index, Number* g) override {
-        P->eval_g(x, g);
+        if (armtd) P->armtd_eval_g(x, g); else P->eval_g(x, g);
         return true;
     }
     bool eval_jac_g(Index n, const Number* x, bool, Index m, Index, Index* iRow, Index* jCol, Number* values) override {
@@ -59,14 +62,14 @@ struct OracleNLP : public TNLP {
                     jCol[i * n + j] = j;
                 }
         } else {
-            P->eval_jac_g(x, values);
+            if (armtd) P->armtd_eval_jac_g(x, values); else P->eval_jac_g(x, values);
         }
         return true;
     }
     void finalize_solution(SolverReturn, Index n, const Number* x, const Number*, const Number*, Index, const Number* g,
                            const Number*, Number, const IpoptData*, IpoptCalculatedQuantities*) override {
         for (Index i = 0; i < n; i++) solution[i] = x[i];
-        feasible = P->verdict(g, &first_violation) != 0;  // KPR/NLPclass.cu:449-537
+        feasible = (armtd ? P->armtd_verdict(g, &first_violation) : P->verdict(g, &first_violation)) != 0;  // NLPclass.cu:449-537
     }
 };
 }  // namespace
@@ -90,4 +93,25 @@ extern "C" int orc_solve(void* h, const double* q_des, int max_iter, double max_
 // the QP sub-solver of the host solver on its own, for tests/test_active_set_qp.py
 extern "C" int orc_qp(int n, double h, const double* c, int nrows, const double* A, const double* b, double* d) {
     return local_qp(n, h, c, nrows, A, b, d, 200);
+}
+
+// the same for the ARMTD comparison planner (KPA/armtd_main.cu:163-205 with the local solver in Ipopt's place; tol as
+// KPA/Parameters.h:43); fills the sliced link centres at the solution like the reference's last eval_g
+extern "C" int orc_armtd_solve(void* h, const double* q_des, int max_iter, double tol, double* k_opt, int* feasible,
+                               int* first_violation, int* iterations) {
+    orc::Problem* P = static_cast<orc::Problem*>(h);
+    OracleNLP nlp(P, q_des, true);
+    LocalSolverOptions opt;
+    if (max_iter > 0) opt.max_iter = max_iter;
+    if (tol > 0) opt.tol = tol;
+    opt.max_wall_time = 1e9;
+    LocalSolverStats st;
+    local_solve(nlp, opt, &st);
+    for (int i = 0; i < orc::NF; i++) k_opt[i] = nlp.solution[i];
+    if (feasible) *feasible = nlp.feasible ? 1 : 0;
+    if (first_violation) *first_violation = nlp.first_violation;
+    if (iterations) *iterations = st.iterations;
+    std::vector<double> g(P->armtd_num_constraints());
+    P->armtd_eval_g(nlp.solution, g.data());
+    return 0;
 }

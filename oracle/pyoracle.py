@@ -261,3 +261,14 @@ class OracleArmtd(OracleProblem):
     def link_tables(self, cap_link=64):
         r = self.export_reachsets(cap_link, 8)
         return r["nl"], r["cl"], r["hl"], r["gl"]
+
+    def solve(self, q_des, max_iter=0, tol=1e-7):
+        """Plan on the CPU (oracle/cpu_planner.cpp: the product's host-side local solver over this oracle, KPA's tolerance).
+        Returns (k_opt, feasible, first violated row, iterations); link_sliced_center() then holds the centres at k_opt."""
+        q_des, k = _f64(q_des), np.empty(NF)
+        ok, first, it = C.c_int(0), C.c_int(-1), C.c_int(0)
+        L = lib()
+        L.orc_armtd_solve.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_double, C.POINTER(C.c_double),
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_armtd_solve(self._h, _dp(q_des), max_iter, tol, _dp(k), C.byref(ok), C.byref(first), C.byref(it))
+        return k, bool(ok.value), first.value, it.value

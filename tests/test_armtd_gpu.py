@@ -78,3 +78,36 @@ def test_argument_errors(built):
     eng = ReachSetEngine(max_problems=1, max_obstacles=2)
     assert eng.lib.armour_armtd_num_constraints(eng._h) < 0  # not an ARMTD context
     eng.close()
+
+
+def test_armtd_main_cli_matches_the_cpu_planner(built, tmp_path):
+    """armtd_main (the drop-in for KPA/armtd_main.cu): armtd.in -> the four output files, against the same local solver
+    driving the oracle on the CPU."""
+    import subprocess
+
+    from armour_b200 import worlds
+    from oracle.pyoracle import OracleArmtd
+    exe = os.path.join(os.path.dirname(HERE), "armour_b200", "armtd_main")
+    q0, qd0, q_des, jrs, kr, obs = worlds.armtd_problem(os.path.join(HERE, "golden", "worlds", "scene_016_006.csv"), seed=1)
+    worlds.write_armtd_in(str(tmp_path / "armtd.in"), q0, qd0, q_des, jrs, kr, obs)
+    res = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    o = OracleArmtd().build(q0, qd0, jrs, kr, obs)
+    k_ref, ok_ref, _, _ = o.solve(q_des)
+    lines = (tmp_path / "armtd.out").read_text().split()
+    if "wall time exceeded" in res.stdout:
+        pytest.skip("the cold process ran into the reference's 0.4 s optimiser budget")
+    assert ok_ref and len(lines) == 8  # 7 x k_opt + the time
+    k = np.array([float(x) for x in lines[:7]])
+    assert np.max(np.abs(k - k_ref)) <= 1e-8
+    cen = np.loadtxt(tmp_path / "armtd_joint_position_center.out").reshape(100, 7, 3)
+    assert np.max(np.abs(cen - o.link_sliced_center())) <= 1e-8
+    rad = np.loadtxt(tmp_path / "armtd_joint_position_radius.out").reshape(100, 7, 3, 6)
+    ref = o.link_gens()  # [T, NJ, 3, 6]
+    assert np.max(np.abs(rad - ref)) <= 1e-8
+    g = np.loadtxt(tmp_path / "armtd_constraints.out")
+    assert g.shape == (o.m,) and np.max(np.abs(g - o.eval_g(k_ref))) <= 1e-5
+    # too many obstacles: a single -1, exit code -1 (255)
+    worlds.write_armtd_in(str(tmp_path / "armtd.in"), q0, qd0, q_des, jrs, kr, np.zeros((41, 12)))
+    res = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode != 0 and (tmp_path / "armtd.out").read_text().strip() == "-1"
