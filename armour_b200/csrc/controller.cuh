@@ -266,14 +266,21 @@ __global__ void k_model_setup(Model* M) {
     }
 }
 
-// passRNEA / passRNEA_Int (MEX/rnea.cpp:6-94 / 96-187) for one state.  sc: sin(-q_i), cos(-q_i) per joint.
+// The joint transforms of one state, Xli[i] = IntTransform(Sb[i], -q[i]).apply(XTree[i].inverse()) (MEX/rnea.cpp:139-146):
+// they depend on the angles only, so the controller update computes them once for its two interval passes.
+template <class T>
+__device__ void rnea_transforms(const Model* M, const double* sn, const double* cs, Xf<T>* Xli) {
+    const JointModel<T>* J = joints<T>(M);
+    for (int i = 0; i < M->nj; i++) Xli[i] = xf_apply(xf_joint(J[i].Sb, sn[i], cs[i]), J[i].Xinv);
+}
+
+// passRNEA / passRNEA_Int (MEX/rnea.cpp:6-94 / 96-187) for one state, given its joint transforms.
 // Requires parent[i] < i (a spanning tree numbered from the base, as the reference's files are).
 template <class T>
-__device__ void rnea(const Model* M, const double* qd, const double* qda, const double* qdd, const double* sn, const double* cs,
-                     bool friction, bool gravity, T* tau) {
+__device__ void rnea_pass(const Model* M, const Xf<T>* Xli, const double* qd, const double* qda, const double* qdd, bool friction,
+                          bool gravity, T* tau) {
     const JointModel<T>* J = joints<T>(M);
     const int nj = M->nj;
-    Xf<T> Xli[MAXJ];
     Wr<T> f[MAXJ];
     Tw<T> v[MAXJ], va[MAXJ], a[MAXJ];
     Tw<T> neg_g;
@@ -284,7 +291,6 @@ __device__ void rnea(const Model* M, const double* qd, const double* qda, const 
     for (int i = 0; i < nj; i++) {
         const int li = M->parent[i];
         const Tw<T> Sb = J[i].Sb;
-        Xli[i] = xf_apply(xf_joint(Sb, sn[i], cs[i]), J[i].Xinv);
         const Tw<T> sqd = tw_scaled(Sb, qd[i]), sqda = tw_scaled(Sb, qda[i]), sqdd = tw_scaled(Sb, qdd[i]);
         if (li == -1) {
             v[i] = sqd;
@@ -321,6 +327,13 @@ __device__ void rnea(const Model* M, const double* qd, const double* qda, const 
             f[li].f = vadd(f[li].f, up.f);
         }
     }
+}
+template <class T>
+__device__ void rnea(const Model* M, const double* qd, const double* qda, const double* qdd, const double* sn, const double* cs,
+                     bool friction, bool gravity, T* tau) {
+    Xf<T> Xli[MAXJ];
+    rnea_transforms<T>(M, sn, cs, Xli);
+    rnea_pass<T>(M, Xli, qd, qda, qdd, friction, gravity, tau);
 }
 
 struct TrigSrc {
@@ -432,7 +445,9 @@ k_controller_update(const Model* __restrict__ M, int n, ControllerGains G, const
     double un[MAXJ];
     Itv ui[MAXJ];
     rnea<double>(M, qdv, qa_d, qa_dd, sn, cs, G.friction != 0, true, un);
-    rnea<Itv>(M, qdv, qa_d, qa_dd, sn, cs, G.friction != 0, true, ui);
+    Xf<Itv> Xli[MAXJ];  // shared by the interval torque pass and the interval M(q) r pass below
+    rnea_transforms<Itv>(M, sn, cs, Xli);
+    rnea_pass<Itv>(M, Xli, qdv, qa_d, qa_dd, G.friction != 0, true, ui);
     int st = 0;
     double bound[MAXJ];
     for (int i = 0; i < nj; i++) {
@@ -445,7 +460,7 @@ k_controller_update(const Model* __restrict__ M, int n, ControllerGains G, const
     const double r_norm = norm_dyn(r, nj);
     if (r_norm > G.r_norm_threshold) {
         Itv Mr[MAXJ];
-        rnea<Itv>(M, zero, zero, r, sn, cs, false, false, Mr);  // M(q) r
+        rnea_pass<Itv>(M, Xli, zero, zero, r, false, false, Mr);  // M(q) r
         Itv V = pt<Itv>(0.0);
         for (int i = 0; i < nj; i++) V = s_add(V, s_muld(Mr[i], 0.5 * r[i]));
         const double h = -V.hi + G.V_max;
