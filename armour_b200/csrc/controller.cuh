@@ -276,7 +276,10 @@ __device__ void rnea_transforms(const Model* M, const double* sn, const double* 
 
 // passRNEA / passRNEA_Int (MEX/rnea.cpp:6-94 / 96-187) for one state, given its joint transforms.
 // Requires parent[i] < i (a spanning tree numbered from the base, as the reference's files are).
-template <class T>
+// ZERO_VEL: the call with qd = qda = 0 (M(q) r of the controller, robust_controller.cpp:148): every velocity twist is the zero
+// interval, so the velocity products are [0, 0] and adding them changes nothing (x + 0 is exact in every rounding direction);
+// they are left out, the result is the reference's.
+template <class T, bool ZERO_VEL = false>
 __device__ void rnea_pass(const Model* M, const Xf<T>* Xli, const double* qd, const double* qda, const double* qdd, bool friction,
                           bool gravity, T* tau) {
     const JointModel<T>* J = joints<T>(M);
@@ -291,7 +294,14 @@ __device__ void rnea_pass(const Model* M, const Xf<T>* Xli, const double* qd, co
     for (int i = 0; i < nj; i++) {
         const int li = M->parent[i];
         const Tw<T> Sb = J[i].Sb;
-        const Tw<T> sqd = tw_scaled(Sb, qd[i]), sqda = tw_scaled(Sb, qda[i]), sqdd = tw_scaled(Sb, qdd[i]);
+        const Tw<T> sqdd = tw_scaled(Sb, qdd[i]);
+        if (ZERO_VEL) {
+            a[i] = li == -1 ? tw_add(xf_apply(Xli[i], neg_g), sqdd) : tw_add(xf_apply(Xli[i], a[li]), sqdd);
+            f[i].tau = vadd(mv(J[i].Ibar, a[i].w), mv(J[i].mch, a[i].v));  // I.apply(a)
+            f[i].f = vsub(vscale(a[i].v, J[i].m), mv(J[i].mch, a[i].w));
+            continue;
+        }
+        const Tw<T> sqd = tw_scaled(Sb, qd[i]), sqda = tw_scaled(Sb, qda[i]);
         if (li == -1) {
             v[i] = sqd;
             va[i] = sqda;
@@ -460,7 +470,7 @@ k_controller_update(const Model* __restrict__ M, int n, ControllerGains G, const
     const double r_norm = norm_dyn(r, nj);
     if (r_norm > G.r_norm_threshold) {
         Itv Mr[MAXJ];
-        rnea_pass<Itv>(M, Xli, zero, zero, r, false, false, Mr);  // M(q) r
+        rnea_pass<Itv, true>(M, Xli, zero, zero, r, false, false, Mr);  // M(q) r
         Itv V = pt<Itv>(0.0);
         for (int i = 0; i < nj; i++) V = s_add(V, s_muld(Mr[i], 0.5 * r[i]));
         const double h = -V.hi + G.V_max;
