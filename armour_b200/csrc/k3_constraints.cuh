@@ -483,6 +483,9 @@ constexpr int K3_UTAB_BYTES = K3_USLOT * 2 + K3_USLOT * 8;
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+#ifndef K3_SKIP_ZERO_DK
+#define K3_SKIP_ZERO_DK 0   // 1: no look-ups / products for d/dk_v with v above the link index (exactly zero); measured: no gain
+#endif
 #ifndef K3_STREAM_STORES
 #define K3_STREAM_STORES 0  // 1: Jacobian rows with st.global.cs (evict-first)
 #endif
@@ -907,11 +910,22 @@ k_constraints(Batch B, const double* __restrict__ kin, double* __restrict__ g, d
         const long long row_i = active ? (long long)(size_t(NF) * T + (size_t(l) * T + tb * TB + tt) * O + o) : -1;
         if (gp && active) gp[row_i] = -max_elt;
 #if K3_DIRECT_J
+#if K3_SKIP_ZERO_DK
+        // the centre of link l depends on k_0 .. k_l only: d/dk_v is exactly zero for v > l, those products are not made
+        // (the rows of a warp pass belong to at most two consecutive links: the bound is the larger one)
+        const int lmax = __reduce_max_sync(0xffffffffu, active ? l : 0);
+#endif
         if (jp && active) {
             double* out = jp + row_i * NF;
             double jv[NF];
 #pragma unroll
             for (int v = 0; v < NF; v++) {
+#if K3_SKIP_ZERO_DK
+                if (v > lmax) {
+                    jv[v] = 0.0;
+                    continue;
+                }
+#endif
                 const double* dk = s_dlc[tt][l][v];
                 // -(C.dk) for a 'pos' winner, +(C.dk) for 'neg' (:286-295); the sign is folded into A
                 jv[v] = A0 * dk[0] + A1 * dk[1] + A2 * dk[2];
