@@ -240,6 +240,9 @@ bool parse_model(const std::string& path, FileModel& F, std::string& err) {
 void convert_model(const FileModel& F, double eps, Model& M) {
     std::memset(&M, 0, sizeof(M));
     M.nj = F.nj;
+    M.chain = 1;
+    for (int i = 0; i < F.nj; i++)
+        if (F.parent[i] != i - 1) M.chain = 0;
     for (int k = 0; k < 3; k++) M.gravity[k] = F.gravity[k];
     const double lowP = 1 - eps, highP = 1 + eps;
     for (int i = 0; i < F.nj; i++) {
