@@ -42,6 +42,10 @@ __device__ int g_k1spill[8];  // arena blocks in global memory, all arena blocks
 #define K1LAT_TAB_16THS 11  // share (in sixteenths) of a group's dynamic shared memory given to the scratch pool
 #endif
 #define K1_TAB_16THS K1LAT_TAB_16THS
+#ifndef K1LAT_DYN_CAP
+#define K1LAT_DYN_CAP -1  // shared memory per group beyond the fixed region: no cap
+#endif
+#define K1_DYN_CAP K1LAT_DYN_CAP
 #define K1_NS k1lat
 #define K1_NT K1LAT_NT
 #define K1_CTAS K1LAT_CTAS
@@ -59,14 +63,19 @@ __device__ int g_k1spill[8];  // arena blocks in global memory, all arena blocks
 #define K1THR_NT 64
 #endif
 #ifndef K1THR_GROUPS
-#define K1THR_GROUPS 12
+#define K1THR_GROUPS 8
 #endif
 #ifndef K1THR_CTAS
-#define K1THR_CTAS 1
+#define K1THR_CTAS 2
 #endif
 #ifndef K1THR_TAB_EIGHTHS
 #define K1THR_TAB_EIGHTHS 4  // share (in eighths) of a group's dynamic shared memory given to the scratch pool
 #endif
+#ifndef K1THR_DYN_CAP
+#define K1THR_DYN_CAP 0  // no shared-memory arena / scratch per group: the global scratch behind a large L1 is faster
+#endif
+#undef K1_DYN_CAP
+#define K1_DYN_CAP K1THR_DYN_CAP
 #undef K1_TAB_EIGHTHS
 #define K1_TAB_EIGHTHS K1THR_TAB_EIGHTHS
 #define K1_TAB_16THS (2 * K1THR_TAB_EIGHTHS)

@@ -1266,6 +1266,9 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
 
 #ifndef ARMOUR_EMU
 // ---- host side: scratch buffers and launch ----------------------------------------------------------
+#ifndef K1_DYN_CAP
+#define K1_DYN_CAP -1
+#endif
 #ifndef K1_TAB_EIGHTHS
 #define K1_TAB_EIGHTHS 5
 #endif
@@ -1305,7 +1308,12 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     int per_cta = (smem_optin + 1024) / CTAS_PER_SM - 1024;
     per_cta &= ~1023;
     const int per_group = ((per_cta - K1_HDR_BYTES) / GROUPS) & ~15;
-    const int dyn = per_group - K1_FIXED_BYTES;
+    int dyn = per_group - K1_FIXED_BYTES;
+    // K1_DYN_CAP: at most this much shared memory per group beyond the fixed region.  What the arena and the scratch do
+    // not hold in shared memory lives in the group's global scratch, i.e. in the L1 cache, which gets the shared memory
+    // the CTAs do not claim (the spill slots of the kernel go through the same cache): see DESIGN.md section 6.
+    if (K1_DYN_CAP >= 0 && dyn > K1_DYN_CAP) dyn = K1_DYN_CAP;
+    if (dyn < 0) return cudaErrorInvalidConfiguration;  // the fixed region of GROUPS groups does not fit
     s->tab_s_bytes = (dyn * K1_TAB_16THS / 16) & ~1023;  // scratch of the merge / hash passes; the rest is the PZ arena
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
     s->group_bytes = K1_FIXED_BYTES + s->arena_words * 8 + s->tab_s_bytes;

@@ -567,7 +567,7 @@ __device__ __forceinline__ void slice_component_pt(const uint16_t* __restrict__ 
         }
     }
 }
-constexpr int K3_LINK_THREADS = 192;
+constexpr int K3_LINK_THREADS = ((TB * 3 * MAXJ + 31) / 32) * 32;  // 192 for TB = 8
 #ifndef K3_TORQUE_LANES_N
 #define K3_TORQUE_LANES_N 2
 #endif
