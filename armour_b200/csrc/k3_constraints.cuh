@@ -1201,6 +1201,19 @@ cudaError_t launch_hyperplanes(const Batch& B, cudaStream_t st, const int* unit_
 }
 cudaError_t launch_constraints(const Batch& B, const double* d_k, double* d_g, double* d_jac, cudaStream_t st) {
     if (B.nprob == 0) return cudaSuccess;
+#ifdef K3_CARVEOUT_KNOB
+    {  // experiment: shared-memory carve-out of the main kernel in per cent of the maximum (ARMOUR_K3_CARVEOUT)
+        static int done = 0;
+        if (!done) {
+            done = 1;
+            const char* v = std::getenv("ARMOUR_K3_CARVEOUT");
+            if (v) {
+                cudaError_t ec = cudaFuncSetAttribute(k_constraints, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(v));
+                std::printf("k_constraints carve-out %s %%: %s\n", v, cudaGetErrorString(ec));
+            }
+        }
+    }
+#endif
     dim3 grid(B.T / TB, B.nprob);
     const int rows_all = B.NJ * TB * B.O;
     const size_t dyn = (K3_STAGE_TABLES ? size_t(TB) * (B.NJ * K3_LTAB_BYTES + NF * K3_UTAB_BYTES) : 0) +
