@@ -74,6 +74,11 @@ __device__ int g_k1spill[8];  // arena blocks in global memory, all arena blocks
 #ifndef K1THR_DYN_CAP
 #define K1THR_DYN_CAP 0  // no shared-memory arena / scratch per group: the global scratch behind a large L1 is faster
 #endif
+#ifndef K1THR_JRS_GLOBAL
+#define K1THR_JRS_GLOBAL 1  // the joint-reachable-set region of a group sits in its global scratch too (only the control block in shared memory)
+#endif
+#undef K1_JRS_GLOBAL
+#define K1_JRS_GLOBAL K1THR_JRS_GLOBAL
 #undef K1_DYN_CAP
 #define K1_DYN_CAP K1THR_DYN_CAP
 #undef K1_TAB_EIGHTHS

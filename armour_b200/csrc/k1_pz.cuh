@@ -64,6 +64,9 @@ constexpr int GROUPS = K1_GROUPS;  // units built side by side by one CTA (CTA =
 // next task of a fixed priority list, waits for its inputs, runs it in its own arena and publishes the results
 // (k1_reachsets.cuh, build_unit_mg).  Without MG the groups build different units in lock step.
 constexpr bool MG = K1_MG != 0;
+#ifndef K1_JRS_GLOBAL
+#define K1_JRS_GLOBAL 0
+#endif
 constexpr int CTAS_PER_SM = K1_CTAS;  // resident CTAs per SM (shared memory is split evenly)
 constexpr int NW = NT / 32;  // warps per CTA
 constexpr int RED_STRIDE = 12;
@@ -193,7 +196,14 @@ inline void k1_sync_cta() {}
 inline K1X& k1x() { return *reinterpret_cast<K1X*>(smem_cta()); }
 #endif
 K1_DI K1S& k1s() { return *reinterpret_cast<K1S*>(smem_base()); }
+// K1_JRS_GLOBAL: the fixed joint-reachable-set region [0, JRS words) of the virtual arena lives at the front of the group's
+// global scratch instead of shared memory (throughput configuration: everything but the control block goes through L1).
+// The virtual offsets do not change: gbase points behind the region, so vptr() resolves both halves to gbase - AW + off.
+#if K1_JRS_GLOBAL
+K1_DI double* arena0() { return k1s().gbase - k1s().AW; }
+#else
 K1_DI double* arena0() { return reinterpret_cast<double*>(smem_base() + K1S_BYTES); }
+#endif
 K1_DI char* tab_s0() { return reinterpret_cast<char*>(arena0() + k1s().AW); }
 
 K1_DI void set_fail_at(int code, int line) {

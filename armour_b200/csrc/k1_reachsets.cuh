@@ -1073,7 +1073,12 @@ K1_DI int run_task(const Batch& B, int p, int t, int kind, int i) {
 #endif  // K1_MG
 
 // ---- kernel ---------------------------------------------------------------------------------------
+#if K1_JRS_GLOBAL
+constexpr int K1_FIXED_BYTES = K1S_BYTES;  // per group: the control block only (the JRS region is in the global scratch)
+static_assert(!MG, "K1_JRS_GLOBAL is a knob of the throughput configuration");
+#else
 constexpr int K1_FIXED_BYTES = K1S_BYTES + JRS_WORDS * 8;  // per group: control block + joint reachable set region
+#endif
 
 __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params P) {
 #ifndef ARMOUR_EMU
@@ -1099,12 +1104,18 @@ __global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) k_reachsets(K1Params
     const int tid = k1_tid();
     const int slot = blockIdx.x * GROUPS + k1_group();  // scratch slot of this group
     if (tid == 0) {
+#if K1_JRS_GLOBAL
+        S.gbase = P.gscr + size_t(slot) * P.gscr_words + JRS_WORDS;  // [JRS region | spill space | F/N scratch]
+        S.AW = JRS_WORDS;
+        S.GW = P.gscr_words - P.fn_words - JRS_WORDS;
+#else
         S.gbase = P.gscr + size_t(slot) * P.gscr_words;
+        S.AW = JRS_WORDS + P.arena_words;
+        S.GW = P.gscr_words - P.fn_words;
+#endif
         S.tab_g = P.gtab + size_t(slot) * P.gtab_bytes;
         S.thr = c_robot.simplify_threshold;
         S.thr2 = threshold_sq(S.thr);
-        S.AW = JRS_WORDS + P.arena_words;
-        S.GW = P.gscr_words - P.fn_words;
         S.FW = P.fn_words;
         S.tab_s_bytes = P.tab_s_bytes;
         S.tab_g_bytes = P.gtab_bytes;
@@ -1313,6 +1324,9 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     // not hold in shared memory lives in the group's global scratch, i.e. in the L1 cache, which gets the shared memory
     // the CTAs do not claim (the spill slots of the kernel go through the same cache): see DESIGN.md section 6.
     if (K1_DYN_CAP >= 0 && dyn > K1_DYN_CAP) dyn = K1_DYN_CAP;
+#if K1_JRS_GLOBAL
+    if (dyn > 0) dyn = 0;  // the arena must start right behind the JRS region, in the global scratch
+#endif
     if (dyn < 0) return cudaErrorInvalidConfiguration;  // the fixed region of GROUPS groups does not fit
     s->tab_s_bytes = (dyn * K1_TAB_16THS / 16) & ~1023;  // scratch of the merge / hash passes; the rest is the PZ arena
     s->arena_words = (dyn - s->tab_s_bytes) / 8;
@@ -1322,7 +1336,7 @@ inline cudaError_t k1_scratch_create(K1Scratch* s, const armour_config& cfg, con
     // per-CTA global scratch: arena spill space, then F_i / N_i of one unit; and the overflow hash-table pool
     const int capw = cfg.cap_work_monomials;
     s->fn_words = 2 * MAXJ * (9 + capw * 2);
-    s->gscr_words = s->fn_words + 24 * capw;
+    s->gscr_words = s->fn_words + 24 * capw + (K1_JRS_GLOBAL ? ((JRS_WORDS + 15) & ~15) : 0);
     s->gtab_bytes = 16 * capw * 8 * 7;  // a cross product table for up to ~10 * capw candidate keys
     if ((e = cudaMalloc(&s->work, 2 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s->work, 0, 2 * sizeof(int), st)) != cudaSuccess) return e;
