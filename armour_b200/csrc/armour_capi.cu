@@ -16,10 +16,13 @@
 #include "bezier.cuh"
 #include "device_constants.cuh"
 // The reach-set kernel is compiled twice (see k1_pz.cuh):
-//   k1lat: one unit per CTA, 256 threads, 2 CTAs per SM  -> lowest latency for one planning problem
-//   k1thr: 12 units per CTA in lock step, 64 threads each -> highest throughput for batches (instruction fetch,
-//          the resource that bounds this kernel, is shared by the 12 units; round-1 sweep on 1 024 problems:
-//          8 groups 535 us per problem, 10: 519, 12: 503, 14: 497, pool share 3/8..5/8 within 2 %)
+//   k1lat: one unit per CTA built by 3 groups of 128 threads (task list, MG mode) -> lowest latency for one planning problem
+//   k1thr: 2 CTAs per SM of 8 units each in lock step, 64 threads per unit -> highest throughput for batches.  Instruction
+//          fetch bounds this kernel: the units of a CTA run the same operation at the same time (without the lock step the
+//          instruction cache thrashes: 2.3x slower), and two lock-step domains per SM overlap each other's barriers.  A unit
+//          keeps only its control block in shared memory; arena, scratch and joint reachable set live in its global scratch,
+//          behind the L1 cache that the unclaimed shared memory becomes (profiles/r3_k1thr_experiments.md: 445 -> 360 us
+//          per problem; round-1 sweep with one CTA per SM: 8 groups 535 us, 10: 519, 12: 503, 14: 497)
 #ifdef K1_PROFILE
 constexpr int K1_PROF_SITES = 512;
 __device__ long long g_k1prof[128 * K1_PROF_SITES * 2];
