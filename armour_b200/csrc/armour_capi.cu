@@ -861,6 +861,13 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
     k_solver_start<<<nprob, SOLVER_THREADS, 0, st>>>(B, S, ctx->d_g);
     CU(cudaGetLastError());
     ctx->launches += 2 + (B.O > 0);
+    // the list of running problems is rebuilt every `compact_every` iterations (a host synchronisation each time; between two
+    // rebuilds the solver kernels skip finished problems themselves, only the constraint kernel still evaluates them)
+    static const int compact_every = [] {
+        const char* v = std::getenv("ARMOUR_SOLVER_COMPACT_EVERY");  // developer knob
+        const int n = v ? std::atoi(v) : 0;
+        return n >= 1 ? n : 4;
+    }();
     Batch Ba = B;      // launches over the problems still running (all of them at first)
     int nactive = nprob;
     for (int it = 0; it < opt.max_iter && nactive > 0; it++) {
@@ -871,7 +878,7 @@ int armour_batch_solve_device(armour_ctx* ctx, int nprob, const double* d_q_des,
         k_solver_accept<<<nactive, SOLVER_THREADS, 0, st>>>(Ba, S, d_gt, it == opt.max_iter - 1 ? 1 : 0);
         CU(cudaGetLastError());  // (covers k_solver_step too: launch errors are sticky until read)
         ctx->launches += 4 + 2 * (B.O > 0);
-        if ((it & 3) == 3 && it + 1 < opt.max_iter) {  // every fourth iteration: who is still running?
+        if ((it + 1) % compact_every == 0 && it + 1 < opt.max_iter) {  // every fourth iteration: who is still running?
             CU(cudaMemsetAsync(d_running, 0, sizeof(int), st));
             k_solver_compact<<<(nprob + 255) / 256, 256, 0, st>>>(S, nprob, d_running, d_list);
             CU(cudaMemcpyAsync(&nactive, d_running, sizeof(int), cudaMemcpyDeviceToHost, st));
