@@ -69,6 +69,9 @@ constexpr bool MG = K1_MG != 0;
 #endif
 constexpr int CTAS_PER_SM = K1_CTAS;  // resident CTAs per SM (shared memory is split evenly)
 constexpr int NW = NT / 32;  // warps per CTA
+static_assert(NT % 32 == 0 && NT >= 32, "a unit is built by whole warps");
+static_assert(GROUPS <= 15, "one named barrier per group besides barrier 0 (16 per CTA)");
+static_assert(GROUPS == 1 || NT >= 64, "several groups of ONE warp per CTA: not finished (profiles/r3_k1thr_experiments.md)");
 constexpr int RED_STRIDE = 12;
 constexpr int MASK_WORDS = 256;  // a merge operation handles up to 32 * MASK_WORDS candidate monomials
 
